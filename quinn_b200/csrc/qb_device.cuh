@@ -1,0 +1,616 @@
+// Device code of the fused MLP log-posterior / gradient evaluation (kernels 1 and 2) that the
+// chain-step, predictive and VI kernels all call.  sm_100a, CUDA cores (FP32 / FP64 FMA pipes).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "qb_plan.h"
+
+// --------------------------------------------------------------------------------------------
+// per-dtype tile constants and 128-bit vector access
+// --------------------------------------------------------------------------------------------
+template <typename T> struct VT;
+template <> struct VT<float>  { static constexpr int TP = 8, TU = 8, LDPAD = 4, PV = 4; };
+template <> struct VT<double> { static constexpr int TP = 4, TU = 4, LDPAD = 2, PV = 2; };
+
+template <int N> __device__ __forceinline__ void ldv(float* d, const float* s) {
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) {
+        float4 v = *reinterpret_cast<const float4*>(s + 4 * q);
+        d[4 * q] = v.x; d[4 * q + 1] = v.y; d[4 * q + 2] = v.z; d[4 * q + 3] = v.w;
+    }
+}
+template <int N> __device__ __forceinline__ void ldv(double* d, const double* s) {
+#pragma unroll
+    for (int q = 0; q < N / 2; ++q) {
+        double2 v = *reinterpret_cast<const double2*>(s + 2 * q);
+        d[2 * q] = v.x; d[2 * q + 1] = v.y;
+    }
+}
+template <int N> __device__ __forceinline__ void stv(float* d, const float* s) {
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q)
+        *reinterpret_cast<float4*>(d + 4 * q) = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
+}
+template <int N> __device__ __forceinline__ void stv(double* d, const double* s) {
+#pragma unroll
+    for (int q = 0; q < N / 2; ++q)
+        *reinterpret_cast<double2*>(d + 2 * q) = make_double2(s[2 * q], s[2 * q + 1]);
+}
+
+// --------------------------------------------------------------------------------------------
+// activations
+// --------------------------------------------------------------------------------------------
+// fp32 tanh = 1 - 2/(exp(2z)+1) with one MUFU.EX2 and one MUFU.RCP (abs. error ~2e-7; MUFU.TANH's
+// 2^-11 relative error does not keep the 1e-4 log-posterior tolerance).
+__device__ __forceinline__ float qb_tanh(float z) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * 2.8853900817779268f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
+}
+__device__ __forceinline__ double qb_tanh(double z) { return tanh(z); }
+__device__ __forceinline__ float qb_exp(float z) { return expf(z); }
+__device__ __forceinline__ double qb_exp(double z) { return exp(z); }
+
+template <int ACT, typename T> __device__ __forceinline__ T qb_act(T z) {
+    if (ACT == QB_ACT_TANH) return qb_tanh(z);
+    if (ACT == QB_ACT_RELU) return z > T(0) ? z : T(0);
+    return z;
+}
+// derivative of the activation expressed through its VALUE a = act(z)
+template <typename T> __device__ __forceinline__ T qb_dact(int act, T a) {
+    if (act == QB_ACT_TANH) return T(1) - a * a;
+    if (act == QB_ACT_RELU) return a > T(0) ? T(1) : T(0);
+    return T(1);
+}
+
+// --------------------------------------------------------------------------------------------
+// deterministic block reduction (fixed order: lane tree, then warps in order)
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ double qb_block_sum(double v, double* red /* >= 33 doubles */) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        const int nw = (blockDim.x + 31) >> 5;
+        for (int w = 0; w < nw; ++w) s += red[w];
+        red[32] = s;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+// --------------------------------------------------------------------------------------------
+// weight staging: flat theta (global) -> Wt / Wr / bias (shared), once per parameter vector
+// --------------------------------------------------------------------------------------------
+template <typename T>
+__device__ void qb_stage_weights(const QbPlan& P, T* sW, const T* theta) {
+    constexpr int TU = VT<T>::TU;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int l = 0; l < P.n_layers; ++l) {
+        const QbLayerPlan& L = P.L[l];
+        // skip layers that alias an earlier layer's staged copy (shared weights, rnet.py:344-347)
+        bool dup = false;
+        for (int m = 0; m < l; ++m) dup = dup || (P.L[m].wt_off == L.wt_off);
+        if (dup) continue;
+        const int UG = L.n_out_pad / TU;
+        const bool gemm = (L.mode == QB_MODE_GEMM);
+        T* Wt = sW + L.wt_off;
+        const int nwt = L.n_in * L.n_out_pad;
+        for (int idx = tid; idx < nwt; idx += nt) {
+            const int i = idx / L.n_out_pad, col = idx - i * L.n_out_pad;
+            const int j = gemm ? (col / TU) + UG * (col % TU) : col;
+            Wt[idx] = (j < L.n_out) ? theta[L.w_off + j * L.n_in + i] : T(0);
+        }
+        T* bs = sW + L.bias_off;
+        for (int col = tid; col < L.n_out_pad; col += nt) {
+            const int j = gemm ? (col / TU) + UG * (col % TU) : col;
+            bs[col] = (j < L.n_out && L.b_off >= 0) ? theta[L.b_off + j] : T(0);
+        }
+        if (L.wr_off >= 0) {
+            const int UGI = L.n_in_pad / TU;
+            T* Wr = sW + L.wr_off;
+            const int nwr = L.n_out * L.n_in_pad;
+            for (int idx = tid; idx < nwr; idx += nt) {
+                const int j = idx / L.n_in_pad, col = idx - j * L.n_in_pad;
+                const int i = (col / TU) + UGI * (col % TU);
+                Wr[idx] = (i < L.n_in) ? theta[L.w_off + j * L.n_in + i] : T(0);
+            }
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// forward layers
+// --------------------------------------------------------------------------------------------
+// GEMM mode: each thread owns a TU x TP register tile (units x points); per input unit i it issues one
+// 128-bit broadcast load of TU weights and TP/4 128-bit loads of activations for TU*TP FMAs.
+template <typename T, int ACT>
+__device__ __forceinline__ void qb_fwd_gemm(const QbLayerPlan& L, const T* sW, const T* Ain, T* Aout,
+                                            int lda, int TM, bool sync_before_store) {
+    constexpr int TP = VT<T>::TP, TU = VT<T>::TU;
+    const int UG = L.n_out_pad / TU, PG = TM / TP, items = UG * PG;
+    const T* Wt = sW + L.wt_off;
+    const T* bias = sW + L.bias_off;
+    const int n_in = L.n_in, ldw = L.n_out_pad;
+    const bool res = L.has_res != 0;
+    const T step = T(L.res_step);
+    for (int base = 0; base < items; base += blockDim.x) {
+        const int item = base + threadIdx.x;
+        const bool valid = item < items;
+        const int pg = item / UG, ug = item - pg * UG;
+        T acc[TU][TP];
+        if (valid) {
+#pragma unroll
+            for (int u = 0; u < TU; ++u)
+#pragma unroll
+                for (int p = 0; p < TP; ++p) acc[u][p] = T(0);
+            const T* ap = Ain + pg * TP;
+            const T* wp = Wt + ug * TU;
+#pragma unroll 2
+            for (int i = 0; i < n_in; ++i) {
+                T a[TP], w[TU];
+                ldv<TP>(a, ap + i * lda);
+                ldv<TU>(w, wp + i * ldw);
+#pragma unroll
+                for (int u = 0; u < TU; ++u)
+#pragma unroll
+                    for (int p = 0; p < TP; ++p) acc[u][p] = fma(w[u], a[p], acc[u][p]);
+            }
+            T b[TU];
+            ldv<TU>(b, bias + ug * TU);
+#pragma unroll
+            for (int u = 0; u < TU; ++u)
+#pragma unroll
+                for (int p = 0; p < TP; ++p) acc[u][p] = qb_act<ACT>(acc[u][p] + b[u]);
+            if (res) {
+#pragma unroll
+                for (int u = 0; u < TU; ++u) {
+                    T r[TP];
+                    ldv<TP>(r, Ain + (ug + UG * u) * lda + pg * TP);
+#pragma unroll
+                    for (int p = 0; p < TP; ++p) acc[u][p] = fma(step, acc[u][p], r[p]);
+                }
+            }
+        }
+        if (sync_before_store) __syncthreads();
+        if (valid) {
+#pragma unroll
+            for (int u = 0; u < TU; ++u) stv<TP>(Aout + (ug + UG * u) * lda + pg * TP, acc[u]);
+        }
+    }
+}
+
+// DOT mode (narrow outputs): one thread per point column, NJ outputs at a time.  A thread only ever
+// touches its own column, so this is in-place safe whenever n_out <= NJ.
+template <typename T, int NJ, int ACT>
+__device__ __forceinline__ void qb_fwd_dot(const QbLayerPlan& L, const T* sW, const T* Ain, T* Aout,
+                                           int lda, int TM) {
+    const T* Wt = sW + L.wt_off;
+    const T* bias = sW + L.bias_off;
+    const int n_in = L.n_in, ldw = L.n_out_pad, n_out = L.n_out;
+    const bool res = L.has_res != 0;
+    const T step = T(L.res_step);
+    for (int p = threadIdx.x; p < TM; p += blockDim.x) {
+        for (int j0 = 0; j0 < n_out; j0 += NJ) {
+            T acc[NJ];
+#pragma unroll
+            for (int q = 0; q < NJ; ++q) acc[q] = bias[j0 + q];
+#pragma unroll 4
+            for (int i = 0; i < n_in; ++i) {
+                const T a = Ain[i * lda + p];
+#pragma unroll
+                for (int q = 0; q < NJ; ++q) acc[q] = fma(Wt[i * ldw + j0 + q], a, acc[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < NJ; ++q) {
+                T v = qb_act<ACT>(acc[q]);
+                if (res && j0 + q < n_out) v = fma(step, v, Ain[(j0 + q) * lda + p]);
+                acc[q] = v;
+            }
+#pragma unroll
+            for (int q = 0; q < NJ; ++q)
+                if (j0 + q < n_out) Aout[(j0 + q) * lda + p] = acc[q];
+        }
+    }
+}
+
+template <typename T>
+__device__ void qb_layer_forward(const QbLayerPlan& L, const T* sW, const T* Ain, T* Aout, int lda, int TM,
+                                 bool inplace) {
+    if (L.mode == QB_MODE_GEMM) {
+        switch (L.act) {
+            case QB_ACT_TANH: qb_fwd_gemm<T, QB_ACT_TANH>(L, sW, Ain, Aout, lda, TM, inplace); break;
+            case QB_ACT_RELU: qb_fwd_gemm<T, QB_ACT_RELU>(L, sW, Ain, Aout, lda, TM, inplace); break;
+            default: qb_fwd_gemm<T, QB_ACT_IDENTITY>(L, sW, Ain, Aout, lda, TM, inplace); break;
+        }
+    } else {
+#define QB_DOT(NJ)                                                                             \
+    switch (L.act) {                                                                           \
+        case QB_ACT_TANH: qb_fwd_dot<T, NJ, QB_ACT_TANH>(L, sW, Ain, Aout, lda, TM); break;     \
+        case QB_ACT_RELU: qb_fwd_dot<T, NJ, QB_ACT_RELU>(L, sW, Ain, Aout, lda, TM); break;     \
+        default: qb_fwd_dot<T, NJ, QB_ACT_IDENTITY>(L, sW, Ain, Aout, lda, TM); break;          \
+    }
+        if (L.nj == 1) { QB_DOT(1) } else if (L.nj == 2) { QB_DOT(2) } else { QB_DOT(4) }
+#undef QB_DOT
+    }
+    __syncthreads();
+}
+
+// x[p0 .. p0+TM) -> rows 0..d-1 of A (zero for points beyond pend)
+template <typename T>
+__device__ __forceinline__ void qb_load_x_tile(const T* __restrict__ x, int d, int64_t p0, int64_t pend,
+                                               T* A, int lda, int TM) {
+    const int n = TM * d;
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        const int p = idx / d, i = idx - p * d;
+        const int64_t gp = p0 + p;
+        A[i * lda + p] = (gp < pend) ? __ldg(x + gp * d + i) : T(0);
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// kernel 1 body: sum of squared residuals of one parameter vector over points [n0, n1)
+// --------------------------------------------------------------------------------------------
+struct QbSmem {
+    double* red;     // 40 doubles
+    void* w;         // staged weights
+    void* act;       // activation rows
+};
+template <typename T> __device__ __forceinline__ QbSmem qb_carve(const QbPlan& P, unsigned char* raw) {
+    QbSmem s;
+    s.red = reinterpret_cast<double*>(raw);
+    s.w = raw + 40 * sizeof(double);
+    s.act = reinterpret_cast<T*>(s.w) + P.w_elems;
+    return s;
+}
+
+// If out_tile != nullptr the network outputs of every tile are also written to
+// out_tile[(p - n0) * out_dim + j] (used by the predictive kernel; y may then be nullptr).
+template <typename T>
+__device__ double qb_eval_value(const QbPlan& P, const QbSmem& S, const T* theta, const T* __restrict__ x,
+                                const T* __restrict__ y, int64_t n0, int64_t n1, bool restage,
+                                T* out_glob /* nullable: [n1-n0, o] */) {
+    T* sW = reinterpret_cast<T*>(S.w);
+    T* A0 = reinterpret_cast<T*>(S.act);
+    const int lda = P.lda, TM = P.TM, o = P.out_dim;
+    T* A1 = P.inplace ? A0 : A0 + (size_t)P.buf_rows * lda;
+    __syncthreads();
+    if (restage) {
+        qb_stage_weights<T>(P, sW, theta);
+        __syncthreads();
+    }
+    T ssq = T(0);
+    for (int64_t p0 = n0; p0 < n1; p0 += TM) {
+        qb_load_x_tile<T>(x, P.in_dim, p0, n1, A0, lda, TM);
+        __syncthreads();
+        T* cur = A0;
+        T* oth = A1;
+        for (int l = 0; l < P.n_layers; ++l) {
+            qb_layer_forward<T>(P.L[l], sW, cur, oth, lda, TM, P.inplace != 0);
+            T* t = cur; cur = oth; oth = t;
+        }
+        // residuals (losses.py:197: sum over all points and outputs)
+        const int n = TM * o;
+        for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+            const int j = idx / TM, p = idx - j * TM;
+            const int64_t gp = p0 + p;
+            if (gp < n1) {
+                T out = cur[j * lda + p];
+                if (P.final_exp) out = qb_exp(out);
+                if (out_glob) out_glob[(gp - n0) * o + j] = out;
+                if (y) {
+                    const T r = __ldg(y + gp * o + j) - out;
+                    ssq = fma(r, r, ssq);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    return qb_block_sum((double)ssq, S.red);
+}
+
+// --------------------------------------------------------------------------------------------
+// kernel 2 body: value + gradient (reverse mode) of the data term
+// --------------------------------------------------------------------------------------------
+// write delta_z of layer Lm for (unit j, TP consecutive points) given delta_a (gradient wrt the layer output)
+template <typename T>
+__device__ __forceinline__ void qb_finish_delta_vec(const QbLayerPlan& Lm, T* R, T* D, int lda, int j, int pcol,
+                                                    T (&da)[VT<T>::TP]) {
+    constexpr int TP = VT<T>::TP;
+    T aout[TP], dz[TP];
+    T* po = R + (size_t)(Lm.row_out + j) * lda + pcol;
+    ldv<TP>(aout, po);
+    if (Lm.has_res) {
+        T ain[TP];
+        ldv<TP>(ain, R + (size_t)(Lm.row_in + j) * lda + pcol);
+        const T step = T(Lm.res_step), inv = T(1) / step;
+#pragma unroll
+        for (int p = 0; p < TP; ++p) {
+            const T t = (aout[p] - ain[p]) * inv;
+            dz[p] = step * da[p] * qb_dact<T>(Lm.act, t);
+        }
+        stv<TP>(D + (size_t)j * lda + pcol, da);
+    } else {
+#pragma unroll
+        for (int p = 0; p < TP; ++p) dz[p] = da[p] * qb_dact<T>(Lm.act, aout[p]);
+    }
+    stv<TP>(po, dz);
+}
+template <typename T>
+__device__ __forceinline__ void qb_finish_delta(const QbLayerPlan& Lm, T* R, T* D, int lda, int j, int p, T da) {
+    T* po = R + (size_t)(Lm.row_out + j) * lda + p;
+    const T aout = *po;
+    T dz;
+    if (Lm.has_res) {
+        const T ain = R[(size_t)(Lm.row_in + j) * lda + p];
+        const T step = T(Lm.res_step);
+        const T t = (aout - ain) / step;
+        dz = step * da * qb_dact<T>(Lm.act, t);
+        D[(size_t)j * lda + p] = da;
+    } else {
+        dz = da * qb_dact<T>(Lm.act, aout);
+    }
+    *po = dz;
+}
+
+// dW_l += delta_z_l (rows) x a_in (rows) over the tile's points; db_l += row sums of delta_z_l.
+// Each thread owns a 4x4 patch of dW (rows interleaved by JG / IG so that the 8 lanes of a quarter
+// warp hit distinct banks) and, for narrow layers, one of `dw_chunks` slices of the points; slices are
+// combined with a fixed-order xor-shuffle tree, so the result is deterministic.
+template <typename T>
+__device__ void qb_dw_accumulate(const QbLayerPlan& L, const T* R, int lda, int TM, T* g) {
+    constexpr int PV = VT<T>::PV;
+    const int JG = (L.n_out + 3) >> 2, IG = (L.n_in + 3) >> 2;
+    const int C = L.dw_chunks, patches = JG * IG, items = patches * C;
+    const int clen = TM / C;
+    const T* Rz = R + (size_t)L.row_out * lda;
+    const T* Ra = R + (size_t)L.row_in * lda;
+    for (int base = 0; base < items; base += blockDim.x) {
+        const int item = base + threadIdx.x;
+        const bool valid = item < items;
+        const int it = valid ? item : 0;
+        const int patch = it / C, chunk = it - patch * C;
+        const int jg = patch / IG, ig = patch - jg * IG;
+        T acc[4][4], bacc[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            bacc[a] = T(0);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = T(0);
+        }
+        const T* zr = Rz + (size_t)jg * lda + chunk * clen;
+        const T* ar = Ra + (size_t)ig * lda + chunk * clen;
+        const size_t zs = (size_t)JG * lda, as = (size_t)IG * lda;
+        for (int p = 0; p < clen; p += PV) {
+            T dz[4][PV], av[4][PV];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                ldv<PV>(dz[c], zr + c * zs + p);
+                ldv<PV>(av[c], ar + c * as + p);
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+#pragma unroll
+                for (int q = 0; q < PV; ++q) bacc[a] += dz[a][q];
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+#pragma unroll
+                    for (int q = 0; q < PV; ++q) acc[a][b] = fma(dz[a][q], av[b][q], acc[a][b]);
+            }
+        }
+        for (int off = C >> 1; off > 0; off >>= 1) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                bacc[a] += __shfl_xor_sync(0xffffffffu, bacc[a], off);
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] += __shfl_xor_sync(0xffffffffu, acc[a][b], off);
+            }
+        }
+        if (valid && chunk == 0) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int j = jg + JG * a;
+                if (j < L.n_out) {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int i = ig + IG * b;
+                        if (i < L.n_in) g[L.w_off + j * L.n_in + i] += acc[a][b];
+                    }
+                    if (ig == 0 && L.b_off >= 0) g[L.b_off + j] += bacc[a];
+                }
+            }
+        }
+    }
+}
+
+// delta_a of layer l's INPUT (= output of layer l-1): W_l^T delta_z_l (+ pass-through if layer l is
+// residual), immediately converted to delta_z of layer l-1 and stored in place over that layer's
+// activations.
+template <typename T>
+__device__ void qb_bwd_gemm(const QbLayerPlan& L, const QbLayerPlan& Lm, const T* sW, T* R, T* D, int lda, int TM) {
+    constexpr int TP = VT<T>::TP, TU = VT<T>::TU;
+    const int UGI = L.n_in_pad / TU, PG = TM / TP, items = UGI * PG;
+    const T* Wr = sW + L.wr_off;
+    const T* Rz = R + (size_t)L.row_out * lda;
+    const int n_out = L.n_out, ldw = L.n_in_pad;
+    for (int base = 0; base < items; base += blockDim.x) {
+        const int item = base + threadIdx.x;
+        if (item >= items) continue;
+        const int pg = item / UGI, ig = item - pg * UGI;
+        T acc[TU][TP];
+#pragma unroll
+        for (int u = 0; u < TU; ++u)
+#pragma unroll
+            for (int p = 0; p < TP; ++p) acc[u][p] = T(0);
+        const T* zp = Rz + pg * TP;
+        const T* wp = Wr + ig * TU;
+#pragma unroll 2
+        for (int j = 0; j < n_out; ++j) {
+            T d[TP], w[TU];
+            ldv<TP>(d, zp + (size_t)j * lda);
+            ldv<TU>(w, wp + j * ldw);
+#pragma unroll
+            for (int u = 0; u < TU; ++u)
+#pragma unroll
+                for (int p = 0; p < TP; ++p) acc[u][p] = fma(w[u], d[p], acc[u][p]);
+        }
+#pragma unroll
+        for (int u = 0; u < TU; ++u) {
+            const int i = ig + UGI * u;
+            if (i < L.n_in) {
+                if (L.has_res) {
+                    T pass[TP];
+                    ldv<TP>(pass, D + (size_t)i * lda + pg * TP);
+#pragma unroll
+                    for (int p = 0; p < TP; ++p) acc[u][p] += pass[p];
+                }
+                qb_finish_delta_vec<T>(Lm, R, D, lda, i, pg * TP, acc[u]);
+            }
+        }
+    }
+}
+
+// value + gradient of the data term for one parameter vector over points [n0, n1):
+// returns sum of squared residuals; g[0..P) receives d/dtheta of  -0.5*ssq/sigma^2  (i.e. of lp's data term).
+// g must be addressable by this block only (one row per (chain, split)).
+template <typename T>
+__device__ double qb_eval_value_grad(const QbPlan& P, const QbSmem& S, const T* theta, const T* __restrict__ x,
+                                     const T* __restrict__ y, int64_t n0, int64_t n1, double inv_sigma2, T* g) {
+    T* sW = reinterpret_cast<T*>(S.w);
+    T* R = reinterpret_cast<T*>(S.act);
+    const int lda = P.lda, TM = P.TM, o = P.out_dim, nl = P.n_layers;
+    T* D = P.d_row >= 0 ? R + (size_t)P.d_row * lda : nullptr;
+    __syncthreads();
+    qb_stage_weights<T>(P, sW, theta);
+    for (int idx = threadIdx.x; idx < P.n_params; idx += blockDim.x) g[idx] = T(0);
+    __syncthreads();
+    T ssq = T(0);
+    const T is2 = T(inv_sigma2);
+    const QbLayerPlan& Ltop = P.L[nl - 1];
+    for (int64_t p0 = n0; p0 < n1; p0 += TM) {
+        qb_load_x_tile<T>(x, P.in_dim, p0, n1, R, lda, TM);
+        __syncthreads();
+        for (int l = 0; l < nl; ++l) {
+            const QbLayerPlan& L = P.L[l];
+            qb_layer_forward<T>(L, sW, R + (size_t)L.row_in * lda, R + (size_t)L.row_out * lda, lda, TM, false);
+        }
+        // residuals -> delta at the top
+        const int n = TM * o;
+        for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+            const int j = idx / TM, p = idx - j * TM;
+            const int64_t gp = p0 + p;
+            T da = T(0);
+            if (gp < n1) {
+                T out = R[(size_t)(Ltop.row_out + j) * lda + p];
+                if (P.final_exp) out = qb_exp(out);
+                const T r = __ldg(y + gp * o + j) - out;
+                ssq = fma(r, r, ssq);
+                da = r * is2;
+                if (P.final_exp) da *= out;
+            }
+            qb_finish_delta<T>(Ltop, R, D, lda, j, p, da);
+        }
+        __syncthreads();
+        for (int l = nl - 1; l >= 0; --l) {
+            const QbLayerPlan& L = P.L[l];
+            qb_dw_accumulate<T>(L, R, lda, TM, g);
+            __syncthreads();
+            if (l > 0) {
+                qb_bwd_gemm<T>(L, P.L[l - 1], sW, R, D, lda, TM);
+                __syncthreads();
+            }
+        }
+    }
+    return qb_block_sum((double)ssq, S.red);
+}
+
+// --------------------------------------------------------------------------------------------
+// likelihood / prior scalars
+// --------------------------------------------------------------------------------------------
+struct QbLikDev {
+    double sigma, inv_sigma2, prior_sigma, prior_scale;
+    const void* anchor;
+    int anchor_per_chain;
+    int has_prior;
+};
+
+// sum_p (theta_p - anchor_p)^2, block-uniform
+template <typename T>
+__device__ double qb_prior_ss(const QbLikDev& lk, const T* theta, int64_t k, int P, double* red) {
+    const T* a = reinterpret_cast<const T*>(lk.anchor);
+    if (a && lk.anchor_per_chain) a += k * (int64_t)P;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const double d = (double)theta[i] - (a ? (double)a[i] : 0.0);
+        s += d * d;
+    }
+    return qb_block_sum(s, red);
+}
+
+__device__ __forceinline__ double qb_lp_from(const QbLikDev& lk, double ssq, int64_t N, double prior_ss, int P) {
+    const double LOG_2PI = 1.8378770664093454835606594728112;
+    double nlp = 0.5 * ssq * lk.inv_sigma2 + 0.5 * (double)N * LOG_2PI + (double)N * log(lk.sigma);
+    if (lk.has_prior) {
+        const double sp2 = lk.prior_sigma * lk.prior_sigma;
+        nlp += lk.prior_scale * (prior_ss / (2.0 * sp2) + 0.5 * (double)P * log(2.0 * 3.14159265358979323846 * sp2));
+    }
+    return -nlp;
+}
+
+// g += d/dtheta of the prior term of lp
+template <typename T>
+__device__ void qb_prior_grad_add(const QbLikDev& lk, const T* theta, int64_t k, int P, T* g) {
+    if (!lk.has_prior) return;
+    const T* a = reinterpret_cast<const T*>(lk.anchor);
+    if (a && lk.anchor_per_chain) a += k * (int64_t)P;
+    const double c = lk.prior_scale / (lk.prior_sigma * lk.prior_sigma);
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const double d = (double)theta[i] - (a ? (double)a[i] : 0.0);
+        g[i] = (T)((double)g[i] - c * d);
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based RNG + Box-Muller
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 qb_philox(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+enum { QB_STREAM_INCR = 0, QB_STREAM_Z0 = 1, QB_STREAM_UNIF = 2, QB_STREAM_VI = 3 };
+
+__device__ __forceinline__ uint4 qb_rand4(uint64_t seed, int64_t chain, int64_t step, int stream, uint32_t idx4) {
+    uint2 key = make_uint2((uint32_t)seed ^ (uint32_t)chain, (uint32_t)(seed >> 32) ^ (uint32_t)((uint64_t)chain >> 32) ^ 0x5851F42Du);
+    uint4 ctr = make_uint4(idx4, (uint32_t)step, (uint32_t)((uint64_t)step >> 32), (uint32_t)stream);
+    return qb_philox(ctr, key);
+}
+__device__ __forceinline__ double qb_u01(uint32_t a) { return ((double)a + 0.5) * 2.3283064365386963e-10; }
+__device__ __forceinline__ void qb_normal4(uint4 r, double (&z)[4]) {
+    const double r1 = sqrt(-2.0 * log(qb_u01(r.x))), r2 = sqrt(-2.0 * log(qb_u01(r.z)));
+    double s1, c1, s2, c2;
+    sincospi(2.0 * qb_u01(r.y), &s1, &c1);
+    sincospi(2.0 * qb_u01(r.w), &s2, &c2);
+    z[0] = r1 * c1; z[1] = r1 * s1; z[2] = r2 * c2; z[3] = r2 * s2;
+}
+__device__ __forceinline__ void qb_normal4(uint4 r, float (&z)[4]) {
+    const float u1 = ((float)(r.x >> 8) + 0.5f) * 5.9604644775390625e-8f;
+    const float u2 = ((float)(r.z >> 8) + 0.5f) * 5.9604644775390625e-8f;
+    const float r1 = sqrtf(-2.0f * __logf(u1)), r2 = sqrtf(-2.0f * __logf(u2));
+    float s1, c1, s2, c2;
+    sincospif(2.0f * ((float)(r.y >> 8) + 0.5f) * 5.9604644775390625e-8f, &s1, &c1);
+    sincospif(2.0f * ((float)(r.w >> 8) + 0.5f) * 5.9604644775390625e-8f, &s2, &c2);
+    z[0] = r1 * c1; z[1] = r1 * s1; z[2] = r2 * c2; z[3] = r2 * s2;
+}

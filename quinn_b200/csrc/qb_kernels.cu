@@ -1,0 +1,977 @@
+// quinn_b200: kernels + C ABI (include/quinn_b200.h).  Build: see quinn_b200/build.py
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 --shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <atomic>
+
+#include "quinn_b200.h"
+#include "qb_plan.h"
+#include "qb_device.cuh"
+
+// =================================================================================================
+// error plumbing
+// =================================================================================================
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+static int qb_fail(const char* fmt, const char* a = "", long long b = 0) {
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return -1;
+}
+#define QB_CUDA(call)                                                                                    \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            snprintf(g_err, sizeof(g_err), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return -2;                                                                                   \
+        }                                                                                                \
+    } while (0)
+
+extern "C" const char* qb_last_error(void) { return g_err; }
+extern "C" int qb_version(void) { return 100; }
+extern "C" int64_t qb_launch_count(void) { return (int64_t)g_launches.load(); }
+
+// =================================================================================================
+// launch planning (host)
+// =================================================================================================
+static inline int rup(int v, int m) { return (v + m - 1) / m * m; }
+static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
+static int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+static const int QB_SMEM_MAX = 227 * 1024;
+static const int QB_SMEM_TWO = 113 * 1024;   // two blocks per SM
+static const int QB_NUM_SMS = 148;
+
+static int validate_net(const qb_net_t* net) {
+    if (!net) return qb_fail("net is NULL");
+    if (net->n_layers < 1 || net->n_layers > QB_MAX_LAYERS) return qb_fail("n_layers out of range%s (%lld)", "", net->n_layers);
+    int width = net->in_dim;
+    for (int l = 0; l < net->n_layers; ++l) {
+        const qb_layer_t& L = net->layers[l];
+        if (L.n_in != width) return qb_fail("layer %s%lld: n_in does not match the previous width", "", l);
+        if (L.n_in < 1 || L.n_out < 1) return qb_fail("layer %s%lld: empty layer", "", l);
+        if (L.act < 0 || L.act > 2) return qb_fail("layer %s%lld: unknown activation", "", l);
+        if (L.res_step != 0.0 && L.n_in != L.n_out) return qb_fail("layer %s%lld: residual layer must be square", "", l);
+        if (L.w_off < 0 || L.w_off + L.n_in * L.n_out > net->n_params) return qb_fail("layer %s%lld: weight offset out of range", "", l);
+        if (L.b_off >= 0 && L.b_off + L.n_out > net->n_params) return qb_fail("layer %s%lld: bias offset out of range", "", l);
+        width = L.n_out;
+    }
+    if (width != net->out_dim) return qb_fail("out_dim does not match the last layer");
+    return 0;
+}
+
+// Fill `P` for tile size TM; returns smem bytes (or -1 if a constraint fails).
+static long long plan_for_tm(const qb_net_t* net, int dtype, bool want_grad, int TM, QbPlan* P) {
+    const int elem = dtype == QB_F64 ? 8 : 4;
+    const int TU = dtype == QB_F64 ? 4 : 8, TP = TU, LDPAD = dtype == QB_F64 ? 2 : 4, PV = dtype == QB_F64 ? 2 : 4;
+    memset(P, 0, sizeof(*P));
+    P->n_layers = net->n_layers; P->in_dim = net->in_dim; P->out_dim = net->out_dim;
+    P->n_params = net->n_params; P->final_exp = net->final_exp;
+    P->TM = TM; P->lda = TM + LDPAD; P->want_grad = want_grad ? 1 : 0; P->elem_size = elem;
+    const int PG = TM / TP;
+    int max_items = 0, woff = 0;
+    bool any_gemm = false;
+    for (int l = 0; l < net->n_layers; ++l) {
+        const qb_layer_t& S = net->layers[l];
+        QbLayerPlan& L = P->L[l];
+        L.n_in = S.n_in; L.n_out = S.n_out; L.n_in_pad = rup(S.n_in, TU); L.n_out_pad = rup(S.n_out, TU);
+        L.w_off = S.w_off; L.b_off = S.b_off; L.act = S.act; L.res_step = S.res_step; L.has_res = S.res_step != 0.0;
+        if (L.has_res) P->has_res = 1;
+        const int UG = L.n_out_pad / TU;
+        L.nj = S.n_out == 1 ? 1 : (S.n_out == 2 ? 2 : 4);
+        const long long cost_g = cdiv((long long)UG * PG, 256) * S.n_in * (TP * TU + 4);
+        const long long cost_d = cdiv(TM, 256) * cdiv(S.n_out, L.nj) * S.n_in * (2 * L.nj + 1);
+        L.mode = (cost_d < cost_g) ? QB_MODE_DOT : QB_MODE_GEMM;
+        if (L.mode == QB_MODE_GEMM) { any_gemm = true; max_items = std::max(max_items, UG * PG); }
+        if (want_grad && l > 0) max_items = std::max(max_items, (L.n_in_pad / TU) * PG), any_gemm = true;
+        // shared weights: reuse an identical earlier staging
+        int dup = -1;
+        for (int m = 0; m < l; ++m) {
+            const qb_layer_t& Sm = net->layers[m];
+            if (Sm.w_off == S.w_off && Sm.b_off == S.b_off && Sm.n_in == S.n_in && Sm.n_out == S.n_out &&
+                P->L[m].mode == L.mode && (P->L[m].wr_off >= 0) == (want_grad && l > 0)) { dup = m; break; }
+        }
+        if (dup >= 0) {
+            L.wt_off = P->L[dup].wt_off; L.bias_off = P->L[dup].bias_off; L.wr_off = P->L[dup].wr_off;
+        } else {
+            L.wt_off = woff; woff += rup(L.n_in * L.n_out_pad, 4);
+            L.bias_off = woff; woff += rup(L.n_out_pad, 4);
+            L.wr_off = -1;
+            if (want_grad && l > 0) { L.wr_off = woff; woff += rup(L.n_out * L.n_in_pad, 4); }
+        }
+    }
+    P->w_elems = woff;
+    int nthreads = any_gemm ? max_items : TM;
+    nthreads = std::min(256, std::max(64, rup(nthreads, 32)));
+    nthreads = env_int("QB_THREADS", nthreads);
+    P->nthreads = nthreads;
+    // value kernel: in place when every GEMM layer is a single pass and DOT layers are single-chunk
+    int inplace = 1, buf_rows = rup(net->in_dim, TU);
+    for (int l = 0; l < net->n_layers; ++l) {
+        QbLayerPlan& L = P->L[l];
+        buf_rows = std::max(buf_rows, std::max(L.n_in_pad, L.n_out_pad));
+        if (L.mode == QB_MODE_GEMM && (L.n_out_pad / TU) * PG > nthreads) inplace = 0;
+        if (L.mode == QB_MODE_DOT && L.n_out > L.nj) inplace = 0;
+        // dW split-K chunks for narrow layers
+        const int patches = ((L.n_out + 3) / 4) * ((L.n_in + 3) / 4);
+        int C = 1;
+        while (C < 32 && patches * C * 2 <= nthreads && TM / (C * 2) >= PV) C *= 2;
+        L.dw_chunks = C;
+    }
+    if (env_int("QB_NO_INPLACE", 0)) inplace = 0;
+    P->inplace = inplace; P->buf_rows = buf_rows;
+    long long act_elems;
+    if (!want_grad) {
+        act_elems = (long long)(inplace ? 1 : 2) * buf_rows * P->lda;
+        P->total_rows = buf_rows; P->d_row = -1;
+    } else {
+        int row = 0, dmax = 0;
+        for (int l = 0; l < net->n_layers; ++l) {
+            QbLayerPlan& L = P->L[l];
+            L.row_in = row;
+            row += (l == 0) ? rup(net->in_dim, TU) : P->L[l - 1].n_out_pad;
+            if (L.has_res) dmax = std::max(dmax, L.n_out_pad);
+        }
+        for (int l = 0; l < net->n_layers; ++l) P->L[l].row_out = (l + 1 < net->n_layers) ? P->L[l + 1].row_in : row;
+        row += P->L[net->n_layers - 1].n_out_pad;
+        P->d_row = dmax ? row : -1;
+        row += dmax;
+        P->total_rows = row;
+        act_elems = (long long)row * P->lda;
+    }
+    P->smem_bytes = 40 * 8 + (long long)woff * elem + act_elems * elem;
+    return P->smem_bytes;
+}
+
+struct QbLaunch { QbPlan plan; int S; long long pts_per_split; };
+
+static int make_launch(const qb_net_t* net, int dtype, bool want_grad, long long K, long long N, bool force_single,
+                       QbLaunch* out) {
+    if (validate_net(net)) return -1;
+    if (dtype != QB_F32 && dtype != QB_F64) return qb_fail("unknown dtype");
+    if (K < 1 || N < 1) return qb_fail("K and N must be positive");
+    const int cands32[] = {256, 128, 64, 32}, cands64[] = {128, 64, 32, 16};
+    const int* cands = dtype == QB_F64 ? cands64 : cands32;
+    const int mintm = cands[3];
+    const int cap = std::max(mintm, rup((int)std::min<long long>(N, 256), mintm));
+    int forced = env_int("QB_TM", 0);
+    int pick = -1;
+    QbPlan tmp;
+    for (int pass = 0; pass < 2 && pick < 0; ++pass) {
+        const int limit = pass == 0 ? QB_SMEM_TWO : QB_SMEM_MAX;
+        for (int c = 0; c < 4; ++c) {
+            int TM = cands[c];
+            if (forced) TM = forced;
+            else if (TM > cap) continue;
+            long long b = plan_for_tm(net, dtype, want_grad, TM, &tmp);
+            if (b <= limit) { pick = TM; break; }
+            if (forced) break;
+        }
+    }
+    if (pick < 0) return qb_fail("network too large for the fused shared-memory path (weights + one tile exceed 227 KB)");
+    plan_for_tm(net, dtype, want_grad, pick, &out->plan);
+    const int TM = out->plan.TM;
+    long long S = 1;
+    if (!force_single) {
+        const long long target = (long long)QB_NUM_SMS * 4;
+        if (K < target) S = std::min(cdiv(N, TM), cdiv(target, K));
+        S = env_int("QB_SPLIT", (int)S);
+        if (S < 1) S = 1;
+    }
+    long long pps = rup((int)cdiv(N, S), TM);
+    S = cdiv(N, pps);
+    out->S = (int)S; out->pts_per_split = pps;
+    return 0;
+}
+
+template <typename K>
+static int set_smem(K kernel, long long bytes) {
+    QB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+static QbLikDev lik_dev(const qb_lik_t* lik) {
+    QbLikDev d;
+    d.sigma = lik->sigma; d.inv_sigma2 = 1.0 / (lik->sigma * lik->sigma);
+    d.prior_sigma = lik->prior_sigma; d.prior_scale = lik->prior_scale;
+    d.anchor = lik->prior_anchor; d.anchor_per_chain = lik->anchor_per_chain;
+    d.has_prior = lik->prior_sigma > 0.0;
+    return d;
+}
+
+// =================================================================================================
+// kernels 1 and 2 (stand-alone entry points)
+// =================================================================================================
+template <typename T> struct EvalArgs {
+    const T* theta; const T* x; const T* y;
+    long long K, N; int S; long long pps;
+    double* part;   // [K,S]
+    T* grad;        // [K,P] (S == 1) or nullptr
+    T* gpart;       // [K,S,P] (S > 1)
+    double* lp;
+    QbLikDev lk;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_logpost(const __grid_constant__ QbPlan P, const EvalArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const QbSmem S = qb_carve<T>(P, smem_raw);
+    const long long k = blockIdx.x, s = blockIdx.y;
+    const long long n0 = s * a.pps, n1 = min(a.N, n0 + a.pps);
+    const double ssq = qb_eval_value<T>(P, S, a.theta + k * P.n_params, a.x, a.y, n0, n1, true, nullptr);
+    if (threadIdx.x == 0) a.part[k * a.S + s] = ssq;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_logpost_grad(const __grid_constant__ QbPlan P, const EvalArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const QbSmem S = qb_carve<T>(P, smem_raw);
+    const long long k = blockIdx.x, s = blockIdx.y;
+    const long long n0 = s * a.pps, n1 = min(a.N, n0 + a.pps);
+    T* g = (a.S == 1) ? a.grad + k * P.n_params : a.gpart + (k * a.S + s) * P.n_params;
+    const double ssq = qb_eval_value_grad<T>(P, S, a.theta + k * P.n_params, a.x, a.y, n0, n1, a.lk.inv_sigma2, g);
+    if (threadIdx.x == 0) a.part[k * a.S + s] = ssq;
+}
+
+// combine the N-splits (fixed order), add constants and the prior
+template <typename T>
+__global__ void __launch_bounds__(128) k_finalize(const EvalArgs<T> a, int P, int want_grad) {
+    __shared__ double red[40];
+    const long long k = blockIdx.x;
+    double ssq = 0.0;
+    for (int s = 0; s < a.S; ++s) ssq += a.part[k * a.S + s];
+    const T* th = a.theta + k * P;
+    double pss = 0.0;
+    if (a.lk.has_prior) pss = qb_prior_ss<T>(a.lk, th, k, P, red);
+    if (threadIdx.x == 0) a.lp[k] = qb_lp_from(a.lk, ssq, a.N, pss, P);
+    if (want_grad) {
+        T* g = a.grad + k * P;
+        if (a.S > 1) {
+            for (int i = threadIdx.x; i < P; i += blockDim.x) {
+                T v = T(0);
+                for (int s = 0; s < a.S; ++s) v += a.gpart[(k * a.S + s) * P + i];
+                g[i] = v;
+            }
+            __syncthreads();
+        }
+        qb_prior_grad_add<T>(a.lk, th, k, P, g);
+    }
+}
+
+template <typename T>
+static int run_eval(const qb_net_t* net, int dtype, const void* theta, int64_t K, const qb_data_t* data,
+                    const qb_lik_t* lik, double* lp, void* grad, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const bool want_grad = grad != nullptr;
+    QbLaunch L;
+    if (make_launch(net, dtype, want_grad, K, data->n, false, &L)) return -1;
+    const size_t need = qb_eval_workspace_bytes(net, dtype, K, data->n, want_grad);
+    if (ws_bytes < need || (need && !ws)) return qb_fail("workspace too small%s (need %lld bytes)", "", (long long)need);
+    EvalArgs<T> a;
+    a.theta = (const T*)theta; a.x = (const T*)data->x; a.y = (const T*)data->y;
+    a.K = K; a.N = data->n; a.S = L.S; a.pps = L.pts_per_split;
+    a.part = (double*)ws;
+    a.grad = (T*)grad;
+    const size_t part_bytes = ((size_t)K * L.S * sizeof(double) + 255) / 256 * 256;
+    a.gpart = (L.S > 1 && want_grad) ? (T*)((char*)ws + part_bytes) : nullptr;
+    a.lp = lp; a.lk = lik_dev(lik);
+    dim3 grid((unsigned)K, (unsigned)L.S);
+    if (want_grad) {
+        if (set_smem(k_logpost_grad<T>, L.plan.smem_bytes)) return -2;
+        k_logpost_grad<T><<<grid, L.plan.nthreads, L.plan.smem_bytes, st>>>(L.plan, a);
+    } else {
+        if (set_smem(k_logpost<T>, L.plan.smem_bytes)) return -2;
+        k_logpost<T><<<grid, L.plan.nthreads, L.plan.smem_bytes, st>>>(L.plan, a);
+    }
+    QB_CUDA(cudaGetLastError());
+    k_finalize<T><<<(unsigned)K, 128, 0, st>>>(a, net->n_params, want_grad ? 1 : 0);
+    QB_CUDA(cudaGetLastError());
+    g_launches += 2;
+    return 0;
+}
+
+extern "C" size_t qb_eval_workspace_bytes(const qb_net_t* net, int dtype, int64_t K, int64_t N, int want_grad) {
+    QbLaunch L;
+    if (make_launch(net, dtype, want_grad != 0, K, N, false, &L)) return 0;
+    size_t b = ((size_t)K * L.S * sizeof(double) + 255) / 256 * 256;
+    if (want_grad && L.S > 1) b += (size_t)K * L.S * net->n_params * (dtype == QB_F64 ? 8 : 4);
+    return b;
+}
+
+extern "C" int qb_plan_info(const qb_net_t* net, int dtype, int64_t K, int64_t N, int want_grad, int64_t* out) {
+    QbLaunch L;
+    if (make_launch(net, dtype, want_grad != 0, K, N, false, &L)) return -1;
+    out[0] = L.plan.TM; out[1] = L.plan.nthreads; out[2] = L.plan.smem_bytes; out[3] = L.S;
+    out[4] = (int64_t)K * L.S; out[5] = L.plan.inplace; out[6] = 0; out[7] = 0;
+    return 0;
+}
+
+extern "C" int qb_logpost(const qb_net_t* net, int dtype, const void* theta, int64_t K, const qb_data_t* data,
+                          const qb_lik_t* lik, double* lp, void* ws, size_t ws_bytes, void* stream) {
+    if (!theta || !data || !lik || !lp) return qb_fail("NULL argument to qb_logpost");
+    if (dtype == QB_F64) return run_eval<double>(net, dtype, theta, K, data, lik, lp, nullptr, ws, ws_bytes, (cudaStream_t)stream);
+    return run_eval<float>(net, dtype, theta, K, data, lik, lp, nullptr, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int qb_logpost_grad(const qb_net_t* net, int dtype, const void* theta, int64_t K, const qb_data_t* data,
+                               const qb_lik_t* lik, double* lp, void* grad, void* ws, size_t ws_bytes, void* stream) {
+    if (!theta || !data || !lik || !lp || !grad) return qb_fail("NULL argument to qb_logpost_grad");
+    if (dtype == QB_F64) return run_eval<double>(net, dtype, theta, K, data, lik, lp, grad, ws, ws_bytes, (cudaStream_t)stream);
+    return run_eval<float>(net, dtype, theta, K, data, lik, lp, grad, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+// =================================================================================================
+// kernel 3: fused chain steps
+// =================================================================================================
+template <typename T> __device__ __forceinline__ T qb_mul(T a, T b);
+template <> __device__ __forceinline__ float qb_mul<float>(float a, float b) { return __fmul_rn(a, b); }
+template <> __device__ __forceinline__ double qb_mul<double>(double a, double b) { return __dmul_rn(a, b); }
+template <typename T> __device__ __forceinline__ T qb_add(T a, T b);
+template <> __device__ __forceinline__ float qb_add<float>(float a, float b) { return __fadd_rn(a, b); }
+template <> __device__ __forceinline__ double qb_add<double>(double a, double b) { return __dadd_rn(a, b); }
+
+template <typename T> struct ChainArgs {
+    long long K, N;
+    const T* x; const T* y;
+    QbLikDev lk;
+    T* theta; double* lp; long long* naccept; T* map_theta; double* map_lp;
+    int rng_mode; unsigned long long seed; long long chain_offset; const T* incr; const double* unif;
+    double* rec_lp; double* rec_alpha; unsigned char* rec_acc; long long rec_ld;
+    T* samples; long long store_every, n_slots;
+    long long t_start, nsteps; int init_lp;
+};
+template <typename T> struct AmcmcArgs {
+    double gamma; long long t0, tadapt; int adapt, track;
+    T* xm; T* cov; T* pscale; T* chol; const T* chol_ini; int* prop_kind; T* prop;
+};
+template <typename T> struct HmcArgs {
+    int method, L; double eps;
+    T* gcur; T* mom; T* prop; T* gprop;
+};
+
+// Metropolis-Hastings accept + bookkeeping (mcmc.py:69-85); all threads hold identical scalars.
+template <typename T>
+__device__ __forceinline__ bool qb_mh_step(const ChainArgs<T>& c, long long k, long long s, int P, double lp_prop,
+                                           double K_cur, double K_prop, T* cur, const T* prop, T* mapth,
+                                           double& lp_cur, double& map_lp, long long& na) {
+    const double cur_H = -lp_cur + K_cur, prop_H = -lp_prop + K_prop;
+    const double mh = exp(cur_H - prop_H);                       // unclipped; inf is normal
+    double u;
+    if (c.rng_mode == QB_RNG_REPLAY) u = c.unif[s * c.K + k];
+    else u = qb_u01(qb_rand4(c.seed, c.chain_offset + k, c.t_start + s, QB_STREAM_UNIF, 0).x);
+    const bool acc = u < mh;                                      // strict <, NaN rejects
+    if (acc) {
+        for (int i = threadIdx.x; i < P; i += blockDim.x) cur[i] = prop[i];
+        lp_cur = lp_prop;
+        na += 1;
+        if (lp_cur >= map_lp) {
+            map_lp = lp_cur;
+            for (int i = threadIdx.x; i < P; i += blockDim.x) mapth[i] = prop[i];
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (c.rec_lp) c.rec_lp[k * c.rec_ld + s] = lp_cur;
+        if (c.rec_alpha) c.rec_alpha[k * c.rec_ld + s] = mh;
+        if (c.rec_acc) c.rec_acc[k * c.rec_ld + s] = acc ? 1 : 0;
+    }
+    __syncthreads();
+    if (c.samples && c.store_every > 0 && (s + 1) % c.store_every == 0) {
+        const long long slot = (s + 1) / c.store_every - 1;
+        if (slot < c.n_slots) {
+            T* dst = c.samples + (k * c.n_slots + slot) * P;
+            for (int i = threadIdx.x; i < P; i += blockDim.x) dst[i] = cur[i];
+        }
+    }
+    return acc;
+}
+
+// in-block Cholesky of fac*(cov + jitter*I) -> lower factor Lf (global, [P,P])
+template <typename T>
+__device__ void qb_cholesky(const T* cov, T* Lf, int P, double fac, double jitter) {
+    for (int idx = threadIdx.x; idx < P * P; idx += blockDim.x) Lf[idx] = T(0);
+    __syncthreads();
+    for (int j = 0; j < P; ++j) {
+        for (int i = j + threadIdx.x; i < P; i += blockDim.x) {
+            double s = fac * ((double)cov[i * P + j] + (i == j ? jitter : 0.0));
+            for (int q = 0; q < j; ++q) s -= (double)Lf[i * P + q] * (double)Lf[j * P + q];
+            Lf[i * P + j] = (T)s;
+        }
+        __syncthreads();
+        const double d = sqrt((double)Lf[j * P + j]);
+        __syncthreads();
+        for (int i = j + threadIdx.x; i < P; i += blockDim.x)
+            Lf[i * P + j] = (i == j) ? (T)d : (T)((double)Lf[i * P + j] / d);
+        __syncthreads();
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_amcmc(const __grid_constant__ QbPlan plan, const ChainArgs<T> c, const AmcmcArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const QbSmem S = qb_carve<T>(plan, smem_raw);
+    const long long k = blockIdx.x;
+    const int P = plan.n_params, tid = threadIdx.x, nt = blockDim.x;
+    T* cur = c.theta + k * P;
+    T* prop = a.prop + k * P;
+    T* mapth = c.map_theta + k * P;
+    T* xm = a.xm ? a.xm + k * P : nullptr;
+    T* pscale = a.pscale + k * P;
+    const bool full = a.track == 2;               // shape of cov: [P,P] (2) or [P] (1)
+    T* cov = a.cov ? a.cov + k * (full ? (long long)P * P : (long long)P) : nullptr;
+    T* chol = a.chol ? a.chol + k * (long long)P * P : nullptr;
+    T* zbuf = reinterpret_cast<T*>(S.act);       // scratch between evaluations
+
+    double lp_cur, map_lp;
+    long long na;
+    if (c.init_lp) {
+        const double ssq = qb_eval_value<T>(plan, S, cur, c.x, c.y, 0, c.N, true, nullptr);
+        double pss = 0.0;
+        if (c.lk.has_prior) pss = qb_prior_ss<T>(c.lk, cur, k, P, S.red);
+        lp_cur = qb_lp_from(c.lk, ssq, c.N, pss, P);
+        map_lp = lp_cur; na = 0;
+        for (int i = tid; i < P; i += nt) mapth[i] = cur[i];
+    } else {
+        lp_cur = c.lp[k]; map_lp = c.map_lp[k]; na = c.naccept[k];
+    }
+    int kind = a.prop_kind[k];
+    __syncthreads();
+
+    for (long long s = 0; s < c.nsteps; ++s) {
+        const long long t = c.t_start + s;
+        // ---- running mean / covariance (admcmc.py:52-59)
+        if (a.track && xm) {
+            if (t == 0) {
+                for (int i = tid; i < P; i += nt) xm[i] = cur[i];
+                if (cov) { const long long n = full ? (long long)P * P : P; for (long long i = tid; i < n; i += nt) cov[i] = T(0); }
+            } else {
+                const double td = (double)t;
+                const T rt = (T)((td - 1.0) / td), st = (T)((td + 1.0) / (td * td));
+                for (int i = tid; i < P; i += nt)
+                    xm[i] = qb_add<T>(qb_mul<T>((T)td, xm[i]), cur[i]) / (T)(td + 1.0);
+                __syncthreads();
+                if (cov && full) {
+                    for (int idx = tid; idx < P * P; idx += nt) {
+                        const int r = idx / P, q = idx - r * P;
+                        const T dr = cur[r] - xm[r], dq = cur[q] - xm[q];
+                        cov[idx] = qb_add<T>(qb_mul<T>(rt, cov[idx]), qb_mul<T>(st, qb_mul<T>(dr, dq)));
+                    }
+                } else if (cov) {
+                    for (int i = tid; i < P; i += nt) {
+                        const T d = cur[i] - xm[i];
+                        cov[i] = qb_add<T>(qb_mul<T>(rt, cov[i]), qb_mul<T>(st, qb_mul<T>(d, d)));
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---- proposal covariance (admcmc.py:61-67)
+        if (t == 0) {
+            if (a.chol_ini) kind = 3;
+            else {
+                kind = 0;
+                for (int i = tid; i < P; i += nt) pscale[i] = (T)sqrt(0.09 * fabs((double)cur[i]));
+            }
+            __syncthreads();
+        } else if (a.adapt != QB_ADAPT_NONE && t > a.t0 && (t % a.tadapt) == 0) {
+            const double fac = a.gamma * 2.4 * 2.4 / (double)P;
+            if (full) { qb_cholesky<T>(cov, chol, P, fac, 1e-8); kind = 2; }
+            else {
+                for (int i = tid; i < P; i += nt) pscale[i] = (T)sqrt(fac * ((double)cov[i] + 1e-8));
+                kind = 1;
+            }
+            __syncthreads();
+        }
+        // ---- proposal (admcmc.py:70)
+        if (c.rng_mode == QB_RNG_REPLAY) {
+            const T* xi = c.incr + (s * c.K + k) * P;
+            for (int i = tid; i < P; i += nt) prop[i] = qb_add<T>(cur[i], xi[i]);
+        } else {
+            const long long chain = c.chain_offset + k;
+            if (kind == 0 || kind == 1) {
+                T z0 = T(0);
+                if (kind == 0) { T zz[4]; qb_normal4(qb_rand4(c.seed, chain, t, QB_STREAM_Z0, 0), zz); z0 = T(0.1) * zz[0]; }
+                for (int i4 = tid; i4 * 4 < P; i4 += nt) {
+                    T z[4];
+                    qb_normal4(qb_rand4(c.seed, chain, t, QB_STREAM_INCR, (uint32_t)i4), z);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int i = i4 * 4 + q;
+                        if (i < P) prop[i] = cur[i] + (z0 + pscale[i] * z[q]);
+                    }
+                }
+            } else {
+                for (int i4 = tid; i4 * 4 < P; i4 += nt) {
+                    T z[4];
+                    qb_normal4(qb_rand4(c.seed, chain, t, QB_STREAM_INCR, (uint32_t)i4), z);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if (i4 * 4 + q < P) zbuf[i4 * 4 + q] = z[q];
+                }
+                __syncthreads();
+                const T* Lf = (kind == 3) ? a.chol_ini : chol;
+                for (int i = tid; i < P; i += nt) {
+                    T acc = T(0);
+                    for (int q = 0; q <= i; ++q) acc = fma(Lf[(long long)i * P + q], zbuf[q], acc);
+                    prop[i] = cur[i] + acc;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- evaluate + accept
+        const double ssq = qb_eval_value<T>(plan, S, prop, c.x, c.y, 0, c.N, true, nullptr);
+        double pss = 0.0;
+        if (c.lk.has_prior) pss = qb_prior_ss<T>(c.lk, prop, k, P, S.red);
+        const double lp_prop = qb_lp_from(c.lk, ssq, c.N, pss, P);
+        qb_mh_step<T>(c, k, s, P, lp_prop, 0.0, 0.0, cur, prop, mapth, lp_cur, map_lp, na);
+        __syncthreads();
+    }
+    if (tid == 0) { c.lp[k] = lp_cur; c.map_lp[k] = map_lp; c.naccept[k] = na; a.prop_kind[k] = kind; }
+}
+
+template <typename T>
+__device__ double qb_full_grad(const QbPlan& plan, const QbSmem& S, const ChainArgs<T>& c, long long k, const T* th, T* g,
+                               double* lp_out) {
+    const int P = plan.n_params;
+    const double ssq = qb_eval_value_grad<T>(plan, S, th, c.x, c.y, 0, c.N, c.lk.inv_sigma2, g);
+    double pss = 0.0;
+    if (c.lk.has_prior) {
+        pss = qb_prior_ss<T>(c.lk, th, k, P, S.red);
+        qb_prior_grad_add<T>(c.lk, th, k, P, g);
+    }
+    __syncthreads();
+    *lp_out = qb_lp_from(c.lk, ssq, c.N, pss, P);
+    return ssq;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_hmc(const __grid_constant__ QbPlan plan, const ChainArgs<T> c, const HmcArgs<T> h) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const QbSmem S = qb_carve<T>(plan, smem_raw);
+    const long long k = blockIdx.x;
+    const int P = plan.n_params, tid = threadIdx.x, nt = blockDim.x;
+    T* cur = c.theta + k * P;
+    T* mapth = c.map_theta + k * P;
+    T* gcur = h.gcur + k * P;
+    T* mom = h.mom + k * P;
+    T* prop = h.prop + k * P;
+    T* gprop = h.gprop + k * P;
+    const T eps = (T)h.eps;
+
+    double lp_cur, map_lp;
+    long long na;
+    if (c.init_lp) {
+        qb_full_grad<T>(plan, S, c, k, cur, gcur, &lp_cur);
+        map_lp = lp_cur; na = 0;
+        for (int i = tid; i < P; i += nt) mapth[i] = cur[i];
+    } else {
+        lp_cur = c.lp[k]; map_lp = c.map_lp[k]; na = c.naccept[k];
+    }
+    __syncthreads();
+
+    for (long long s = 0; s < c.nsteps; ++s) {
+        const long long t = c.t_start + s;
+        // momentum draw (hmc.py:43 / mala.py:42)
+        double ksum = 0.0;
+        if (c.rng_mode == QB_RNG_REPLAY) {
+            const T* p0 = c.incr + (s * c.K + k) * P;
+            for (int i = tid; i < P; i += nt) { const T v = p0[i]; mom[i] = v; ksum += (double)v * (double)v; }
+        } else {
+            const long long chain = c.chain_offset + k;
+            for (int i4 = tid; i4 * 4 < P; i4 += nt) {
+                T z[4];
+                qb_normal4(qb_rand4(c.seed, chain, t, QB_STREAM_INCR, (uint32_t)i4), z);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int i = i4 * 4 + q;
+                    if (i < P) { mom[i] = z[q]; ksum += (double)z[q] * (double)z[q]; }
+                }
+            }
+        }
+        const double K_cur = qb_block_sum(ksum, S.red) / 2.0;
+        double lp_prop;
+        if (h.method == 0) {
+            // leapfrog (hmc.py:48-60); each thread only touches its own elements between evaluations
+            for (int i = tid; i < P; i += nt) {
+                mom[i] = qb_add<T>(mom[i], qb_mul<T>(eps, gcur[i]) / T(2));
+                prop[i] = cur[i];
+            }
+            for (int jj = 0; jj < h.L; ++jj) {
+                for (int i = tid; i < P; i += nt) prop[i] = qb_add<T>(prop[i], qb_mul<T>(eps, mom[i]));
+                __syncthreads();
+                qb_full_grad<T>(plan, S, c, k, prop, gprop, &lp_prop);
+                if (jj != h.L - 1) {
+                    for (int i = tid; i < P; i += nt) mom[i] = qb_add<T>(mom[i], qb_mul<T>(eps, gprop[i]));
+                } else {
+                    for (int i = tid; i < P; i += nt) mom[i] = qb_add<T>(mom[i], qb_mul<T>(eps, gprop[i]) / T(2));
+                }
+            }
+        } else {
+            // MALA (mala.py:44-51)
+            const T c2 = qb_mul<T>(T(0.5), qb_mul<T>(eps, eps));
+            for (int i = tid; i < P; i += nt)
+                prop[i] = qb_add<T>(cur[i], qb_add<T>(qb_mul<T>(c2, gcur[i]), qb_mul<T>(eps, mom[i])));
+            __syncthreads();
+            qb_full_grad<T>(plan, S, c, k, prop, gprop, &lp_prop);
+            for (int i = tid; i < P; i += nt)
+                mom[i] = qb_add<T>(mom[i], qb_mul<T>(eps, qb_add<T>(gcur[i], gprop[i])) / T(2));
+        }
+        double k2 = 0.0;
+        for (int i = tid; i < P; i += nt) { const double v = (double)mom[i]; k2 += v * v; }
+        const double K_prop = qb_block_sum(k2, S.red) / 2.0;
+        const bool acc = qb_mh_step<T>(c, k, s, P, lp_prop, K_cur, K_prop, cur, prop, mapth, lp_cur, map_lp, na);
+        if (acc) for (int i = tid; i < P; i += nt) gcur[i] = gprop[i];
+        __syncthreads();
+    }
+    if (tid == 0) { c.lp[k] = lp_cur; c.map_lp[k] = map_lp; c.naccept[k] = na; }
+}
+
+template <typename T>
+static void fill_chain_args(ChainArgs<T>& c, const qb_data_t* data, const qb_lik_t* lik, const qb_chain_t* ch,
+                            const qb_rng_t* rng, const qb_record_t* rec, int64_t t_start, int64_t nsteps, int init_lp) {
+    c.K = ch->K; c.N = data->n; c.x = (const T*)data->x; c.y = (const T*)data->y; c.lk = lik_dev(lik);
+    c.theta = (T*)ch->theta; c.lp = ch->lp; c.naccept = (long long*)ch->naccept; c.map_theta = (T*)ch->map_theta; c.map_lp = ch->map_lp;
+    c.rng_mode = rng->mode; c.seed = rng->seed; c.chain_offset = rng->chain_offset; c.incr = (const T*)rng->incr; c.unif = rng->unif;
+    c.rec_lp = rec ? rec->logpost : nullptr; c.rec_alpha = rec ? rec->alpha : nullptr; c.rec_acc = rec ? rec->accepted : nullptr;
+    c.rec_ld = rec ? rec->ld : 0; c.samples = rec ? (T*)rec->samples : nullptr;
+    c.store_every = rec ? rec->store_every : 0; c.n_slots = rec ? rec->n_slots : 0;
+    c.t_start = t_start; c.nsteps = nsteps; c.init_lp = init_lp;
+}
+
+static int check_chain_common(const qb_data_t* data, const qb_lik_t* lik, const qb_chain_t* ch, const qb_rng_t* rng) {
+    if (!data || !lik || !ch || !rng) return qb_fail("NULL argument to chain run");
+    if (!ch->theta || !ch->lp || !ch->naccept || !ch->map_theta || !ch->map_lp) return qb_fail("chain state has NULL arrays");
+    if (rng->mode == QB_RNG_REPLAY && (!rng->incr || !rng->unif)) return qb_fail("replay mode needs incr and unif");
+    if (ch->K < 1) return qb_fail("K must be positive");
+    return 0;
+}
+
+template <typename T>
+static int run_amcmc(const qb_net_t* net, int dtype, const qb_data_t* data, const qb_lik_t* lik, qb_chain_t* ch,
+                     qb_amcmc_t* am, const qb_rng_t* rng, const qb_record_t* rec, int64_t t_start, int64_t nsteps,
+                     int init_lp, void* scratch, cudaStream_t st) {
+    QbLaunch L;
+    if (make_launch(net, dtype, false, ch->K, data->n, true, &L)) return -1;
+    const int P = net->n_params;
+    if (am->adapt == QB_ADAPT_FULL || am->chol_ini) {
+        const long long act_elems = (L.plan.smem_bytes - 40 * 8) / L.plan.elem_size - L.plan.w_elems;
+        if (P > act_elems) return qb_fail("full-covariance proposals need P <= tile scratch%s (P=%lld)", "", P);
+    }
+    ChainArgs<T> c; fill_chain_args<T>(c, data, lik, ch, rng, rec, t_start, nsteps, init_lp);
+    AmcmcArgs<T> a;
+    a.gamma = am->gamma; a.t0 = am->t0; a.tadapt = am->tadapt; a.adapt = am->adapt;
+    a.track = am->track_moments;
+    if (am->adapt == QB_ADAPT_DIAG) a.track = 1;
+    if (am->adapt == QB_ADAPT_FULL) a.track = 2;
+    if (a.track < 0 || a.track > 2) return qb_fail("track_moments must be 0, 1 (diagonal cov) or 2 (full cov)");
+    if (a.track && !am->cov) return qb_fail("moment tracking needs cov");
+    a.xm = (T*)am->xm; a.cov = (T*)am->cov; a.pscale = (T*)am->pscale; a.chol = (T*)am->chol;
+    a.chol_ini = (const T*)am->chol_ini; a.prop_kind = am->prop_kind; a.prop = (T*)scratch;
+    if (a.track && (!a.xm)) return qb_fail("moment tracking needs xm");
+    if (am->adapt != QB_ADAPT_NONE && !a.cov) return qb_fail("adaptation needs cov");
+    if (am->adapt == QB_ADAPT_FULL && !a.chol) return qb_fail("full adaptation needs chol");
+    if (!a.pscale || !a.prop_kind || !a.prop) return qb_fail("amcmc needs pscale, prop_kind and scratch");
+    if (set_smem(k_amcmc<T>, L.plan.smem_bytes)) return -2;
+    k_amcmc<T><<<(unsigned)ch->K, L.plan.nthreads, L.plan.smem_bytes, st>>>(L.plan, c, a);
+    QB_CUDA(cudaGetLastError());
+    g_launches += 1;
+    return 0;
+}
+
+extern "C" int qb_amcmc_run(const qb_net_t* net, int dtype, const qb_data_t* data, const qb_lik_t* lik,
+                            qb_chain_t* chain, qb_amcmc_t* am, const qb_rng_t* rng, const qb_record_t* rec,
+                            int64_t t_start, int64_t nsteps, int init_lp, void* scratch, void* stream) {
+    if (check_chain_common(data, lik, chain, rng) || !am) return g_err[0] ? -1 : qb_fail("NULL amcmc state");
+    if (dtype == QB_F64) return run_amcmc<double>(net, dtype, data, lik, chain, am, rng, rec, t_start, nsteps, init_lp, scratch, (cudaStream_t)stream);
+    return run_amcmc<float>(net, dtype, data, lik, chain, am, rng, rec, t_start, nsteps, init_lp, scratch, (cudaStream_t)stream);
+}
+
+template <typename T>
+static int run_hmc(const qb_net_t* net, int dtype, const qb_data_t* data, const qb_lik_t* lik, qb_chain_t* ch,
+                   qb_hmc_t* hm, const qb_rng_t* rng, const qb_record_t* rec, int64_t t_start, int64_t nsteps,
+                   int init_lp, cudaStream_t st) {
+    QbLaunch L;
+    if (make_launch(net, dtype, true, ch->K, data->n, true, &L)) return -1;
+    if (!hm->grad_cur || !hm->mom || !hm->prop || !hm->grad_prop) return qb_fail("hmc state has NULL arrays");
+    if (hm->method == 0 && hm->L < 1) return qb_fail("HMC needs L >= 1");
+    ChainArgs<T> c; fill_chain_args<T>(c, data, lik, ch, rng, rec, t_start, nsteps, init_lp);
+    HmcArgs<T> h;
+    h.method = hm->method; h.L = hm->L; h.eps = hm->epsilon;
+    h.gcur = (T*)hm->grad_cur; h.mom = (T*)hm->mom; h.prop = (T*)hm->prop; h.gprop = (T*)hm->grad_prop;
+    if (set_smem(k_hmc<T>, L.plan.smem_bytes)) return -2;
+    k_hmc<T><<<(unsigned)ch->K, L.plan.nthreads, L.plan.smem_bytes, st>>>(L.plan, c, h);
+    QB_CUDA(cudaGetLastError());
+    g_launches += 1;
+    return 0;
+}
+
+extern "C" int qb_hmc_run(const qb_net_t* net, int dtype, const qb_data_t* data, const qb_lik_t* lik,
+                          qb_chain_t* chain, qb_hmc_t* hm, const qb_rng_t* rng, const qb_record_t* rec,
+                          int64_t t_start, int64_t nsteps, int init_lp, void* stream) {
+    if (check_chain_common(data, lik, chain, rng) || !hm) return g_err[0] ? -1 : qb_fail("NULL hmc state");
+    if (dtype == QB_F64) return run_hmc<double>(net, dtype, data, lik, chain, hm, rng, rec, t_start, nsteps, init_lp, (cudaStream_t)stream);
+    return run_hmc<float>(net, dtype, data, lik, chain, hm, rng, rec, t_start, nsteps, init_lp, (cudaStream_t)stream);
+}
+
+// =================================================================================================
+// kernel 4: posterior predictive
+// =================================================================================================
+template <typename T> struct PredArgs {
+    const T* theta; const T* x; long long M, N;
+    T* out; T* mean; T* var;
+    int fused;     // 1: block = point tile, loops over all members, Welford in registers
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_predict(const __grid_constant__ QbPlan P, const PredArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const QbSmem S = qb_carve<T>(P, smem_raw);
+    T* sW = reinterpret_cast<T*>(S.w);
+    T* A0 = reinterpret_cast<T*>(S.act);
+    const int lda = P.lda, TM = P.TM, o = P.out_dim;
+    T* A1 = P.inplace ? A0 : A0 + (size_t)P.buf_rows * lda;
+    const long long p0 = (long long)blockIdx.x * TM;
+    const long long m_lo = a.fused ? 0 : blockIdx.y, m_hi = a.fused ? a.M : m_lo + 1;
+    constexpr int QMAX = 4;
+    T wmean[QMAX], wm2[QMAX];
+#pragma unroll
+    for (int q = 0; q < QMAX; ++q) { wmean[q] = T(0); wm2[q] = T(0); }
+    const int n = TM * o;
+    for (long long m = m_lo; m < m_hi; ++m) {
+        __syncthreads();
+        qb_stage_weights<T>(P, sW, a.theta + m * P.n_params);
+        qb_load_x_tile<T>(a.x, P.in_dim, p0, a.N, A0, lda, TM);
+        __syncthreads();
+        T* cur = A0; T* oth = A1;
+        for (int l = 0; l < P.n_layers; ++l) {
+            qb_layer_forward<T>(P.L[l], sW, cur, oth, lda, TM, P.inplace != 0);
+            T* t = cur; cur = oth; oth = t;
+        }
+        if (!a.fused) {
+            for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+                const int p = idx / o, j = idx - p * o;
+                const long long gp = p0 + p;
+                if (gp < a.N) {
+                    T v = cur[j * lda + p];
+                    if (P.final_exp) v = qb_exp(v);
+                    a.out[(m * a.N + gp) * o + j] = v;
+                }
+            }
+            continue;
+        }
+        const T inv_n = T(1) / (T)(m + 1);
+#pragma unroll
+        for (int q = 0; q < QMAX; ++q) {
+            const int idx = threadIdx.x + q * blockDim.x;
+            if (idx < n) {
+                // idx = p * o + j : consecutive threads write consecutive addresses of out[m, p0+p, j]
+                const int p = idx / o, j = idx - p * o;
+                const long long gp = p0 + p;
+                if (gp < a.N) {
+                    T v = cur[j * lda + p];
+                    if (P.final_exp) v = qb_exp(v);
+                    if (a.out) a.out[(m * a.N + gp) * o + j] = v;
+                    const T d = v - wmean[q];
+                    wmean[q] += d * inv_n;
+                    wm2[q] = fma(d, v - wmean[q], wm2[q]);
+                }
+            }
+        }
+    }
+    if (a.fused) {
+#pragma unroll
+        for (int q = 0; q < QMAX; ++q) {
+            const int idx = threadIdx.x + q * blockDim.x;
+            if (idx < n) {
+                const int p = idx / o, j = idx - p * o;
+                const long long gp = p0 + p;
+                if (gp < a.N) {
+                    if (a.mean) a.mean[gp * o + j] = wmean[q];
+                    if (a.var) a.var[gp * o + j] = a.M > 1 ? wm2[q] / (T)(a.M - 1) : T(NAN);
+                }
+            }
+        }
+    }
+}
+
+// mean / var(ddof=1) over the leading axis of out[M, n]  (HBM-bound, coalesced over n)
+template <typename T>
+__global__ void k_moments(const T* out, long long M, long long n, T* mean, T* var) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    T mu = T(0), m2 = T(0);
+    for (long long m = 0; m < M; ++m) {
+        const T v = out[m * n + i];
+        const T d = v - mu;
+        mu += d / (T)(m + 1);
+        m2 = fma(d, v - mu, m2);
+    }
+    if (mean) mean[i] = mu;
+    if (var) var[i] = M > 1 ? m2 / (T)(M - 1) : T(NAN);
+}
+
+template <typename T>
+static int run_predict(const qb_net_t* net, int dtype, const void* theta, int64_t M, const void* x, int64_t N,
+                       void* out, void* mean, void* var, cudaStream_t st) {
+    QbLaunch L;
+    if (make_launch(net, dtype, false, M, N, true, &L)) return -1;
+    const QbPlan& P = L.plan;
+    const long long tiles = cdiv(N, P.TM);
+    const bool want_mom = mean || var;
+    const bool can_fuse = (long long)P.TM * P.out_dim <= 4LL * P.nthreads;
+    bool fused = want_mom && can_fuse && (tiles >= 2 * QB_NUM_SMS || !out);
+    if (want_mom && !fused && !out) return qb_fail("moments without `out` need TM*out_dim <= 4*threads; pass an `out` buffer");
+    if (!fused && M > 65535) return qb_fail("member-parallel predictive supports M <= 65535; chunk the call");
+    PredArgs<T> a;
+    a.theta = (const T*)theta; a.x = (const T*)x; a.M = M; a.N = N;
+    a.out = (T*)out; a.mean = (T*)mean; a.var = (T*)var; a.fused = fused ? 1 : 0;
+    if (set_smem(k_predict<T>, P.smem_bytes)) return -2;
+    dim3 grid((unsigned)tiles, fused ? 1u : (unsigned)M);
+    k_predict<T><<<grid, P.nthreads, P.smem_bytes, st>>>(P, a);
+    QB_CUDA(cudaGetLastError());
+    g_launches += 1;
+    if (want_mom && !fused) {
+        const long long n = N * P.out_dim;
+        k_moments<T><<<(unsigned)cdiv(n, 256), 256, 0, st>>>((const T*)out, M, n, (T*)mean, (T*)var);
+        QB_CUDA(cudaGetLastError());
+        g_launches += 1;
+    }
+    return 0;
+}
+
+extern "C" int qb_predict(const qb_net_t* net, int dtype, const void* theta, int64_t M, const void* x, int64_t N,
+                          void* out, void* mean, void* var, void* stream) {
+    if (!theta || !x) return qb_fail("NULL argument to qb_predict");
+    if (!out && !mean && !var) return qb_fail("qb_predict: nothing to compute");
+    if (dtype == QB_F64) return run_predict<double>(net, dtype, theta, M, x, N, out, mean, var, (cudaStream_t)stream);
+    return run_predict<float>(net, dtype, theta, M, x, N, out, mean, var, (cudaStream_t)stream);
+}
+
+// =================================================================================================
+// variational inference element-wise kernels
+// =================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) k_vi_sample(const T* mu, const T* rho, T* eps, long long nsam, long long P, double pi,
+                                                   double s1, double s2, unsigned long long seed, unsigned long long step,
+                                                   T* w, double* logq, double* logp) {
+    __shared__ double red[40];
+    const long long s = blockIdx.x;
+    const double LOG_SQRT_2PI = 0.91893853320467274178;
+    double lq = 0.0, lpr = 0.0;
+    if (seed) {
+        for (long long i4 = threadIdx.x; i4 * 4 < P; i4 += blockDim.x) {
+            T z[4];
+            qb_normal4(qb_rand4(seed, s, (long long)step, QB_STREAM_VI, (uint32_t)i4), z);
+            for (int q = 0; q < 4; ++q) if (i4 * 4 + q < P) eps[s * P + i4 * 4 + q] = z[q];
+        }
+        __syncthreads();
+    }
+    for (long long i = threadIdx.x; i < P; i += blockDim.x) {
+        const double m = (double)mu[i], r = (double)rho[i], e = (double)eps[s * P + i];
+        const double sig = exp(r);
+        const T wv = (T)(m + sig * e);
+        w[s * P + i] = wv;
+        const double wd = (double)wv;
+        // Gaussian_1d.log_prob (rvs.py:124-126)
+        const double dq = wd - m;
+        lq += -LOG_SQRT_2PI - log(sig) - dq * dq / (2.0 * sig * sig);
+        // GMM2_1d.log_prob (rvs.py:169-171): exp-then-log, not log-sum-exp
+        const double p1 = exp(-wd * wd / (2.0 * s1 * s1) - log(s1) - LOG_SQRT_2PI);
+        const double p2 = exp(-wd * wd / (2.0 * s2 * s2) - log(s2) - LOG_SQRT_2PI);
+        lpr += log(pi * p1 + (1.0 - pi) * p2);
+    }
+    lq = qb_block_sum(lq, red);
+    lpr = qb_block_sum(lpr, red);
+    if (threadIdx.x == 0) { logq[s] = lq; logp[s] = lpr; }
+}
+
+template <typename T>
+__global__ void k_vi_backward(const T* mu, const T* rho, const T* eps, const T* w, const T* glp, long long nsam, long long P,
+                              double pi, double s1, double s2, double c_nll, double inv_nsam_nb, double gout, T* gmu, T* grho) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const double LOG_SQRT_2PI = 0.91893853320467274178;
+    const double sig = exp((double)rho[i]);
+    double am = 0.0, ar = 0.0;
+    for (long long s = 0; s < nsam; ++s) {
+        const double wd = (double)w[s * P + i], e = (double)eps[s * P + i];
+        const double p1 = pi * exp(-wd * wd / (2.0 * s1 * s1) - log(s1) - LOG_SQRT_2PI);
+        const double p2 = (1.0 - pi) * exp(-wd * wd / (2.0 * s2 * s2) - log(s2) - LOG_SQRT_2PI);
+        const double dlogp = (p1 * (-wd / (s1 * s1)) + p2 * (-wd / (s2 * s2))) / (p1 + p2);
+        const double dw = c_nll * (-2.0 * (double)glp[s * P + i]) - dlogp * inv_nsam_nb;
+        am += dw;
+        ar += dw * sig * e - inv_nsam_nb;
+    }
+    gmu[i] = (T)(gout * am);
+    grho[i] = (T)(gout * ar);
+}
+
+extern "C" int qb_vi_sample(int dtype, const void* mu, const void* rho, void* eps, int64_t nsam, int64_t P, double pi,
+                            double sigma1, double sigma2, uint64_t seed, uint64_t step, void* w, double* logq,
+                            double* logp, void* stream) {
+    if (!mu || !rho || !eps || !w || !logq || !logp) return qb_fail("NULL argument to qb_vi_sample");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == QB_F64)
+        k_vi_sample<double><<<(unsigned)nsam, 256, 0, st>>>((const double*)mu, (const double*)rho, (double*)eps, nsam, P, pi, sigma1, sigma2, seed, step, (double*)w, logq, logp);
+    else
+        k_vi_sample<float><<<(unsigned)nsam, 256, 0, st>>>((const float*)mu, (const float*)rho, (float*)eps, nsam, P, pi, sigma1, sigma2, seed, step, (float*)w, logq, logp);
+    QB_CUDA(cudaGetLastError());
+    g_launches += 1;
+    return 0;
+}
+
+extern "C" int qb_vi_backward(int dtype, const void* mu, const void* rho, const void* eps, const void* w, const void* glp,
+                              int64_t nsam, int64_t P, double pi, double sigma1, double sigma2, double c_nll,
+                              double inv_nsam_nb, double grad_out, void* gmu, void* grho, void* stream) {
+    if (!mu || !rho || !eps || !w || !glp || !gmu || !grho) return qb_fail("NULL argument to qb_vi_backward");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned blocks = (unsigned)cdiv(P, 128);
+    if (dtype == QB_F64)
+        k_vi_backward<double><<<blocks, 128, 0, st>>>((const double*)mu, (const double*)rho, (const double*)eps, (const double*)w, (const double*)glp, nsam, P, pi, sigma1, sigma2, c_nll, inv_nsam_nb, grad_out, (double*)gmu, (double*)grho);
+    else
+        k_vi_backward<float><<<blocks, 128, 0, st>>>((const float*)mu, (const float*)rho, (const float*)eps, (const float*)w, (const float*)glp, nsam, P, pi, sigma1, sigma2, c_nll, inv_nsam_nb, grad_out, (float*)gmu, (float*)grho);
+    QB_CUDA(cudaGetLastError());
+    g_launches += 1;
+    return 0;
+}
+
+// =================================================================================================
+// FMA peak micro-benchmark (roofline denominator for the CUDA-core kernels)
+// =================================================================================================
+template <typename T, int CH>
+__global__ void __launch_bounds__(256) k_fma_peak(long long iters, T* sink) {
+    T a[CH];
+    const T b = T(1.0000001) + T(threadIdx.x) * T(1e-9), c = T(1e-7);
+#pragma unroll
+    for (int q = 0; q < CH; ++q) a[q] = T(q) * T(0.01) + T(threadIdx.x) * T(1e-6);
+    for (long long it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int q = 0; q < CH; ++q) a[q] = fma(a[q], b, c);
+    }
+    T s = T(0);
+#pragma unroll
+    for (int q = 0; q < CH; ++q) s += a[q];
+    if (s == T(123.456)) sink[0] = s;
+}
+
+extern "C" int qb_fma_peak(int dtype, int variant, int64_t iters, double* flops_out_host, void* sink, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = QB_NUM_SMS * 8, threads = 256;
+    const int CH = variant == 1 ? 16 : 8;
+    if (dtype == QB_F64) {
+        if (variant == 1) k_fma_peak<double, 16><<<blocks, threads, 0, st>>>(iters, (double*)sink);
+        else k_fma_peak<double, 8><<<blocks, threads, 0, st>>>(iters, (double*)sink);
+    } else {
+        if (variant == 1) k_fma_peak<float, 16><<<blocks, threads, 0, st>>>(iters, (float*)sink);
+        else k_fma_peak<float, 8><<<blocks, threads, 0, st>>>(iters, (float*)sink);
+    }
+    QB_CUDA(cudaGetLastError());
+    g_launches += 1;
+    if (flops_out_host) *flops_out_host = 2.0 * (double)blocks * threads * (double)iters * 8.0 * CH;
+    return 0;
+}

@@ -51,3 +51,16 @@ def oracle_layers(spec):
 
 def load(name):
     return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+def netdesc_from_spec(spec):
+    """quinn_b200 NetDesc for a NET_CASES spec (built from the oracle's layer list, no torch module)."""
+    from quinn_b200.netdesc import NetDesc, Layer
+    layers, P = oracle_layers(spec)
+    return netdesc_from_layers(layers, P)
+
+
+def netdesc_from_layers(layers, P, final_exp=False):
+    from quinn_b200.netdesc import NetDesc, Layer
+    ls = [Layer(L['n_in'], L['n_out'], L['w_off'], L['b_off'], L['act'], L['res_step']) for L in layers]
+    return NetDesc(ls[0].n_in, ls[-1].n_out, P, ls, final_exp)
