@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""Benchmark of the posterior-sampling hot path (contract: task statement "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c2|c3|c4] [--impl native|reference]
+
+Default workload = BASELINE.json configs[4] / north_star target ("c5"): AMCMC, 10^5 chains TOTAL (sharded
+over the N GPUs: strong scaling), MLP 3->64->64->1 (P=4481), N=10^4 synthetic points, fp32.  A "step" is one
+AMCMC chain step of every chain (propose + log-posterior + accept, fused kernel 3).
+metric = chain-steps/s, whole job.  Other workloads are selectable for the record:
+  c2  HMC(L=3) 1,024 chains, MLP 2->32->32->1, N=1,000            (chain-steps/s)
+  c3  256-member ensemble predictive mean/var over 10^6 points, MLP 10->128->128->1   (member-points/s)
+  c4  VI ELBO value+grad, 128 MC samples, same net, N=10^5        (MC-sample evals/s)
+One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic data
+# ------------------------------------------------------------------------------------------------
+def scale01(xx, lo, hi):
+    return xx * (hi - lo) + lo
+
+
+def workload_spec(name):
+    if name == 'c5':
+        return dict(name='c5', d=3, hls=(64, 64), N=10_000, K=100_000, sigma=0.05, sampler='amcmc',
+                    desc='AMCMC 1e5 chains (total), MLP 3-64-64-1 tanh, N=1e4 Sine data, gamma=0.01 t0=100 tadapt=1000')
+    if name == 'c2':
+        return dict(name='c2', d=2, hls=(32, 32), N=1_000, K=1_024, sigma=0.02, sampler='hmc', L=3, eps=1e-4,
+                    desc='HMC L=3 eps=1e-4, 1024 chains, MLP 2-32-32-1 tanh, N=1e3 Ackley data')
+    if name == 'c3':
+        return dict(name='c3', d=10, hls=(128, 128), N=1_000_000, K=256, sigma=0.05, sampler='predict',
+                    desc='256-member ensemble predictive mean+var, MLP 10-128-128-1 tanh, 1e6 test points')
+    if name == 'c4':
+        return dict(name='c4', d=10, hls=(128, 128), N=100_000, K=128, sigma=0.05, sampler='vi',
+                    desc='VI ELBO value+grad, 128 MC weight samples, MLP 10-128-128-1 tanh, N=1e5 Sine data')
+    raise SystemExit(f'unknown workload {name}')
+
+
+def make_data(spec):
+    rs = np.random.RandomState(0)
+    d, N = spec['d'], spec['N']
+    if spec['name'] == 'c2':
+        x = scale01(rs.rand(N, d), -1.5, 1.5)
+        y = 0.02 * rs.randn(N)
+        for i in range(d - 1):          # Ackley (func/funcs.py:90-109)
+            y += np.exp(-0.2) * np.sqrt(x[:, i] ** 2 + x[:, i + 1] ** 2) + 3 * (np.cos(2 * x[:, i]) + np.sin(2 * x[:, i + 1]))
+        return x, y.reshape(-1, 1)
+    if spec['name'] == 'c5':
+        x = scale01(rs.rand(N, d), -math.pi, math.pi)
+    else:
+        x = rs.rand(N, d)
+    y = spec['sigma'] * rs.randn(N, 1) + np.sum(np.sin(x), axis=1).reshape(-1, 1)     # Sine (funcs.py:29-45)
+    return x, y
+
+
+def mlp_desc(d, hls, o=1):
+    from quinn_b200.netdesc import NetDesc, Layer
+    widths = [d] + list(hls) + [o]
+    layers, off = [], 0
+    for l in range(len(widths) - 1):
+        w = off
+        off += widths[l] * widths[l + 1]
+        b = off
+        off += widths[l + 1]
+        layers.append(Layer(widths[l], widths[l + 1], w, b, 'tanh' if l < len(widths) - 2 else 'identity', 0.0))
+    return NetDesc(d, o, off, layers)
+
+
+def theta_init(spec, P, lo, hi):
+    """theta0[k] for global chains lo..hi-1.  c5: rand(P); c2: 0.1*randn(P); c3/c4: U(+-1/sqrt(fan_in))-like."""
+    rs = np.random.RandomState(1234 + lo)
+    n = hi - lo
+    if spec['name'] == 'c5':
+        return rs.rand(n, P).astype(np.float32)
+    if spec['name'] == 'c2':
+        return (0.1 * rs.randn(n, P)).astype(np.float32)
+    return ((2 * rs.rand(n, P) - 1) / math.sqrt(spec['hls'][0])).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md: the clocks line)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            f = [c.strip() for c in r.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[3:7]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline (oracle port of the reference flow, timed on the host cores)
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(spec, budget_s=18.0):
+    import torch
+    from oracle.torch_port import RefPort, amcmc_proposal_draw
+    torch.set_num_threads(os.cpu_count() or 1)
+    x, y = make_data(spec)
+    port = RefPort(spec['d'], 1, spec['hls'], 'tanh')
+    ylist = [r for r in y]
+    rs = np.random.RandomState(7)
+    th = rs.rand(port.pdim)
+    cores = torch.get_num_threads()
+    if spec['sampler'] == 'predict':
+        n = min(spec['N'], 200_000)
+        t0 = time.perf_counter()
+        port.forward(th, x[:n])
+        dt = time.perf_counter() - t0
+        return dict(value=n / dt, unit='member-points/s', cores=cores, kind='port',
+                    sample=f'1 member x {n} points of {spec["N"]} (reference: Learner.predict per member, sequential)')
+
+    def rate(fn, budget):
+        for _ in range(2):
+            fn()
+        n, t0 = 0, time.perf_counter()
+        while True:
+            fn()
+            n += 1
+            dt = time.perf_counter() - t0
+            if dt > budget or n >= 400:
+                return dt / n
+    if spec['sampler'] == 'amcmc':
+        t_lp = rate(lambda: port.logpost(th, x, ylist, spec['sigma']), 5.0)
+        t0 = time.perf_counter()
+        amcmc_proposal_draw(th)                     # one dense-covariance draw (SVD of PxP), admcmc.py:70
+        t_draw = time.perf_counter() - t0
+        return dict(value=1.0 / (t_lp + t_draw), unit='chain-steps/s', cores=cores, kind='port',
+                    sample=f'1 chain of {spec["K"]}: {t_lp * 1e3:.2f} ms/logpost (avg over ~5 s) + {t_draw:.2f} s/proposal draw '
+                           f'(1 draw, PxP SVD); logpost-only rate {1.0 / t_lp:.1f} evals/s',
+                    logpost_only_evals_per_s=1.0 / t_lp, proposal_draw_s=t_draw)
+    if spec['sampler'] == 'hmc':
+        t_g = rate(lambda: port.logpostgrad(th, x, ylist, spec['sigma']), 6.0)
+        t_v = rate(lambda: port.logpost(th, x, ylist, spec['sigma']), 3.0)
+        step = (spec['L'] + 1) * t_g + t_v          # hmc.py: L+1 gradients + 1 value per step
+        return dict(value=1.0 / step, unit='chain-steps/s', cores=cores, kind='port',
+                    sample=f'1 chain of {spec["K"]}: {(spec["L"] + 1)} grads ({t_g * 1e3:.2f} ms) + 1 value ({t_v * 1e3:.2f} ms) per step')
+    # vi: value+grad per MC sample
+    t_g = rate(lambda: port.logpostgrad(th, x, ylist, spec['sigma']), 10.0)
+    return dict(value=1.0 / t_g, unit='MC-sample evals/s', cores=cores, kind='port',
+                sample='viloss fwd+bwd per MC weight sample, sequential over samples (bnet.py:202-205)')
+
+
+def run_reference_arm(args, spec):
+    """--impl reference: the reference's CPU algorithm for this path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    vals = []
+    base = None
+    for _ in range(max(1, min(args.steps, 3))):
+        base = cpu_baseline(spec, budget_s=10.0)
+        vals.append(base['value'])
+    v = float(np.mean(vals))
+    base['value'] = v
+    line = dict(impl='reference', metric=metric_name(spec), value=v, unit=base['unit'], n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 / v if v > 0 else None, higher_is_better=True, scaling='strong',
+                vs_baseline=None, dtype='f64', data='synthetic', config=dict(workload=spec['desc']),
+                cpu_baseline=base, e2e=dict(value=v, unit=base['unit'], h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                wall_s=time.perf_counter() - t0)
+    print(json.dumps(line), flush=True)
+
+
+def metric_name(spec):
+    return {'amcmc': 'MCMC chain-steps/sec', 'hmc': 'MCMC chain-steps/sec', 'predict': 'predictive member-points/sec',
+            'vi': 'VI MC-sample evals/sec'}[spec['sampler']]
+
+
+# ------------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--workload', default='c5')
+    ap.add_argument('--impl', default='native')
+    ap.add_argument('--chains', type=int, default=0, help='override the total chain count (development)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    spec = workload_spec(args.workload)
+    if args.chains:
+        spec['K'] = args.chains
+    if args.impl == 'reference':
+        run_reference_arm(args, spec)
+        return
+
+    import torch
+    from quinn_b200 import ops, dist, _lib
+    rank, world, local = dist.init()
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py (native arm) needs a CUDA device; there is no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    lib = _lib.load()
+    args.warmup = max(args.warmup, 3)
+    desc = mlp_desc(spec['d'], spec['hls'])
+    P, S = desc.n_params, desc.macs_per_point()
+    x, y = make_data(spec)
+    lo, hi = dist.shard_range(spec['K'], rank, world)
+    Kloc = hi - lo
+    N = spec['N']
+    dt = torch.float32
+    F_v = 2.0 * N * S
+    F_vg = 6.0 * N * S - 2.0 * N * desc.layers[0].n_in * desc.layers[0].n_out
+
+    th0_host = torch.from_numpy(theta_init(spec, P, lo, hi)).pin_memory()
+    launches0 = lib.qb_launch_count()
+
+    if spec['sampler'] in ('amcmc', 'hmc'):
+        prob = ops.Problem(desc, x, y, spec['sigma'], dtype=dt, device=dev)
+        st = ops.ChainState(prob, th0_host)
+        if spec['sampler'] == 'amcmc':
+            samp = ops.AmcmcState(st, gamma=0.01, t0=100, tadapt=1000, adapt='diag')
+            advance = lambda n: ops.amcmc_run(st, samp, n, None, seed=2026, chain_offset=lo)      # noqa: E731
+            flop_per_unit, kernel_name = F_v, 'k_amcmc<float>'
+        else:
+            samp = ops.HmcState(st, epsilon=spec['eps'], L=spec['L'], method='hmc')
+            advance = lambda n: ops.hmc_run(st, samp, n, None, seed=2026, chain_offset=lo)        # noqa: E731
+            flop_per_unit, kernel_name = spec['L'] * F_vg, 'k_hmc<float>'
+        units_per_step = spec['K']
+        plan = prob.plan_info(Kloc, spec['sampler'] == 'hmc')
+    elif spec['sampler'] == 'predict':
+        # members stay whole on every rank; the 10^6 test points are sharded (no collective needed)
+        plo, phi = dist.shard_range(N, rank, world)
+        xs = torch.as_tensor(x[plo:phi], dtype=dt, device=dev)
+        th = torch.as_tensor(theta_init(spec, P, 0, spec['K']), device=dev)
+        cnet = desc.to_c()
+        advance = lambda n: [ops.predict(desc, th, xs, dtype=dt, device=dev, want_out=False, want_moments=True, cnet=cnet) for _ in range(n)]  # noqa: E731
+        flop_per_unit, kernel_name = 2.0 * S, 'k_predict<float>'
+        units_per_step = spec['K'] * N
+        plan = {}
+    else:   # vi
+        prob = ops.Problem(desc, x, y, 1.0, dtype=dt, device=dev)
+        mu = torch.as_tensor(theta_init(spec, P, 0, 1)[0], device=dev)
+        rho = torch.full((P,), -4.5, dtype=dt, device=dev)
+        B = N
+        c_ssq = 0.5 * B / (Kloc * world * B) / spec['sigma'] ** 2
+
+        def advance(n):
+            for i in range(n):
+                w, eps, logq, logp = ops.vi_sample(mu, rho, Kloc, 0.5, 1.0, 1.0, seed=11 + rank, step=i + 1)
+                lp, glp = ops.logpost_grad(prob, w)
+                ops.vi_backward(mu, rho, eps, w, glp, 0.5, 1.0, 1.0, c_ssq, -1.0 / spec['K'], 1.0 / spec['K'])
+        flop_per_unit, kernel_name = F_vg, 'k_logpost_grad<float>'
+        units_per_step = spec['K']
+        plan = prob.plan_info(Kloc, True)
+
+    # ---- FP32 FMA peak, measured live (the roofline denominator; MEASURED_PEAKS.json has no such entry)
+    fma_peak = ops.fma_peak(dt, 0, iters=20000, device=dev)
+
+    # ---- warm-up, then the timed region (device-timed, barrier + sync on both sides, max over ranks)
+    advance(args.warmup)
+    torch.cuda.synchronize()
+    dist.barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = lib.qb_launch_count()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    advance(args.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms_local = e0.elapsed_time(e1)
+    launches = lib.qb_launch_count() - l0
+    ms = dist.max_over_ranks(ms_local)
+    clk = clocks.stop() if rank == 0 else None
+
+    # cross-chain diagnostic reduced over NVLink (R-hat of the log-posterior needs per-chain moments; here the
+    # acceptance-rate mean/variance as a cheap collective sanity number)
+    diag = None
+    if spec['sampler'] in ('amcmc', 'hmc'):
+        acc = st.naccept.double() / float(st.t)
+        s = torch.stack([acc.sum(), (acc * acc).sum(), torch.tensor(float(Kloc), device=dev, dtype=torch.float64)])
+        dist._allreduce(s)
+        diag = dict(mean_accept_rate=(s[0] / s[2]).item())
+
+    value = units_per_step * args.steps / (ms * 1e-3)
+    achieved = (Kloc if spec['sampler'] != 'predict' else spec['K'] * (xs.shape[0])) * args.steps * flop_per_unit / (ms_local * 1e-3)
+    roofline = dict(bound='fp32', kernel=kernel_name, achieved=achieved / 1e12, peak=fma_peak / 1e12, unit='TFLOP/s',
+                    frac=achieved / fma_peak, traffic=None,
+                    note='FP32 CUDA-core FMA bound (not hbm/tensor): peak = live FMA micro-benchmark qb_fma_peak; '
+                         'achieved = algorithmic GEMM flops (2 flop/MAC, SURVEY 8d) / CUDA-event time of the timed launches')
+
+    # ---- end to end through the public API with host buffers
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(spec, desc, x, y, th0_host, lo, args, dev, world)
+
+    if rank == 0:
+        cb = None
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_baseline(spec)
+        line = dict(metric=metric_name(spec), value=value, unit=cpu_unit(spec), n_gpus=world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling='strong',
+                    vs_baseline=None, dtype='f32', data='synthetic',
+                    config=dict(workload=spec['desc'], chains_or_units_total=spec['K'], per_rank=Kloc, N=N, P=P,
+                                macs_per_point=S, plan=plan, l2='inputs larger than L2 (per-chain state %.2f GB)' % (Kloc * P * 4 / 1e9)
+                                if spec['sampler'] in ('amcmc', 'hmc') else 'inputs larger than L2 or re-staged per member'),
+                    clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cb, diagnostics=diag)
+        print(json.dumps(line), flush=True)
+
+
+def cpu_unit(spec):
+    return {'amcmc': 'chain-steps/s', 'hmc': 'chain-steps/s', 'predict': 'member-points/s', 'vi': 'MC-sample evals/s'}[spec['sampler']]
+
+
+def run_e2e(spec, desc, x, y, th0_host, lo, args, dev, world):
+    """Same metric through the public API (the reference-facing classes) with HOST inputs and outputs."""
+    import torch
+    from quinn_b200 import dist
+    from quinn_b200.mcmc import AMCMC, HMC, DeviceLogPost
+    from quinn_b200 import ops
+    steps = args.steps
+    P = desc.n_params
+    if spec['sampler'] in ('amcmc', 'hmc'):
+        sam = AMCMC(gamma=0.01, t0=100, tadapt=1000, adapt='diag') if spec['sampler'] == 'amcmc' else HMC(epsilon=spec['eps'], L=spec['L'])
+        out_host = torch.empty((th0_host.shape[0], P), dtype=torch.float32).pin_memory()
+
+        def once():
+            prob = ops.Problem(desc, x, y, spec['sigma'], dtype=torch.float32, device=dev)        # H2D of x, y
+            sam.setLogPost(DeviceLogPost(prob), None)
+            res = sam.run(steps, th0_host, seed=5, store_every=steps, chain_offset=lo, verbose=False, keep_on_device=True)
+            out_host.copy_(res['chain'][:, -1, :], non_blocking=True)                           # D2H final states
+            lp = res['logpost'].cpu()
+            acc = res['accrate'].cpu()
+            torch.cuda.synchronize()
+            return lp, acc
+        once()
+        dist.barrier()
+        t0 = time.perf_counter()
+        once()
+        dist.barrier()
+        dtm = dist.max_over_ranks(time.perf_counter() - t0)
+        h2d = (th0_host.numel() * 4 + x.size * 4 + y.size * 4) / steps
+        d2h = (out_host.numel() * 4 + th0_host.shape[0] * (steps + 1) * 8 + th0_host.shape[0] * 8) / steps
+        return dict(value=spec['K'] * steps / dtm, unit='chain-steps/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                    api='AMCMC/HMC.run(nmcmc=steps, param_ini=host[K,P]) -> host final states + logpost + accrate')
+    if spec['sampler'] == 'predict':
+        plo, phi = dist.shard_range(spec['N'], *dist.env_rank_world()[:2])
+        xh = torch.from_numpy(np.ascontiguousarray(x[plo:phi], dtype=np.float32)).pin_memory()
+        thh = torch.from_numpy(theta_init(spec, P, 0, spec['K'])).pin_memory()
+
+        def once():
+            _, m, v = ops.predict(desc, thh, xh, dtype=torch.float32, device=dev, want_out=False, want_moments=True)
+            return m.cpu(), v.cpu()
+        once()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            once()
+        dist.barrier()
+        dtm = dist.max_over_ranks(time.perf_counter() - t0)
+        return dict(value=spec['K'] * spec['N'] * steps / dtm, unit='member-points/s', h2d_bytes_per_step=xh.numel() * 4 + thh.numel() * 4,
+                    d2h_bytes_per_step=2 * xh.shape[0] * 4, api='ops.predict(host theta, host x) -> host mean, var')
+    return None
+
+
+if __name__ == '__main__':
+    main()

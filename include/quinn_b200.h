@@ -203,15 +203,15 @@ int qb_vi_sample(int dtype, const void* mu, const void* rho, void* eps, int64_t 
                  double pi, double sigma1, double sigma2, uint64_t rng_seed_or_0, uint64_t rng_step,
                  void* w, double* logq, double* logp, void* stream);
 
-/* Chain rule of BNet.viloss (bnet.py:219-232) back to (mu, rho):
- * given glp[s,:] = d lp_data(sigma=1)/d w_s (from qb_logpost_grad, so d ssq/dw = -2 glp),
- * c_nll = 0.5*B/(nsam*B*o)/datanoise^2, and the mixture prior parameters,
- * gmu[p]  = sum_s ( -2 c_nll glp - dlogp/dw /(nsam*nb) )
- * grho[p] = sum_s ( (-2 c_nll glp - dlogp/dw /(nsam*nb)) * exp(rho) eps  - 1/(nsam*nb) )
- * scaled by grad_out (the upstream gradient of the scalar loss). */
+/* Chain rule of BNet.sample_elbo / viloss (bnet.py:181-232) back to (mu, rho).  With
+ * glp[s,:] = d lp_data(sigma=1)/d w_s from qb_logpost_grad (so d ssq_s/dw = -2 glp), for a scalar
+ *   L = c_ssq * sum_s ssq_s + c_logp * sum_s logp_s + c_logq * sum_s logq_s
+ * it returns gmu[p] = sum_s dL/dw_sp and grho[p] = sum_s (dL/dw_sp * exp(rho_p) eps_sp) - nsam*c_logq
+ * (the total derivative of log q wrt mu is 0 and wrt rho is -1 per sample).
+ * viloss uses c_ssq = 0.5*B/(nsam*B*o)/datanoise^2, c_logp = -1/(nsam*num_batches), c_logq = -c_logp. */
 int qb_vi_backward(int dtype, const void* mu, const void* rho, const void* eps, const void* w,
                    const void* glp, int64_t nsam, int64_t P, double pi, double sigma1, double sigma2,
-                   double c_nll, double inv_nsam_nb, double grad_out, void* gmu, void* grho, void* stream);
+                   double c_ssq, double c_logp, double c_logq, void* gmu, void* grho, void* stream);
 
 /* ---- measurement helper --------------------------------------------------------------------------
  * Dependent-chain FMA micro-benchmark used as the FP32 / FP64 CUDA-core roofline denominator

@@ -890,7 +890,7 @@ __global__ void __launch_bounds__(256) k_vi_sample(const T* mu, const T* rho, T*
 
 template <typename T>
 __global__ void k_vi_backward(const T* mu, const T* rho, const T* eps, const T* w, const T* glp, long long nsam, long long P,
-                              double pi, double s1, double s2, double c_nll, double inv_nsam_nb, double gout, T* gmu, T* grho) {
+                              double pi, double s1, double s2, double c_ssq, double c_logp, double c_logq, T* gmu, T* grho) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     const double LOG_SQRT_2PI = 0.91893853320467274178;
@@ -901,12 +901,12 @@ __global__ void k_vi_backward(const T* mu, const T* rho, const T* eps, const T* 
         const double p1 = pi * exp(-wd * wd / (2.0 * s1 * s1) - log(s1) - LOG_SQRT_2PI);
         const double p2 = (1.0 - pi) * exp(-wd * wd / (2.0 * s2 * s2) - log(s2) - LOG_SQRT_2PI);
         const double dlogp = (p1 * (-wd / (s1 * s1)) + p2 * (-wd / (s2 * s2))) / (p1 + p2);
-        const double dw = c_nll * (-2.0 * (double)glp[s * P + i]) - dlogp * inv_nsam_nb;
+        const double dw = c_ssq * (-2.0 * (double)glp[s * P + i]) + c_logp * dlogp;
         am += dw;
-        ar += dw * sig * e - inv_nsam_nb;
+        ar += dw * sig * e - c_logq;      // log q: total derivative wrt mu is 0, wrt rho is -1 per sample
     }
-    gmu[i] = (T)(gout * am);
-    grho[i] = (T)(gout * ar);
+    gmu[i] = (T)am;
+    grho[i] = (T)ar;
 }
 
 extern "C" int qb_vi_sample(int dtype, const void* mu, const void* rho, void* eps, int64_t nsam, int64_t P, double pi,
@@ -924,15 +924,15 @@ extern "C" int qb_vi_sample(int dtype, const void* mu, const void* rho, void* ep
 }
 
 extern "C" int qb_vi_backward(int dtype, const void* mu, const void* rho, const void* eps, const void* w, const void* glp,
-                              int64_t nsam, int64_t P, double pi, double sigma1, double sigma2, double c_nll,
-                              double inv_nsam_nb, double grad_out, void* gmu, void* grho, void* stream) {
+                              int64_t nsam, int64_t P, double pi, double sigma1, double sigma2, double c_ssq,
+                              double c_logp, double c_logq, void* gmu, void* grho, void* stream) {
     if (!mu || !rho || !eps || !w || !glp || !gmu || !grho) return qb_fail("NULL argument to qb_vi_backward");
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned blocks = (unsigned)cdiv(P, 128);
     if (dtype == QB_F64)
-        k_vi_backward<double><<<blocks, 128, 0, st>>>((const double*)mu, (const double*)rho, (const double*)eps, (const double*)w, (const double*)glp, nsam, P, pi, sigma1, sigma2, c_nll, inv_nsam_nb, grad_out, (double*)gmu, (double*)grho);
+        k_vi_backward<double><<<blocks, 128, 0, st>>>((const double*)mu, (const double*)rho, (const double*)eps, (const double*)w, (const double*)glp, nsam, P, pi, sigma1, sigma2, c_ssq, c_logp, c_logq, (double*)gmu, (double*)grho);
     else
-        k_vi_backward<float><<<blocks, 128, 0, st>>>((const float*)mu, (const float*)rho, (const float*)eps, (const float*)w, (const float*)glp, nsam, P, pi, sigma1, sigma2, c_nll, inv_nsam_nb, grad_out, (float*)gmu, (float*)grho);
+        k_vi_backward<float><<<blocks, 128, 0, st>>>((const float*)mu, (const float*)rho, (const float*)eps, (const float*)w, (const float*)glp, nsam, P, pi, sigma1, sigma2, c_ssq, c_logp, c_logq, (float*)gmu, (float*)grho);
     QB_CUDA(cudaGetLastError());
     g_launches += 1;
     return 0;

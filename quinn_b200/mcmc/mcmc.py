@@ -1,0 +1,188 @@
+"""MCMCBase: chain driver with the reference's interface (quinn/mcmc/mcmc.py:9-114), running K chains
+at once on the GPU.
+
+``setLogPost`` accepts
+  * a ``DeviceLogPost`` handle, or ``NN_MCMC.logpost`` / ``logpostgrad`` bound methods with ``lpinfo=``
+    (what the reference's NN_MCMC.fit passes, nn_mcmc.py:130-135): the whole run is ONE fused kernel per
+    segment -- propose, evaluate, accept on the device, no host round trip per step (kernel 3);
+  * any other Python callable (the reference's own sampler tests pass numpy closures,
+    tests/test_mcmc.py:10-22): propose/accept still run on the GPU (torch tensors), the callable is
+    invoked once per sweep -- batched over chains if it has attribute ``batched = True`` and takes/returns
+    CUDA tensors, else chain by chain on numpy rows.  This adapter exists for API conformance only.
+
+``run(nmcmc, param_ini)``: ``param_ini`` of shape (P,) reproduces the reference's result dict exactly
+('chain' (M+1,P), 'mapparams', 'maxpost', 'accrate', 'logpost', 'alphas', mcmc.py:92-99); shape (K,P)
+adds a leading K axis to every entry.
+"""
+import numpy as np
+import torch
+
+from .. import ops
+
+
+class DeviceLogPost:
+    """A log-posterior that lives on the GPU: network + data + likelihood (an ops.Problem)."""
+
+    def __init__(self, problem: ops.Problem):
+        self.problem = problem
+
+    def __call__(self, theta, **_):
+        lp = ops.logpost(self.problem, theta)
+        return float(lp[0].item()) if np.ndim(theta) == 1 else lp
+
+    def grad(self, theta, **_):
+        _, g = ops.logpost_grad(self.problem, theta)
+        return g[0].double().cpu().numpy() if np.ndim(theta) == 1 else g
+
+
+class MCMCBase(object):
+    def __init__(self):
+        self.logPost = None
+        self.logPostGrad = None
+        self.postInfo = {}
+        self._device_lp = None
+
+    def setLogPost(self, logPost, logPostGrad, **postInfo):
+        self.logPost = logPost
+        self.logPostGrad = logPostGrad
+        self.postInfo = postInfo
+        self._device_lp = None
+        if isinstance(logPost, DeviceLogPost):
+            self._device_lp = logPost
+        else:
+            owner = getattr(logPost, '__self__', None)
+            if owner is not None and hasattr(owner, 'device_logpost') and 'lpinfo' in postInfo:
+                self._device_lp = owner.device_logpost(postInfo['lpinfo'])
+
+    # ------------------------------------------------------------------ public driver
+    def run(self, nmcmc, param_ini, *, seed=None, store_every=1, replay=None, chain_offset=0, verbose=True,
+            keep_on_device=False):
+        """nmcmc steps for every row of param_ini.
+
+        Extensions (keyword-only): ``seed`` Philox seed (default: drawn from np.random so np.random.seed
+        controls it), ``store_every`` thinning of the returned chain, ``replay=dict(incr=[M,(K,)P],
+        unif=[M,(K)])`` to consume recorded draws instead of Philox, ``chain_offset`` global index of the
+        first chain (multi-GPU sharding), ``keep_on_device`` return CUDA tensors.
+        """
+        assert self.logPost is not None
+        if not torch.is_tensor(param_ini):          # tensors (e.g. pinned host memory) are passed through untouched
+            param_ini = np.asarray(param_ini, dtype=np.float64)
+        single = param_ini.ndim == 1
+        theta0 = param_ini[None, :] if single else param_ini
+        if seed is None:
+            seed = int(np.random.randint(1, 2 ** 31 - 1))
+        if self._device_lp is not None:
+            res = self._run_fused(int(nmcmc), theta0, int(seed), int(store_every), replay, int(chain_offset), verbose)
+        else:
+            res = self._run_generic(int(nmcmc), theta0, int(seed), int(store_every), verbose)
+        return self._finish(res, single, keep_on_device)
+
+    # ------------------------------------------------------------------ fused path (kernel 3)
+    def _run_fused(self, nmcmc, theta0, seed, store_every, replay, chain_offset, verbose):
+        prob = self._device_lp.problem
+        st = ops.ChainState(prob, theta0)
+        K, P = st.K, st.P
+        samp = self._device_sampler_state(st)
+        incr = unif = None
+        if replay is not None:
+            incr = ops.as_device(np.asarray(replay['incr']).reshape(nmcmc, K, P), prob.dtype, prob.device)
+            unif = ops.as_device(np.asarray(replay['unif']).reshape(nmcmc, K), torch.float64, prob.device)
+        nseg = 10 if (verbose and nmcmc >= 10) else 1
+        bounds = [int(round(i * nmcmc / nseg)) for i in range(nseg + 1)]
+        if store_every > 1:          # segment boundaries must fall on stored steps
+            bounds = sorted(set([0, nmcmc] + [b - b % store_every for b in bounds[1:-1]]))
+        recs = []
+        th0 = st.theta.clone()
+        lp0 = ops.logpost(prob, th0)        # log-posterior of the initial state (mcmc.py:55-61)
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            if b <= a:
+                continue
+            rec = ops.Recorder(st, b - a, store_every=store_every)
+            kw = dict(seed=seed, chain_offset=chain_offset)
+            if incr is not None:
+                kw.update(incr=incr[a:b].contiguous(), unif=unif[a:b].contiguous())
+            self._device_advance(st, samp, b - a, rec, kw)
+            recs.append(rec)
+            if verbose:
+                acc = st.naccept.double().mean().item() / b
+                print('%d / %d completed, acceptance rate %lg' % (b, nmcmc, acc))
+        self._device_export(st, samp)
+        chain = torch.cat([th0[:, None, :]] + [r.samples for r in recs if r.samples is not None], dim=1)
+        logpost = torch.cat([lp0[:, None]] + [r.logpost for r in recs], dim=1)
+        alphas = torch.cat([torch.zeros((K, 1), dtype=torch.float64, device=prob.device)] + [r.alpha for r in recs], dim=1)
+        accepted = torch.cat([r.accepted for r in recs], dim=1)
+        return dict(chain=chain, mapparams=st.map_theta, maxpost=st.map_lp, accrate=st.naccept.double() / nmcmc,
+                    logpost=logpost, alphas=alphas, accepted=accepted, state=st)
+
+    # hooks the samplers implement for the fused path
+    def _device_sampler_state(self, st):
+        raise NotImplementedError
+
+    def _device_advance(self, st, samp, nsteps, rec, kw):
+        raise NotImplementedError
+
+    def _device_export(self, st, samp):
+        pass
+
+    # ------------------------------------------------------------------ generic-callable adapter
+    def _eval_generic(self, fn, theta):
+        """theta: CUDA [K,P] float64 -> CUDA [K] (logPost) or [K,P] (logPostGrad)."""
+        if getattr(fn, 'batched', False):
+            return fn(theta, **self.postInfo)
+        rows = theta.cpu().numpy()
+        vals = [np.asarray(fn(r, **self.postInfo), dtype=np.float64) for r in rows]
+        return torch.as_tensor(np.stack(vals), dtype=torch.float64, device=theta.device)
+
+    def _run_generic(self, nmcmc, theta0, seed, store_every, verbose):
+        if not torch.cuda.is_available():
+            raise RuntimeError('quinn_b200 samplers need a CUDA device (there is no CPU fallback)')
+        dev = torch.device('cuda')
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(seed)
+        cur = torch.as_tensor(theta0).to(device=dev, dtype=torch.float64).clone()
+        K, P = cur.shape
+        cur_U = -self._eval_generic(self.logPost, cur)
+        cmode, pmode = cur.clone(), -cur_U.clone()
+        samples, alphas, logposts, accs = [cur.clone()], [torch.zeros(K, dtype=torch.float64, device=dev)], [-cur_U], []
+        na = torch.zeros(K, dtype=torch.float64, device=dev)
+        self._gen = gen
+        for imcmc in range(nmcmc):
+            prop, K_cur, K_prop = self.sampler(cur, imcmc)
+            prop_U = -self._eval_generic(self.logPost, prop)
+            mh = torch.exp((cur_U + K_cur) - (prop_U + K_prop))
+            u = torch.rand(K, dtype=torch.float64, device=dev, generator=gen)
+            acc = u < mh
+            na += acc
+            cur = torch.where(acc[:, None], prop, cur)
+            cur_U = torch.where(acc, prop_U, cur_U)
+            better = acc & (-cur_U >= pmode)
+            pmode = torch.where(better, -cur_U, pmode)
+            cmode = torch.where(better[:, None], cur, cmode)
+            if (imcmc + 1) % store_every == 0:
+                samples.append(cur.clone())
+            alphas.append(mh)
+            logposts.append(-cur_U)
+            accs.append(acc)
+            if verbose and nmcmc >= 10 and ((imcmc + 2) % (nmcmc // 10) == 0):
+                print('%d / %d completed, acceptance rate %lg' % (imcmc + 2, nmcmc, na.mean().item() / (imcmc + 1)))
+        return dict(chain=torch.stack(samples, 1), mapparams=cmode, maxpost=pmode, accrate=na / max(nmcmc, 1),
+                    logpost=torch.stack(logposts, 1), alphas=torch.stack(alphas, 1),
+                    accepted=torch.stack(accs, 1) if accs else torch.zeros((K, 0), dtype=torch.bool, device=dev))
+
+    def sampler(self, current, imcmc):
+        """Generic-path proposal for all chains: (proposal[K,P], current_K[K], proposed_K[K])."""
+        raise NotImplementedError("sampler method not implemented in the base class and should be implemented in children.")
+
+    # ------------------------------------------------------------------ result dict
+    def _finish(self, res, single, keep_on_device):
+        self.last_state = res.pop('state', None)
+        if keep_on_device:
+            return res
+        out = {}
+        for k, v in res.items():
+            a = v.detach().double().cpu().numpy() if v.dtype != torch.uint8 and v.dtype != torch.bool else v.cpu().numpy().astype(bool)
+            out[k] = a[0] if single else a
+        if single:
+            out['maxpost'] = float(out['maxpost'])
+            out['accrate'] = float(out['accrate'])
+        return out

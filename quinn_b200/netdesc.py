@@ -79,7 +79,7 @@ def _act_of(m):
 def _from_sequential(seq, prefix, offs, layers):
     """Linear [act] Linear [act] ... ; an activation directly follows the Linear it applies to."""
     final_exp = False
-    mods = list(seq.named_children())
+    mods = list(seq._modules.items())      # NOT named_children(): MLP reuses one activation module (mlp.py:65,76)
     for name, m in mods:
         if isinstance(m, torch.nn.Linear):
             w = offs[f'{prefix}{name}.weight']
@@ -94,7 +94,7 @@ def _from_sequential(seq, prefix, offs, layers):
                 raise NotImplementedError('two activations in a row are not supported')
             layers[-1].act = _act_of(m)
         elif type(m).__name__ == 'Expon':
-            if (name, m) != mods[-1]:
+            if name != mods[-1][0]:
                 raise NotImplementedError('Expon is only supported as the final transform')
             final_exp = True
         else:

@@ -334,14 +334,14 @@ def vi_sample(mu, rho, nsam, pi, sigma1, sigma2, eps=None, seed=0, step=0):
     return w, eps, logq, logp
 
 
-def vi_backward(mu, rho, eps, w, glp, pi, sigma1, sigma2, c_nll, inv_nsam_nb, grad_out=1.0):
+def vi_backward(mu, rho, eps, w, glp, pi, sigma1, sigma2, c_ssq, c_logp, c_logq):
     nsam, P = w.shape
     gmu = torch.empty_like(mu)
     grho = torch.empty_like(rho)
     with torch.cuda.device(mu.device):
         rc = _lib.load().qb_vi_backward(qb_dtype(mu.dtype), _ptr(mu), _ptr(rho), _ptr(eps), _ptr(w), _ptr(glp), nsam, P,
-                                        float(pi), float(sigma1), float(sigma2), float(c_nll), float(inv_nsam_nb),
-                                        float(grad_out), _ptr(gmu), _ptr(grho), _stream())
+                                        float(pi), float(sigma1), float(sigma2), float(c_ssq), float(c_logp),
+                                        float(c_logq), _ptr(gmu), _ptr(grho), _stream())
     _lib.check(rc, 'qb_vi_backward')
     return gmu, grho
 

@@ -1,0 +1,4 @@
+from .quinn import QUiNNBase
+from .nn_mcmc import NN_MCMC
+from .nn_ens import NN_Ens
+from .nn_vi import NN_VI

@@ -303,7 +303,7 @@ def test_vi_loss_and_grads_golden(name, net):
     c_nll = 0.5 * B / (nsam * B * o) / dn ** 2
     loss = (logq.mean() - logp.mean()) / nb + B * np.log(dn) + 0.5 * B * np.log(2 * np.pi) + c_nll * ssq.sum()
     assert abs(loss.item() - float(g['loss'])) <= 1e-10 * abs(float(g['loss']))
-    gmu, grho = ops.vi_backward(mu, rho, eps, w, glp, pi, s1, s2, c_nll, 1.0 / (nsam * nb))
+    gmu, grho = ops.vi_backward(mu, rho, eps, w, glp, pi, s1, s2, c_nll, -1.0 / (nsam * nb), 1.0 / (nsam * nb))
     np.testing.assert_allclose(gmu.cpu().numpy(), g['gmu'], rtol=1e-8, atol=1e-9 * np.abs(g['gmu']).max())
     np.testing.assert_allclose(grho.cpu().numpy(), g['grho'], rtol=1e-8, atol=1e-9 * np.abs(g['grho']).max())
 

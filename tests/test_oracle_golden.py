@@ -129,3 +129,18 @@ def test_ensemble_predictive():
     np.testing.assert_allclose(c, g['ycov'], rtol=1e-10, atol=1e-16)
     m1, v1, _ = qo.predict_moments(ye, msc=1)
     np.testing.assert_allclose(v1, g['yvar'], rtol=1e-10, atol=1e-16)
+
+
+def test_torch_port_matches_golden():
+    """oracle/torch_port.py (the CPU-baseline flow) computes the same numbers as the reference."""
+    from oracle.torch_port import RefPort
+    for name in ('mlp_c2', 'mlp_tanh_o2'):
+        spec = NET_CASES[name]
+        g = load(f'logpost_{name}.npz')
+        port = RefPort(spec['indim'], spec['outdim'], spec['hls'], spec['activ'])
+        x, y = make_inputs(spec)
+        th = make_thetas(spec, port.pdim)
+        lp = port.logpost(th[0], x, [r for r in y], spec['sigma'])
+        assert abs(lp - g['lp'][0]) <= 1e-12 * abs(g['lp'][0])
+        gr = port.logpostgrad(th[0], x, [r for r in y], spec['sigma'])
+        assert np.abs(gr - g['grad'][0]).max() <= 1e-11 * np.abs(g['grad'][0]).max()
