@@ -432,13 +432,16 @@ __device__ void qb_dw_accumulate(const QbLayerPlan& L, const T* R, int lda, int 
 // delta_a of layer l's INPUT (= output of layer l-1): W_l^T delta_z_l (+ pass-through if layer l is
 // residual), immediately converted to delta_z of layer l-1 and stored in place over that layer's
 // activations.
-template <typename T>
-__device__ void qb_bwd_gemm(const QbLayerPlan& L, const QbLayerPlan& Lm, const T* sW, T* R, T* D, int lda, int TM) {
+// GLOBALW: the (rare) fallback when Wt and Wr do not both fit in shared memory: W is read straight from
+// the flat parameter vector in global memory / L1 with contiguous (un-permuted) units.
+template <typename T, bool GLOBALW>
+__device__ void qb_bwd_gemm(const QbLayerPlan& L, const QbLayerPlan& Lm, const T* sW, const T* theta, T* R, T* D,
+                            int lda, int TM) {
     constexpr int TP = VT<T>::TP, TU = VT<T>::TU;
     const int UGI = L.n_in_pad / TU, PG = TM / TP, items = UGI * PG;
-    const T* Wr = sW + L.wr_off;
+    const T* Wr = GLOBALW ? theta + L.w_off : sW + L.wr_off;
     const T* Rz = R + (size_t)L.row_out * lda;
-    const int n_out = L.n_out, ldw = L.n_in_pad;
+    const int n_out = L.n_out, ldw = GLOBALW ? L.n_in : L.n_in_pad;
     for (int base = 0; base < items; base += blockDim.x) {
         const int item = base + threadIdx.x;
         if (item >= items) continue;
@@ -454,7 +457,12 @@ __device__ void qb_bwd_gemm(const QbLayerPlan& L, const QbLayerPlan& Lm, const T
         for (int j = 0; j < n_out; ++j) {
             T d[TP], w[TU];
             ldv<TP>(d, zp + (size_t)j * lda);
-            ldv<TU>(w, wp + j * ldw);
+            if (GLOBALW) {
+#pragma unroll
+                for (int u = 0; u < TU; ++u) w[u] = (ig * TU + u < L.n_in) ? wp[j * ldw + u] : T(0);
+            } else {
+                ldv<TU>(w, wp + j * ldw);
+            }
 #pragma unroll
             for (int u = 0; u < TU; ++u)
 #pragma unroll
@@ -462,7 +470,7 @@ __device__ void qb_bwd_gemm(const QbLayerPlan& L, const QbLayerPlan& Lm, const T
         }
 #pragma unroll
         for (int u = 0; u < TU; ++u) {
-            const int i = ig + UGI * u;
+            const int i = GLOBALW ? ig * TU + u : ig + UGI * u;
             if (i < L.n_in) {
                 if (L.has_res) {
                     T pass[TP];
@@ -522,7 +530,8 @@ __device__ double qb_eval_value_grad(const QbPlan& P, const QbSmem& S, const T* 
             qb_dw_accumulate<T>(L, R, lda, TM, g);
             __syncthreads();
             if (l > 0) {
-                qb_bwd_gemm<T>(L, P.L[l - 1], sW, R, D, lda, TM);
+                if (L.wr_off >= 0) qb_bwd_gemm<T, false>(L, P.L[l - 1], sW, theta, R, D, lda, TM);
+                else qb_bwd_gemm<T, true>(L, P.L[l - 1], sW, theta, R, D, lda, TM);
                 __syncthreads();
             }
         }

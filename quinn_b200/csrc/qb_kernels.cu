@@ -67,7 +67,7 @@ static int validate_net(const qb_net_t* net) {
 }
 
 // Fill `P` for tile size TM; returns smem bytes (or -1 if a constraint fails).
-static long long plan_for_tm(const qb_net_t* net, int dtype, bool want_grad, int TM, QbPlan* P) {
+static long long plan_for_tm(const qb_net_t* net, int dtype, bool want_grad, int TM, QbPlan* P, bool wr_global = false) {
     const int elem = dtype == QB_F64 ? 8 : 4;
     const int TU = dtype == QB_F64 ? 4 : 8, TP = TU, LDPAD = dtype == QB_F64 ? 2 : 4, PV = dtype == QB_F64 ? 2 : 4;
     memset(P, 0, sizeof(*P));
@@ -95,7 +95,7 @@ static long long plan_for_tm(const qb_net_t* net, int dtype, bool want_grad, int
         for (int m = 0; m < l; ++m) {
             const qb_layer_t& Sm = net->layers[m];
             if (Sm.w_off == S.w_off && Sm.b_off == S.b_off && Sm.n_in == S.n_in && Sm.n_out == S.n_out &&
-                P->L[m].mode == L.mode && (P->L[m].wr_off >= 0) == (want_grad && l > 0)) { dup = m; break; }
+                P->L[m].mode == L.mode && (P->L[m].wr_off >= 0) == (want_grad && l > 0 && !wr_global)) { dup = m; break; }
         }
         if (dup >= 0) {
             L.wt_off = P->L[dup].wt_off; L.bias_off = P->L[dup].bias_off; L.wr_off = P->L[dup].wr_off;
@@ -103,7 +103,7 @@ static long long plan_for_tm(const qb_net_t* net, int dtype, bool want_grad, int
             L.wt_off = woff; woff += rup(L.n_in * L.n_out_pad, 4);
             L.bias_off = woff; woff += rup(L.n_out_pad, 4);
             L.wr_off = -1;
-            if (want_grad && l > 0) { L.wr_off = woff; woff += rup(L.n_out * L.n_in_pad, 4); }
+            if (want_grad && l > 0 && !wr_global) { L.wr_off = woff; woff += rup(L.n_out * L.n_in_pad, 4); }
         }
     }
     P->w_elems = woff;
@@ -163,19 +163,23 @@ static int make_launch(const qb_net_t* net, int dtype, bool want_grad, long long
     int forced = env_int("QB_TM", 0);
     int pick = -1;
     QbPlan tmp;
-    for (int pass = 0; pass < 2 && pick < 0; ++pass) {
+    bool wr_global = false;
+    for (int pass = 0; pass < 3 && pick < 0; ++pass) {
+        // pass 0: two blocks per SM; pass 1: one block per SM; pass 2 (gradient only): drop the shared copy
+        // of W used by back-propagation and read it from global memory instead
         const int limit = pass == 0 ? QB_SMEM_TWO : QB_SMEM_MAX;
+        if (pass == 2) { if (!want_grad) break; wr_global = true; }
         for (int c = 0; c < 4; ++c) {
             int TM = cands[c];
             if (forced) TM = forced;
             else if (TM > cap) continue;
-            long long b = plan_for_tm(net, dtype, want_grad, TM, &tmp);
+            long long b = plan_for_tm(net, dtype, want_grad, TM, &tmp, wr_global);
             if (b <= limit) { pick = TM; break; }
             if (forced) break;
         }
     }
     if (pick < 0) return qb_fail("network too large for the fused shared-memory path (weights + one tile exceed 227 KB)");
-    plan_for_tm(net, dtype, want_grad, pick, &out->plan);
+    plan_for_tm(net, dtype, want_grad, pick, &out->plan, wr_global);
     const int TM = out->plan.TM;
     long long S = 1;
     if (!force_single) {

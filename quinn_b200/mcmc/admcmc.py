@@ -43,6 +43,13 @@ class AMCMC(MCMCBase):
             Lf = samp.chol[0].double().cpu().numpy()
             self._propcov = Lf @ Lf.T
 
+    @staticmethod
+    def _factor(cov):
+        """A with A A^T = cov for a positive SEMI-definite cov (the reference's numpy draw goes through an SVD,
+        admcmc.py:70, so singular matrices such as the initial 0.01 + diag(0.09|0|) are legal)."""
+        s, v = torch.linalg.eigh(cov)
+        return v * s.clamp_min(0.0).sqrt()[..., None, :]
+
     # ---- generic-callable adapter: same recursion, batched over chains with torch ops
     def sampler(self, current, imcmc):
         K, P = current.shape
@@ -53,7 +60,7 @@ class AMCMC(MCMCBase):
                 pc = torch.as_tensor(np.asarray(self.cov_ini), dtype=current.dtype, device=current.device).expand(K, P, P)
             else:
                 pc = 0.01 + torch.diag_embed(0.09 * current.abs())
-            self._gchol = torch.linalg.cholesky(pc)
+            self._gchol = self._factor(pc)
         else:
             self._gXm = (imcmc * self._gXm + current) / (imcmc + 1.0)
             rt, stt = (imcmc - 1.0) / imcmc, (imcmc + 1.0) / imcmc ** 2
@@ -61,7 +68,7 @@ class AMCMC(MCMCBase):
             self._gcov = rt * self._gcov + stt * d[:, :, None] * d[:, None, :]
             if imcmc > self.t0 and imcmc % self.tadapt == 0:
                 eye = torch.eye(P, dtype=current.dtype, device=current.device)
-                self._gchol = torch.linalg.cholesky((self.gamma * 2.4 ** 2 / P) * (self._gcov + 1e-8 * eye))
+                self._gchol = self._factor((self.gamma * 2.4 ** 2 / P) * (self._gcov + 1e-8 * eye))
         z = torch.randn((K, P), dtype=current.dtype, device=current.device, generator=self._gen)
         prop = current + torch.einsum('kab,kb->ka', self._gchol, z)
         zero = torch.zeros(K, dtype=current.dtype, device=current.device)

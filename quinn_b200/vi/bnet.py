@@ -26,7 +26,7 @@ class _ElboTerms(torch.autograd.Function):
         w, eps, logq, logp = ops.vi_sample(mu.detach(), rho.detach(), nsam, bnet.pi, bnet.sigma1, bnet.sigma2, eps=eps,
                                            seed=0 if eps is not None else bnet.seed, step=bnet._step)
         B = x.shape[0]
-        need_grad = torch.is_grad_enabled() and (mu.requires_grad or rho.requires_grad)
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]     # False under torch.no_grad()
         if need_grad:
             lp, glp = ops.logpost_grad(prob, w)
             ctx.save_for_backward(mu.detach(), rho.detach(), eps, w, glp)

@@ -158,8 +158,13 @@ def test_nn_mcmc_solver_flow_like_reference_tests():
     lp = uq.logpost(uq.cmode, uq.lpinfo)
     assert isinstance(lp, float) and np.isfinite(lp)
     assert uq.logpostgrad(uq.cmode, uq.lpinfo).shape == (uq.pdim,)
-    m, v, c = uq.predict_mom_sample(xt, msc=1, nsam=20)         # thinning with nburn=1000 > chain length is the
-    assert m.shape == (10, 1)                                   # reference's behaviour too; just check shapes
+    with pytest.raises(IndexError):                             # nburn=1000 > chain length: the reference raises too
+        uq.predict_mom_sample(xt, msc=1, nsam=20)               # (quinn.py:84 -> nn_mcmc.py:194-196)
+    uq.fit(x, y, nmcmc=1400, sampler='amcmc', zflag=False, sampler_params={})
+    m, v, c = uq.predict_mom_sample(xt, msc=1, nsam=20)
+    ref = uq.predict_ens(xt, nens=20, nburn=1000)
+    np.testing.assert_allclose(m, ref.mean(0), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(v, ref.var(0, ddof=1), rtol=1e-7, atol=1e-14)
     # MALA is reachable (the reference's docstring promises it, nn_mcmc.py:110) and zflag uses the analytic gradient
     uq.fit(x, y, nmcmc=50, sampler='mala', zflag=True, sampler_params={'epsilon': 0.002})
     assert uq.samples.shape == (51, uq.pdim)
