@@ -6,12 +6,18 @@
 #include <math.h>
 #include "qb_plan.h"
 
+#ifndef QB_UNROLL
+#define QB_UNROLL 2
+#endif
+#define QB_STR_(x) #x
+#define QB_PRAGMA_UNROLL(n) _Pragma(QB_STR_(unroll n))
+
 // --------------------------------------------------------------------------------------------
 // per-dtype tile constants and 128-bit vector access
 // --------------------------------------------------------------------------------------------
 template <typename T> struct VT;
-template <> struct VT<float>  { static constexpr int TP = 8, TU = 8, LDPAD = 4, PV = 4; };
-template <> struct VT<double> { static constexpr int TP = 4, TU = 4, LDPAD = 2, PV = 2; };
+template <> struct VT<float>  { static constexpr int TP = 8, TU = 8, LDPAD = 4, PV = 4, VW = 4; };
+template <> struct VT<double> { static constexpr int TP = 4, TU = 4, LDPAD = 2, PV = 2, VW = 2; };
 
 template <int N> __device__ __forceinline__ void ldv(float* d, const float* s) {
 #pragma unroll
@@ -38,6 +44,25 @@ template <int N> __device__ __forceinline__ void stv(double* d, const double* s)
         *reinterpret_cast<double2*>(d + 2 * q) = make_double2(s[2 * q], s[2 * q + 1]);
 }
 
+// Column permutation of the staged weight rows.  Thread tile `g` (of G) owns units g + G*u, u = 0..TU-1; its TU
+// weights are fetched with TU/VW 128-bit loads.  Load number h of all G tiles is laid out contiguously
+// (col = h*G*VW + g*VW + q, u = h*VW + q) so that the lanes of a quarter warp (consecutive g) read 128
+// contiguous bytes: one conflict-free wavefront (the first layout, col = g*TU + u, strided the lanes by
+// 32 B and measured 8 wavefronts per LDS.128 in ncu, profiles/r1_amcmc_v0.md).
+template <typename T> __device__ __forceinline__ int qb_col_to_unit(int col, int G) {
+    constexpr int VW = VT<T>::VW;
+    const int h = col / (G * VW), rem = col - h * (G * VW);
+    const int g = rem / VW, q = rem - g * VW;
+    return g + G * (h * VW + q);
+}
+// load the TU weights of tile g from a staged row
+template <typename T> __device__ __forceinline__ void qb_ld_wrow(T (&w)[VT<T>::TU], const T* row, int g, int G) {
+    constexpr int VW = VT<T>::VW, TU = VT<T>::TU;
+#pragma unroll
+    for (int h = 0; h < TU / VW; ++h) ldv<VW>(&w[h * VW], row + h * G * VW + g * VW);
+}
+
+
 // --------------------------------------------------------------------------------------------
 // activations
 // --------------------------------------------------------------------------------------------
@@ -53,8 +78,33 @@ __device__ __forceinline__ double qb_tanh(double z) { return tanh(z); }
 __device__ __forceinline__ float qb_exp(float z) { return expf(z); }
 __device__ __forceinline__ double qb_exp(double z) { return exp(z); }
 
+// tanh of a pre-activation that was already multiplied by 2*log2(e) (folded into the staged fp32 weights)
+__device__ __forceinline__ float qb_tanh_prescaled(float z2) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z2));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
+}
+__device__ __forceinline__ double qb_tanh_prescaled(double z) { return tanh(z); }   // never folded in fp64
+template <typename T> __device__ __forceinline__ T qb_tanh_fold() { return T(1); }
+template <> __device__ __forceinline__ float qb_tanh_fold<float>() { return 2.8853900817779268f; }
+
+// Who cooperates on a tile: the whole block (p_base = 0, p_count = TM) or, in warp-synchronous mode, one warp
+// that owns WP consecutive points of the tile for ALL layers (no block barrier inside the tile loop).
+struct QbScope {
+    int nthr, tid, p_base, p_count;
+    bool warp;
+    __device__ __forceinline__ void sync() const { if (warp) __syncwarp(); else __syncthreads(); }
+};
+__device__ __forceinline__ QbScope qb_block_scope(int TM) {
+    QbScope s; s.nthr = blockDim.x; s.tid = threadIdx.x; s.p_base = 0; s.p_count = TM; s.warp = false; return s;
+}
+__device__ __forceinline__ QbScope qb_warp_scope(int WP) {
+    QbScope s; s.nthr = 32; s.tid = threadIdx.x & 31; s.p_base = (threadIdx.x >> 5) * WP; s.p_count = WP; s.warp = true; return s;
+}
+
 template <int ACT, typename T> __device__ __forceinline__ T qb_act(T z) {
-    if (ACT == QB_ACT_TANH) return qb_tanh(z);
+    if (ACT == QB_ACT_TANH) return qb_tanh_prescaled(z);
     if (ACT == QB_ACT_RELU) return z > T(0) ? z : T(0);
     return z;
 }
@@ -102,15 +152,16 @@ __device__ void qb_stage_weights(const QbPlan& P, T* sW, const T* theta) {
         const bool gemm = (L.mode == QB_MODE_GEMM);
         T* Wt = sW + L.wt_off;
         const int nwt = L.n_in * L.n_out_pad;
+        const T fold = (L.act == QB_ACT_TANH) ? qb_tanh_fold<T>() : T(1);      // 2*log2(e) for fp32 tanh layers
         for (int idx = tid; idx < nwt; idx += nt) {
             const int i = idx / L.n_out_pad, col = idx - i * L.n_out_pad;
-            const int j = gemm ? (col / TU) + UG * (col % TU) : col;
-            Wt[idx] = (j < L.n_out) ? theta[L.w_off + j * L.n_in + i] : T(0);
+            const int j = gemm ? qb_col_to_unit<T>(col, UG) : col;
+            Wt[idx] = (j < L.n_out) ? theta[L.w_off + j * L.n_in + i] * fold : T(0);
         }
         T* bs = sW + L.bias_off;
         for (int col = tid; col < L.n_out_pad; col += nt) {
-            const int j = gemm ? (col / TU) + UG * (col % TU) : col;
-            bs[col] = (j < L.n_out && L.b_off >= 0) ? theta[L.b_off + j] : T(0);
+            const int j = gemm ? qb_col_to_unit<T>(col, UG) : col;
+            bs[col] = (j < L.n_out && L.b_off >= 0) ? theta[L.b_off + j] * fold : T(0);
         }
         if (L.wr_off >= 0) {
             const int UGI = L.n_in_pad / TU;
@@ -118,7 +169,7 @@ __device__ void qb_stage_weights(const QbPlan& P, T* sW, const T* theta) {
             const int nwr = L.n_out * L.n_in_pad;
             for (int idx = tid; idx < nwr; idx += nt) {
                 const int j = idx / L.n_in_pad, col = idx - j * L.n_in_pad;
-                const int i = (col / TU) + UGI * (col % TU);
+                const int i = qb_col_to_unit<T>(col, UGI);
                 Wr[idx] = (i < L.n_in) ? theta[L.w_off + j * L.n_in + i] : T(0);
             }
         }
@@ -132,38 +183,41 @@ __device__ void qb_stage_weights(const QbPlan& P, T* sW, const T* theta) {
 // 128-bit broadcast load of TU weights and TP/4 128-bit loads of activations for TU*TP FMAs.
 template <typename T, int ACT>
 __device__ __forceinline__ void qb_fwd_gemm(const QbLayerPlan& L, const T* sW, const T* Ain, T* Aout,
-                                            int lda, int TM, bool sync_before_store) {
+                                            int lda, const QbScope& sc, bool sync_before_store) {
     constexpr int TP = VT<T>::TP, TU = VT<T>::TU;
-    const int UG = L.n_out_pad / TU, PG = TM / TP, items = UG * PG;
+    const int UG = L.n_out_pad / TU, PG = sc.p_count / TP, items = UG * PG;
     const T* Wt = sW + L.wt_off;
     const T* bias = sW + L.bias_off;
     const int n_in = L.n_in, ldw = L.n_out_pad;
     const bool res = L.has_res != 0;
     const T step = T(L.res_step);
-    for (int base = 0; base < items; base += blockDim.x) {
-        const int item = base + threadIdx.x;
+    for (int base = 0; base < items; base += sc.nthr) {
+        const int item = base + sc.tid;
         const bool valid = item < items;
         const int pg = item / UG, ug = item - pg * UG;
+        const int pcol = sc.p_base + pg * TP;
         T acc[TU][TP];
         if (valid) {
 #pragma unroll
             for (int u = 0; u < TU; ++u)
 #pragma unroll
                 for (int p = 0; p < TP; ++p) acc[u][p] = T(0);
-            const T* ap = Ain + pg * TP;
-            const T* wp = Wt + ug * TU;
-#pragma unroll 2
+            const T* ap = Ain + pcol;
+            const T* wp = Wt;
+QB_PRAGMA_UNROLL(QB_UNROLL)
             for (int i = 0; i < n_in; ++i) {
                 T a[TP], w[TU];
-                ldv<TP>(a, ap + i * lda);
-                ldv<TU>(w, wp + i * ldw);
+                ldv<TP>(a, ap);
+                qb_ld_wrow<T>(w, wp, ug, UG);
+                ap += lda;
+                wp += ldw;
 #pragma unroll
                 for (int u = 0; u < TU; ++u)
 #pragma unroll
                     for (int p = 0; p < TP; ++p) acc[u][p] = fma(w[u], a[p], acc[u][p]);
             }
             T b[TU];
-            ldv<TU>(b, bias + ug * TU);
+            qb_ld_wrow<T>(b, bias, ug, UG);
 #pragma unroll
             for (int u = 0; u < TU; ++u)
 #pragma unroll
@@ -172,16 +226,16 @@ __device__ __forceinline__ void qb_fwd_gemm(const QbLayerPlan& L, const T* sW, c
 #pragma unroll
                 for (int u = 0; u < TU; ++u) {
                     T r[TP];
-                    ldv<TP>(r, Ain + (ug + UG * u) * lda + pg * TP);
+                    ldv<TP>(r, Ain + (ug + UG * u) * lda + pcol);
 #pragma unroll
                     for (int p = 0; p < TP; ++p) acc[u][p] = fma(step, acc[u][p], r[p]);
                 }
             }
         }
-        if (sync_before_store) __syncthreads();
+        if (sync_before_store) sc.sync();
         if (valid) {
 #pragma unroll
-            for (int u = 0; u < TU; ++u) stv<TP>(Aout + (ug + UG * u) * lda + pg * TP, acc[u]);
+            for (int u = 0; u < TU; ++u) stv<TP>(Aout + (ug + UG * u) * lda + pcol, acc[u]);
         }
     }
 }
@@ -190,13 +244,14 @@ __device__ __forceinline__ void qb_fwd_gemm(const QbLayerPlan& L, const T* sW, c
 // touches its own column, so this is in-place safe whenever n_out <= NJ.
 template <typename T, int NJ, int ACT>
 __device__ __forceinline__ void qb_fwd_dot(const QbLayerPlan& L, const T* sW, const T* Ain, T* Aout,
-                                           int lda, int TM) {
+                                           int lda, const QbScope& sc) {
     const T* Wt = sW + L.wt_off;
     const T* bias = sW + L.bias_off;
     const int n_in = L.n_in, ldw = L.n_out_pad, n_out = L.n_out;
     const bool res = L.has_res != 0;
     const T step = T(L.res_step);
-    for (int p = threadIdx.x; p < TM; p += blockDim.x) {
+    for (int pl = sc.tid; pl < sc.p_count; pl += sc.nthr) {
+        const int p = sc.p_base + pl;
         for (int j0 = 0; j0 < n_out; j0 += NJ) {
             T acc[NJ];
 #pragma unroll
@@ -221,36 +276,37 @@ __device__ __forceinline__ void qb_fwd_dot(const QbLayerPlan& L, const T* sW, co
 }
 
 template <typename T>
-__device__ void qb_layer_forward(const QbLayerPlan& L, const T* sW, const T* Ain, T* Aout, int lda, int TM,
+__device__ void qb_layer_forward(const QbLayerPlan& L, const T* sW, const T* Ain, T* Aout, int lda, const QbScope& sc,
                                  bool inplace) {
     if (L.mode == QB_MODE_GEMM) {
         switch (L.act) {
-            case QB_ACT_TANH: qb_fwd_gemm<T, QB_ACT_TANH>(L, sW, Ain, Aout, lda, TM, inplace); break;
-            case QB_ACT_RELU: qb_fwd_gemm<T, QB_ACT_RELU>(L, sW, Ain, Aout, lda, TM, inplace); break;
-            default: qb_fwd_gemm<T, QB_ACT_IDENTITY>(L, sW, Ain, Aout, lda, TM, inplace); break;
+            case QB_ACT_TANH: qb_fwd_gemm<T, QB_ACT_TANH>(L, sW, Ain, Aout, lda, sc, inplace); break;
+            case QB_ACT_RELU: qb_fwd_gemm<T, QB_ACT_RELU>(L, sW, Ain, Aout, lda, sc, inplace); break;
+            default: qb_fwd_gemm<T, QB_ACT_IDENTITY>(L, sW, Ain, Aout, lda, sc, inplace); break;
         }
     } else {
-#define QB_DOT(NJ)                                                                             \
-    switch (L.act) {                                                                           \
-        case QB_ACT_TANH: qb_fwd_dot<T, NJ, QB_ACT_TANH>(L, sW, Ain, Aout, lda, TM); break;     \
-        case QB_ACT_RELU: qb_fwd_dot<T, NJ, QB_ACT_RELU>(L, sW, Ain, Aout, lda, TM); break;     \
-        default: qb_fwd_dot<T, NJ, QB_ACT_IDENTITY>(L, sW, Ain, Aout, lda, TM); break;          \
+#define QB_DOT(NJ)                                                                            \
+    switch (L.act) {                                                                          \
+        case QB_ACT_TANH: qb_fwd_dot<T, NJ, QB_ACT_TANH>(L, sW, Ain, Aout, lda, sc); break;     \
+        case QB_ACT_RELU: qb_fwd_dot<T, NJ, QB_ACT_RELU>(L, sW, Ain, Aout, lda, sc); break;     \
+        default: qb_fwd_dot<T, NJ, QB_ACT_IDENTITY>(L, sW, Ain, Aout, lda, sc); break;          \
     }
         if (L.nj == 1) { QB_DOT(1) } else if (L.nj == 2) { QB_DOT(2) } else { QB_DOT(4) }
 #undef QB_DOT
     }
-    __syncthreads();
+    sc.sync();
 }
 
-// x[p0 .. p0+TM) -> rows 0..d-1 of A (zero for points beyond pend)
+// x[p0 + p_base .. + p_count) -> rows 0..d-1 of A (zero for points beyond pend)
 template <typename T>
 __device__ __forceinline__ void qb_load_x_tile(const T* __restrict__ x, int d, int64_t p0, int64_t pend,
-                                               T* A, int lda, int TM) {
-    const int n = TM * d;
-    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+                                               T* A, int lda, const QbScope& sc) {
+    const int n = sc.p_count * d;
+    const int64_t g0 = p0 + sc.p_base;
+    for (int idx = sc.tid; idx < n; idx += sc.nthr) {
         const int p = idx / d, i = idx - p * d;
-        const int64_t gp = p0 + p;
-        A[i * lda + p] = (gp < pend) ? __ldg(x + gp * d + i) : T(0);
+        const int64_t gp = g0 + p;
+        A[i * lda + sc.p_base + p] = (gp < pend) ? __ldg(x + gp * d + i) : T(0);
     }
 }
 
@@ -286,19 +342,20 @@ __device__ double qb_eval_value(const QbPlan& P, const QbSmem& S, const T* theta
         __syncthreads();
     }
     T ssq = T(0);
+    const QbScope sc = P.ws ? qb_warp_scope(P.WP) : qb_block_scope(TM);
     for (int64_t p0 = n0; p0 < n1; p0 += TM) {
-        qb_load_x_tile<T>(x, P.in_dim, p0, n1, A0, lda, TM);
-        __syncthreads();
+        qb_load_x_tile<T>(x, P.in_dim, p0, n1, A0, lda, sc);
+        sc.sync();
         T* cur = A0;
         T* oth = A1;
         for (int l = 0; l < P.n_layers; ++l) {
-            qb_layer_forward<T>(P.L[l], sW, cur, oth, lda, TM, P.inplace != 0);
+            qb_layer_forward<T>(P.L[l], sW, cur, oth, lda, sc, P.inplace != 0);
             T* t = cur; cur = oth; oth = t;
         }
         // residuals (losses.py:197: sum over all points and outputs)
-        const int n = TM * o;
-        for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-            const int j = idx / TM, p = idx - j * TM;
+        const int n = sc.p_count * o;
+        for (int idx = sc.tid; idx < n; idx += sc.nthr) {
+            const int j = idx / sc.p_count, p = sc.p_base + (idx - j * sc.p_count);
             const int64_t gp = p0 + p;
             if (gp < n1) {
                 T out = cur[j * lda + p];
@@ -310,7 +367,7 @@ __device__ double qb_eval_value(const QbPlan& P, const QbSmem& S, const T* theta
                 }
             }
         }
-        __syncthreads();
+        sc.sync();
     }
     return qb_block_sum((double)ssq, S.red);
 }
@@ -452,17 +509,19 @@ __device__ void qb_bwd_gemm(const QbLayerPlan& L, const QbLayerPlan& Lm, const T
 #pragma unroll
             for (int p = 0; p < TP; ++p) acc[u][p] = T(0);
         const T* zp = Rz + pg * TP;
-        const T* wp = Wr + ig * TU;
-#pragma unroll 2
+        const T* wp = GLOBALW ? Wr + ig * TU : Wr;
+QB_PRAGMA_UNROLL(QB_UNROLL)
         for (int j = 0; j < n_out; ++j) {
             T d[TP], w[TU];
-            ldv<TP>(d, zp + (size_t)j * lda);
+            ldv<TP>(d, zp);
             if (GLOBALW) {
 #pragma unroll
-                for (int u = 0; u < TU; ++u) w[u] = (ig * TU + u < L.n_in) ? wp[j * ldw + u] : T(0);
+                for (int u = 0; u < TU; ++u) w[u] = (ig * TU + u < L.n_in) ? wp[u] : T(0);
             } else {
-                ldv<TU>(w, wp + j * ldw);
+                qb_ld_wrow<T>(w, wp, ig, UGI);
             }
+            zp += lda;
+            wp += ldw;
 #pragma unroll
             for (int u = 0; u < TU; ++u)
 #pragma unroll
@@ -501,12 +560,13 @@ __device__ double qb_eval_value_grad(const QbPlan& P, const QbSmem& S, const T* 
     T ssq = T(0);
     const T is2 = T(inv_sigma2);
     const QbLayerPlan& Ltop = P.L[nl - 1];
+    const QbScope bsc = qb_block_scope(TM);
     for (int64_t p0 = n0; p0 < n1; p0 += TM) {
-        qb_load_x_tile<T>(x, P.in_dim, p0, n1, R, lda, TM);
+        qb_load_x_tile<T>(x, P.in_dim, p0, n1, R, lda, bsc);
         __syncthreads();
         for (int l = 0; l < nl; ++l) {
             const QbLayerPlan& L = P.L[l];
-            qb_layer_forward<T>(L, sW, R + (size_t)L.row_in * lda, R + (size_t)L.row_out * lda, lda, TM, false);
+            qb_layer_forward<T>(L, sW, R + (size_t)L.row_in * lda, R + (size_t)L.row_out * lda, lda, bsc, false);
         }
         // residuals -> delta at the top
         const int n = TM * o;

@@ -125,6 +125,29 @@ static long long plan_for_tm(const qb_net_t* net, int dtype, bool want_grad, int
         L.dw_chunks = C;
     }
     if (env_int("QB_NO_INPLACE", 0)) inplace = 0;
+    // Warp-synchronous value kernel: when every GEMM layer's unit groups divide a warp, one warp can own WP
+    // consecutive points for ALL layers (its lanes cover every unit of those points), so the tile loop needs
+    // no block barrier and warps drift apart (MUFU / FMA / LDS phases of different warps overlap).
+    P->ws = 0; P->WP = 0;
+    if (!want_grad && any_gemm && !env_int("QB_NO_WS", 0)) {
+        int ugmax = 0; bool ok = true;
+        for (int l = 0; l < net->n_layers; ++l) {
+            const QbLayerPlan& L = P->L[l];
+            if (L.mode == QB_MODE_GEMM) {
+                const int UG = L.n_out_pad / TU;
+                if (UG > 32 || 32 % UG) ok = false;
+                ugmax = std::max(ugmax, UG);
+            } else if (L.n_out > L.nj) ok = false;
+        }
+        if (ok) {
+            const int WP = (32 / ugmax) * TP;
+            if (TM % WP == 0 && TM / WP >= 1 && TM / WP <= 8) {
+                P->ws = 1; P->WP = WP; inplace = 1;
+                nthreads = 32 * (TM / WP);
+                P->nthreads = nthreads;
+            }
+        }
+    }
     P->inplace = inplace; P->buf_rows = buf_rows;
     long long act_elems;
     if (!want_grad) {
@@ -223,7 +246,7 @@ template <typename T> struct EvalArgs {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_logpost(const __grid_constant__ QbPlan P, const EvalArgs<T> a) {
+__global__ void __launch_bounds__(256, 2) k_logpost(const __grid_constant__ QbPlan P, const EvalArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const QbSmem S = qb_carve<T>(P, smem_raw);
     const long long k = blockIdx.x, s = blockIdx.y;
@@ -233,7 +256,7 @@ __global__ void __launch_bounds__(256) k_logpost(const __grid_constant__ QbPlan 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_logpost_grad(const __grid_constant__ QbPlan P, const EvalArgs<T> a) {
+__global__ void __launch_bounds__(256, 2) k_logpost_grad(const __grid_constant__ QbPlan P, const EvalArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const QbSmem S = qb_carve<T>(P, smem_raw);
     const long long k = blockIdx.x, s = blockIdx.y;
@@ -415,7 +438,7 @@ __device__ void qb_cholesky(const T* cov, T* Lf, int P, double fac, double jitte
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_amcmc(const __grid_constant__ QbPlan plan, const ChainArgs<T> c, const AmcmcArgs<T> a) {
+__global__ void __launch_bounds__(256, 2) k_amcmc(const __grid_constant__ QbPlan plan, const ChainArgs<T> c, const AmcmcArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const QbSmem S = qb_carve<T>(plan, smem_raw);
     const long long k = blockIdx.x;
@@ -552,7 +575,7 @@ __device__ double qb_full_grad(const QbPlan& plan, const QbSmem& S, const ChainA
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_hmc(const __grid_constant__ QbPlan plan, const ChainArgs<T> c, const HmcArgs<T> h) {
+__global__ void __launch_bounds__(256, 2) k_hmc(const __grid_constant__ QbPlan plan, const ChainArgs<T> c, const HmcArgs<T> h) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const QbSmem S = qb_carve<T>(plan, smem_raw);
     const long long k = blockIdx.x;
@@ -730,7 +753,7 @@ template <typename T> struct PredArgs {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_predict(const __grid_constant__ QbPlan P, const PredArgs<T> a) {
+__global__ void __launch_bounds__(256, 2) k_predict(const __grid_constant__ QbPlan P, const PredArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const QbSmem S = qb_carve<T>(P, smem_raw);
     T* sW = reinterpret_cast<T*>(S.w);
@@ -744,16 +767,19 @@ __global__ void __launch_bounds__(256) k_predict(const __grid_constant__ QbPlan 
 #pragma unroll
     for (int q = 0; q < QMAX; ++q) { wmean[q] = T(0); wm2[q] = T(0); }
     const int n = TM * o;
+    const QbScope sc = P.ws ? qb_warp_scope(P.WP) : qb_block_scope(TM);
     for (long long m = m_lo; m < m_hi; ++m) {
         __syncthreads();
         qb_stage_weights<T>(P, sW, a.theta + m * P.n_params);
-        qb_load_x_tile<T>(a.x, P.in_dim, p0, a.N, A0, lda, TM);
         __syncthreads();
+        qb_load_x_tile<T>(a.x, P.in_dim, p0, a.N, A0, lda, sc);
+        sc.sync();
         T* cur = A0; T* oth = A1;
         for (int l = 0; l < P.n_layers; ++l) {
-            qb_layer_forward<T>(P.L[l], sW, cur, oth, lda, TM, P.inplace != 0);
+            qb_layer_forward<T>(P.L[l], sW, cur, oth, lda, sc, P.inplace != 0);
             T* t = cur; cur = oth; oth = t;
         }
+        __syncthreads();          // the copy-out below reads points of every warp
         if (!a.fused) {
             for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
                 const int p = idx / o, j = idx - p * o;
@@ -858,7 +884,7 @@ extern "C" int qb_predict(const qb_net_t* net, int dtype, const void* theta, int
 // variational inference element-wise kernels
 // =================================================================================================
 template <typename T>
-__global__ void __launch_bounds__(256) k_vi_sample(const T* mu, const T* rho, T* eps, long long nsam, long long P, double pi,
+__global__ void __launch_bounds__(256, 2) k_vi_sample(const T* mu, const T* rho, T* eps, long long nsam, long long P, double pi,
                                                    double s1, double s2, unsigned long long seed, unsigned long long step,
                                                    T* w, double* logq, double* logp) {
     __shared__ double red[40];
@@ -946,7 +972,7 @@ extern "C" int qb_vi_backward(int dtype, const void* mu, const void* rho, const 
 // FMA peak micro-benchmark (roofline denominator for the CUDA-core kernels)
 // =================================================================================================
 template <typename T, int CH>
-__global__ void __launch_bounds__(256) k_fma_peak(long long iters, T* sink) {
+__global__ void __launch_bounds__(256, 2) k_fma_peak(long long iters, T* sink) {
     T a[CH];
     const T b = T(1.0000001) + T(threadIdx.x) * T(1e-9), c = T(1e-7);
 #pragma unroll

@@ -37,6 +37,7 @@ struct QbPlan {
     int want_grad;
     int has_res;
     int elem_size;
+    int ws, WP;         // value kernel: warp-synchronous mode, points owned by one warp
     long long smem_bytes;
     QbLayerPlan L[QB_MAX_LAYERS];
 };
