@@ -9,6 +9,9 @@
 #ifndef QB_UNROLL
 #define QB_UNROLL 2
 #endif
+#ifndef QB_TAIL_UNROLL
+#define QB_TAIL_UNROLL 2
+#endif
 #define QB_STR_(x) #x
 #define QB_PRAGMA_UNROLL(n) _Pragma(QB_STR_(unroll n))
 
@@ -179,65 +182,187 @@ __device__ void qb_stage_weights(const QbPlan& P, T* sW, const T* theta) {
 // --------------------------------------------------------------------------------------------
 // forward layers
 // --------------------------------------------------------------------------------------------
-// GEMM mode: each thread owns a TU x TP register tile (units x points); per input unit i it issues one
-// 128-bit broadcast load of TU weights and TP/4 128-bit loads of activations for TU*TP FMAs.
+// GEMM mode: each thread owns a TU x TP register tile (units x points); per input unit i it issues TU/VW
+// 128-bit loads of weights and TP/VW 128-bit loads of activations for TU*TP FMAs.  Operands of step i+1 are
+// fetched before the FMAs of step i (register double buffering).  Accumulators start from the bias.
+//
+// Fused tail (tail != nullptr): the NEXT layer is a narrow linear output layer (n_out <= 4, identity): instead of
+// storing this layer's activations, every thread dots its TU x TP activations with the tail weights, the UG lanes
+// that share the same points combine with an xor-shuffle tree (UG is a power of two in this mode) and the lane
+// with ug == 0 receives tail_out[q][p] = sum_j Wtail[q][j] h[j][p] (bias not yet added).
+template <typename T> struct QbTailCtx {   // what the fused tail needs to turn outputs into squared residuals
+    const QbLayerPlan* tail;
+    const T* y;
+    int64_t p0, n1;
+    int o, final_exp;
+};
+
+// acc[u][p] = bias[u] + sum_i Wt[i][unit u of tile ug] * Ain[i][pcol + p]      (the one hot loop of the library)
+template <typename T>
+__device__ __forceinline__ void qb_gemm_accumulate(T (&acc)[VT<T>::TU][VT<T>::TP], const T* __restrict__ Wt,
+                                                   const T* __restrict__ bias, const T* __restrict__ ap, int n_in,
+                                                   int lda, int ldw, int ug, int UG) {
+    constexpr int TP = VT<T>::TP, TU = VT<T>::TU;
+    {
+        T b[TU];
+        qb_ld_wrow<T>(b, bias, ug, UG);
+#pragma unroll
+        for (int u = 0; u < TU; ++u)
+#pragma unroll
+            for (int p = 0; p < TP; ++p) acc[u][p] = b[u];
+    }
+    const T* wp = Wt;
+    T a0[TP], w0[TU], a1[TP], w1[TU];
+    ldv<TP>(a0, ap);
+    qb_ld_wrow<T>(w0, wp, ug, UG);
+    int i = 0;
+#pragma unroll 1
+    for (; i + 2 <= n_in; i += 2) {
+        ldv<TP>(a1, ap + lda);
+        qb_ld_wrow<T>(w1, wp + ldw, ug, UG);
+#pragma unroll
+        for (int u = 0; u < TU; ++u)
+#pragma unroll
+            for (int p = 0; p < TP; ++p) acc[u][p] = fma(w0[u], a0[p], acc[u][p]);
+        ap += 2 * lda;
+        wp += 2 * ldw;
+        if (i + 2 < n_in) {
+            ldv<TP>(a0, ap);
+            qb_ld_wrow<T>(w0, wp, ug, UG);
+        }
+#pragma unroll
+        for (int u = 0; u < TU; ++u)
+#pragma unroll
+            for (int p = 0; p < TP; ++p) acc[u][p] = fma(w1[u], a1[p], acc[u][p]);
+    }
+    if (i < n_in) {
+#pragma unroll
+        for (int u = 0; u < TU; ++u)
+#pragma unroll
+            for (int p = 0; p < TP; ++p) acc[u][p] = fma(w0[u], a0[p], acc[u][p]);
+    }
+}
+
+// activation (+ residual) of one accumulator row
 template <typename T, int ACT>
-__device__ __forceinline__ void qb_fwd_gemm(const QbLayerPlan& L, const T* sW, const T* Ain, T* Aout,
-                                            int lda, const QbScope& sc, bool sync_before_store) {
+__device__ __forceinline__ void qb_act_row(T (&h)[VT<T>::TP], const T (&accrow)[VT<T>::TP], bool res, T step,
+                                           const T* ain_row) {
+    constexpr int TP = VT<T>::TP;
+#pragma unroll
+    for (int p = 0; p < TP; ++p) h[p] = qb_act<ACT>(accrow[p]);
+    if (res) {
+        T r[TP];
+        ldv<TP>(r, ain_row);
+#pragma unroll
+        for (int p = 0; p < TP; ++p) h[p] = fma(step, h[p], r[p]);
+    }
+}
+
+template <typename T, int ACT>
+__device__ __forceinline__ void qb_epilogue_store(const T (&acc)[VT<T>::TU][VT<T>::TP], const T* Ain, T* Aout, int lda,
+                                                  int pcol, int ug, int UG, bool res, T step) {
+    constexpr int TP = VT<T>::TP, TU = VT<T>::TU;
+#pragma unroll
+    for (int u = 0; u < TU; ++u) {
+        const int j = ug + UG * u;
+        T h[TP];
+        qb_act_row<T, ACT>(h, acc[u], res, step, Ain + j * lda + pcol);
+        stv<TP>(Aout + j * lda + pcol, h);
+    }
+}
+
+template <typename T, int ACT, int NT>
+__device__ __forceinline__ void qb_epilogue_tail(const T (&acc)[VT<T>::TU][VT<T>::TP], const T* Ain, int lda, int pcol,
+                                                 int ug, int UG, bool res, T step, int n_out, const T* Wl, int ldl,
+                                                 int n_tail, T (&part)[NT][VT<T>::TP]) {
+    constexpr int TP = VT<T>::TP, TU = VT<T>::TU;
+#pragma unroll
+    for (int u = 0; u < TU; ++u) {
+        const int j = ug + UG * u;
+        T h[TP];
+        qb_act_row<T, ACT>(h, acc[u], res, step, Ain + j * lda + pcol);
+        if (j < n_out) {
+#pragma unroll
+            for (int q = 0; q < NT; ++q) {
+                const T wq = Wl[j * ldl + q];          // columns >= n_tail of the staged tail weights are zero
+#pragma unroll
+                for (int p = 0; p < TP; ++p) part[q][p] = fma(wq, h[p], part[q][p]);
+            }
+        }
+        asm volatile("" ::: "memory");      // keep the rows in order: hoisting all TU weight loads costs 64 registers
+    }
+}
+
+// NT = 0: store the activations; NT = 1, 2, 4: fused tail with up to NT outputs
+template <typename T, int NT>
+__device__ __forceinline__ T qb_fwd_gemm(const QbLayerPlan& L, const T* sW, const T* Ain, T* Aout,
+                                         int lda, const QbScope& sc, bool sync_before_store,
+                                         const QbTailCtx<T>* tc) {
     constexpr int TP = VT<T>::TP, TU = VT<T>::TU;
     const int UG = L.n_out_pad / TU, PG = sc.p_count / TP, items = UG * PG;
     const T* Wt = sW + L.wt_off;
     const T* bias = sW + L.bias_off;
-    const int n_in = L.n_in, ldw = L.n_out_pad;
+    const int n_in = L.n_in, ldw = L.n_out_pad, act = L.act;
     const bool res = L.has_res != 0;
     const T step = T(L.res_step);
+    T ssq = T(0);
+    const QbLayerPlan* tail = tc ? tc->tail : nullptr;
     for (int base = 0; base < items; base += sc.nthr) {
         const int item = base + sc.tid;
         const bool valid = item < items;
-        const int pg = item / UG, ug = item - pg * UG;
+        int pg, ug;
+        if (L.ug_shift >= 0) { pg = item >> L.ug_shift; ug = item & (UG - 1); }
+        else { pg = item / UG; ug = item - pg * UG; }
         const int pcol = sc.p_base + pg * TP;
         T acc[TU][TP];
-        if (valid) {
+        if (valid) qb_gemm_accumulate<T>(acc, Wt, bias, Ain + pcol, n_in, lda, ldw, ug, UG);
+        if (sync_before_store) sc.sync();       // every lane has finished READING the input rows
+        if (NT > 0) {
+            constexpr int NTA = NT > 0 ? NT : 1;
+            T part[NTA][TP];
 #pragma unroll
-            for (int u = 0; u < TU; ++u)
+            for (int q = 0; q < NTA; ++q)
 #pragma unroll
-                for (int p = 0; p < TP; ++p) acc[u][p] = T(0);
-            const T* ap = Ain + pcol;
-            const T* wp = Wt;
-QB_PRAGMA_UNROLL(QB_UNROLL)
-            for (int i = 0; i < n_in; ++i) {
-                T a[TP], w[TU];
-                ldv<TP>(a, ap);
-                qb_ld_wrow<T>(w, wp, ug, UG);
-                ap += lda;
-                wp += ldw;
-#pragma unroll
-                for (int u = 0; u < TU; ++u)
-#pragma unroll
-                    for (int p = 0; p < TP; ++p) acc[u][p] = fma(w[u], a[p], acc[u][p]);
+                for (int p = 0; p < TP; ++p) part[q][p] = T(0);
+            if (valid) {
+                const T* Wl = sW + tail->wt_off;
+                const int ldl = tail->n_out_pad, nt = tail->n_out;
+                if (act == QB_ACT_TANH) qb_epilogue_tail<T, QB_ACT_TANH, NTA>(acc, Ain, lda, pcol, ug, UG, res, step, L.n_out, Wl, ldl, nt, part);
+                else if (act == QB_ACT_RELU) qb_epilogue_tail<T, QB_ACT_RELU, NTA>(acc, Ain, lda, pcol, ug, UG, res, step, L.n_out, Wl, ldl, nt, part);
+                else qb_epilogue_tail<T, QB_ACT_IDENTITY, NTA>(acc, Ain, lda, pcol, ug, UG, res, step, L.n_out, Wl, ldl, nt, part);
             }
-            T b[TU];
-            qb_ld_wrow<T>(b, bias, ug, UG);
+            // combine the UG lanes that hold the same points (consecutive lanes; fixed order => deterministic)
+            for (int off = UG >> 1; off > 0; off >>= 1) {
 #pragma unroll
-            for (int u = 0; u < TU; ++u)
+                for (int q = 0; q < NTA; ++q)
 #pragma unroll
-                for (int p = 0; p < TP; ++p) acc[u][p] = qb_act<ACT>(acc[u][p] + b[u]);
-            if (res) {
+                    for (int p = 0; p < TP; ++p) part[q][p] += __shfl_xor_sync(0xffffffffu, part[q][p], off);
+            }
+            if (valid && ug == 0) {
+                const T* bo = sW + tail->bias_off;
 #pragma unroll
-                for (int u = 0; u < TU; ++u) {
-                    T r[TP];
-                    ldv<TP>(r, Ain + (ug + UG * u) * lda + pcol);
+                for (int q = 0; q < NTA; ++q) {
+                    if (q < tc->o) {
 #pragma unroll
-                    for (int p = 0; p < TP; ++p) acc[u][p] = fma(step, acc[u][p], r[p]);
+                        for (int p = 0; p < TP; ++p) {
+                            const int64_t gp = tc->p0 + pcol + p;
+                            if (gp < tc->n1) {
+                                T out = part[q][p] + bo[q];
+                                if (tc->final_exp) out = qb_exp(out);
+                                const T r = __ldg(tc->y + gp * tc->o + q) - out;
+                                ssq = fma(r, r, ssq);
+                            }
+                        }
+                    }
                 }
             }
-        }
-        if (sync_before_store) sc.sync();
-        if (valid) {
-#pragma unroll
-            for (int u = 0; u < TU; ++u) stv<TP>(Aout + (ug + UG * u) * lda + pcol, acc[u]);
+        } else if (valid) {
+            if (act == QB_ACT_TANH) qb_epilogue_store<T, QB_ACT_TANH>(acc, Ain, Aout, lda, pcol, ug, UG, res, step);
+            else if (act == QB_ACT_RELU) qb_epilogue_store<T, QB_ACT_RELU>(acc, Ain, Aout, lda, pcol, ug, UG, res, step);
+            else qb_epilogue_store<T, QB_ACT_IDENTITY>(acc, Ain, Aout, lda, pcol, ug, UG, res, step);
         }
     }
+    return ssq;
 }
 
 // DOT mode (narrow outputs): one thread per point column, NJ outputs at a time.  A thread only ever
@@ -279,11 +404,7 @@ template <typename T>
 __device__ void qb_layer_forward(const QbLayerPlan& L, const T* sW, const T* Ain, T* Aout, int lda, const QbScope& sc,
                                  bool inplace) {
     if (L.mode == QB_MODE_GEMM) {
-        switch (L.act) {
-            case QB_ACT_TANH: qb_fwd_gemm<T, QB_ACT_TANH>(L, sW, Ain, Aout, lda, sc, inplace); break;
-            case QB_ACT_RELU: qb_fwd_gemm<T, QB_ACT_RELU>(L, sW, Ain, Aout, lda, sc, inplace); break;
-            default: qb_fwd_gemm<T, QB_ACT_IDENTITY>(L, sW, Ain, Aout, lda, sc, inplace); break;
-        }
+        qb_fwd_gemm<T, 0>(L, sW, Ain, Aout, lda, sc, inplace, nullptr);
     } else {
 #define QB_DOT(NJ)                                                                            \
     switch (L.act) {                                                                          \
@@ -326,12 +447,9 @@ template <typename T> __device__ __forceinline__ QbSmem qb_carve(const QbPlan& P
     return s;
 }
 
-// If out_tile != nullptr the network outputs of every tile are also written to
-// out_tile[(p - n0) * out_dim + j] (used by the predictive kernel; y may then be nullptr).
 template <typename T>
-__device__ double qb_eval_value(const QbPlan& P, const QbSmem& S, const T* theta, const T* __restrict__ x,
-                                const T* __restrict__ y, int64_t n0, int64_t n1, bool restage,
-                                T* out_glob /* nullable: [n1-n0, o] */) {
+__device__ __forceinline__ double qb_eval_value(const QbPlan& P, const QbSmem& S, const T* theta, const T* __restrict__ x,
+                                const T* __restrict__ y, int64_t n0, int64_t n1, bool restage) {
     T* sW = reinterpret_cast<T*>(S.w);
     T* A0 = reinterpret_cast<T*>(S.act);
     const int lda = P.lda, TM = P.TM, o = P.out_dim;
@@ -348,20 +466,32 @@ __device__ double qb_eval_value(const QbPlan& P, const QbSmem& S, const T* theta
         sc.sync();
         T* cur = A0;
         T* oth = A1;
-        for (int l = 0; l < P.n_layers; ++l) {
+        const int nfull = P.fuse_tail ? P.n_layers - 2 : P.n_layers;
+        for (int l = 0; l < nfull; ++l) {
             qb_layer_forward<T>(P.L[l], sW, cur, oth, lda, sc, P.inplace != 0);
             T* t = cur; cur = oth; oth = t;
         }
-        // residuals (losses.py:197: sum over all points and outputs)
-        const int n = sc.p_count * o;
-        for (int idx = sc.tid; idx < n; idx += sc.nthr) {
-            const int j = idx / sc.p_count, p = sc.p_base + (idx - j * sc.p_count);
-            const int64_t gp = p0 + p;
-            if (gp < n1) {
-                T out = cur[j * lda + p];
-                if (P.final_exp) out = qb_exp(out);
-                if (out_glob) out_glob[(gp - n0) * o + j] = out;
-                if (y) {
+#ifndef QB_NOTAILCODE
+        if (P.fuse_tail) {
+            // last hidden layer + narrow linear output layer + residuals, without storing the hidden activations
+            const QbLayerPlan& Lh = P.L[P.n_layers - 2];
+            const QbLayerPlan& Lo = P.L[P.n_layers - 1];
+            QbTailCtx<T> tc;
+            tc.tail = &Lo; tc.y = y; tc.p0 = p0; tc.n1 = n1; tc.o = o; tc.final_exp = P.final_exp;
+            if (Lo.nj == 1) ssq += qb_fwd_gemm<T, 1>(Lh, sW, cur, oth, lda, sc, P.inplace != 0, &tc);
+            else if (Lo.nj == 2) ssq += qb_fwd_gemm<T, 2>(Lh, sW, cur, oth, lda, sc, P.inplace != 0, &tc);
+            else ssq += qb_fwd_gemm<T, 4>(Lh, sW, cur, oth, lda, sc, P.inplace != 0, &tc);
+        } else
+#endif
+        {
+            // residuals (losses.py:197: sum over all points and outputs)
+            const int n = sc.p_count * o;
+            for (int idx = sc.tid; idx < n; idx += sc.nthr) {
+                const int j = idx / sc.p_count, p = sc.p_base + (idx - j * sc.p_count);
+                const int64_t gp = p0 + p;
+                if (gp < n1) {
+                    T out = cur[j * lda + p];
+                    if (P.final_exp) out = qb_exp(out);
                     const T r = __ldg(y + gp * o + j) - out;
                     ssq = fma(r, r, ssq);
                 }

@@ -46,6 +46,7 @@ static int env_int(const char* name, int dflt) {
 
 static const int QB_SMEM_MAX = 227 * 1024;
 static const int QB_SMEM_TWO = 113 * 1024;   // two blocks per SM
+static const int QB_SMEM_FOUR = 56 * 1024;   // four blocks per SM
 static const int QB_NUM_SMS = 148;
 
 static int validate_net(const qb_net_t* net) {
@@ -84,6 +85,8 @@ static long long plan_for_tm(const qb_net_t* net, int dtype, bool want_grad, int
         L.w_off = S.w_off; L.b_off = S.b_off; L.act = S.act; L.res_step = S.res_step; L.has_res = S.res_step != 0.0;
         if (L.has_res) P->has_res = 1;
         const int UG = L.n_out_pad / TU;
+        L.ug_shift = -1;
+        for (int sft = 0; sft < 16; ++sft) if ((1 << sft) == UG) L.ug_shift = sft;
         L.nj = S.n_out == 1 ? 1 : (S.n_out == 2 ? 2 : 4);
         const long long cost_g = cdiv((long long)UG * PG, 256) * S.n_in * (TP * TU + 4);
         const long long cost_d = cdiv(TM, 256) * cdiv(S.n_out, L.nj) * S.n_in * (2 * L.nj + 1);
@@ -149,6 +152,17 @@ static long long plan_for_tm(const qb_net_t* net, int dtype, bool want_grad, int
         }
     }
     P->inplace = inplace; P->buf_rows = buf_rows;
+    // fused tail: ... -> GEMM hidden layer -> narrow linear output layer (identity, no residual, n_out <= 4)
+    P->fuse_tail = 0;
+    // (off by default: the first implementation made ptxas keep the accumulators in local memory -- 8x slower,
+    //  profiles/r1_notes.md; kept behind QB_TAIL=1 for the next round)
+    if (P->ws && net->n_layers >= 2 && env_int("QB_TAIL", 0)) {
+        const QbLayerPlan& Lh = P->L[net->n_layers - 2];
+        const QbLayerPlan& Lo = P->L[net->n_layers - 1];
+        if (Lh.mode == QB_MODE_GEMM && Lo.mode == QB_MODE_DOT && Lo.n_out <= 4 && Lo.act == QB_ACT_IDENTITY &&
+            !Lo.has_res && Lh.ug_shift >= 0)
+            P->fuse_tail = 1;
+    }
     long long act_elems;
     if (!want_grad) {
         act_elems = (long long)(inplace ? 1 : 2) * buf_rows * P->lda;
@@ -187,10 +201,12 @@ static int make_launch(const qb_net_t* net, int dtype, bool want_grad, long long
     int pick = -1;
     QbPlan tmp;
     bool wr_global = false;
-    for (int pass = 0; pass < 3 && pick < 0; ++pass) {
-        // pass 0: two blocks per SM; pass 1: one block per SM; pass 2 (gradient only): drop the shared copy
-        // of W used by back-propagation and read it from global memory instead
-        const int limit = pass == 0 ? QB_SMEM_TWO : QB_SMEM_MAX;
+    for (int pass = -1; pass < 3 && pick < 0; ++pass) {
+        // pass -1 (value kernel): four blocks per SM (measured best on config 5: more, smaller blocks overlap their
+        // MUFU / FMA phases); pass 0: two blocks per SM; pass 1: one block per SM; pass 2 (gradient only): drop the
+        // shared copy of W used by back-propagation and read it from global memory instead
+        if (pass == -1 && want_grad) continue;
+        const int limit = pass == -1 ? QB_SMEM_FOUR : (pass == 0 ? QB_SMEM_TWO : QB_SMEM_MAX);
         if (pass == 2) { if (!want_grad) break; wr_global = true; }
         for (int c = 0; c < 4; ++c) {
             int TM = cands[c];
@@ -251,7 +267,7 @@ __global__ void __launch_bounds__(256, 2) k_logpost(const __grid_constant__ QbPl
     const QbSmem S = qb_carve<T>(P, smem_raw);
     const long long k = blockIdx.x, s = blockIdx.y;
     const long long n0 = s * a.pps, n1 = min(a.N, n0 + a.pps);
-    const double ssq = qb_eval_value<T>(P, S, a.theta + k * P.n_params, a.x, a.y, n0, n1, true, nullptr);
+    const double ssq = qb_eval_value<T>(P, S, a.theta + k * P.n_params, a.x, a.y, n0, n1, true);
     if (threadIdx.x == 0) a.part[k * a.S + s] = ssq;
 }
 
@@ -453,23 +469,19 @@ __global__ void __launch_bounds__(256, 2) k_amcmc(const __grid_constant__ QbPlan
     T* chol = a.chol ? a.chol + k * (long long)P * P : nullptr;
     T* zbuf = reinterpret_cast<T*>(S.act);       // scratch between evaluations
 
-    double lp_cur, map_lp;
-    long long na;
-    if (c.init_lp) {
-        const double ssq = qb_eval_value<T>(plan, S, cur, c.x, c.y, 0, c.N, true, nullptr);
-        double pss = 0.0;
-        if (c.lk.has_prior) pss = qb_prior_ss<T>(c.lk, cur, k, P, S.red);
-        lp_cur = qb_lp_from(c.lk, ssq, c.N, pss, P);
-        map_lp = lp_cur; na = 0;
-        for (int i = tid; i < P; i += nt) mapth[i] = cur[i];
-    } else {
-        lp_cur = c.lp[k]; map_lp = c.map_lp[k]; na = c.naccept[k];
-    }
+    // One evaluation call site: step s == -1 (only when init_lp) evaluates the incoming state itself
+    // (mcmc.py:55-56) and initialises the MAP bookkeeping.
+    double lp_cur = 0.0, map_lp = 0.0;
+    long long na = 0;
+    if (!c.init_lp) { lp_cur = c.lp[k]; map_lp = c.map_lp[k]; na = c.naccept[k]; }
     int kind = a.prop_kind[k];
     __syncthreads();
 
-    for (long long s = 0; s < c.nsteps; ++s) {
+    for (long long s = c.init_lp ? -1 : 0; s < c.nsteps; ++s) {
         const long long t = c.t_start + s;
+        const bool init_step = s < 0;
+        const T* evalp = init_step ? cur : prop;
+        if (!init_step) {
         // ---- running mean / covariance (admcmc.py:52-59)
         if (a.track && xm) {
             if (t == 0) {
@@ -547,13 +559,19 @@ __global__ void __launch_bounds__(256, 2) k_amcmc(const __grid_constant__ QbPlan
                 }
             }
         }
+        }   // !init_step
         __syncthreads();
         // ---- evaluate + accept
-        const double ssq = qb_eval_value<T>(plan, S, prop, c.x, c.y, 0, c.N, true, nullptr);
+        const double ssq = qb_eval_value<T>(plan, S, evalp, c.x, c.y, 0, c.N, true);
         double pss = 0.0;
-        if (c.lk.has_prior) pss = qb_prior_ss<T>(c.lk, prop, k, P, S.red);
+        if (c.lk.has_prior) pss = qb_prior_ss<T>(c.lk, evalp, k, P, S.red);
         const double lp_prop = qb_lp_from(c.lk, ssq, c.N, pss, P);
-        qb_mh_step<T>(c, k, s, P, lp_prop, 0.0, 0.0, cur, prop, mapth, lp_cur, map_lp, na);
+        if (init_step) {
+            lp_cur = lp_prop; map_lp = lp_prop; na = 0;
+            for (int i = tid; i < P; i += nt) mapth[i] = cur[i];
+        } else {
+            qb_mh_step<T>(c, k, s, P, lp_prop, 0.0, 0.0, cur, prop, mapth, lp_cur, map_lp, na);
+        }
         __syncthreads();
     }
     if (tid == 0) { c.lp[k] = lp_cur; c.map_lp[k] = map_lp; c.naccept[k] = na; a.prop_kind[k] = kind; }

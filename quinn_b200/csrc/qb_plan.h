@@ -22,7 +22,7 @@ struct QbLayerPlan {
     int wt_off, wr_off, bias_off; // element offsets in the shared weight area (wr_off < 0: absent)
     int row_in, row_out;          // row offsets of this layer's input / output activations (grad kernel)
     int act, mode, nj, dw_chunks;
-    int has_res, pad_;
+    int has_res, ug_shift;        // ug_shift: log2(n_out_pad/TU) if that is a power of two, else -1
     double res_step;
 };
 
@@ -38,6 +38,7 @@ struct QbPlan {
     int has_res;
     int elem_size;
     int ws, WP;         // value kernel: warp-synchronous mode, points owned by one warp
+    int fuse_tail;      // value kernel: last (narrow linear) layer folded into the epilogue of the last hidden layer
     long long smem_bytes;
     QbLayerPlan L[QB_MAX_LAYERS];
 };
