@@ -21,6 +21,12 @@ import sys
 import threading
 import time
 
+if 'reference' in sys.argv or any(a.startswith('--impl=ref') for a in sys.argv):
+    # the reference arm uses every host thread; torchrun exports OMP_NUM_THREADS=1, which would also pin
+    # numpy's LAPACK (the PxP SVD of admcmc.py:70) to one core -- undo that before numpy is imported
+    for _v in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OPENBLAS_NUM_THREADS'):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -350,6 +356,9 @@ def main():
                                 if spec['sampler'] in ('amcmc', 'hmc') else 'inputs larger than L2 or re-staged per member'),
                     clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cb, diagnostics=diag)
         print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as td
+        td.destroy_process_group()
 
 
 def cpu_unit(spec):
