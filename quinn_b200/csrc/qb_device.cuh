@@ -197,12 +197,40 @@ template <typename T> struct QbTailCtx {   // what the fused tail needs to turn 
     int o, final_exp;
 };
 
+// acc[u][p] += w[u] * a[p] for the whole register tile.  fp32 uses Blackwell's packed FFMA2 (two FMAs per lane
+// per issued instruction, scalar operand broadcast by the hardware): the kernel is issue-bound, so halving the
+// FMA instruction count is what lets the FMA pipe, not the scheduler, set the pace.
+template <typename T>
+__device__ __forceinline__ void qb_fma_tile(T (&acc)[VT<T>::TU][VT<T>::TP], const T (&w)[VT<T>::TU], const T (&a)[VT<T>::TP]) {
+#pragma unroll
+    for (int u = 0; u < VT<T>::TU; ++u)
+#pragma unroll
+        for (int p = 0; p < VT<T>::TP; ++p) acc[u][p] = fma(w[u], a[p], acc[u][p]);
+}
+#ifndef QB_NO_FFMA2
+template <>
+__device__ __forceinline__ void qb_fma_tile<float>(float (&acc)[8][8], const float (&w)[8], const float (&a)[8]) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int p = 0; p < 8; p += 2) {
+            const float2 r = __ffma2_rn(make_float2(a[p], a[p + 1]), make_float2(w[u], w[u]),
+                                        make_float2(acc[u][p], acc[u][p + 1]));
+            acc[u][p] = r.x;
+            acc[u][p + 1] = r.y;
+        }
+}
+#endif
+
 // acc[u][p] = bias[u] + sum_i Wt[i][unit u of tile ug] * Ain[i][pcol + p]      (the one hot loop of the library)
+// Three running pointers (activations, first / second half of the weight row) advanced by constant strides and a
+// down-counter keep the loop overhead to a handful of integer instructions per 128 FMAs.
 template <typename T>
 __device__ __forceinline__ void qb_gemm_accumulate(T (&acc)[VT<T>::TU][VT<T>::TP], const T* __restrict__ Wt,
                                                    const T* __restrict__ bias, const T* __restrict__ ap, int n_in,
                                                    int lda, int ldw, int ug, int UG) {
-    constexpr int TP = VT<T>::TP, TU = VT<T>::TU;
+    constexpr int TP = VT<T>::TP, TU = VT<T>::TU, VW = VT<T>::VW;
+    static_assert(TU == 2 * VW && TP == 2 * VW, "tile = two 128-bit vectors per operand");
     {
         T b[TU];
         qb_ld_wrow<T>(b, bias, ug, UG);
@@ -211,36 +239,34 @@ __device__ __forceinline__ void qb_gemm_accumulate(T (&acc)[VT<T>::TU][VT<T>::TP
 #pragma unroll
             for (int p = 0; p < TP; ++p) acc[u][p] = b[u];
     }
-    const T* wp = Wt;
+    const T* w0p = Wt + ug * VW;                 // units u = 0..VW-1 of this tile
+    const T* w1p = Wt + UG * VW + ug * VW;       // units u = VW..TU-1
+    const int lda2 = 2 * lda, ldw2 = 2 * ldw;
     T a0[TP], w0[TU], a1[TP], w1[TU];
     ldv<TP>(a0, ap);
-    qb_ld_wrow<T>(w0, wp, ug, UG);
-    int i = 0;
+    ldv<VW>(&w0[0], w0p);
+    ldv<VW>(&w0[VW], w1p);
+    int pairs = n_in >> 1;
 #pragma unroll 1
-    for (; i + 2 <= n_in; i += 2) {
+    while (pairs > 0) {
         ldv<TP>(a1, ap + lda);
-        qb_ld_wrow<T>(w1, wp + ldw, ug, UG);
-#pragma unroll
-        for (int u = 0; u < TU; ++u)
-#pragma unroll
-            for (int p = 0; p < TP; ++p) acc[u][p] = fma(w0[u], a0[p], acc[u][p]);
-        ap += 2 * lda;
-        wp += 2 * ldw;
-        if (i + 2 < n_in) {
+        ldv<VW>(&w1[0], w0p + ldw);
+        ldv<VW>(&w1[VW], w1p + ldw);
+        qb_fma_tile<T>(acc, w0, a0);
+        ap += lda2;
+        w0p += ldw2;
+        w1p += ldw2;
+        --pairs;
+        // the row after the last one is never used; reading it stays inside the staged arrays (weights are
+        // followed by the bias / next layer, activations by the next row or the pad) unless this is the very end
+        if (pairs > 0 || (n_in & 1)) {
             ldv<TP>(a0, ap);
-            qb_ld_wrow<T>(w0, wp, ug, UG);
+            ldv<VW>(&w0[0], w0p);
+            ldv<VW>(&w0[VW], w1p);
         }
-#pragma unroll
-        for (int u = 0; u < TU; ++u)
-#pragma unroll
-            for (int p = 0; p < TP; ++p) acc[u][p] = fma(w1[u], a1[p], acc[u][p]);
+        qb_fma_tile<T>(acc, w1, a1);
     }
-    if (i < n_in) {
-#pragma unroll
-        for (int u = 0; u < TU; ++u)
-#pragma unroll
-            for (int p = 0; p < TP; ++p) acc[u][p] = fma(w0[u], a0[p], acc[u][p]);
-    }
+    if (n_in & 1) qb_fma_tile<T>(acc, w0, a0);
 }
 
 // activation (+ residual) of one accumulator row
@@ -289,7 +315,6 @@ __device__ __forceinline__ void qb_epilogue_tail(const T (&acc)[VT<T>::TU][VT<T>
                 for (int p = 0; p < TP; ++p) part[q][p] = fma(wq, h[p], part[q][p]);
             }
         }
-        asm volatile("" ::: "memory");      // keep the rows in order: hoisting all TU weight loads costs 64 registers
     }
 }
 

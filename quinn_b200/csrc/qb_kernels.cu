@@ -11,6 +11,11 @@
 #include "qb_plan.h"
 #include "qb_device.cuh"
 
+#ifndef QB_LB_T
+#define QB_LB_T 256
+#define QB_LB_B 2
+#endif
+
 // =================================================================================================
 // error plumbing
 // =================================================================================================
@@ -262,7 +267,7 @@ template <typename T> struct EvalArgs {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(256, 2) k_logpost(const __grid_constant__ QbPlan P, const EvalArgs<T> a) {
+__global__ void __launch_bounds__(QB_LB_T, QB_LB_B) k_logpost(const __grid_constant__ QbPlan P, const EvalArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const QbSmem S = qb_carve<T>(P, smem_raw);
     const long long k = blockIdx.x, s = blockIdx.y;
@@ -454,7 +459,7 @@ __device__ void qb_cholesky(const T* cov, T* Lf, int P, double fac, double jitte
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256, 2) k_amcmc(const __grid_constant__ QbPlan plan, const ChainArgs<T> c, const AmcmcArgs<T> a) {
+__global__ void __launch_bounds__(QB_LB_T, QB_LB_B) k_amcmc(const __grid_constant__ QbPlan plan, const ChainArgs<T> c, const AmcmcArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const QbSmem S = qb_carve<T>(plan, smem_raw);
     const long long k = blockIdx.x;
@@ -1007,9 +1012,34 @@ __global__ void __launch_bounds__(256, 2) k_fma_peak(long long iters, T* sink) {
     if (s == T(123.456)) sink[0] = s;
 }
 
+// variant 2 (fp32 only): packed FFMA2 chains -- the Blackwell-specific way to issue FP32 FMAs
+__global__ void __launch_bounds__(256, 2) k_fma2_peak(long long iters, float* sink) {
+    float2 a[8];
+    const float2 b = make_float2(1.0000001f + threadIdx.x * 1e-9f, 1.0000002f), c = make_float2(1e-7f, 2e-7f);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a[q] = make_float2(q * 0.01f + threadIdx.x * 1e-6f, q * 0.02f);
+    for (long long it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) a[q] = __ffma2_rn(a[q], b, c);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += a[q].x + a[q].y;
+    if (s == 123.456f) sink[0] = s;
+}
+
 extern "C" int qb_fma_peak(int dtype, int variant, int64_t iters, double* flops_out_host, void* sink, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int blocks = QB_NUM_SMS * 8, threads = 256;
+    if (dtype == QB_F32 && variant == 2) {
+        k_fma2_peak<<<blocks, threads, 0, st>>>(iters, (float*)sink);
+        QB_CUDA(cudaGetLastError());
+        g_launches += 1;
+        if (flops_out_host) *flops_out_host = 2.0 * (double)blocks * threads * (double)iters * 8.0 * 8 * 2;
+        return 0;
+    }
     const int CH = variant == 1 ? 16 : 8;
     if (dtype == QB_F64) {
         if (variant == 1) k_fma_peak<double, 16><<<blocks, threads, 0, st>>>(iters, (double*)sink);
