@@ -269,6 +269,66 @@ __device__ __forceinline__ void qb_gemm_accumulate(T (&acc)[VT<T>::TU][VT<T>::TP
     if (n_in & 1) qb_fma_tile<T>(acc, w0, a0);
 }
 
+#ifndef QB_NO_FFMA2
+// fp32 specialisation: the accumulators live as float2 values (aligned register pairs) for the whole loop so that
+// FFMA2 reads and writes them in place (the generic version made ptxas shuffle pairs: 0.6 MOV per FFMA2).
+__device__ __forceinline__ void qb_ld8(float2 (&d)[4], const float* s) {
+    const float4 lo = *reinterpret_cast<const float4*>(s), hi = *reinterpret_cast<const float4*>(s + 4);
+    d[0] = make_float2(lo.x, lo.y); d[1] = make_float2(lo.z, lo.w);
+    d[2] = make_float2(hi.x, hi.y); d[3] = make_float2(hi.z, hi.w);
+}
+__device__ __forceinline__ void qb_ldw8(float (&w)[8], const float* w0p, const float* w1p) {
+    const float4 lo = *reinterpret_cast<const float4*>(w0p), hi = *reinterpret_cast<const float4*>(w1p);
+    w[0] = lo.x; w[1] = lo.y; w[2] = lo.z; w[3] = lo.w; w[4] = hi.x; w[5] = hi.y; w[6] = hi.z; w[7] = hi.w;
+}
+__device__ __forceinline__ void qb_fma2_tile(float2 (&c)[8][4], const float (&w)[8], const float2 (&a)[4]) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) c[u][q] = __ffma2_rn(a[q], make_float2(w[u], w[u]), c[u][q]);
+}
+template <>
+__device__ __forceinline__ void qb_gemm_accumulate<float>(float (&acc)[8][8], const float* __restrict__ Wt,
+                                                          const float* __restrict__ bias, const float* __restrict__ ap,
+                                                          int n_in, int lda, int ldw, int ug, int UG) {
+    float2 c[8][4];
+    {
+        float b[8];
+        qb_ldw8(b, bias + ug * 4, bias + UG * 4 + ug * 4);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) c[u][q] = make_float2(b[u], b[u]);
+    }
+    const float* w0p = Wt + ug * 4;
+    const float* w1p = Wt + UG * 4 + ug * 4;
+    const int lda2 = 2 * lda, ldw2 = 2 * ldw;
+    float2 a0[4], a1[4];
+    float w0[8], w1[8];
+    qb_ld8(a0, ap);
+    qb_ldw8(w0, w0p, w1p);
+    int pairs = n_in >> 1;
+#pragma unroll 1
+    while (pairs > 0) {
+        qb_ld8(a1, ap + lda);
+        qb_ldw8(w1, w0p + ldw, w1p + ldw);
+        qb_fma2_tile(c, w0, a0);
+        ap += lda2;
+        w0p += ldw2;
+        w1p += ldw2;
+        --pairs;
+        qb_ld8(a0, ap);              // after the last pair this reads one row past the end: the plan pads for it
+        qb_ldw8(w0, w0p, w1p);
+        qb_fma2_tile(c, w1, a1);
+    }
+    if (n_in & 1) qb_fma2_tile(c, w0, a0);
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { acc[u][2 * q] = c[u][q].x; acc[u][2 * q + 1] = c[u][q].y; }
+}
+#endif
+
 // activation (+ residual) of one accumulator row
 template <typename T, int ACT>
 __device__ __forceinline__ void qb_act_row(T (&h)[VT<T>::TP], const T (&accrow)[VT<T>::TP], bool res, T step,
@@ -310,16 +370,19 @@ __device__ __forceinline__ void qb_epilogue_tail(const T (&acc)[VT<T>::TU][VT<T>
         if (j < n_out) {
 #pragma unroll
             for (int q = 0; q < NT; ++q) {
-                const T wq = Wl[j * ldl + q];          // columns >= n_tail of the staged tail weights are zero
+                if (q < n_tail) {                      // uniform
+                    const T wq = Wl[j * ldl + q];
 #pragma unroll
-                for (int p = 0; p < TP; ++p) part[q][p] = fma(wq, h[p], part[q][p]);
+                    for (int p = 0; p < TP; ++p) part[q][p] = fma(wq, h[p], part[q][p]);
+                }
             }
         }
     }
 }
 
-// NT = 0: store the activations; NT = 1, 2, 4: fused tail with up to NT outputs
-template <typename T, int NT>
+// tc == nullptr: store the activations; else fused tail with up to 4 outputs.  ONE instance of the hot loop serves
+// both (separate template instances of the tail made ptxas spill the accumulators inside the loop).
+template <typename T>
 __device__ __forceinline__ T qb_fwd_gemm(const QbLayerPlan& L, const T* sW, const T* Ain, T* Aout,
                                          int lda, const QbScope& sc, bool sync_before_store,
                                          const QbTailCtx<T>* tc) {
@@ -342,8 +405,8 @@ __device__ __forceinline__ T qb_fwd_gemm(const QbLayerPlan& L, const T* sW, cons
         T acc[TU][TP];
         if (valid) qb_gemm_accumulate<T>(acc, Wt, bias, Ain + pcol, n_in, lda, ldw, ug, UG);
         if (sync_before_store) sc.sync();       // every lane has finished READING the input rows
-        if (NT > 0) {
-            constexpr int NTA = NT > 0 ? NT : 1;
+        if (tc) {
+            constexpr int NTA = 4;
             T part[NTA][TP];
 #pragma unroll
             for (int q = 0; q < NTA; ++q)
@@ -359,9 +422,12 @@ __device__ __forceinline__ T qb_fwd_gemm(const QbLayerPlan& L, const T* sW, cons
             // combine the UG lanes that hold the same points (consecutive lanes; fixed order => deterministic)
             for (int off = UG >> 1; off > 0; off >>= 1) {
 #pragma unroll
-                for (int q = 0; q < NTA; ++q)
+                for (int q = 0; q < NTA; ++q) {
+                    if (q < tail->n_out) {
 #pragma unroll
-                    for (int p = 0; p < TP; ++p) part[q][p] += __shfl_xor_sync(0xffffffffu, part[q][p], off);
+                        for (int p = 0; p < TP; ++p) part[q][p] += __shfl_xor_sync(0xffffffffu, part[q][p], off);
+                    }
+                }
             }
             if (valid && ug == 0) {
                 const T* bo = sW + tail->bias_off;
@@ -426,10 +492,11 @@ __device__ __forceinline__ void qb_fwd_dot(const QbLayerPlan& L, const T* sW, co
 }
 
 template <typename T>
-__device__ void qb_layer_forward(const QbLayerPlan& L, const T* sW, const T* Ain, T* Aout, int lda, const QbScope& sc,
-                                 bool inplace) {
+__device__ T qb_layer_forward(const QbLayerPlan& L, const T* sW, const T* Ain, T* Aout, int lda, const QbScope& sc,
+                              bool inplace, const QbTailCtx<T>* tc = nullptr) {
+    T ssq = T(0);
     if (L.mode == QB_MODE_GEMM) {
-        qb_fwd_gemm<T, 0>(L, sW, Ain, Aout, lda, sc, inplace, nullptr);
+        ssq = qb_fwd_gemm<T>(L, sW, Ain, Aout, lda, sc, inplace, tc);
     } else {
 #define QB_DOT(NJ)                                                                            \
     switch (L.act) {                                                                          \
@@ -441,6 +508,7 @@ __device__ void qb_layer_forward(const QbLayerPlan& L, const T* sW, const T* Ain
 #undef QB_DOT
     }
     sc.sync();
+    return ssq;
 }
 
 // x[p0 + p_base .. + p_count) -> rows 0..d-1 of A (zero for points beyond pend)
@@ -491,24 +559,16 @@ __device__ __forceinline__ double qb_eval_value(const QbPlan& P, const QbSmem& S
         sc.sync();
         T* cur = A0;
         T* oth = A1;
-        const int nfull = P.fuse_tail ? P.n_layers - 2 : P.n_layers;
+        const int nfull = P.fuse_tail ? P.n_layers - 1 : P.n_layers;
+        QbTailCtx<T> tc;
+        tc.tail = &P.L[P.n_layers - 1]; tc.y = y; tc.p0 = p0; tc.n1 = n1; tc.o = o; tc.final_exp = P.final_exp;
         for (int l = 0; l < nfull; ++l) {
-            qb_layer_forward<T>(P.L[l], sW, cur, oth, lda, sc, P.inplace != 0);
+            // with fuse_tail the last hidden layer also applies the narrow linear output layer and the residuals
+            const QbTailCtx<T>* tcp = (P.fuse_tail && l == nfull - 1) ? &tc : nullptr;
+            ssq += qb_layer_forward<T>(P.L[l], sW, cur, oth, lda, sc, P.inplace != 0, tcp);
             T* t = cur; cur = oth; oth = t;
         }
-#ifndef QB_NOTAILCODE
-        if (P.fuse_tail) {
-            // last hidden layer + narrow linear output layer + residuals, without storing the hidden activations
-            const QbLayerPlan& Lh = P.L[P.n_layers - 2];
-            const QbLayerPlan& Lo = P.L[P.n_layers - 1];
-            QbTailCtx<T> tc;
-            tc.tail = &Lo; tc.y = y; tc.p0 = p0; tc.n1 = n1; tc.o = o; tc.final_exp = P.final_exp;
-            if (Lo.nj == 1) ssq += qb_fwd_gemm<T, 1>(Lh, sW, cur, oth, lda, sc, P.inplace != 0, &tc);
-            else if (Lo.nj == 2) ssq += qb_fwd_gemm<T, 2>(Lh, sW, cur, oth, lda, sc, P.inplace != 0, &tc);
-            else ssq += qb_fwd_gemm<T, 4>(Lh, sW, cur, oth, lda, sc, P.inplace != 0, &tc);
-        } else
-#endif
-        {
+        if (!P.fuse_tail) {
             // residuals (losses.py:197: sum over all points and outputs)
             const int n = sc.p_count * o;
             for (int idx = sc.tid; idx < n; idx += sc.nthr) {

@@ -187,6 +187,7 @@ static long long plan_for_tm(const qb_net_t* net, int dtype, bool want_grad, int
         P->total_rows = row;
         act_elems = (long long)row * P->lda;
     }
+    act_elems += P->lda;      // one pad row: the double-buffered hot loop prefetches one row past the end
     P->smem_bytes = 40 * 8 + (long long)woff * elem + act_elems * elem;
     return P->smem_bytes;
 }
