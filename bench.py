@@ -334,8 +334,11 @@ def main():
 
     value = units_per_step * args.steps / (ms * 1e-3)
     achieved = (Kloc if spec['sampler'] != 'predict' else spec['K'] * (xs.shape[0])) * args.steps * flop_per_unit / (ms_local * 1e-3)
+    # DRAM bytes per launch: from the ncu --set full capture profiles/r1_amcmc_r1d (653.0 MB for 4736 chain-steps of this
+    # kernel = 137.9 KB per chain-step: theta / proposal / Xm / var / pscale rows), scaled to this launch; null elsewhere
+    traffic = 137.9e3 * Kloc * args.steps if spec['sampler'] == 'amcmc' else None
     roofline = dict(bound='fp32', kernel=kernel_name, achieved=achieved / 1e12, peak=fma_peak / 1e12, unit='TFLOP/s',
-                    frac=achieved / fma_peak, traffic=None,
+                    frac=achieved / fma_peak, traffic=traffic,
                     note='FP32 CUDA-core FMA bound (not hbm/tensor): peak = live FMA micro-benchmark qb_fma_peak; '
                          'achieved = algorithmic GEMM flops (2 flop/MAC, SURVEY 8d) / CUDA-event time of the timed launches')
 

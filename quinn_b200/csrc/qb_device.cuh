@@ -233,11 +233,11 @@ __device__ __forceinline__ void qb_gemm_accumulate(T (&acc)[VT<T>::TU][VT<T>::TP
     static_assert(TU == 2 * VW && TP == 2 * VW, "tile = two 128-bit vectors per operand");
     {
         T b[TU];
-        qb_ld_wrow<T>(b, bias, ug, UG);
+        if (bias) qb_ld_wrow<T>(b, bias, ug, UG);
 #pragma unroll
         for (int u = 0; u < TU; ++u)
 #pragma unroll
-            for (int p = 0; p < TP; ++p) acc[u][p] = b[u];
+            for (int p = 0; p < TP; ++p) acc[u][p] = bias ? b[u] : T(0);
     }
     const T* w0p = Wt + ug * VW;                 // units u = 0..VW-1 of this tile
     const T* w1p = Wt + UG * VW + ug * VW;       // units u = VW..TU-1
@@ -294,11 +294,11 @@ __device__ __forceinline__ void qb_gemm_accumulate<float>(float (&acc)[8][8], co
     float2 c[8][4];
     {
         float b[8];
-        qb_ldw8(b, bias + ug * 4, bias + UG * 4 + ug * 4);
+        if (bias) qb_ldw8(b, bias + ug * 4, bias + UG * 4 + ug * 4);
 #pragma unroll
         for (int u = 0; u < 8; ++u)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) c[u][q] = make_float2(b[u], b[u]);
+            for (int q = 0; q < 4; ++q) c[u][q] = bias ? make_float2(b[u], b[u]) : make_float2(0.f, 0.f);
     }
     const float* w0p = Wt + ug * 4;
     const float* w1p = Wt + UG * 4 + ug * 4;
@@ -631,6 +631,49 @@ __device__ __forceinline__ void qb_finish_delta(const QbLayerPlan& Lm, T* R, T* 
     *po = dz;
 }
 
+// one PV-point step of the dW patch: acc[a][b] += sum_q dz[a][q]*av[b][q].  fp32: the (q, q+1) pairs that come out of
+// the 128-bit loads feed FFMA2 directly; even and odd q accumulate separately (acc / acc2) and are folded at the end.
+template <typename T>
+__device__ __forceinline__ void qb_dw_fma(T (&acc)[4][4], T (&acc2)[4][4], T (&bacc)[4], const T (&dz)[4][VT<T>::PV],
+                                          const T (&av)[4][VT<T>::PV], bool want_bias) {
+    constexpr int PV = VT<T>::PV;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        if (want_bias) {
+#pragma unroll
+            for (int q = 0; q < PV; ++q) bacc[a] += dz[a][q];
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int q = 0; q < PV; ++q) acc[a][b] = fma(dz[a][q], av[b][q], acc[a][b]);
+    }
+}
+#ifndef QB_NO_FFMA2
+template <>
+__device__ __forceinline__ void qb_dw_fma<float>(float (&acc)[4][4], float (&acc2)[4][4], float (&bacc)[4],
+                                                 const float (&dz)[4][4], const float (&av)[4][4], bool want_bias) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        if (want_bias) bacc[a] += (dz[a][0] + dz[a][1]) + (dz[a][2] + dz[a][3]);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            float2 c = make_float2(acc[a][b], acc2[a][b]);
+            c = __ffma2_rn(make_float2(dz[a][0], dz[a][1]), make_float2(av[b][0], av[b][1]), c);
+            c = __ffma2_rn(make_float2(dz[a][2], dz[a][3]), make_float2(av[b][2], av[b][3]), c);
+            acc[a][b] = c.x;
+            acc2[a][b] = c.y;
+        }
+    }
+}
+#endif
+template <typename T> __device__ __forceinline__ void qb_dw_fold(T (&acc)[4][4], const T (&acc2)[4][4]) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] += acc2[a][b];
+}
+
 // dW_l += delta_z_l (rows) x a_in (rows) over the tile's points; db_l += row sums of delta_z_l.
 // Each thread owns a 4x4 patch of dW (rows interleaved by JG / IG so that the 8 lanes of a quarter
 // warp hit distinct banks) and, for narrow layers, one of `dw_chunks` slices of the points; slices are
@@ -649,12 +692,27 @@ __device__ void qb_dw_accumulate(const QbLayerPlan& L, const T* R, int lda, int 
         const int it = valid ? item : 0;
         const int patch = it / C, chunk = it - patch * C;
         const int jg = patch / IG, ig = patch - jg * IG;
-        T acc[4][4], bacc[4];
+        T acc[4][4], acc2[4][4], bacc[4];      // acc2: odd-q partial sums of the packed fp32 path
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             bacc[a] = T(0);
 #pragma unroll
-            for (int b = 0; b < 4; ++b) acc[a][b] = T(0);
+            for (int b = 0; b < 4; ++b) { acc[a][b] = T(0); acc2[a][b] = T(0); }
+        }
+        const bool want_bias = (ig == 0) && L.b_off >= 0;
+        const bool writer = valid && chunk == 0;
+        // the running gradient entries this thread owns: fetched BEFORE the point loop so the global-memory
+        // latency hides behind it (they were 30 % of the kernel's stall samples as a load-add-store at the end)
+        T gold[4][4], bold[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int j = jg + JG * a;
+            bold[a] = (writer && want_bias && j < L.n_out) ? g[L.b_off + j] : T(0);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int i = ig + IG * b;
+                gold[a][b] = (writer && j < L.n_out && i < L.n_in) ? g[L.w_off + j * L.n_in + i] : T(0);
+            }
         }
         const T* zr = Rz + (size_t)jg * lda + chunk * clen;
         const T* ar = Ra + (size_t)ig * lda + chunk * clen;
@@ -666,16 +724,9 @@ __device__ void qb_dw_accumulate(const QbLayerPlan& L, const T* R, int lda, int 
                 ldv<PV>(dz[c], zr + c * zs + p);
                 ldv<PV>(av[c], ar + c * as + p);
             }
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-#pragma unroll
-                for (int q = 0; q < PV; ++q) bacc[a] += dz[a][q];
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-#pragma unroll
-                    for (int q = 0; q < PV; ++q) acc[a][b] = fma(dz[a][q], av[b][q], acc[a][b]);
-            }
+            qb_dw_fma<T>(acc, acc2, bacc, dz, av, want_bias);
         }
+        qb_dw_fold<T>(acc, acc2);
         for (int off = C >> 1; off > 0; off >>= 1) {
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
@@ -684,7 +735,7 @@ __device__ void qb_dw_accumulate(const QbLayerPlan& L, const T* R, int lda, int 
                 for (int b = 0; b < 4; ++b) acc[a][b] += __shfl_xor_sync(0xffffffffu, acc[a][b], off);
             }
         }
-        if (valid && chunk == 0) {
+        if (writer) {
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
                 const int j = jg + JG * a;
@@ -692,9 +743,9 @@ __device__ void qb_dw_accumulate(const QbLayerPlan& L, const T* R, int lda, int 
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
                         const int i = ig + IG * b;
-                        if (i < L.n_in) g[L.w_off + j * L.n_in + i] += acc[a][b];
+                        if (i < L.n_in) g[L.w_off + j * L.n_in + i] = gold[a][b] + acc[a][b];
                     }
-                    if (ig == 0 && L.b_off >= 0) g[L.b_off + j] += bacc[a];
+                    if (want_bias) g[L.b_off + j] = bold[a] + bacc[a];
                 }
             }
         }
@@ -719,28 +770,28 @@ __device__ void qb_bwd_gemm(const QbLayerPlan& L, const QbLayerPlan& Lm, const T
         if (item >= items) continue;
         const int pg = item / UGI, ig = item - pg * UGI;
         T acc[TU][TP];
-#pragma unroll
-        for (int u = 0; u < TU; ++u)
-#pragma unroll
-            for (int p = 0; p < TP; ++p) acc[u][p] = T(0);
-        const T* zp = Rz + pg * TP;
-        const T* wp = GLOBALW ? Wr + ig * TU : Wr;
-QB_PRAGMA_UNROLL(QB_UNROLL)
-        for (int j = 0; j < n_out; ++j) {
-            T d[TP], w[TU];
-            ldv<TP>(d, zp);
-            if (GLOBALW) {
-#pragma unroll
-                for (int u = 0; u < TU; ++u) w[u] = (ig * TU + u < L.n_in) ? wp[u] : T(0);
-            } else {
-                qb_ld_wrow<T>(w, wp, ig, UGI);
-            }
-            zp += lda;
-            wp += ldw;
+        if (!GLOBALW) {
+            // same hot loop as the forward pass: rows = output units j, "weights" = staged Wr, no bias
+            qb_gemm_accumulate<T>(acc, Wr, (const T*)nullptr, Rz + pg * TP, n_out, lda, ldw, ig, UGI);
+        } else {
 #pragma unroll
             for (int u = 0; u < TU; ++u)
 #pragma unroll
-                for (int p = 0; p < TP; ++p) acc[u][p] = fma(w[u], d[p], acc[u][p]);
+                for (int p = 0; p < TP; ++p) acc[u][p] = T(0);
+            const T* zp = Rz + pg * TP;
+            const T* wp = Wr + ig * TU;
+            for (int j = 0; j < n_out; ++j) {
+                T d[TP], w[TU];
+                ldv<TP>(d, zp);
+#pragma unroll
+                for (int u = 0; u < TU; ++u) w[u] = (ig * TU + u < L.n_in) ? wp[u] : T(0);
+                zp += lda;
+                wp += ldw;
+#pragma unroll
+                for (int u = 0; u < TU; ++u)
+#pragma unroll
+                    for (int p = 0; p < TP; ++p) acc[u][p] = fma(w[u], d[p], acc[u][p]);
+            }
         }
 #pragma unroll
         for (int u = 0; u < TU; ++u) {

@@ -50,8 +50,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 static const int QB_SMEM_MAX = 227 * 1024;
-static const int QB_SMEM_TWO = 113 * 1024;   // two blocks per SM
-static const int QB_SMEM_FOUR = 56 * 1024;   // four blocks per SM
+static const int QB_SMEM_SM = 228 * 1024;    // shared memory per SM
 static const int QB_NUM_SMS = 148;
 
 static int validate_net(const qb_net_t* net) {
@@ -116,7 +115,7 @@ static long long plan_for_tm(const qb_net_t* net, int dtype, bool want_grad, int
     }
     P->w_elems = woff;
     int nthreads = any_gemm ? max_items : TM;
-    nthreads = std::min(256, std::max(64, rup(nthreads, 32)));
+    nthreads = std::min(want_grad ? 256 : 512, std::max(64, rup(nthreads, 32)));
     nthreads = env_int("QB_THREADS", nthreads);
     P->nthreads = nthreads;
     // value kernel: in place when every GEMM layer is a single pass and DOT layers are single-chunk
@@ -149,7 +148,7 @@ static long long plan_for_tm(const qb_net_t* net, int dtype, bool want_grad, int
         }
         if (ok) {
             const int WP = (32 / ugmax) * TP;
-            if (TM % WP == 0 && TM / WP >= 1 && TM / WP <= 8) {
+            if (TM % WP == 0 && TM / WP >= 1 && TM / WP <= 16) {
                 P->ws = 1; P->WP = WP; inplace = 1;
                 nthreads = 32 * (TM / WP);
                 P->nthreads = nthreads;
@@ -204,22 +203,34 @@ static int make_launch(const qb_net_t* net, int dtype, bool want_grad, long long
     const int mintm = cands[3];
     const int cap = std::max(mintm, rup((int)std::min<long long>(N, 256), mintm));
     int forced = env_int("QB_TM", 0);
-    int pick = -1;
-    QbPlan tmp;
+    // Score every tile size by resident warps per SM (limited by shared memory, 128 registers/thread and 2048
+    // threads); ties go to more, smaller blocks for the value kernel (their MUFU / FMA phases overlap better,
+    // measured on config 5) and to larger tiles for the gradient kernel (fewer block barriers per point).
+    // Gradient only: if nothing fits, drop the shared copy of W used by back-propagation (read from global).
+    int pick = -1, best_score = -1;
     bool wr_global = false;
-    for (int pass = -1; pass < 3 && pick < 0; ++pass) {
-        // pass -1 (value kernel): four blocks per SM (measured best on config 5: more, smaller blocks overlap their
-        // MUFU / FMA phases); pass 0: two blocks per SM; pass 1: one block per SM; pass 2 (gradient only): drop the
-        // shared copy of W used by back-propagation and read it from global memory instead
-        if (pass == -1 && want_grad) continue;
-        const int limit = pass == -1 ? QB_SMEM_FOUR : (pass == 0 ? QB_SMEM_TWO : QB_SMEM_MAX);
-        if (pass == 2) { if (!want_grad) break; wr_global = true; }
+    QbPlan tmp;
+    for (int g = 0; g < 2 && pick < 0; ++g) {
+        if (g == 1 && !want_grad) break;
         for (int c = 0; c < 4; ++c) {
             int TM = cands[c];
             if (forced) TM = forced;
             else if (TM > cap) continue;
-            long long b = plan_for_tm(net, dtype, want_grad, TM, &tmp, wr_global);
-            if (b <= limit) { pick = TM; break; }
+            const long long b = plan_for_tm(net, dtype, want_grad, TM, &tmp, g == 1);
+            if (b <= QB_SMEM_MAX) {
+                const int by_smem = (int)(QB_SMEM_SM / (b + 1024));
+                const int by_regs = 512 / tmp.nthreads;
+                const int blocks = std::max(1, std::min(std::min(by_smem, by_regs), 16));
+                int score;
+                if (want_grad) {
+                    // gradient kernel (block barriers per layer): the largest tile that still leaves two blocks per SM,
+                    // else the largest tile that fits at all
+                    score = (blocks >= 2 ? 1000 : 0) + (3 - c);
+                } else {
+                    score = blocks * (tmp.nthreads / 32) * 16 + std::min(blocks, 8);
+                }
+                if (score > best_score) { best_score = score; pick = TM; wr_global = (g == 1); }
+            }
             if (forced) break;
         }
     }
@@ -268,7 +279,7 @@ template <typename T> struct EvalArgs {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(QB_LB_T, QB_LB_B) k_logpost(const __grid_constant__ QbPlan P, const EvalArgs<T> a) {
+__global__ void __launch_bounds__(512, 1) k_logpost(const __grid_constant__ QbPlan P, const EvalArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const QbSmem S = qb_carve<T>(P, smem_raw);
     const long long k = blockIdx.x, s = blockIdx.y;
@@ -460,7 +471,7 @@ __device__ void qb_cholesky(const T* cov, T* Lf, int P, double fac, double jitte
 }
 
 template <typename T>
-__global__ void __launch_bounds__(QB_LB_T, QB_LB_B) k_amcmc(const __grid_constant__ QbPlan plan, const ChainArgs<T> c, const AmcmcArgs<T> a) {
+__global__ void __launch_bounds__(512, 1) k_amcmc(const __grid_constant__ QbPlan plan, const ChainArgs<T> c, const AmcmcArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const QbSmem S = qb_carve<T>(plan, smem_raw);
     const long long k = blockIdx.x;
@@ -774,25 +785,56 @@ template <typename T> struct PredArgs {
     const T* theta; const T* x; long long M, N;
     T* out; T* mean; T* var;
     int fused;     // 1: block = point tile, loops over all members, Welford in registers
+    long long tiles_per_block;   // member-parallel mode
 };
 
 template <typename T>
-__global__ void __launch_bounds__(256, 2) k_predict(const __grid_constant__ QbPlan P, const PredArgs<T> a) {
+__global__ void __launch_bounds__(512, 1) k_predict(const __grid_constant__ QbPlan P, const PredArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const QbSmem S = qb_carve<T>(P, smem_raw);
     T* sW = reinterpret_cast<T*>(S.w);
     T* A0 = reinterpret_cast<T*>(S.act);
     const int lda = P.lda, TM = P.TM, o = P.out_dim;
     T* A1 = P.inplace ? A0 : A0 + (size_t)P.buf_rows * lda;
+    const int n = TM * o;
+    const QbScope sc = P.ws ? qb_warp_scope(P.WP) : qb_block_scope(TM);
+    if (!a.fused) {
+        // member-parallel: this block owns member blockIdx.y and a chunk of consecutive tiles; the weights are
+        // staged once and every warp (warp-synchronous plans) copies out its own points without a block barrier
+        const long long m = blockIdx.y;
+        const long long ntiles = (a.N + TM - 1) / TM;
+        const long long t0 = (long long)blockIdx.x * a.tiles_per_block, t1 = min(ntiles, t0 + a.tiles_per_block);
+        qb_stage_weights<T>(P, sW, a.theta + m * P.n_params);
+        __syncthreads();
+        for (long long t = t0; t < t1; ++t) {
+            const long long p0 = t * TM;
+            qb_load_x_tile<T>(a.x, P.in_dim, p0, a.N, A0, lda, sc);
+            sc.sync();
+            T* cur = A0; T* oth = A1;
+            for (int l = 0; l < P.n_layers; ++l) {
+                qb_layer_forward<T>(P.L[l], sW, cur, oth, lda, sc, P.inplace != 0);
+                T* tt = cur; cur = oth; oth = tt;
+            }
+            const int nn = sc.p_count * o;
+            for (int idx = sc.tid; idx < nn; idx += sc.nthr) {
+                const int pl = idx / o, j = idx - pl * o, p = sc.p_base + pl;
+                const long long gp = p0 + p;
+                if (gp < a.N) {
+                    T v = cur[j * lda + p];
+                    if (P.final_exp) v = qb_exp(v);
+                    a.out[(m * a.N + gp) * o + j] = v;
+                }
+            }
+            sc.sync();
+        }
+        return;
+    }
     const long long p0 = (long long)blockIdx.x * TM;
-    const long long m_lo = a.fused ? 0 : blockIdx.y, m_hi = a.fused ? a.M : m_lo + 1;
     constexpr int QMAX = 4;
     T wmean[QMAX], wm2[QMAX];
 #pragma unroll
     for (int q = 0; q < QMAX; ++q) { wmean[q] = T(0); wm2[q] = T(0); }
-    const int n = TM * o;
-    const QbScope sc = P.ws ? qb_warp_scope(P.WP) : qb_block_scope(TM);
-    for (long long m = m_lo; m < m_hi; ++m) {
+    for (long long m = 0; m < a.M; ++m) {
         __syncthreads();
         qb_stage_weights<T>(P, sW, a.theta + m * P.n_params);
         __syncthreads();
@@ -803,19 +845,7 @@ __global__ void __launch_bounds__(256, 2) k_predict(const __grid_constant__ QbPl
             qb_layer_forward<T>(P.L[l], sW, cur, oth, lda, sc, P.inplace != 0);
             T* t = cur; cur = oth; oth = t;
         }
-        __syncthreads();          // the copy-out below reads points of every warp
-        if (!a.fused) {
-            for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-                const int p = idx / o, j = idx - p * o;
-                const long long gp = p0 + p;
-                if (gp < a.N) {
-                    T v = cur[j * lda + p];
-                    if (P.final_exp) v = qb_exp(v);
-                    a.out[(m * a.N + gp) * o + j] = v;
-                }
-            }
-            continue;
-        }
+        __syncthreads();          // the accumulation below reads points of every warp
         const T inv_n = T(1) / (T)(m + 1);
 #pragma unroll
         for (int q = 0; q < QMAX; ++q) {
@@ -876,14 +906,21 @@ static int run_predict(const qb_net_t* net, int dtype, const void* theta, int64_
     const long long tiles = cdiv(N, P.TM);
     const bool want_mom = mean || var;
     const bool can_fuse = (long long)P.TM * P.out_dim <= 4LL * P.nthreads;
-    bool fused = want_mom && can_fuse && (tiles >= 2 * QB_NUM_SMS || !out);
+    bool fused = want_mom && can_fuse && !out;     // with an `out` buffer: member-parallel + k_moments (weights staged once)
     if (want_mom && !fused && !out) return qb_fail("moments without `out` need TM*out_dim <= 4*threads; pass an `out` buffer");
     if (!fused && M > 65535) return qb_fail("member-parallel predictive supports M <= 65535; chunk the call");
     PredArgs<T> a;
     a.theta = (const T*)theta; a.x = (const T*)x; a.M = M; a.N = N;
     a.out = (T*)out; a.mean = (T*)mean; a.var = (T*)var; a.fused = fused ? 1 : 0;
     if (set_smem(k_predict<T>, P.smem_bytes)) return -2;
-    dim3 grid((unsigned)tiles, fused ? 1u : (unsigned)M);
+    long long chunks = tiles;
+    a.tiles_per_block = 1;
+    if (!fused) {
+        chunks = std::max<long long>(1, std::min<long long>(tiles, cdiv((long long)QB_NUM_SMS * 8, M)));
+        a.tiles_per_block = cdiv(tiles, chunks);
+        chunks = cdiv(tiles, a.tiles_per_block);
+    }
+    dim3 grid((unsigned)chunks, fused ? 1u : (unsigned)M);
     k_predict<T><<<grid, P.nthreads, P.smem_bytes, st>>>(P, a);
     QB_CUDA(cudaGetLastError());
     g_launches += 1;

@@ -152,7 +152,10 @@ def predict(desc: NetDesc, theta, x, dtype=torch.float32, device='cuda', want_ou
     M, N, o = theta.shape[0], x.shape[0], desc.out_dim
     if theta.shape[1] != desc.n_params or x.shape[1] != desc.in_dim:
         raise ValueError('theta / x do not match the network')
-    out = torch.empty((M, N, o), dtype=dtype, device=device) if want_out else None
+    # moments of many members: run member-parallel (weights staged once per block) into a scratch array and reduce it
+    # with k_moments, unless the scratch would be huge; then fall back to the fused per-tile member loop
+    scratch = want_moments and not want_out and M > 1 and M * N * o * theta.element_size() <= 16 * 2 ** 30
+    out = torch.empty((M, N, o), dtype=dtype, device=device) if (want_out or scratch) else None
     mean = torch.empty((N, o), dtype=dtype, device=device) if want_moments else None
     var = torch.empty((N, o), dtype=dtype, device=device) if want_moments else None
     cnet = cnet if cnet is not None else desc.to_c()
@@ -167,7 +170,7 @@ def predict(desc: NetDesc, theta, x, dtype=torch.float32, device='cuda', want_ou
                                 _ptr(var), _stream())
             out = None
     _lib.check(rc, 'qb_predict')
-    return out, mean, var
+    return (out if want_out else None), mean, var
 
 
 class ChainState:
