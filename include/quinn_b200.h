@@ -136,6 +136,7 @@ typedef struct {
     void*    samples;
     int64_t  store_every;
     int64_t  n_slots;
+    double*  logpost0;     /* [K], optional: log-posterior of the incoming state, written when init_lp != 0 (mcmc.py:55-61) */
 } qb_record_t;
 
 enum { QB_ADAPT_NONE = 0, QB_ADAPT_DIAG = 1, QB_ADAPT_FULL = 2 };

@@ -46,7 +46,7 @@ class qb_rng_t(C.Structure):
 
 class qb_record_t(C.Structure):
     _fields_ = [('logpost', C.c_void_p), ('alpha', C.c_void_p), ('accepted', C.c_void_p), ('ld', C.c_int64),
-                ('samples', C.c_void_p), ('store_every', C.c_int64), ('n_slots', C.c_int64)]
+                ('samples', C.c_void_p), ('store_every', C.c_int64), ('n_slots', C.c_int64), ('logpost0', C.c_void_p)]
 
 
 class qb_amcmc_t(C.Structure):

@@ -401,7 +401,7 @@ template <typename T> struct ChainArgs {
     QbLikDev lk;
     T* theta; double* lp; long long* naccept; T* map_theta; double* map_lp;
     int rng_mode; unsigned long long seed; long long chain_offset; const T* incr; const double* unif;
-    double* rec_lp; double* rec_alpha; unsigned char* rec_acc; long long rec_ld;
+    double* rec_lp; double* rec_alpha; unsigned char* rec_acc; long long rec_ld; double* rec_lp0;
     T* samples; long long store_every, n_slots;
     long long t_start, nsteps; int init_lp;
 };
@@ -585,6 +585,7 @@ __global__ void __launch_bounds__(512, 1) k_amcmc(const __grid_constant__ QbPlan
         const double lp_prop = qb_lp_from(c.lk, ssq, c.N, pss, P);
         if (init_step) {
             lp_cur = lp_prop; map_lp = lp_prop; na = 0;
+            if (tid == 0 && c.rec_lp0) c.rec_lp0[k] = lp_cur;
             for (int i = tid; i < P; i += nt) mapth[i] = cur[i];
         } else {
             qb_mh_step<T>(c, k, s, P, lp_prop, 0.0, 0.0, cur, prop, mapth, lp_cur, map_lp, na);
@@ -628,6 +629,7 @@ __global__ void __launch_bounds__(256, 2) k_hmc(const __grid_constant__ QbPlan p
     if (c.init_lp) {
         qb_full_grad<T>(plan, S, c, k, cur, gcur, &lp_cur);
         map_lp = lp_cur; na = 0;
+        if (tid == 0 && c.rec_lp0) c.rec_lp0[k] = lp_cur;
         for (int i = tid; i < P; i += nt) mapth[i] = cur[i];
     } else {
         lp_cur = c.lp[k]; map_lp = c.map_lp[k]; na = c.naccept[k];
@@ -698,7 +700,7 @@ static void fill_chain_args(ChainArgs<T>& c, const qb_data_t* data, const qb_lik
     c.theta = (T*)ch->theta; c.lp = ch->lp; c.naccept = (long long*)ch->naccept; c.map_theta = (T*)ch->map_theta; c.map_lp = ch->map_lp;
     c.rng_mode = rng->mode; c.seed = rng->seed; c.chain_offset = rng->chain_offset; c.incr = (const T*)rng->incr; c.unif = rng->unif;
     c.rec_lp = rec ? rec->logpost : nullptr; c.rec_alpha = rec ? rec->alpha : nullptr; c.rec_acc = rec ? rec->accepted : nullptr;
-    c.rec_ld = rec ? rec->ld : 0; c.samples = rec ? (T*)rec->samples : nullptr;
+    c.rec_ld = rec ? rec->ld : 0; c.samples = rec ? (T*)rec->samples : nullptr; c.rec_lp0 = rec ? rec->logpost0 : nullptr;
     c.store_every = rec ? rec->store_every : 0; c.n_slots = rec ? rec->n_slots : 0;
     c.t_start = t_start; c.nsteps = nsteps; c.init_lp = init_lp;
 }

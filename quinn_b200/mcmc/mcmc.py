@@ -93,7 +93,6 @@ class MCMCBase(object):
             bounds = sorted(set([0, nmcmc] + [b - b % store_every for b in bounds[1:-1]]))
         recs = []
         th0 = st.theta.clone()
-        lp0 = ops.logpost(prob, th0)        # log-posterior of the initial state (mcmc.py:55-61)
         for a, b in zip(bounds[:-1], bounds[1:]):
             if b <= a:
                 continue
@@ -108,6 +107,7 @@ class MCMCBase(object):
                 print('%d / %d completed, acceptance rate %lg' % (b, nmcmc, acc))
         self._device_export(st, samp)
         chain = torch.cat([th0[:, None, :]] + [r.samples for r in recs if r.samples is not None], dim=1)
+        lp0 = recs[0].logpost0              # log-posterior of the initial state (mcmc.py:55-61), recorded by the kernel
         logpost = torch.cat([lp0[:, None]] + [r.logpost for r in recs], dim=1)
         alphas = torch.cat([torch.zeros((K, 1), dtype=torch.float64, device=prob.device)] + [r.alpha for r in recs], dim=1)
         accepted = torch.cat([r.accepted for r in recs], dim=1)

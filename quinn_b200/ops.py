@@ -220,6 +220,7 @@ class Recorder:
         self.accepted = torch.empty((K, nsteps), dtype=torch.uint8, device=dev) if record_scalars else None
         self.samples = (torch.empty((K, self.n_slots, P), dtype=state.prob.dtype, device=dev)
                         if self.n_slots > 0 else None)
+        self.logpost0 = torch.empty(K, dtype=torch.float64, device=dev)     # filled by the first segment of a run
 
     def c(self):
         r = _lib.qb_record_t()
@@ -230,6 +231,7 @@ class Recorder:
             r.samples = self.samples.data_ptr()
         r.store_every = self.store_every
         r.n_slots = self.n_slots
+        r.logpost0 = self.logpost0.data_ptr()
         return r
 
 
