@@ -112,6 +112,11 @@ template <int ACT, typename T> __device__ __forceinline__ T qb_act(T z) {
     return z;
 }
 // derivative of the activation expressed through its VALUE a = act(z)
+template <int ACT, typename T> __device__ __forceinline__ T qb_dact_c(T a) {
+    if (ACT == QB_ACT_TANH) return T(1) - a * a;
+    if (ACT == QB_ACT_RELU) return a > T(0) ? T(1) : T(0);
+    return T(1);
+}
 template <typename T> __device__ __forceinline__ T qb_dact(int act, T a) {
     if (act == QB_ACT_TANH) return T(1) - a * a;
     if (act == QB_ACT_RELU) return a > T(0) ? T(1) : T(0);
@@ -197,143 +202,130 @@ template <typename T> struct QbTailCtx {   // what the fused tail needs to turn 
     int o, final_exp;
 };
 
-// acc[u][p] += w[u] * a[p] for the whole register tile.  fp32 uses Blackwell's packed FFMA2 (two FMAs per lane
-// per issued instruction, scalar operand broadcast by the hardware): the kernel is issue-bound, so halving the
-// FMA instruction count is what lets the FMA pipe, not the scheduler, set the pace.
-template <typename T>
-__device__ __forceinline__ void qb_fma_tile(T (&acc)[VT<T>::TU][VT<T>::TP], const T (&w)[VT<T>::TU], const T (&a)[VT<T>::TP]) {
+// ---- the hot loop of the library:  acc[u][p] = bias[u] + sum_i W[i][unit u of tile ug] * A[i][pcol + p] ----------
+// Thread tile = TU units x TP points (TP = 8 in the value / predictive kernels, 4 in the gradient kernel, whose
+// blocks need twice the threads per tile to reach 4 warps per scheduler).  Three running pointers (activation
+// row, two halves of the weight row) advance by constant strides; the operands of step i+1 are fetched before
+// the FMAs of step i (register double buffering; after the last pair one row past the end is read, the plan pads
+// for it).
+//
+// fp32: the accumulators live as float2 values (aligned register pairs along the point axis) and every FMA is
+// Blackwell's packed FFMA2 (two FMAs per lane per issued instruction, weight broadcast by the hardware:
+// SASS `FFMA2 Rd, Ra.F32x2.HI_LO, Rb.F32, Rc.F32x2.HI_LO`).  The kernels are issue-bound, so halving the FMA
+// instruction count is what lets the FMA pipe, not the scheduler, set the pace.
+template <int TP> __device__ __forceinline__ void qb_ldp(float2 (&d)[TP / 2], const float* s) {
 #pragma unroll
-    for (int u = 0; u < VT<T>::TU; ++u)
-#pragma unroll
-        for (int p = 0; p < VT<T>::TP; ++p) acc[u][p] = fma(w[u], a[p], acc[u][p]);
-}
-#ifndef QB_NO_FFMA2
-template <>
-__device__ __forceinline__ void qb_fma_tile<float>(float (&acc)[8][8], const float (&w)[8], const float (&a)[8]) {
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
-#pragma unroll
-        for (int p = 0; p < 8; p += 2) {
-            const float2 r = __ffma2_rn(make_float2(a[p], a[p + 1]), make_float2(w[u], w[u]),
-                                        make_float2(acc[u][p], acc[u][p + 1]));
-            acc[u][p] = r.x;
-            acc[u][p + 1] = r.y;
-        }
-}
-#endif
-
-// acc[u][p] = bias[u] + sum_i Wt[i][unit u of tile ug] * Ain[i][pcol + p]      (the one hot loop of the library)
-// Three running pointers (activations, first / second half of the weight row) advanced by constant strides and a
-// down-counter keep the loop overhead to a handful of integer instructions per 128 FMAs.
-template <typename T>
-__device__ __forceinline__ void qb_gemm_accumulate(T (&acc)[VT<T>::TU][VT<T>::TP], const T* __restrict__ Wt,
-                                                   const T* __restrict__ bias, const T* __restrict__ ap, int n_in,
-                                                   int lda, int ldw, int ug, int UG) {
-    constexpr int TP = VT<T>::TP, TU = VT<T>::TU, VW = VT<T>::VW;
-    static_assert(TU == 2 * VW && TP == 2 * VW, "tile = two 128-bit vectors per operand");
-    {
-        T b[TU];
-        if (bias) qb_ld_wrow<T>(b, bias, ug, UG);
-#pragma unroll
-        for (int u = 0; u < TU; ++u)
-#pragma unroll
-            for (int p = 0; p < TP; ++p) acc[u][p] = bias ? b[u] : T(0);
+    for (int q = 0; q < TP / 4; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(s + 4 * q);
+        d[2 * q] = make_float2(v.x, v.y);
+        d[2 * q + 1] = make_float2(v.z, v.w);
     }
-    const T* w0p = Wt + ug * VW;                 // units u = 0..VW-1 of this tile
-    const T* w1p = Wt + UG * VW + ug * VW;       // units u = VW..TU-1
-    const int lda2 = 2 * lda, ldw2 = 2 * ldw;
-    T a0[TP], w0[TU], a1[TP], w1[TU];
-    ldv<TP>(a0, ap);
-    ldv<VW>(&w0[0], w0p);
-    ldv<VW>(&w0[VW], w1p);
-    int pairs = n_in >> 1;
-#pragma unroll 1
-    while (pairs > 0) {
-        ldv<TP>(a1, ap + lda);
-        ldv<VW>(&w1[0], w0p + ldw);
-        ldv<VW>(&w1[VW], w1p + ldw);
-        qb_fma_tile<T>(acc, w0, a0);
-        ap += lda2;
-        w0p += ldw2;
-        w1p += ldw2;
-        --pairs;
-        // the row after the last one is never used; reading it stays inside the staged arrays (weights are
-        // followed by the bias / next layer, activations by the next row or the pad) unless this is the very end
-        if (pairs > 0 || (n_in & 1)) {
-            ldv<TP>(a0, ap);
-            ldv<VW>(&w0[0], w0p);
-            ldv<VW>(&w0[VW], w1p);
-        }
-        qb_fma_tile<T>(acc, w1, a1);
-    }
-    if (n_in & 1) qb_fma_tile<T>(acc, w0, a0);
-}
-
-#ifndef QB_NO_FFMA2
-// fp32 specialisation: the accumulators live as float2 values (aligned register pairs) for the whole loop so that
-// FFMA2 reads and writes them in place (the generic version made ptxas shuffle pairs: 0.6 MOV per FFMA2).
-__device__ __forceinline__ void qb_ld8(float2 (&d)[4], const float* s) {
-    const float4 lo = *reinterpret_cast<const float4*>(s), hi = *reinterpret_cast<const float4*>(s + 4);
-    d[0] = make_float2(lo.x, lo.y); d[1] = make_float2(lo.z, lo.w);
-    d[2] = make_float2(hi.x, hi.y); d[3] = make_float2(hi.z, hi.w);
 }
 __device__ __forceinline__ void qb_ldw8(float (&w)[8], const float* w0p, const float* w1p) {
     const float4 lo = *reinterpret_cast<const float4*>(w0p), hi = *reinterpret_cast<const float4*>(w1p);
     w[0] = lo.x; w[1] = lo.y; w[2] = lo.z; w[3] = lo.w; w[4] = hi.x; w[5] = hi.y; w[6] = hi.z; w[7] = hi.w;
 }
-__device__ __forceinline__ void qb_fma2_tile(float2 (&c)[8][4], const float (&w)[8], const float2 (&a)[4]) {
+template <int TP> __device__ __forceinline__ void qb_fma2_tile(float2 (&c)[8][TP / 2], const float (&w)[8], const float2 (&a)[TP / 2]) {
 #pragma unroll
     for (int u = 0; u < 8; ++u)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) c[u][q] = __ffma2_rn(a[q], make_float2(w[u], w[u]), c[u][q]);
+        for (int q = 0; q < TP / 2; ++q) c[u][q] = __ffma2_rn(a[q], make_float2(w[u], w[u]), c[u][q]);
 }
-template <>
-__device__ __forceinline__ void qb_gemm_accumulate<float>(float (&acc)[8][8], const float* __restrict__ Wt,
-                                                          const float* __restrict__ bias, const float* __restrict__ ap,
-                                                          int n_in, int lda, int ldw, int ug, int UG) {
-    float2 c[8][4];
+template <int TP>
+__device__ __forceinline__ void qb_gemm_accumulate(float (&acc)[8][TP], const float* __restrict__ Wt,
+                                                   const float* __restrict__ bias, const float* __restrict__ ap,
+                                                   int n_in, int lda, int ldw, int ug, int UG) {
+    float2 c[8][TP / 2];
     {
         float b[8];
         if (bias) qb_ldw8(b, bias + ug * 4, bias + UG * 4 + ug * 4);
 #pragma unroll
         for (int u = 0; u < 8; ++u)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) c[u][q] = bias ? make_float2(b[u], b[u]) : make_float2(0.f, 0.f);
+            for (int q = 0; q < TP / 2; ++q) c[u][q] = bias ? make_float2(b[u], b[u]) : make_float2(0.f, 0.f);
     }
     const float* w0p = Wt + ug * 4;
     const float* w1p = Wt + UG * 4 + ug * 4;
     const int lda2 = 2 * lda, ldw2 = 2 * ldw;
-    float2 a0[4], a1[4];
+    float2 a0[TP / 2], a1[TP / 2];
     float w0[8], w1[8];
-    qb_ld8(a0, ap);
+    qb_ldp<TP>(a0, ap);
     qb_ldw8(w0, w0p, w1p);
     int pairs = n_in >> 1;
 #pragma unroll 1
     while (pairs > 0) {
-        qb_ld8(a1, ap + lda);
+        qb_ldp<TP>(a1, ap + lda);
         qb_ldw8(w1, w0p + ldw, w1p + ldw);
-        qb_fma2_tile(c, w0, a0);
+        qb_fma2_tile<TP>(c, w0, a0);
         ap += lda2;
         w0p += ldw2;
         w1p += ldw2;
         --pairs;
-        qb_ld8(a0, ap);              // after the last pair this reads one row past the end: the plan pads for it
+        qb_ldp<TP>(a0, ap);          // after the last pair this reads one row past the end: the plan pads for it
         qb_ldw8(w0, w0p, w1p);
-        qb_fma2_tile(c, w1, a1);
+        qb_fma2_tile<TP>(c, w1, a1);
     }
-    if (n_in & 1) qb_fma2_tile(c, w0, a0);
+    if (n_in & 1) qb_fma2_tile<TP>(c, w0, a0);
 #pragma unroll
     for (int u = 0; u < 8; ++u)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { acc[u][2 * q] = c[u][q].x; acc[u][2 * q + 1] = c[u][q].y; }
+        for (int q = 0; q < TP / 2; ++q) { acc[u][2 * q] = c[u][q].x; acc[u][2 * q + 1] = c[u][q].y; }
 }
-#endif
+
+// fp64: 4 x 4 tile, scalar DFMA
+template <int TP>
+__device__ __forceinline__ void qb_gemm_accumulate(double (&acc)[4][TP], const double* __restrict__ Wt,
+                                                   const double* __restrict__ bias, const double* __restrict__ ap,
+                                                   int n_in, int lda, int ldw, int ug, int UG) {
+    static_assert(TP == 4, "fp64 tiles are 4 x 4");
+    {
+        double b[4];
+        if (bias) { ldv<2>(&b[0], bias + ug * 2); ldv<2>(&b[2], bias + UG * 2 + ug * 2); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[u][p] = bias ? b[u] : 0.0;
+    }
+    const double* w0p = Wt + ug * 2;
+    const double* w1p = Wt + UG * 2 + ug * 2;
+    double a0[4], w0[4], a1[4], w1[4];
+    ldv<4>(a0, ap);
+    ldv<2>(&w0[0], w0p);
+    ldv<2>(&w0[2], w1p);
+    int pairs = n_in >> 1;
+#pragma unroll 1
+    while (pairs > 0) {
+        ldv<4>(a1, ap + lda);
+        ldv<2>(&w1[0], w0p + ldw);
+        ldv<2>(&w1[2], w1p + ldw);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[u][p] = fma(w0[u], a0[p], acc[u][p]);
+        ap += 2 * lda;
+        w0p += 2 * ldw;
+        w1p += 2 * ldw;
+        --pairs;
+        ldv<4>(a0, ap);
+        ldv<2>(&w0[0], w0p);
+        ldv<2>(&w0[2], w1p);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[u][p] = fma(w1[u], a1[p], acc[u][p]);
+    }
+    if (n_in & 1) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[u][p] = fma(w0[u], a0[p], acc[u][p]);
+    }
+}
 
 // activation (+ residual) of one accumulator row
-template <typename T, int ACT>
-__device__ __forceinline__ void qb_act_row(T (&h)[VT<T>::TP], const T (&accrow)[VT<T>::TP], bool res, T step,
+template <typename T, int ACT, int TP>
+__device__ __forceinline__ void qb_act_row(T (&h)[TP], const T (&accrow)[TP], bool res, T step,
                                            const T* ain_row) {
-    constexpr int TP = VT<T>::TP;
 #pragma unroll
     for (int p = 0; p < TP; ++p) h[p] = qb_act<ACT>(accrow[p]);
     if (res) {
@@ -344,29 +336,29 @@ __device__ __forceinline__ void qb_act_row(T (&h)[VT<T>::TP], const T (&accrow)[
     }
 }
 
-template <typename T, int ACT>
-__device__ __forceinline__ void qb_epilogue_store(const T (&acc)[VT<T>::TU][VT<T>::TP], const T* Ain, T* Aout, int lda,
+template <typename T, int ACT, int TP>
+__device__ __forceinline__ void qb_epilogue_store(const T (&acc)[VT<T>::TU][TP], const T* Ain, T* Aout, int lda,
                                                   int pcol, int ug, int UG, bool res, T step) {
-    constexpr int TP = VT<T>::TP, TU = VT<T>::TU;
+    constexpr int TU = VT<T>::TU;
 #pragma unroll
     for (int u = 0; u < TU; ++u) {
         const int j = ug + UG * u;
         T h[TP];
-        qb_act_row<T, ACT>(h, acc[u], res, step, Ain + j * lda + pcol);
+        qb_act_row<T, ACT, TP>(h, acc[u], res, step, Ain + j * lda + pcol);
         stv<TP>(Aout + j * lda + pcol, h);
     }
 }
 
-template <typename T, int ACT, int NT>
-__device__ __forceinline__ void qb_epilogue_tail(const T (&acc)[VT<T>::TU][VT<T>::TP], const T* Ain, int lda, int pcol,
+template <typename T, int ACT, int NT, int TP>
+__device__ __forceinline__ void qb_epilogue_tail(const T (&acc)[VT<T>::TU][TP], const T* Ain, int lda, int pcol,
                                                  int ug, int UG, bool res, T step, int n_out, const T* Wl, int ldl,
-                                                 int n_tail, T (&part)[NT][VT<T>::TP]) {
-    constexpr int TP = VT<T>::TP, TU = VT<T>::TU;
+                                                 int n_tail, T (&part)[NT][TP]) {
+    constexpr int TU = VT<T>::TU;
 #pragma unroll
     for (int u = 0; u < TU; ++u) {
         const int j = ug + UG * u;
         T h[TP];
-        qb_act_row<T, ACT>(h, acc[u], res, step, Ain + j * lda + pcol);
+        qb_act_row<T, ACT, TP>(h, acc[u], res, step, Ain + j * lda + pcol);
         if (j < n_out) {
 #pragma unroll
             for (int q = 0; q < NT; ++q) {
@@ -382,11 +374,11 @@ __device__ __forceinline__ void qb_epilogue_tail(const T (&acc)[VT<T>::TU][VT<T>
 
 // tc == nullptr: store the activations; else fused tail with up to 4 outputs.  ONE instance of the hot loop serves
 // both (separate template instances of the tail made ptxas spill the accumulators inside the loop).
-template <typename T>
+template <typename T, int TP>
 __device__ __forceinline__ T qb_fwd_gemm(const QbLayerPlan& L, const T* sW, const T* Ain, T* Aout,
                                          int lda, const QbScope& sc, bool sync_before_store,
                                          const QbTailCtx<T>* tc) {
-    constexpr int TP = VT<T>::TP, TU = VT<T>::TU;
+    constexpr int TU = VT<T>::TU;
     const int UG = L.n_out_pad / TU, PG = sc.p_count / TP, items = UG * PG;
     const T* Wt = sW + L.wt_off;
     const T* bias = sW + L.bias_off;
@@ -403,7 +395,7 @@ __device__ __forceinline__ T qb_fwd_gemm(const QbLayerPlan& L, const T* sW, cons
         else { pg = item / UG; ug = item - pg * UG; }
         const int pcol = sc.p_base + pg * TP;
         T acc[TU][TP];
-        if (valid) qb_gemm_accumulate<T>(acc, Wt, bias, Ain + pcol, n_in, lda, ldw, ug, UG);
+        if (valid) qb_gemm_accumulate<TP>(acc, Wt, bias, Ain + pcol, n_in, lda, ldw, ug, UG);
         if (sync_before_store) sc.sync();       // every lane has finished READING the input rows
         if (tc) {
             constexpr int NTA = 4;
@@ -415,9 +407,9 @@ __device__ __forceinline__ T qb_fwd_gemm(const QbLayerPlan& L, const T* sW, cons
             if (valid) {
                 const T* Wl = sW + tail->wt_off;
                 const int ldl = tail->n_out_pad, nt = tail->n_out;
-                if (act == QB_ACT_TANH) qb_epilogue_tail<T, QB_ACT_TANH, NTA>(acc, Ain, lda, pcol, ug, UG, res, step, L.n_out, Wl, ldl, nt, part);
-                else if (act == QB_ACT_RELU) qb_epilogue_tail<T, QB_ACT_RELU, NTA>(acc, Ain, lda, pcol, ug, UG, res, step, L.n_out, Wl, ldl, nt, part);
-                else qb_epilogue_tail<T, QB_ACT_IDENTITY, NTA>(acc, Ain, lda, pcol, ug, UG, res, step, L.n_out, Wl, ldl, nt, part);
+                if (act == QB_ACT_TANH) qb_epilogue_tail<T, QB_ACT_TANH, NTA, TP>(acc, Ain, lda, pcol, ug, UG, res, step, L.n_out, Wl, ldl, nt, part);
+                else if (act == QB_ACT_RELU) qb_epilogue_tail<T, QB_ACT_RELU, NTA, TP>(acc, Ain, lda, pcol, ug, UG, res, step, L.n_out, Wl, ldl, nt, part);
+                else qb_epilogue_tail<T, QB_ACT_IDENTITY, NTA, TP>(acc, Ain, lda, pcol, ug, UG, res, step, L.n_out, Wl, ldl, nt, part);
             }
             // combine the UG lanes that hold the same points (consecutive lanes; fixed order => deterministic)
             for (int off = UG >> 1; off > 0; off >>= 1) {
@@ -448,9 +440,9 @@ __device__ __forceinline__ T qb_fwd_gemm(const QbLayerPlan& L, const T* sW, cons
                 }
             }
         } else if (valid) {
-            if (act == QB_ACT_TANH) qb_epilogue_store<T, QB_ACT_TANH>(acc, Ain, Aout, lda, pcol, ug, UG, res, step);
-            else if (act == QB_ACT_RELU) qb_epilogue_store<T, QB_ACT_RELU>(acc, Ain, Aout, lda, pcol, ug, UG, res, step);
-            else qb_epilogue_store<T, QB_ACT_IDENTITY>(acc, Ain, Aout, lda, pcol, ug, UG, res, step);
+            if (act == QB_ACT_TANH) qb_epilogue_store<T, QB_ACT_TANH, TP>(acc, Ain, Aout, lda, pcol, ug, UG, res, step);
+            else if (act == QB_ACT_RELU) qb_epilogue_store<T, QB_ACT_RELU, TP>(acc, Ain, Aout, lda, pcol, ug, UG, res, step);
+            else qb_epilogue_store<T, QB_ACT_IDENTITY, TP>(acc, Ain, Aout, lda, pcol, ug, UG, res, step);
         }
     }
     return ssq;
@@ -491,12 +483,12 @@ __device__ __forceinline__ void qb_fwd_dot(const QbLayerPlan& L, const T* sW, co
     }
 }
 
-template <typename T>
+template <typename T, int TP = VT<T>::TP>
 __device__ T qb_layer_forward(const QbLayerPlan& L, const T* sW, const T* Ain, T* Aout, int lda, const QbScope& sc,
                               bool inplace, const QbTailCtx<T>* tc = nullptr) {
     T ssq = T(0);
     if (L.mode == QB_MODE_GEMM) {
-        ssq = qb_fwd_gemm<T>(L, sW, Ain, Aout, lda, sc, inplace, tc);
+        ssq = qb_fwd_gemm<T, TP>(L, sW, Ain, Aout, lda, sc, inplace, tc);
     } else {
 #define QB_DOT(NJ)                                                                            \
     switch (L.act) {                                                                          \
@@ -591,10 +583,9 @@ __device__ __forceinline__ double qb_eval_value(const QbPlan& P, const QbSmem& S
 // kernel 2 body: value + gradient (reverse mode) of the data term
 // --------------------------------------------------------------------------------------------
 // write delta_z of layer Lm for (unit j, TP consecutive points) given delta_a (gradient wrt the layer output)
-template <typename T>
+template <typename T, int TP, int ACT>
 __device__ __forceinline__ void qb_finish_delta_vec(const QbLayerPlan& Lm, T* R, T* D, int lda, int j, int pcol,
-                                                    T (&da)[VT<T>::TP]) {
-    constexpr int TP = VT<T>::TP;
+                                                    T (&da)[TP]) {
     T aout[TP], dz[TP];
     T* po = R + (size_t)(Lm.row_out + j) * lda + pcol;
     ldv<TP>(aout, po);
@@ -605,12 +596,12 @@ __device__ __forceinline__ void qb_finish_delta_vec(const QbLayerPlan& Lm, T* R,
 #pragma unroll
         for (int p = 0; p < TP; ++p) {
             const T t = (aout[p] - ain[p]) * inv;
-            dz[p] = step * da[p] * qb_dact<T>(Lm.act, t);
+            dz[p] = step * da[p] * qb_dact_c<ACT, T>(t);
         }
         stv<TP>(D + (size_t)j * lda + pcol, da);
     } else {
 #pragma unroll
-        for (int p = 0; p < TP; ++p) dz[p] = da[p] * qb_dact<T>(Lm.act, aout[p]);
+        for (int p = 0; p < TP; ++p) dz[p] = da[p] * qb_dact_c<ACT, T>(aout[p]);
     }
     stv<TP>(po, dz);
 }
@@ -634,15 +625,11 @@ __device__ __forceinline__ void qb_finish_delta(const QbLayerPlan& Lm, T* R, T* 
 // one PV-point step of the dW patch: acc[a][b] += sum_q dz[a][q]*av[b][q].  fp32: the (q, q+1) pairs that come out of
 // the 128-bit loads feed FFMA2 directly; even and odd q accumulate separately (acc / acc2) and are folded at the end.
 template <typename T>
-__device__ __forceinline__ void qb_dw_fma(T (&acc)[4][4], T (&acc2)[4][4], T (&bacc)[4], const T (&dz)[4][VT<T>::PV],
-                                          const T (&av)[4][VT<T>::PV], bool want_bias) {
+__device__ __forceinline__ void qb_dw_fma(T (&acc)[4][4], T (&acc2)[4][4], const T (&dz)[4][VT<T>::PV],
+                                          const T (&av)[4][VT<T>::PV]) {
     constexpr int PV = VT<T>::PV;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-        if (want_bias) {
-#pragma unroll
-            for (int q = 0; q < PV; ++q) bacc[a] += dz[a][q];
-        }
 #pragma unroll
         for (int b = 0; b < 4; ++b)
 #pragma unroll
@@ -651,11 +638,10 @@ __device__ __forceinline__ void qb_dw_fma(T (&acc)[4][4], T (&acc2)[4][4], T (&b
 }
 #ifndef QB_NO_FFMA2
 template <>
-__device__ __forceinline__ void qb_dw_fma<float>(float (&acc)[4][4], float (&acc2)[4][4], float (&bacc)[4],
-                                                 const float (&dz)[4][4], const float (&av)[4][4], bool want_bias) {
+__device__ __forceinline__ void qb_dw_fma<float>(float (&acc)[4][4], float (&acc2)[4][4],
+                                                 const float (&dz)[4][4], const float (&av)[4][4]) {
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-        if (want_bias) bacc[a] += (dz[a][0] + dz[a][1]) + (dz[a][2] + dz[a][3]);
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             float2 c = make_float2(acc[a][b], acc2[a][b]);
@@ -690,24 +676,22 @@ __device__ void qb_dw_accumulate(const QbLayerPlan& L, const T* R, int lda, int 
         const int item = base + threadIdx.x;
         const bool valid = item < items;
         const int it = valid ? item : 0;
-        const int patch = it / C, chunk = it - patch * C;
-        const int jg = patch / IG, ig = patch - jg * IG;
-        T acc[4][4], acc2[4][4], bacc[4];      // acc2: odd-q partial sums of the packed fp32 path
+        const int patch = it >> L.c_shift, chunk = it & (C - 1);          // C is a power of two
+        int jg, ig;
+        if (L.ig_shift >= 0) { jg = patch >> L.ig_shift; ig = patch & (IG - 1); }
+        else { jg = patch / IG; ig = patch - jg * IG; }
+        T acc[4][4], acc2[4][4];      // acc2: odd-q partial sums of the packed fp32 path
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            bacc[a] = T(0);
+        for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) { acc[a][b] = T(0); acc2[a][b] = T(0); }
-        }
-        const bool want_bias = (ig == 0) && L.b_off >= 0;
         const bool writer = valid && chunk == 0;
         // the running gradient entries this thread owns: fetched BEFORE the point loop so the global-memory
         // latency hides behind it (they were 30 % of the kernel's stall samples as a load-add-store at the end)
-        T gold[4][4], bold[4];
+        T gold[4][4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             const int j = jg + JG * a;
-            bold[a] = (writer && want_bias && j < L.n_out) ? g[L.b_off + j] : T(0);
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 const int i = ig + IG * b;
@@ -724,16 +708,14 @@ __device__ void qb_dw_accumulate(const QbLayerPlan& L, const T* R, int lda, int 
                 ldv<PV>(dz[c], zr + c * zs + p);
                 ldv<PV>(av[c], ar + c * as + p);
             }
-            qb_dw_fma<T>(acc, acc2, bacc, dz, av, want_bias);
+            qb_dw_fma<T>(acc, acc2, dz, av);
         }
         qb_dw_fold<T>(acc, acc2);
         for (int off = C >> 1; off > 0; off >>= 1) {
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                bacc[a] += __shfl_xor_sync(0xffffffffu, bacc[a], off);
+            for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int b = 0; b < 4; ++b) acc[a][b] += __shfl_xor_sync(0xffffffffu, acc[a][b], off);
-            }
         }
         if (writer) {
 #pragma unroll
@@ -745,9 +727,29 @@ __device__ void qb_dw_accumulate(const QbLayerPlan& L, const T* R, int lda, int 
                         const int i = ig + IG * b;
                         if (i < L.n_in) g[L.w_off + j * L.n_in + i] = gold[a][b] + acc[a][b];
                     }
-                    if (want_bias) g[L.b_off + j] = bold[a] + bacc[a];
                 }
             }
+        }
+    }
+    // db[j] += sum_p delta_z[j][p]: one warp per row, lanes stride the points, fixed-order shuffle tree.  (Kept out
+    // of the patch loop: a per-lane "this patch also owns the bias" test made every warp run the loop twice.)
+    if (L.b_off >= 0) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for (int jb = 0; jb < L.n_out; jb += nw * 32) {        // rows jb + warp + nw*r, r = 0..31, belong to this warp
+            T mine = T(0);
+            int nr = 0;
+            for (int r = 0; r < 32; ++r) {
+                const int j = jb + warp + nw * r;
+                if (j >= L.n_out) break;
+                const T* zr = Rz + (size_t)j * lda;
+                T sacc = T(0);
+                for (int p = lane; p < TM; p += 32) sacc += zr[p];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, off);
+                if (lane == r) mine = sacc;
+                nr = r + 1;
+            }
+            if (lane < nr) g[L.b_off + jb + warp + nw * lane] += mine;      // one parallel read-modify-write per warp
         }
     }
 }
@@ -757,10 +759,10 @@ __device__ void qb_dw_accumulate(const QbLayerPlan& L, const T* R, int lda, int 
 // activations.
 // GLOBALW: the (rare) fallback when Wt and Wr do not both fit in shared memory: W is read straight from
 // the flat parameter vector in global memory / L1 with contiguous (un-permuted) units.
-template <typename T, bool GLOBALW>
-__device__ void qb_bwd_gemm(const QbLayerPlan& L, const QbLayerPlan& Lm, const T* sW, const T* theta, T* R, T* D,
-                            int lda, int TM) {
-    constexpr int TP = VT<T>::TP, TU = VT<T>::TU;
+template <typename T, bool GLOBALW, int TP, int ACTM>
+__device__ void qb_bwd_gemm_a(const QbLayerPlan& L, const QbLayerPlan& Lm, const T* sW, const T* theta, T* R, T* D,
+                              int lda, int TM) {
+    constexpr int TU = VT<T>::TU;
     const int UGI = L.n_in_pad / TU, PG = TM / TP, items = UGI * PG;
     const T* Wr = GLOBALW ? theta + L.w_off : sW + L.wr_off;
     const T* Rz = R + (size_t)L.row_out * lda;
@@ -768,11 +770,13 @@ __device__ void qb_bwd_gemm(const QbLayerPlan& L, const QbLayerPlan& Lm, const T
     for (int base = 0; base < items; base += blockDim.x) {
         const int item = base + threadIdx.x;
         if (item >= items) continue;
-        const int pg = item / UGI, ig = item - pg * UGI;
+        int pg, ig;
+        if (L.ugi_shift >= 0) { pg = item >> L.ugi_shift; ig = item & (UGI - 1); }
+        else { pg = item / UGI; ig = item - pg * UGI; }
         T acc[TU][TP];
         if (!GLOBALW) {
             // same hot loop as the forward pass: rows = output units j, "weights" = staged Wr, no bias
-            qb_gemm_accumulate<T>(acc, Wr, (const T*)nullptr, Rz + pg * TP, n_out, lda, ldw, ig, UGI);
+            qb_gemm_accumulate<TP>(acc, Wr, (const T*)nullptr, Rz + pg * TP, n_out, lda, ldw, ig, UGI);
         } else {
 #pragma unroll
             for (int u = 0; u < TU; ++u)
@@ -803,17 +807,26 @@ __device__ void qb_bwd_gemm(const QbLayerPlan& L, const QbLayerPlan& Lm, const T
 #pragma unroll
                     for (int p = 0; p < TP; ++p) acc[u][p] += pass[p];
                 }
-                qb_finish_delta_vec<T>(Lm, R, D, lda, i, pg * TP, acc[u]);
+                qb_finish_delta_vec<T, TP, ACTM>(Lm, R, D, lda, i, pg * TP, acc[u]);
             }
         }
     }
 }
 
+template <typename T, bool GLOBALW, int TP>
+__device__ __forceinline__ void qb_bwd_gemm(const QbLayerPlan& L, const QbLayerPlan& Lm, const T* sW, const T* theta,
+                                            T* R, T* D, int lda, int TM) {
+    if (Lm.act == QB_ACT_TANH) qb_bwd_gemm_a<T, GLOBALW, TP, QB_ACT_TANH>(L, Lm, sW, theta, R, D, lda, TM);
+    else if (Lm.act == QB_ACT_RELU) qb_bwd_gemm_a<T, GLOBALW, TP, QB_ACT_RELU>(L, Lm, sW, theta, R, D, lda, TM);
+    else qb_bwd_gemm_a<T, GLOBALW, TP, QB_ACT_IDENTITY>(L, Lm, sW, theta, R, D, lda, TM);
+}
+
 // value + gradient of the data term for one parameter vector over points [n0, n1):
 // returns sum of squared residuals; g[0..P) receives d/dtheta of  -0.5*ssq/sigma^2  (i.e. of lp's data term).
 // g must be addressable by this block only (one row per (chain, split)).
-template <typename T>
-__device__ double qb_eval_value_grad(const QbPlan& P, const QbSmem& S, const T* theta, const T* __restrict__ x,
+// TPG = points per thread tile in the gradient kernel: 4 (twice the threads per tile, for layers >= 64 wide) or 8
+template <typename T, int TPG>
+__device__ double qb_eval_value_grad_t(const QbPlan& P, const QbSmem& S, const T* theta, const T* __restrict__ x,
                                      const T* __restrict__ y, int64_t n0, int64_t n1, double inv_sigma2, T* g) {
     T* sW = reinterpret_cast<T*>(S.w);
     T* R = reinterpret_cast<T*>(S.act);
@@ -832,7 +845,7 @@ __device__ double qb_eval_value_grad(const QbPlan& P, const QbSmem& S, const T* 
         __syncthreads();
         for (int l = 0; l < nl; ++l) {
             const QbLayerPlan& L = P.L[l];
-            qb_layer_forward<T>(L, sW, R + (size_t)L.row_in * lda, R + (size_t)L.row_out * lda, lda, bsc, false);
+            qb_layer_forward<T, TPG>(L, sW, R + (size_t)L.row_in * lda, R + (size_t)L.row_out * lda, lda, bsc, false);
         }
         // residuals -> delta at the top
         const int n = TM * o;
@@ -856,13 +869,20 @@ __device__ double qb_eval_value_grad(const QbPlan& P, const QbSmem& S, const T* 
             qb_dw_accumulate<T>(L, R, lda, TM, g);
             __syncthreads();
             if (l > 0) {
-                if (L.wr_off >= 0) qb_bwd_gemm<T, false>(L, P.L[l - 1], sW, theta, R, D, lda, TM);
-                else qb_bwd_gemm<T, true>(L, P.L[l - 1], sW, theta, R, D, lda, TM);
+                if (L.wr_off >= 0) qb_bwd_gemm<T, false, TPG>(L, P.L[l - 1], sW, theta, R, D, lda, TM);
+                else qb_bwd_gemm<T, true, TPG>(L, P.L[l - 1], sW, theta, R, D, lda, TM);
                 __syncthreads();
             }
         }
     }
     return qb_block_sum((double)ssq, S.red);
+}
+
+template <typename T>
+__device__ double qb_eval_value_grad(const QbPlan& P, const QbSmem& S, const T* theta, const T* __restrict__ x,
+                                     const T* __restrict__ y, int64_t n0, int64_t n1, double inv_sigma2, T* g) {
+    if (sizeof(T) == 4 && P.tpg == 8) return qb_eval_value_grad_t<T, VT<T>::TP>(P, S, theta, x, y, n0, n1, inv_sigma2, g);
+    return qb_eval_value_grad_t<T, 4>(P, S, theta, x, y, n0, n1, inv_sigma2, g);
 }
 
 // --------------------------------------------------------------------------------------------

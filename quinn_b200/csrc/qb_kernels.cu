@@ -74,11 +74,17 @@ static int validate_net(const qb_net_t* net) {
 // Fill `P` for tile size TM; returns smem bytes (or -1 if a constraint fails).
 static long long plan_for_tm(const qb_net_t* net, int dtype, bool want_grad, int TM, QbPlan* P, bool wr_global = false) {
     const int elem = dtype == QB_F64 ? 8 : 4;
-    const int TU = dtype == QB_F64 ? 4 : 8, TP = TU, LDPAD = dtype == QB_F64 ? 2 : 4, PV = dtype == QB_F64 ? 2 : 4;
+    const int TU = dtype == QB_F64 ? 4 : 8, LDPAD = dtype == QB_F64 ? 2 : 4, PV = dtype == QB_F64 ? 2 : 4;
+    // gradient kernel: TU x 4 thread tiles (twice the threads per tile) when some layer is >= 64 wide, else TU x 8
+    int widest = 0;
+    for (int l = 0; l < net->n_layers; ++l) widest = std::max(widest, net->layers[l].n_out);
+    const int tpg = (dtype == QB_F64 || widest >= 64) ? 4 : 8;
+    const int TP = want_grad ? env_int("QB_TPG", tpg) : TU;
     memset(P, 0, sizeof(*P));
     P->n_layers = net->n_layers; P->in_dim = net->in_dim; P->out_dim = net->out_dim;
     P->n_params = net->n_params; P->final_exp = net->final_exp;
     P->TM = TM; P->lda = TM + LDPAD; P->want_grad = want_grad ? 1 : 0; P->elem_size = elem;
+    P->tpg = TP;
     const int PG = TM / TP;
     int max_items = 0, woff = 0;
     bool any_gemm = false;
@@ -89,8 +95,12 @@ static long long plan_for_tm(const qb_net_t* net, int dtype, bool want_grad, int
         L.w_off = S.w_off; L.b_off = S.b_off; L.act = S.act; L.res_step = S.res_step; L.has_res = S.res_step != 0.0;
         if (L.has_res) P->has_res = 1;
         const int UG = L.n_out_pad / TU;
-        L.ug_shift = -1;
-        for (int sft = 0; sft < 16; ++sft) if ((1 << sft) == UG) L.ug_shift = sft;
+        L.ug_shift = L.ugi_shift = L.ig_shift = -1;
+        for (int sft = 0; sft < 16; ++sft) {
+            if ((1 << sft) == UG) L.ug_shift = sft;
+            if ((1 << sft) == L.n_in_pad / TU) L.ugi_shift = sft;
+            if ((1 << sft) == (S.n_in + 3) / 4) L.ig_shift = sft;
+        }
         L.nj = S.n_out == 1 ? 1 : (S.n_out == 2 ? 2 : 4);
         const long long cost_g = cdiv((long long)UG * PG, 256) * S.n_in * (TP * TU + 4);
         const long long cost_d = cdiv(TM, 256) * cdiv(S.n_out, L.nj) * S.n_in * (2 * L.nj + 1);
@@ -130,6 +140,8 @@ static long long plan_for_tm(const qb_net_t* net, int dtype, bool want_grad, int
         int C = 1;
         while (C < 32 && patches * C * 2 <= nthreads && TM / (C * 2) >= PV) C *= 2;
         L.dw_chunks = C;
+        L.c_shift = 0;
+        while ((1 << L.c_shift) < C) ++L.c_shift;
     }
     if (env_int("QB_NO_INPLACE", 0)) inplace = 0;
     // Warp-synchronous value kernel: when every GEMM layer's unit groups divide a warp, one warp can own WP

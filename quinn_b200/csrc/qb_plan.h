@@ -23,6 +23,7 @@ struct QbLayerPlan {
     int row_in, row_out;          // row offsets of this layer's input / output activations (grad kernel)
     int act, mode, nj, dw_chunks;
     int has_res, ug_shift;        // ug_shift: log2(n_out_pad/TU) if that is a power of two, else -1
+    int ugi_shift, ig_shift, c_shift, pad2_;   // same for n_in_pad/TU, ceil(n_in/4), dw_chunks
     double res_step;
 };
 
@@ -38,6 +39,7 @@ struct QbPlan {
     int has_res;
     int elem_size;
     int ws, WP;         // value kernel: warp-synchronous mode, points owned by one warp
+    int tpg;            // gradient kernel: points per thread tile (4 or 8)
     int fuse_tail;      // value kernel: last (narrow linear) layer folded into the epilogue of the last hidden layer
     long long smem_bytes;
     QbLayerPlan L[QB_MAX_LAYERS];
