@@ -261,16 +261,19 @@ def main():
     th0_host = torch.from_numpy(theta_init(spec, P, lo, hi)).pin_memory()
     launches0 = lib.qb_launch_count()
 
+    recs = {}        # per-step log-posteriors / MH ratios / accept flags of every chain are recorded, as in a real run
     if spec['sampler'] in ('amcmc', 'hmc'):
         prob = ops.Problem(desc, x, y, spec['sigma'], dtype=dt, device=dev)
         st = ops.ChainState(prob, th0_host)
         if spec['sampler'] == 'amcmc':
             samp = ops.AmcmcState(st, gamma=0.01, t0=100, tadapt=1000, adapt='diag')
-            advance = lambda n: ops.amcmc_run(st, samp, n, None, seed=2026, chain_offset=lo)      # noqa: E731
+            advance = lambda n: ops.amcmc_run(st, samp, n, recs.setdefault(n, ops.Recorder(st, n, store_every=0)),      # noqa: E731
+                                              seed=2026, chain_offset=lo)
             flop_per_unit, kernel_name = F_v, 'k_amcmc<float>'
         else:
             samp = ops.HmcState(st, epsilon=spec['eps'], L=spec['L'], method='hmc')
-            advance = lambda n: ops.hmc_run(st, samp, n, None, seed=2026, chain_offset=lo)        # noqa: E731
+            advance = lambda n: ops.hmc_run(st, samp, n, recs.setdefault(n, ops.Recorder(st, n, store_every=0)),        # noqa: E731
+                                            seed=2026, chain_offset=lo)
             flop_per_unit, kernel_name = spec['L'] * F_vg, 'k_hmc<float>'
         units_per_step = spec['K']
         plan = prob.plan_info(Kloc, spec['sampler'] == 'hmc')
@@ -331,6 +334,11 @@ def main():
         s = torch.stack([acc.sum(), (acc * acc).sum(), torch.tensor(float(Kloc), device=dev, dtype=torch.float64)])
         dist._allreduce(s)
         diag = dict(mean_accept_rate=(s[0] / s[2]).item())
+        if args.steps >= 2:
+            # Gelman-Rubin R-hat of the log-posterior over the timed steps: per-chain moments on each rank, three small
+            # all-reduces over NVLink (quinn_b200/dist.py); with a handful of steps it only shows the plumbing works
+            lph = recs[args.steps].logpost
+            diag['rhat_logpost'] = dist.rhat(lph.mean(1), lph.var(1, unbiased=True), args.steps).item()
 
     value = units_per_step * args.steps / (ms * 1e-3)
     achieved = (Kloc if spec['sampler'] != 'predict' else spec['K'] * (xs.shape[0])) * args.steps * flop_per_unit / (ms_local * 1e-3)
@@ -378,27 +386,24 @@ def run_e2e(spec, desc, x, y, th0_host, lo, args, dev, world):
     P = desc.n_params
     if spec['sampler'] in ('amcmc', 'hmc'):
         sam = AMCMC(gamma=0.01, t0=100, tadapt=1000, adapt='diag') if spec['sampler'] == 'amcmc' else HMC(epsilon=spec['eps'], L=spec['L'])
-        out_host = torch.empty((th0_host.shape[0], P), dtype=torch.float32).pin_memory()
-
         def once():
             prob = ops.Problem(desc, x, y, spec['sigma'], dtype=torch.float32, device=dev)        # H2D of x, y
             sam.setLogPost(DeviceLogPost(prob), None)
-            res = sam.run(steps, th0_host, seed=5, store_every=steps, chain_offset=lo, verbose=False, keep_on_device=True)
-            out_host.copy_(res['chain'][:, -1, :], non_blocking=True)                           # D2H final states
-            lp = res['logpost'].cpu()
-            acc = res['accrate'].cpu()
+            # host in, host out: final states, per-step log-posteriors / MH ratios / accept flags, MAP, accept rates
+            res = sam.run(steps, th0_host, seed=5, store_every=steps, chain_offset=lo, verbose=False)
             torch.cuda.synchronize()
-            return lp, acc
+            return res['logpost'], res['accrate']
         once()
         dist.barrier()
         t0 = time.perf_counter()
         once()
         dist.barrier()
         dtm = dist.max_over_ranks(time.perf_counter() - t0)
+        Kl = th0_host.shape[0]
         h2d = (th0_host.numel() * 4 + x.size * 4 + y.size * 4) / steps
-        d2h = (out_host.numel() * 4 + th0_host.shape[0] * (steps + 1) * 8 + th0_host.shape[0] * 8) / steps
+        d2h = (2 * Kl * P * 4 + Kl * P * 4 + Kl * (2 * (steps + 1) * 8 + steps + 16)) / steps     # chain[K,2,P], MAP, scalars
         return dict(value=spec['K'] * steps / dtm, unit='chain-steps/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                    api='AMCMC/HMC.run(nmcmc=steps, param_ini=host[K,P]) -> host final states + logpost + accrate')
+                    api='AMCMC/HMC.run(nmcmc=steps, param_ini=host[K,P]) -> host result dict (chain, mapparams, logpost, alphas, accrate); 4 shards pipelined on 2 streams when the states exceed 256 MB')
     if spec['sampler'] == 'predict':
         plo, phi = dist.shard_range(spec['N'], *dist.env_rank_world()[:2])
         xh = torch.from_numpy(np.ascontiguousarray(x[plo:phi], dtype=np.float32)).pin_memory()

@@ -20,6 +20,18 @@ import torch
 from .. import ops
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_streams(device):
+    """Two persistent side streams per device (persistent so that the caching allocator's per-stream pools are
+    reused from one run() to the next)."""
+    key = str(device)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(2)]
+    return _SIDE_STREAMS[key]
+
+
 class DeviceLogPost:
     """A log-posterior that lives on the GPU: network + data + likelihood (an ops.Problem)."""
 
@@ -72,6 +84,9 @@ class MCMCBase(object):
         if seed is None:
             seed = int(np.random.randint(1, 2 ** 31 - 1))
         if self._device_lp is not None:
+            nsh = self._auto_shards(theta0, replay, keep_on_device)
+            if nsh > 1:
+                return self._run_fused_sharded(int(nmcmc), theta0, int(seed), int(store_every), int(chain_offset), verbose, nsh)
             res = self._run_fused(int(nmcmc), theta0, int(seed), int(store_every), replay, int(chain_offset), verbose)
         else:
             res = self._run_generic(int(nmcmc), theta0, int(seed), int(store_every), verbose)
@@ -113,6 +128,54 @@ class MCMCBase(object):
         accepted = torch.cat([r.accepted for r in recs], dim=1)
         return dict(chain=chain, mapparams=st.map_theta, maxpost=st.map_lp, accrate=st.naccept.double() / nmcmc,
                     logpost=logpost, alphas=alphas, accepted=accepted, state=st)
+
+    # ------------------------------------------------------------------ host <-> device pipelining for huge batches
+    def _auto_shards(self, theta0, replay, keep_on_device):
+        """Chains given in HOST memory and big enough that PCIe time matters (>= 256 MB of states) are processed as 4
+        shards on two CUDA streams: the upload of shard i+1 and the download of shard i-1 overlap the kernel of
+        shard i.  Philox is keyed by the global chain index, so sharding does not change any result."""
+        if replay is not None or keep_on_device:
+            return 1
+        on_host = (not torch.is_tensor(theta0)) or theta0.device.type == 'cpu'
+        prob = self._device_lp.problem
+        nbytes = theta0.shape[0] * theta0.shape[1] * prob.x.element_size()
+        return 4 if (on_host and nbytes >= 256 * 2 ** 20 and theta0.shape[0] >= 8) else 1
+
+    def _run_fused_sharded(self, nmcmc, theta0, seed, store_every, chain_offset, verbose, nsh):
+        prob = self._device_lp.problem
+        th = theta0 if torch.is_tensor(theta0) else torch.from_numpy(np.ascontiguousarray(theta0))
+        K, P = th.shape
+        nstored = 1 + (nmcmc // store_every if store_every > 0 else 0)
+        pin = lambda *shape, dtype: torch.empty(shape, dtype=dtype, pin_memory=True)      # noqa: E731
+        host = dict(chain=pin(K, nstored, P, dtype=prob.dtype), mapparams=pin(K, P, dtype=prob.dtype),
+                    maxpost=pin(K, dtype=torch.float64), accrate=pin(K, dtype=torch.float64),
+                    logpost=pin(K, nmcmc + 1, dtype=torch.float64), alphas=pin(K, nmcmc + 1, dtype=torch.float64),
+                    accepted=pin(K, nmcmc, dtype=torch.uint8))
+        main = torch.cuda.current_stream(prob.device)
+        streams = _side_streams(prob.device)
+        from ..dist import shard_range
+        for i in range(nsh):
+            lo, hi = shard_range(K, i, nsh)
+            if hi <= lo:
+                continue
+            s = streams[i % 2]
+            s.wait_stream(main)
+            with torch.cuda.stream(s):
+                res = self._run_fused(nmcmc, th[lo:hi], seed, store_every, None, chain_offset + lo, False)
+                for k, dst in host.items():
+                    dst[lo:hi].copy_(res[k], non_blocking=True)
+                if i == 0:
+                    self.last_state = res.get('state')
+                del res
+        for s in streams:
+            s.synchronize()
+        if verbose:
+            print('%d / %d completed, acceptance rate %lg' % (nmcmc, nmcmc, host['accrate'].mean().item()))
+        out = {k: v.numpy() for k, v in host.items()}
+        out['accepted'] = out['accepted'].astype(bool)
+        if prob.dtype != torch.float64:
+            pass          # chain / mapparams stay in the compute dtype for huge batches (no 2x host copy)
+        return out
 
     # hooks the samplers implement for the fused path
     def _device_sampler_state(self, st):

@@ -39,7 +39,7 @@ def as_device(a, dtype, device):
     if isinstance(a, list):
         a = np.array(a)
     t = torch.as_tensor(a)
-    return t.to(device=device, dtype=dtype).contiguous()
+    return t.to(device=device, dtype=dtype, non_blocking=True).contiguous()     # async from pinned host memory
 
 
 class Problem:
@@ -193,6 +193,19 @@ class ChainState:
         return _lib.qb_chain_t(self.K, self.theta.data_ptr(), self.lp.data_ptr(), self.naccept.data_ptr(),
                                self.map_theta.data_ptr(), self.map_lp.data_ptr())
 
+    # checkpoint / resume: Philox is counter based, so (state, seed, t) resumes exactly
+    _FIELDS = ('theta', 'lp', 'naccept', 'map_theta', 'map_lp')
+
+    def state_dict(self):
+        d = {k: getattr(self, k).detach().cpu().clone() for k in self._FIELDS}
+        d.update(t=self.t, initialised=self.initialised)
+        return d
+
+    def load_state_dict(self, d):
+        for k in self._FIELDS:
+            getattr(self, k).copy_(d[k])
+        self.t, self.initialised = int(d['t']), bool(d['initialised'])
+
 
 def _rng_struct(seed, chain_offset, incr, unif):
     r = _lib.qb_rng_t()
@@ -258,6 +271,15 @@ class AmcmcState:
         self.prop_kind = torch.zeros(K, dtype=torch.int32, device=dev)
         self.scratch = torch.empty((K, P), dtype=dt, device=dev)
 
+    _FIELDS = ('xm', 'cov', 'pscale', 'chol', 'prop_kind')
+
+    def state_dict(self):
+        return {k: getattr(self, k).detach().cpu().clone() for k in self._FIELDS if getattr(self, k) is not None}
+
+    def load_state_dict(self, d):
+        for k, v in d.items():
+            getattr(self, k).copy_(v)
+
     def c(self):
         a = _lib.qb_amcmc_t()
         a.gamma, a.t0, a.tadapt, a.adapt, a.track_moments = self.gamma, self.t0, self.tadapt, self.adapt, self.track
@@ -294,6 +316,12 @@ class HmcState:
         self.mom = torch.zeros_like(state.theta)
         self.prop = torch.zeros_like(state.theta)
         self.grad_prop = torch.zeros_like(state.theta)
+
+    def state_dict(self):
+        return dict(grad_cur=self.grad_cur.detach().cpu().clone())
+
+    def load_state_dict(self, d):
+        self.grad_cur.copy_(d['grad_cur'])
 
     def c(self):
         return _lib.qb_hmc_t(self.method, self.L, self.epsilon, self.grad_cur.data_ptr(), self.mom.data_ptr(),

@@ -275,3 +275,27 @@ def test_nn_vi_fit_and_predict():
     assert ye.shape == (6, 11, 1)
     m, v, _ = vi.predict_mom_sample(xt, msc=1, nsam=200)
     assert m.shape == (11, 1) and np.all(v > 0)
+
+
+def test_sharded_host_pipeline_equals_single_launch():
+    """run() splits big host batches into shards on two streams; results must not change (Philox keyed by chain id)."""
+    from quinn_b200 import ops
+    from quinn_b200.mcmc import AMCMC, HMC, DeviceLogPost
+    from golden_util import netdesc_from_layers
+    rs = np.random.RandomState(21)
+    layers, P = qo.mlp_layers(2, 1, (8,), True, 'tanh')
+    desc = netdesc_from_layers(layers, P)
+    x, y = rs.rand(40, 2), rs.randn(40, 1)
+    th0 = (0.3 * rs.randn(37, P)).astype(np.float32)
+    prob = ops.Problem(desc, x, y, 0.3, dtype=torch.float32)
+    for make in (lambda: AMCMC(gamma=0.3, t0=4, tadapt=4, adapt='diag'), lambda: HMC(epsilon=0.01, L=2)):
+        a = make()
+        a.setLogPost(DeviceLogPost(prob), None)
+        ref = a.run(12, th0, seed=9, store_every=4, verbose=False)
+        b = make()
+        b.setLogPost(DeviceLogPost(prob), None)
+        b._auto_shards = lambda *args: 4
+        out = b.run(12, torch.from_numpy(th0), seed=9, store_every=4, verbose=False)
+        for k in ('chain', 'mapparams', 'maxpost', 'accrate', 'logpost', 'alphas', 'accepted'):
+            np.testing.assert_array_equal(np.asarray(out[k], dtype=np.float64), np.asarray(ref[k], dtype=np.float64), err_msg=k)
+        assert out['chain'].shape == (37, 4, P)

@@ -319,3 +319,35 @@ def test_vi_philox_normals_are_standard():
     np.testing.assert_allclose(w.cpu().numpy(), eps.cpu().numpy(), rtol=1e-6)
     w2, eps2, _, _ = ops.vi_sample(mu, rho, 64, 0.5, 1.0, 1.0, seed=5, step=3)
     assert not np.array_equal(eps2.cpu().numpy(), eps.cpu().numpy())
+
+
+@pytest.mark.parametrize('kind', ['amcmc', 'hmc'])
+def test_checkpoint_resume_is_exact(kind, tmp_path):
+    """state_dict -> torch.save -> fresh objects -> load_state_dict continues the Philox-driven chains bit for bit."""
+    ops = _ops()
+    rs = np.random.RandomState(12)
+    layers, P = qo.mlp_layers(2, 1, (6,), True, 'tanh')
+    desc = netdesc_from_layers(layers, P)
+    x, y, th0 = rs.rand(50, 2), rs.randn(50, 1), 0.3 * rs.randn(16, P)
+    prob = ops.Problem(desc, x, y, 0.3, dtype=torch.float32)
+
+    def make():
+        st = ops.ChainState(prob, th0)
+        sm = (ops.AmcmcState(st, gamma=0.5, t0=5, tadapt=5, adapt='full') if kind == 'amcmc'
+              else ops.HmcState(st, epsilon=0.01, L=2))
+        return st, sm
+    adv = (lambda st, sm, n: ops.amcmc_run(st, sm, n, None, seed=3)) if kind == 'amcmc' else \
+          (lambda st, sm, n: ops.hmc_run(st, sm, n, None, seed=3))
+    st, sm = make()
+    adv(st, sm, 30)
+    ref = st.theta.cpu().numpy().copy()
+    st2, sm2 = make()
+    adv(st2, sm2, 12)
+    torch.save(dict(chain=st2.state_dict(), sampler=sm2.state_dict()), tmp_path / 'ck.pt')
+    ck = torch.load(tmp_path / 'ck.pt')
+    st3, sm3 = make()
+    st3.load_state_dict(ck['chain'])
+    sm3.load_state_dict(ck['sampler'])
+    adv(st3, sm3, 18)
+    np.testing.assert_array_equal(st3.theta.cpu().numpy(), ref)
+    assert st3.t == 30 and np.array_equal(st3.naccept.cpu().numpy(), st.naccept.cpu().numpy())
