@@ -734,22 +734,24 @@ __device__ void qb_dw_accumulate(const QbLayerPlan& L, const T* R, int lda, int 
     // db[j] += sum_p delta_z[j][p]: one warp per row, lanes stride the points, fixed-order shuffle tree.  (Kept out
     // of the patch loop: a per-lane "this patch also owns the bias" test made every warp run the loop twice.)
     if (L.b_off >= 0) {
+        // 8 rows per warp at a time, 4 lanes per row, each lane sums every 4th vector of the row
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-        for (int jb = 0; jb < L.n_out; jb += nw * 32) {        // rows jb + warp + nw*r, r = 0..31, belong to this warp
-            T mine = T(0);
-            int nr = 0;
-            for (int r = 0; r < 32; ++r) {
-                const int j = jb + warp + nw * r;
-                if (j >= L.n_out) break;
+        const int rloc = lane >> 2, q = lane & 3;
+        for (int jb = warp * 8; jb < L.n_out; jb += nw * 8) {
+            const int j = jb + rloc;
+            T sacc = T(0);
+            if (j < L.n_out) {
                 const T* zr = Rz + (size_t)j * lda;
-                T sacc = T(0);
-                for (int p = lane; p < TM; p += 32) sacc += zr[p];
+                for (int p = q * PV; p < TM; p += 4 * PV) {
+                    T v[PV];
+                    ldv<PV>(v, zr + p);
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, off);
-                if (lane == r) mine = sacc;
-                nr = r + 1;
+                    for (int e = 0; e < PV; ++e) sacc += v[e];
+                }
             }
-            if (lane < nr) g[L.b_off + jb + warp + nw * lane] += mine;      // one parallel read-modify-write per warp
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+            if (q == 0 && j < L.n_out) g[L.b_off + j] += sacc;
         }
     }
 }
