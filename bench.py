@@ -267,14 +267,14 @@ def main():
         st = ops.ChainState(prob, th0_host)
         if spec['sampler'] == 'amcmc':
             samp = ops.AmcmcState(st, gamma=0.01, t0=100, tadapt=1000, adapt='diag')
-            advance = lambda n: ops.amcmc_run(st, samp, n, recs.setdefault(n, ops.Recorder(st, n, store_every=0)),      # noqa: E731
-                                              seed=2026, chain_offset=lo)
+            advance = lambda n: ops.amcmc_run(st, samp, n, recs[n], seed=2026, chain_offset=lo)      # noqa: E731
             flop_per_unit, kernel_name = F_v, 'k_amcmc<float>'
         else:
             samp = ops.HmcState(st, epsilon=spec['eps'], L=spec['L'], method='hmc')
-            advance = lambda n: ops.hmc_run(st, samp, n, recs.setdefault(n, ops.Recorder(st, n, store_every=0)),        # noqa: E731
-                                            seed=2026, chain_offset=lo)
+            advance = lambda n: ops.hmc_run(st, samp, n, recs[n], seed=2026, chain_offset=lo)        # noqa: E731
             flop_per_unit, kernel_name = spec['L'] * F_vg, 'k_hmc<float>'
+        for n in {args.warmup, args.steps}:           # record buffers are allocated outside the timed region
+            recs[n] = ops.Recorder(st, n, store_every=0)
         units_per_step = spec['K']
         plan = prob.plan_info(Kloc, spec['sampler'] == 'hmc')
     elif spec['sampler'] == 'predict':
