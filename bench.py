@@ -298,7 +298,10 @@ def main():
             for i in range(n):
                 w, eps, logq, logp = ops.vi_sample(mu, rho, Kloc, 0.5, 1.0, 1.0, seed=11 + rank, step=i + 1)
                 lp, glp = ops.logpost_grad(prob, w)
-                ops.vi_backward(mu, rho, eps, w, glp, 0.5, 1.0, 1.0, c_ssq, -1.0 / spec['K'], 1.0 / spec['K'])
+                gmu, grho = ops.vi_backward(mu, rho, eps, w, glp, 0.5, 1.0, 1.0, c_ssq, -1.0 / spec['K'], 1.0 / spec['K'])
+                if world > 1:          # the MC samples are sharded over ranks: sum their gradient contributions (2P floats)
+                    dist._allreduce(gmu)
+                    dist._allreduce(grho)
         flop_per_unit, kernel_name = F_vg, 'k_logpost_grad<float>'
         units_per_step = spec['K']
         plan = prob.plan_info(Kloc, True)
