@@ -112,6 +112,7 @@ static long long plan_for_tm(const qb_net_t* net, int dtype, bool want_grad, int
         for (int m = 0; m < l; ++m) {
             const qb_layer_t& Sm = net->layers[m];
             if (Sm.w_off == S.w_off && Sm.b_off == S.b_off && Sm.n_in == S.n_in && Sm.n_out == S.n_out &&
+                (Sm.act == QB_ACT_TANH) == (S.act == QB_ACT_TANH) &&      // fp32 tanh layers stage W * 2log2(e)
                 P->L[m].mode == L.mode && (P->L[m].wr_off >= 0) == (want_grad && l > 0 && !wr_global)) { dup = m; break; }
         }
         if (dup >= 0) {
