@@ -1,12 +1,13 @@
 #!/usr/bin/env python
 """Benchmark of the posterior-sampling hot path (contract: task statement "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c2|c3|c4] [--impl native|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c5h|c2|c3|c4] [--impl native|reference]
 
 Default workload = BASELINE.json configs[4] / north_star target ("c5"): AMCMC, 10^5 chains TOTAL (sharded
 over the N GPUs: strong scaling), MLP 3->64->64->1 (P=4481), N=10^4 synthetic points, fp32.  A "step" is one
 AMCMC chain step of every chain (propose + log-posterior + accept, fused kernel 3).
 metric = chain-steps/s, whole job.  Other workloads are selectable for the record:
+  c5h HMC(L=3) on the config-5 shape (1e5 chains)                  (chain-steps/s)
   c2  HMC(L=3) 1,024 chains, MLP 2->32->32->1, N=1,000            (chain-steps/s)
   c3  256-member ensemble predictive mean/var over 10^6 points, MLP 10->128->128->1   (member-points/s)
   c4  VI ELBO value+grad, 128 MC samples, same net, N=10^5        (MC-sample evals/s)
@@ -44,6 +45,9 @@ def workload_spec(name):
     if name == 'c5':
         return dict(name='c5', d=3, hls=(64, 64), N=10_000, K=100_000, sigma=0.05, sampler='amcmc',
                     desc='AMCMC 1e5 chains (total), MLP 3-64-64-1 tanh, N=1e4 Sine data, gamma=0.01 t0=100 tadapt=1000')
+    if name == 'c5h':
+        return dict(name='c5', d=3, hls=(64, 64), N=10_000, K=100_000, sigma=0.05, sampler='hmc', L=3, eps=2e-6,
+                    desc='HMC L=3 eps=2e-6, 1e5 chains (total), MLP 3-64-64-1 tanh, N=1e4 Sine data (north_star target shape)')
     if name == 'c2':
         return dict(name='c2', d=2, hls=(32, 32), N=1_000, K=1_024, sigma=0.02, sampler='hmc', L=3, eps=1e-4,
                     desc='HMC L=3 eps=1e-4, 1024 chains, MLP 2-32-32-1 tanh, N=1e3 Ackley data')

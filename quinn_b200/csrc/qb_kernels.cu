@@ -637,70 +637,83 @@ __global__ void __launch_bounds__(256, 2) k_hmc(const __grid_constant__ QbPlan p
     T* gprop = h.gprop + k * P;
     const T eps = (T)h.eps;
 
-    double lp_cur, map_lp;
-    long long na;
-    if (c.init_lp) {
-        qb_full_grad<T>(plan, S, c, k, cur, gcur, &lp_cur);
-        map_lp = lp_cur; na = 0;
-        if (tid == 0 && c.rec_lp0) c.rec_lp0[k] = lp_cur;
-        for (int i = tid; i < P; i += nt) mapth[i] = cur[i];
-    } else {
-        lp_cur = c.lp[k]; map_lp = c.map_lp[k]; na = c.naccept[k];
-    }
+    // ONE gradient-evaluation call site (the inlined kernel-2 body is ~9k instructions): step s == -1 (only when
+    // init_lp) evaluates the incoming state; every other step runs `nsub` sub-iterations, each a position update,
+    // one evaluation and a momentum update.
+    double lp_cur = 0.0, map_lp = 0.0;
+    long long na = 0;
+    if (!c.init_lp) { lp_cur = c.lp[k]; map_lp = c.map_lp[k]; na = c.naccept[k]; }
+    const T c2 = qb_mul<T>(T(0.5), qb_mul<T>(eps, eps));
     __syncthreads();
 
-    for (long long s = 0; s < c.nsteps; ++s) {
+    for (long long s = c.init_lp ? -1 : 0; s < c.nsteps; ++s) {
         const long long t = c.t_start + s;
-        // momentum draw (hmc.py:43 / mala.py:42)
-        double ksum = 0.0;
-        if (c.rng_mode == QB_RNG_REPLAY) {
-            const T* p0 = c.incr + (s * c.K + k) * P;
-            for (int i = tid; i < P; i += nt) { const T v = p0[i]; mom[i] = v; ksum += (double)v * (double)v; }
-        } else {
-            const long long chain = c.chain_offset + k;
-            for (int i4 = tid; i4 * 4 < P; i4 += nt) {
-                T z[4];
-                qb_normal4(qb_rand4(c.seed, chain, t, QB_STREAM_INCR, (uint32_t)i4), z);
+        const bool init_step = s < 0;
+        double K_cur = 0.0;
+        if (!init_step) {
+            // momentum draw (hmc.py:43 / mala.py:42)
+            double ksum = 0.0;
+            if (c.rng_mode == QB_RNG_REPLAY) {
+                const T* p0 = c.incr + (s * c.K + k) * P;
+                for (int i = tid; i < P; i += nt) { const T v = p0[i]; mom[i] = v; ksum += (double)v * (double)v; }
+            } else {
+                const long long chain = c.chain_offset + k;
+                for (int i4 = tid; i4 * 4 < P; i4 += nt) {
+                    T z[4];
+                    qb_normal4(qb_rand4(c.seed, chain, t, QB_STREAM_INCR, (uint32_t)i4), z);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int i = i4 * 4 + q;
-                    if (i < P) { mom[i] = z[q]; ksum += (double)z[q] * (double)z[q]; }
+                    for (int q = 0; q < 4; ++q) {
+                        const int i = i4 * 4 + q;
+                        if (i < P) { mom[i] = z[q]; ksum += (double)z[q] * (double)z[q]; }
+                    }
+                }
+            }
+            K_cur = qb_block_sum(ksum, S.red) / 2.0;
+            if (h.method == 0) {
+                // first half step of the leapfrog (hmc.py:48); each thread only touches its own elements
+                for (int i = tid; i < P; i += nt) {
+                    mom[i] = qb_add<T>(mom[i], qb_mul<T>(eps, gcur[i]) / T(2));
+                    prop[i] = cur[i];
                 }
             }
         }
-        const double K_cur = qb_block_sum(ksum, S.red) / 2.0;
-        double lp_prop;
-        if (h.method == 0) {
-            // leapfrog (hmc.py:48-60); each thread only touches its own elements between evaluations
-            for (int i = tid; i < P; i += nt) {
-                mom[i] = qb_add<T>(mom[i], qb_mul<T>(eps, gcur[i]) / T(2));
-                prop[i] = cur[i];
-            }
-            for (int jj = 0; jj < h.L; ++jj) {
-                for (int i = tid; i < P; i += nt) prop[i] = qb_add<T>(prop[i], qb_mul<T>(eps, mom[i]));
-                __syncthreads();
-                qb_full_grad<T>(plan, S, c, k, prop, gprop, &lp_prop);
-                if (jj != h.L - 1) {
-                    for (int i = tid; i < P; i += nt) mom[i] = qb_add<T>(mom[i], qb_mul<T>(eps, gprop[i]));
-                } else {
-                    for (int i = tid; i < P; i += nt) mom[i] = qb_add<T>(mom[i], qb_mul<T>(eps, gprop[i]) / T(2));
+        const int nsub = init_step ? 1 : (h.method == 0 ? h.L : 1);
+        double lp_eval = 0.0;
+        for (int jj = 0; jj < nsub; ++jj) {
+            if (!init_step) {
+                if (h.method == 0) {          // hmc.py:52
+                    for (int i = tid; i < P; i += nt) prop[i] = qb_add<T>(prop[i], qb_mul<T>(eps, mom[i]));
+                } else {                      // mala.py:45
+                    for (int i = tid; i < P; i += nt)
+                        prop[i] = qb_add<T>(cur[i], qb_add<T>(qb_mul<T>(c2, gcur[i]), qb_mul<T>(eps, mom[i])));
                 }
             }
-        } else {
-            // MALA (mala.py:44-51)
-            const T c2 = qb_mul<T>(T(0.5), qb_mul<T>(eps, eps));
-            for (int i = tid; i < P; i += nt)
-                prop[i] = qb_add<T>(cur[i], qb_add<T>(qb_mul<T>(c2, gcur[i]), qb_mul<T>(eps, mom[i])));
             __syncthreads();
-            qb_full_grad<T>(plan, S, c, k, prop, gprop, &lp_prop);
-            for (int i = tid; i < P; i += nt)
-                mom[i] = qb_add<T>(mom[i], qb_mul<T>(eps, qb_add<T>(gcur[i], gprop[i])) / T(2));
+            qb_full_grad<T>(plan, S, c, k, init_step ? cur : prop, init_step ? gcur : gprop, &lp_eval);
+            if (!init_step) {
+                if (h.method == 0) {          // hmc.py:57 / :60
+                    if (jj != nsub - 1) {
+                        for (int i = tid; i < P; i += nt) mom[i] = qb_add<T>(mom[i], qb_mul<T>(eps, gprop[i]));
+                    } else {
+                        for (int i = tid; i < P; i += nt) mom[i] = qb_add<T>(mom[i], qb_mul<T>(eps, gprop[i]) / T(2));
+                    }
+                } else {                      // mala.py:50
+                    for (int i = tid; i < P; i += nt)
+                        mom[i] = qb_add<T>(mom[i], qb_mul<T>(eps, qb_add<T>(gcur[i], gprop[i])) / T(2));
+                }
+            }
         }
-        double k2 = 0.0;
-        for (int i = tid; i < P; i += nt) { const double v = (double)mom[i]; k2 += v * v; }
-        const double K_prop = qb_block_sum(k2, S.red) / 2.0;
-        const bool acc = qb_mh_step<T>(c, k, s, P, lp_prop, K_cur, K_prop, cur, prop, mapth, lp_cur, map_lp, na);
-        if (acc) for (int i = tid; i < P; i += nt) gcur[i] = gprop[i];
+        if (init_step) {
+            lp_cur = lp_eval; map_lp = lp_eval; na = 0;
+            if (tid == 0 && c.rec_lp0) c.rec_lp0[k] = lp_cur;
+            for (int i = tid; i < P; i += nt) mapth[i] = cur[i];
+        } else {
+            double k2 = 0.0;
+            for (int i = tid; i < P; i += nt) { const double v = (double)mom[i]; k2 += v * v; }
+            const double K_prop = qb_block_sum(k2, S.red) / 2.0;
+            const bool acc = qb_mh_step<T>(c, k, s, P, lp_eval, K_cur, K_prop, cur, prop, mapth, lp_cur, map_lp, na);
+            if (acc) for (int i = tid; i < P; i += nt) gcur[i] = gprop[i];
+        }
         __syncthreads();
     }
     if (tid == 0) { c.lp[k] = lp_cur; c.map_lp[k] = map_lp; c.naccept[k] = na; }
