@@ -252,8 +252,10 @@ static int make_launch(const qb_net_t* net, int dtype, bool want_grad, long long
     const int TM = out->plan.TM;
     long long S = 1;
     if (!force_single) {
-        const long long target = (long long)QB_NUM_SMS * 4;
-        if (K < target) S = std::min(cdiv(N, TM), cdiv(target, K));
+        // few chains: split the data axis so that the grid is >= 8 waves of one block per SM (tail effect < 10 %),
+        // keeping at least two tiles per block; partial sums / gradients are combined in fixed order by k_finalize
+        const long long target = (long long)QB_NUM_SMS * 8;
+        if (K < target) S = std::max<long long>(1, std::min(cdiv(N, 2LL * TM), cdiv(target, K)));
         S = env_int("QB_SPLIT", (int)S);
         if (S < 1) S = 1;
     }
