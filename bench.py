@@ -91,14 +91,22 @@ def mlp_desc(d, hls, o=1):
 
 
 def theta_init(spec, P, lo, hi):
-    """theta0[k] for global chains lo..hi-1.  c5: rand(P); c2: 0.1*randn(P); c3/c4: U(+-1/sqrt(fan_in))-like."""
-    rs = np.random.RandomState(1234 + lo)
-    n = hi - lo
-    if spec['name'] == 'c5':
-        return rs.rand(n, P).astype(np.float32)
-    if spec['name'] == 'c2':
-        return (0.1 * rs.randn(n, P)).astype(np.float32)
-    return ((2 * rs.rand(n, P) - 1) / math.sqrt(spec['hls'][0])).astype(np.float32)
+    """theta0[k] for global chains lo..hi-1, a function of the GLOBAL chain index only (generated in blocks of 1024
+    chains seeded by the block index), so the job is the same however it is sharded over GPUs.
+    c5: rand(P) (nn_mcmc.py:124); c2: 0.1*randn(P); c3/c4: U(+-1/sqrt(fan_in))-like."""
+    out = np.empty((hi - lo, P), dtype=np.float32)
+    B = 1024
+    for blk in range(lo // B, (hi + B - 1) // B):
+        rs = np.random.RandomState(1234 + blk)
+        if spec['name'] == 'c5':
+            vals = rs.rand(B, P)
+        elif spec['name'] == 'c2':
+            vals = 0.1 * rs.randn(B, P)
+        else:
+            vals = (2 * rs.rand(B, P) - 1) / math.sqrt(spec['hls'][0])
+        a, b = max(lo, blk * B), min(hi, (blk + 1) * B)
+        out[a - lo:b - lo] = vals[a - blk * B:b - blk * B]
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

@@ -85,8 +85,9 @@ class MCMCBase(object):
             seed = int(np.random.randint(1, 2 ** 31 - 1))
         if self._device_lp is not None:
             nsh = self._auto_shards(theta0, replay, keep_on_device)
-            if nsh > 1:
-                return self._run_fused_sharded(int(nmcmc), theta0, int(seed), int(store_every), int(chain_offset), verbose, nsh)
+            if nsh != 1:
+                return self._run_fused_sharded(int(nmcmc), theta0, int(seed), int(store_every), int(chain_offset), verbose,
+                                               max(nsh, 1))
             res = self._run_fused(int(nmcmc), theta0, int(seed), int(store_every), replay, int(chain_offset), verbose)
         else:
             res = self._run_generic(int(nmcmc), theta0, int(seed), int(store_every), verbose)
@@ -139,7 +140,10 @@ class MCMCBase(object):
         on_host = (not torch.is_tensor(theta0)) or theta0.device.type == 'cpu'
         prob = self._device_lp.problem
         nbytes = theta0.shape[0] * theta0.shape[1] * prob.x.element_size()
-        return 4 if (on_host and nbytes >= 256 * 2 ** 20 and theta0.shape[0] >= 8) else 1
+        if not on_host or nbytes < 8 * 2 ** 20:
+            return 1
+        # >= 8 MB of states: results go straight into pinned host buffers (path below); >= 256 MB: 4 pipelined shards
+        return 4 if (nbytes >= 256 * 2 ** 20 and theta0.shape[0] >= 8) else -1
 
     def _run_fused_sharded(self, nmcmc, theta0, seed, store_every, chain_offset, verbose, nsh):
         prob = self._device_lp.problem
@@ -171,10 +175,8 @@ class MCMCBase(object):
             s.synchronize()
         if verbose:
             print('%d / %d completed, acceptance rate %lg' % (nmcmc, nmcmc, host['accrate'].mean().item()))
-        out = {k: v.numpy() for k, v in host.items()}
+        out = {k: v.numpy() for k, v in host.items()}          # chain / mapparams stay in the compute dtype
         out['accepted'] = out['accepted'].astype(bool)
-        if prob.dtype != torch.float64:
-            pass          # chain / mapparams stay in the compute dtype for huge batches (no 2x host copy)
         return out
 
     # hooks the samplers implement for the fused path
@@ -243,7 +245,7 @@ class MCMCBase(object):
             return res
         out = {}
         for k, v in res.items():
-            a = v.detach().double().cpu().numpy() if v.dtype != torch.uint8 and v.dtype != torch.bool else v.cpu().numpy().astype(bool)
+            a = v.detach().cpu().numpy() if v.dtype != torch.uint8 and v.dtype != torch.bool else v.cpu().numpy().astype(bool)
             out[k] = a[0] if single else a
         if single:
             out['maxpost'] = float(out['maxpost'])
