@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, 'csrc', 'qb_kernels.cu')
-DEPS = [SRC, os.path.join(HERE, 'csrc', 'qb_device.cuh'), os.path.join(HERE, 'csrc', 'qb_plan.h'),
+DEPS = [SRC, os.path.join(HERE, 'csrc', 'qb_device.cuh'), os.path.join(HERE, 'csrc', 'qb_tc.cuh'), os.path.join(HERE, 'csrc', 'qb_plan.h'),
         os.path.join(ROOT, 'include', 'quinn_b200.h')]
 OUT = os.path.join(HERE, 'lib', 'libquinn_b200.so')
 

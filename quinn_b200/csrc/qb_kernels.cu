@@ -10,6 +10,7 @@
 #include "quinn_b200.h"
 #include "qb_plan.h"
 #include "qb_device.cuh"
+#include "qb_tc.cuh"
 
 #ifndef QB_LB_T
 #define QB_LB_T 256
@@ -265,6 +266,55 @@ static int make_launch(const qb_net_t* net, int dtype, bool want_grad, long long
     return 0;
 }
 
+
+// Tensor-core (tcgen05 3xTF32) plan for the value path; returns false when the network is not eligible:
+// fp32, >= 3 layers, no residual layers, n_in <= 15, hidden widths multiples of 16 (<= 128), <= 4 outputs.
+static bool make_tc_plan(const qb_net_t* net, int dtype, QbTcPlan* tp) {
+    memset(tp, 0, sizeof(*tp));
+    if (dtype != QB_F32 || env_int("QB_NO_TC", 0)) return false;
+    const int nl = net->n_layers;
+    if (nl < 3 || net->in_dim > 15 || net->out_dim > 4) return false;
+    int kmax = 0, nmax = 0;
+    for (int l = 0; l < nl; ++l) {
+        const qb_layer_t& S = net->layers[l];
+        if (S.res_step != 0.0) return false;
+        if (l < nl - 1 && (S.n_out % 16 != 0 || S.n_out < 16 || S.n_out > 128)) return false;
+        if (l >= 1 && l < nl - 1) { kmax = std::max(kmax, S.n_in); nmax = std::max(nmax, S.n_out); }
+    }
+    const int cols = 2 * kmax + nmax;
+    if (cols > 512) return false;
+    tp->n_layers = nl; tp->in_dim = net->in_dim; tp->out_dim = net->out_dim; tp->n_params = net->n_params;
+    tp->ni = net->in_dim < 4 ? 4 : (net->in_dim < 8 ? 8 : 16);
+    tp->h0 = net->layers[0].n_out; tp->kl = net->layers[nl - 1].n_in;
+    tp->act0 = net->layers[0].act; tp->act_last = net->layers[nl - 1].act; tp->final_exp = net->final_exp;
+    tp->w0_off = net->layers[0].w_off; tp->b0_off = net->layers[0].b_off;
+    tp->wl_off = net->layers[nl - 1].w_off; tp->bl_off = net->layers[nl - 1].b_off;
+    tp->a_lo_col = kmax; tp->d_col = 2 * kmax;
+    tp->tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+    int off = QB_TC_HDR_BYTES;
+    for (int l = 1; l < nl - 1; ++l) {
+        const qb_layer_t& S = net->layers[l];
+        QbTcLayer& L = tp->L[l];
+        L.n_in = S.n_in; L.n_out = S.n_out; L.w_off = S.w_off; L.b_off = S.b_off; L.act = S.act;
+        L.bhi = off; off += S.n_in * S.n_out * 4;
+        L.blo = off; off += S.n_in * S.n_out * 4;
+    }
+    tp->fl_base = off;
+    int f = 0;
+    tp->w0 = f; f += tp->h0 * tp->ni;
+    for (int l = 1; l < nl - 1; ++l) { tp->L[l].bias = f; f += rup(tp->L[l].n_out, 4); }
+    tp->wl = f; f += rup(tp->out_dim * tp->kl, 4);
+    tp->bl = f; f += 4;
+    const long long bytes = (long long)off + (long long)f * 4;
+    if (bytes > QB_SMEM_MAX) return false;
+    // tensor memory is 512 columns per SM: request enough shared memory that no more blocks than 512/tmem_cols
+    // become resident (a further block would spin in tcgen05.alloc)
+    const int max_blocks = 512 / tp->tmem_cols;
+    const long long floor_bytes = QB_SMEM_SM / (max_blocks + 1) + 1;
+    tp->smem_bytes = (int)std::min<long long>(QB_SMEM_MAX, std::max(bytes, floor_bytes));
+    return true;
+}
+
 template <typename K>
 static int set_smem(K kernel, long long bytes) {
     QB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -295,7 +345,7 @@ template <typename T> struct EvalArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(512, 1) k_logpost(const __grid_constant__ QbPlan P, const EvalArgs<T> a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const QbSmem S = qb_carve<T>(P, smem_raw);
     const long long k = blockIdx.x, s = blockIdx.y;
     const long long n0 = s * a.pps, n1 = min(a.N, n0 + a.pps);
@@ -305,13 +355,35 @@ __global__ void __launch_bounds__(512, 1) k_logpost(const __grid_constant__ QbPl
 
 template <typename T>
 __global__ void __launch_bounds__(256, 2) k_logpost_grad(const __grid_constant__ QbPlan P, const EvalArgs<T> a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const QbSmem S = qb_carve<T>(P, smem_raw);
     const long long k = blockIdx.x, s = blockIdx.y;
     const long long n0 = s * a.pps, n1 = min(a.N, n0 + a.pps);
     T* g = (a.S == 1) ? a.grad + k * P.n_params : a.gpart + (k * a.S + s) * P.n_params;
     const double ssq = qb_eval_value_grad<T>(P, S, a.theta + k * P.n_params, a.x, a.y, n0, n1, a.lk.inv_sigma2, g);
     if (threadIdx.x == 0) a.part[k * a.S + s] = ssq;
+}
+
+
+// kernel 1 on the tensor cores (fp32 eligible networks, see qb_tc.cuh)
+__global__ void __launch_bounds__(128, 2) k_logpost_tc(const __grid_constant__ QbTcPlan tp, const EvalArgs<float> a) {
+    extern __shared__ __align__(128) unsigned char smem_tc[];
+    QbTcCtx cx;
+    qb_tc_init(tp, smem_tc, cx);
+    const long long k = blockIdx.x, s = blockIdx.y;
+    const long long n0 = s * a.pps, n1 = min(a.N, n0 + a.pps);
+    qb_tc_stage(tp, smem_tc, a.theta + k * tp.n_params);
+    __syncthreads();
+    const double ssq = qb_tc_eval(tp, cx, smem_tc, a.x, a.y, n0, n1);
+    if (threadIdx.x == 0) a.part[k * a.S + s] = ssq;
+    qb_tc_fini(tp, cx);
+}
+
+template <typename T> static int launch_logpost_tc(const QbTcPlan&, const EvalArgs<T>&, dim3, cudaStream_t) { return qb_fail("tensor-core path is fp32 only"); }
+template <> int launch_logpost_tc<float>(const QbTcPlan& tp, const EvalArgs<float>& a, dim3 grid, cudaStream_t st) {
+    if (set_smem(k_logpost_tc, tp.smem_bytes)) return -2;
+    k_logpost_tc<<<grid, 128, tp.smem_bytes, st>>>(tp, a);
+    return 0;
 }
 
 // combine the N-splits (fixed order), add constants and the prior
@@ -360,8 +432,13 @@ static int run_eval(const qb_net_t* net, int dtype, const void* theta, int64_t K
         if (set_smem(k_logpost_grad<T>, L.plan.smem_bytes)) return -2;
         k_logpost_grad<T><<<grid, L.plan.nthreads, L.plan.smem_bytes, st>>>(L.plan, a);
     } else {
-        if (set_smem(k_logpost<T>, L.plan.smem_bytes)) return -2;
-        k_logpost<T><<<grid, L.plan.nthreads, L.plan.smem_bytes, st>>>(L.plan, a);
+        QbTcPlan tp;
+        if (make_tc_plan(net, dtype, &tp)) {
+            if (launch_logpost_tc<T>(tp, a, grid, st)) return -2;
+        } else {
+            if (set_smem(k_logpost<T>, L.plan.smem_bytes)) return -2;
+            k_logpost<T><<<grid, L.plan.nthreads, L.plan.smem_bytes, st>>>(L.plan, a);
+        }
     }
     QB_CUDA(cudaGetLastError());
     k_finalize<T><<<(unsigned)K, 128, 0, st>>>(a, net->n_params, want_grad ? 1 : 0);
@@ -485,10 +562,20 @@ __device__ void qb_cholesky(const T* cov, T* Lf, int P, double fac, double jitte
     }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(512, 1) k_amcmc(const __grid_constant__ QbPlan plan, const ChainArgs<T> c, const AmcmcArgs<T> a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const QbSmem S = qb_carve<T>(plan, smem_raw);
+// TC = 1 (fp32 only): the evaluation runs on the tensor cores (qb_tc.cuh), 128 threads, two blocks per SM.
+template <typename T, int TC>
+__global__ void __launch_bounds__(TC ? 128 : 512, TC ? 2 : 1)
+k_amcmc(const __grid_constant__ QbPlan plan, const __grid_constant__ QbTcPlan tp, const ChainArgs<T> c, const AmcmcArgs<T> a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    QbSmem S;
+    QbTcCtx cx;
+    if constexpr (TC) {
+        S.red = reinterpret_cast<double*>(smem_raw); S.w = nullptr;
+        S.act = smem_raw + tp.fl_base;       // never used as scratch: full-covariance proposals take the SIMT kernel
+        qb_tc_init(tp, smem_raw, cx);
+    } else {
+        S = qb_carve<T>(plan, smem_raw);
+    }
     const long long k = blockIdx.x;
     const int P = plan.n_params, tid = threadIdx.x, nt = blockDim.x;
     T* cur = c.theta + k * P;
@@ -594,7 +681,14 @@ __global__ void __launch_bounds__(512, 1) k_amcmc(const __grid_constant__ QbPlan
         }   // !init_step
         __syncthreads();
         // ---- evaluate + accept
-        const double ssq = qb_eval_value<T>(plan, S, evalp, c.x, c.y, 0, c.N, true);
+        double ssq;
+        if constexpr (TC) {
+            qb_tc_stage(tp, smem_raw, evalp);
+            __syncthreads();
+            ssq = qb_tc_eval(tp, cx, smem_raw, c.x, c.y, 0, c.N);
+        } else {
+            ssq = qb_eval_value<T>(plan, S, evalp, c.x, c.y, 0, c.N, true);
+        }
         double pss = 0.0;
         if (c.lk.has_prior) pss = qb_prior_ss<T>(c.lk, evalp, k, P, S.red);
         const double lp_prop = qb_lp_from(c.lk, ssq, c.N, pss, P);
@@ -608,6 +702,17 @@ __global__ void __launch_bounds__(512, 1) k_amcmc(const __grid_constant__ QbPlan
         __syncthreads();
     }
     if (tid == 0) { c.lp[k] = lp_cur; c.map_lp[k] = map_lp; c.naccept[k] = na; a.prop_kind[k] = kind; }
+    if constexpr (TC) qb_tc_fini(tp, cx);
+}
+
+template <typename T> static int launch_amcmc_tc(const QbPlan&, const QbTcPlan&, const ChainArgs<T>&, const AmcmcArgs<T>&, long long, cudaStream_t) {
+    return qb_fail("tensor-core path is fp32 only");
+}
+template <> int launch_amcmc_tc<float>(const QbPlan& plan, const QbTcPlan& tp, const ChainArgs<float>& c, const AmcmcArgs<float>& a,
+                                       long long K, cudaStream_t st) {
+    if (set_smem(k_amcmc<float, 1>, tp.smem_bytes)) return -2;
+    k_amcmc<float, 1><<<(unsigned)K, 128, tp.smem_bytes, st>>>(plan, tp, c, a);
+    return 0;
 }
 
 template <typename T>
@@ -627,7 +732,7 @@ __device__ double qb_full_grad(const QbPlan& plan, const QbSmem& S, const ChainA
 
 template <typename T>
 __global__ void __launch_bounds__(256, 2) k_hmc(const __grid_constant__ QbPlan plan, const ChainArgs<T> c, const HmcArgs<T> h) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const QbSmem S = qb_carve<T>(plan, smem_raw);
     const long long k = blockIdx.x;
     const int P = plan.n_params, tid = threadIdx.x, nt = blockDim.x;
@@ -766,8 +871,15 @@ static int run_amcmc(const qb_net_t* net, int dtype, const qb_data_t* data, cons
     if (am->adapt != QB_ADAPT_NONE && !a.cov) return qb_fail("adaptation needs cov");
     if (am->adapt == QB_ADAPT_FULL && !a.chol) return qb_fail("full adaptation needs chol");
     if (!a.pscale || !a.prop_kind || !a.prop) return qb_fail("amcmc needs pscale, prop_kind and scratch");
-    if (set_smem(k_amcmc<T>, L.plan.smem_bytes)) return -2;
-    k_amcmc<T><<<(unsigned)ch->K, L.plan.nthreads, L.plan.smem_bytes, st>>>(L.plan, c, a);
+    QbTcPlan tp;
+    const bool tc = am->adapt != QB_ADAPT_FULL && !am->chol_ini && make_tc_plan(net, dtype, &tp);
+    if (tc) {
+        if (launch_amcmc_tc<T>(L.plan, tp, c, a, ch->K, st)) return -2;
+    } else {
+        memset(&tp, 0, sizeof(tp));
+        if (set_smem(k_amcmc<T, 0>, L.plan.smem_bytes)) return -2;
+        k_amcmc<T, 0><<<(unsigned)ch->K, L.plan.nthreads, L.plan.smem_bytes, st>>>(L.plan, tp, c, a);
+    }
     QB_CUDA(cudaGetLastError());
     g_launches += 1;
     return 0;
@@ -820,7 +932,7 @@ template <typename T> struct PredArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(512, 1) k_predict(const __grid_constant__ QbPlan P, const PredArgs<T> a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const QbSmem S = qb_carve<T>(P, smem_raw);
     T* sW = reinterpret_cast<T*>(S.w);
     T* A0 = reinterpret_cast<T*>(S.act);
