@@ -281,15 +281,18 @@ static bool make_tc_plan(const qb_net_t* net, int dtype, QbTcPlan* tp) {
         if (l < nl - 1 && (S.n_out % 16 != 0 || S.n_out < 16 || S.n_out > 128)) return false;
         if (l >= 1 && l < nl - 1) { kmax = std::max(kmax, S.n_in); nmax = std::max(nmax, S.n_out); }
     }
-    const int cols = 2 * kmax + nmax;
+    const bool pipe = nl == 3 && kmax <= 64 && nmax <= 64 && net->layers[0].act == net->layers[1].act &&
+                      (net->layers[0].act == QB_ACT_TANH || net->layers[0].act == QB_ACT_RELU) && !env_int("QB_NO_PIPE", 0);
+    const int cols = 2 * kmax + (pipe ? 2 : 1) * nmax;       // pipelined path: the accumulator is double-buffered
     if (cols > 512) return false;
     tp->n_layers = nl; tp->in_dim = net->in_dim; tp->out_dim = net->out_dim; tp->n_params = net->n_params;
-    tp->ni = net->in_dim < 4 ? 4 : (net->in_dim < 8 ? 8 : 16);
+    tp->ni = net->in_dim < 4 ? 4 : 16;
     tp->h0 = net->layers[0].n_out; tp->kl = net->layers[nl - 1].n_in;
     tp->act0 = net->layers[0].act; tp->act_last = net->layers[nl - 1].act; tp->final_exp = net->final_exp;
     tp->w0_off = net->layers[0].w_off; tp->b0_off = net->layers[0].b_off;
     tp->wl_off = net->layers[nl - 1].w_off; tp->bl_off = net->layers[nl - 1].b_off;
     tp->a_lo_col = kmax; tp->d_col = 2 * kmax;
+    tp->pipe = pipe ? 1 : 0;
     tp->tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
     int off = QB_TC_HDR_BYTES;
     for (int l = 1; l < nl - 1; ++l) {
@@ -305,7 +308,10 @@ static bool make_tc_plan(const qb_net_t* net, int dtype, QbTcPlan* tp) {
     for (int l = 1; l < nl - 1; ++l) { tp->L[l].bias = f; f += rup(tp->L[l].n_out, 4); }
     tp->wl = f; f += rup(tp->out_dim * tp->kl, 4);
     tp->bl = f; f += 4;
-    const long long bytes = (long long)off + (long long)f * 4;
+    long long bytes = (long long)off + (long long)f * 4;
+    bytes = (bytes + 15) / 16 * 16;
+    tp->ybuf = (int)bytes; bytes += 2 * 4 * 128 * 4;
+    tp->nthreads = tp->pipe ? 256 : 128;
     if (bytes > QB_SMEM_MAX) return false;
     // tensor memory is 512 columns per SM: request enough shared memory that no more blocks than 512/tmem_cols
     // become resident (a further block would spin in tcgen05.alloc)
@@ -366,7 +372,7 @@ __global__ void __launch_bounds__(256, 2) k_logpost_grad(const __grid_constant__
 
 
 // kernel 1 on the tensor cores (fp32 eligible networks, see qb_tc.cuh)
-__global__ void __launch_bounds__(128, 2) k_logpost_tc(const __grid_constant__ QbTcPlan tp, const EvalArgs<float> a) {
+__global__ void __launch_bounds__(256, 2) k_logpost_tc(const __grid_constant__ QbTcPlan tp, const EvalArgs<float> a) {
     extern __shared__ __align__(128) unsigned char smem_tc[];
     QbTcCtx cx;
     qb_tc_init(tp, smem_tc, cx);
@@ -382,7 +388,7 @@ __global__ void __launch_bounds__(128, 2) k_logpost_tc(const __grid_constant__ Q
 template <typename T> static int launch_logpost_tc(const QbTcPlan&, const EvalArgs<T>&, dim3, cudaStream_t) { return qb_fail("tensor-core path is fp32 only"); }
 template <> int launch_logpost_tc<float>(const QbTcPlan& tp, const EvalArgs<float>& a, dim3 grid, cudaStream_t st) {
     if (set_smem(k_logpost_tc, tp.smem_bytes)) return -2;
-    k_logpost_tc<<<grid, 128, tp.smem_bytes, st>>>(tp, a);
+    k_logpost_tc<<<grid, tp.nthreads, tp.smem_bytes, st>>>(tp, a);
     return 0;
 }
 
@@ -562,45 +568,23 @@ __device__ void qb_cholesky(const T* cov, T* Lf, int P, double fac, double jitte
     }
 }
 
-// TC = 1 (fp32 only): the evaluation runs on the tensor cores (qb_tc.cuh), 128 threads, two blocks per SM.
-template <typename T, int TC>
-__global__ void __launch_bounds__(TC ? 128 : 512, TC ? 2 : 1)
-k_amcmc(const __grid_constant__ QbPlan plan, const __grid_constant__ QbTcPlan tp, const ChainArgs<T> c, const AmcmcArgs<T> a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    QbSmem S;
-    QbTcCtx cx;
-    if constexpr (TC) {
-        S.red = reinterpret_cast<double*>(smem_raw); S.w = nullptr;
-        S.act = smem_raw + tp.fl_base;       // never used as scratch: full-covariance proposals take the SIMT kernel
-        qb_tc_init(tp, smem_raw, cx);
-    } else {
-        S = qb_carve<T>(plan, smem_raw);
-    }
-    const long long k = blockIdx.x;
-    const int P = plan.n_params, tid = threadIdx.x, nt = blockDim.x;
+// per-chain scalars that live across the evaluation (kept in a struct so that the cold step logic can be compiled
+// out of line for the tensor-core kernel, whose hot loop needs every register)
+struct QbAmcmcLocal { double lp_cur, map_lp; long long na; int kind; };
+
+// one AMCMC step up to the proposal (admcmc.py:52-70): moments, proposal covariance, proposal -> a.prop
+template <typename T>
+__device__ __forceinline__ void qb_amcmc_pre(const ChainArgs<T>& c, const AmcmcArgs<T>& a, int P, long long k, long long s,
+                                             int& kind, T* zbuf) {
+    const int tid = threadIdx.x, nt = blockDim.x;
     T* cur = c.theta + k * P;
     T* prop = a.prop + k * P;
-    T* mapth = c.map_theta + k * P;
     T* xm = a.xm ? a.xm + k * P : nullptr;
     T* pscale = a.pscale + k * P;
     const bool full = a.track == 2;               // shape of cov: [P,P] (2) or [P] (1)
     T* cov = a.cov ? a.cov + k * (full ? (long long)P * P : (long long)P) : nullptr;
     T* chol = a.chol ? a.chol + k * (long long)P * P : nullptr;
-    T* zbuf = reinterpret_cast<T*>(S.act);       // scratch between evaluations
-
-    // One evaluation call site: step s == -1 (only when init_lp) evaluates the incoming state itself
-    // (mcmc.py:55-56) and initialises the MAP bookkeeping.
-    double lp_cur = 0.0, map_lp = 0.0;
-    long long na = 0;
-    if (!c.init_lp) { lp_cur = c.lp[k]; map_lp = c.map_lp[k]; na = c.naccept[k]; }
-    int kind = a.prop_kind[k];
-    __syncthreads();
-
-    for (long long s = c.init_lp ? -1 : 0; s < c.nsteps; ++s) {
-        const long long t = c.t_start + s;
-        const bool init_step = s < 0;
-        const T* evalp = init_step ? cur : prop;
-        if (!init_step) {
+    const long long t = c.t_start + s;
         // ---- running mean / covariance (admcmc.py:52-59)
         if (a.track && xm) {
             if (t == 0) {
@@ -678,8 +662,74 @@ k_amcmc(const __grid_constant__ QbPlan plan, const __grid_constant__ QbTcPlan tp
                 }
             }
         }
-        }   // !init_step
-        __syncthreads();
+    __syncthreads();
+}
+template <typename T>
+__device__ __noinline__ void qb_amcmc_pre_cold(const ChainArgs<T>& c, const AmcmcArgs<T>& a, int P, long long k, long long s,
+                                               int& kind, T* zbuf) {
+    qb_amcmc_pre<T>(c, a, P, k, s, kind, zbuf);
+}
+
+// accept / reject and bookkeeping after the evaluation (mcmc.py:55-61 for the initial state, 69-85 per step)
+template <typename T>
+__device__ __forceinline__ void qb_amcmc_post(const ChainArgs<T>& c, const AmcmcArgs<T>& a, int P, long long k, long long s,
+                                              double ssq, double* red, QbAmcmcLocal& st) {
+    T* cur = c.theta + k * P;
+    T* prop = a.prop + k * P;
+    T* mapth = c.map_theta + k * P;
+    double pss = 0.0;
+    if (c.lk.has_prior) pss = qb_prior_ss<T>(c.lk, s < 0 ? cur : prop, k, P, red);
+    const double lp_prop = qb_lp_from(c.lk, ssq, c.N, pss, P);
+    if (s < 0) {
+        st.lp_cur = lp_prop; st.map_lp = lp_prop; st.na = 0;
+        if (threadIdx.x == 0 && c.rec_lp0) c.rec_lp0[k] = lp_prop;
+        for (int i = threadIdx.x; i < P; i += blockDim.x) mapth[i] = cur[i];
+    } else {
+        qb_mh_step<T>(c, k, s, P, lp_prop, 0.0, 0.0, cur, prop, mapth, st.lp_cur, st.map_lp, st.na);
+    }
+    __syncthreads();
+}
+template <typename T>
+__device__ __noinline__ void qb_amcmc_post_cold(const ChainArgs<T>& c, const AmcmcArgs<T>& a, int P, long long k, long long s,
+                                                double ssq, double* red, QbAmcmcLocal& st) {
+    qb_amcmc_post<T>(c, a, P, k, s, ssq, red, st);
+}
+
+// TC = 1 (fp32 only): the evaluation runs on the tensor cores (qb_tc.cuh), 128 or 256 threads, two blocks per SM.
+template <typename T, int TC>
+__global__ void __launch_bounds__(TC ? 256 : 512, TC ? 2 : 1)
+k_amcmc(const __grid_constant__ QbPlan plan, const __grid_constant__ QbTcPlan tp, const __grid_constant__ ChainArgs<T> c,
+        const __grid_constant__ AmcmcArgs<T> a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    QbSmem S;
+    QbTcCtx cx;
+    if constexpr (TC) {
+        S.red = reinterpret_cast<double*>(smem_raw); S.w = nullptr;
+        S.act = smem_raw + tp.fl_base;       // never used as scratch: full-covariance proposals take the SIMT kernel
+        qb_tc_init(tp, smem_raw, cx);
+    } else {
+        S = qb_carve<T>(plan, smem_raw);
+    }
+    const long long k = blockIdx.x;
+    const int P = plan.n_params;
+    T* zbuf = reinterpret_cast<T*>(S.act);       // scratch between evaluations
+
+    // One evaluation call site: step s == -1 (only when init_lp) evaluates the incoming state itself
+    // (mcmc.py:55-56) and initialises the MAP bookkeeping.
+    QbAmcmcLocal st;
+    st.lp_cur = 0.0; st.map_lp = 0.0; st.na = 0;
+    if (!c.init_lp) { st.lp_cur = c.lp[k]; st.map_lp = c.map_lp[k]; st.na = c.naccept[k]; }
+    st.kind = a.prop_kind[k];
+    __syncthreads();
+
+    for (long long s = c.init_lp ? -1 : 0; s < c.nsteps; ++s) {
+        const T* evalp = (s < 0 ? c.theta : a.prop) + k * P;
+        if (s >= 0) {
+            if constexpr (TC) qb_amcmc_pre_cold<T>(c, a, P, k, s, st.kind, zbuf);
+            else qb_amcmc_pre<T>(c, a, P, k, s, st.kind, zbuf);
+        } else {
+            __syncthreads();
+        }
         // ---- evaluate + accept
         double ssq;
         if constexpr (TC) {
@@ -689,19 +739,10 @@ k_amcmc(const __grid_constant__ QbPlan plan, const __grid_constant__ QbTcPlan tp
         } else {
             ssq = qb_eval_value<T>(plan, S, evalp, c.x, c.y, 0, c.N, true);
         }
-        double pss = 0.0;
-        if (c.lk.has_prior) pss = qb_prior_ss<T>(c.lk, evalp, k, P, S.red);
-        const double lp_prop = qb_lp_from(c.lk, ssq, c.N, pss, P);
-        if (init_step) {
-            lp_cur = lp_prop; map_lp = lp_prop; na = 0;
-            if (tid == 0 && c.rec_lp0) c.rec_lp0[k] = lp_cur;
-            for (int i = tid; i < P; i += nt) mapth[i] = cur[i];
-        } else {
-            qb_mh_step<T>(c, k, s, P, lp_prop, 0.0, 0.0, cur, prop, mapth, lp_cur, map_lp, na);
-        }
-        __syncthreads();
+        if constexpr (TC) qb_amcmc_post_cold<T>(c, a, P, k, s, ssq, S.red, st);
+        else qb_amcmc_post<T>(c, a, P, k, s, ssq, S.red, st);
     }
-    if (tid == 0) { c.lp[k] = lp_cur; c.map_lp[k] = map_lp; c.naccept[k] = na; a.prop_kind[k] = kind; }
+    if (threadIdx.x == 0) { c.lp[k] = st.lp_cur; c.map_lp[k] = st.map_lp; c.naccept[k] = st.na; a.prop_kind[k] = st.kind; }
     if constexpr (TC) qb_tc_fini(tp, cx);
 }
 
@@ -711,7 +752,7 @@ template <typename T> static int launch_amcmc_tc(const QbPlan&, const QbTcPlan&,
 template <> int launch_amcmc_tc<float>(const QbPlan& plan, const QbTcPlan& tp, const ChainArgs<float>& c, const AmcmcArgs<float>& a,
                                        long long K, cudaStream_t st) {
     if (set_smem(k_amcmc<float, 1>, tp.smem_bytes)) return -2;
-    k_amcmc<float, 1><<<(unsigned)K, 128, tp.smem_bytes, st>>>(plan, tp, c, a);
+    k_amcmc<float, 1><<<(unsigned)K, tp.nthreads, tp.smem_bytes, st>>>(plan, tp, c, a);
     return 0;
 }
 

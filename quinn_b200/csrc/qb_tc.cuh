@@ -12,7 +12,8 @@
 //                          D back with tcgen05.ld, adds the bias, applies the activation and either writes the next
 //                          A operand or, for the last hidden layer, feeds
 //   last layer (n_out<=4): a per-thread dot product with weights broadcast from shared memory, then the residual.
-// Tensor-memory columns: [0,Kmax) A_hi, [Kmax,2Kmax) A_lo, [2Kmax, 2Kmax+Nmax) D.
+// Tensor-memory columns: [0,Kmax) A_hi, [Kmax,2Kmax) A_lo, [2Kmax, 2Kmax+Nmax) D (pipelined path: a second D buffer
+// follows).
 // The tensor pipe of one block overlaps with the CUDA-core phases of the other block(s) resident on the SM.
 #pragma once
 #include <stdint.h>
@@ -25,21 +26,25 @@ struct QbTcLayer {
 };
 struct QbTcPlan {
     int n_layers;                       // layers 1 .. n_layers-2 run on the tensor cores
-    int in_dim, ni, out_dim, n_params;  // ni: padded input width (4, 8 or 16; slot in_dim carries the bias)
+    int in_dim, ni, out_dim, n_params;  // ni: padded input width (4 or 16; slot in_dim carries the bias)
     int h0, kl;                         // width after layer 0; n_in of the last layer
     int act0, act_last, final_exp;
+    int pipe;                           // one tensor-core layer, widths <= 64: software-pipelined tile loop
     int w0, wl, bl;                     // float indices: layer-0 rows [h0][ni], last-layer W [out][kl], last bias
     int w0_off, b0_off, wl_off, bl_off; // offsets in theta (b*_off < 0: no bias)
-    int fl_base;                        // byte offset of the float area
+    int fl_base, ybuf;                  // byte offsets of the float area and of the partial-output exchange buffer
+    int nthreads;                       // 256 (pipelined) or 128
     int a_lo_col, d_col, tmem_cols;
     int smem_bytes;
     QbTcLayer L[QB_MAX_LAYERS];
 };
 
 #ifdef __CUDACC__
-enum { QB_TC_RED_BYTES = 320, QB_TC_BAR_OFF = 320, QB_TC_SLOT_OFF = 328, QB_TC_HDR_BYTES = 384 };
+// shared-memory header: [0,320) reduction scratch, mbarriers, tensor-memory base, MMA descriptor table (<= 48 entries)
+enum { QB_TC_RED_BYTES = 320, QB_TC_BAR_OFF = 320, QB_TC_SLOT_OFF = 328, QB_TC_ABAR_OFF = 336, QB_TC_DTAB_OFF = 384,
+       QB_TC_HDR_BYTES = 768 };
 
-struct QbTcCtx { uint32_t tmem, bar, phase; };
+struct QbTcCtx { uint32_t tmem, bar, phase, abar, aphase; };
 
 __device__ __forceinline__ uint32_t qb_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -66,15 +71,20 @@ __device__ __forceinline__ void qb_tmem_st_wait() { asm volatile("tcgen05.wait::
 __device__ __forceinline__ void qb_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void qb_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// bounded wait: a lost commit traps instead of hanging the GPU
+// bounded wait: a lost arrival traps after ~2 s instead of hanging the GPU
 __device__ __forceinline__ void qb_mbar_wait(uint32_t bar, uint32_t parity) {
-    for (int it = 0; it < (1 << 24); ++it) {
+    long long t0 = 0;
+    for (uint32_t it = 0;; ++it) {
         uint32_t ok;
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
         if (ok) return;
+        if ((it & 63u) == 63u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) __trap();
+        }
     }
-    __trap();
 }
 
 // all threads; allocates tensor memory and initialises the mbarrier
@@ -86,6 +96,7 @@ __device__ __forceinline__ void qb_tc_init(const QbTcPlan& tp, unsigned char* sm
     }
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(qb_smem_u32(smem + QB_TC_BAR_OFF)), "r"(1u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(qb_smem_u32(smem + QB_TC_ABAR_OFF)), "r"((uint32_t)blockDim.x) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     qb_tc_fence_before();
@@ -93,7 +104,8 @@ __device__ __forceinline__ void qb_tc_init(const QbTcPlan& tp, unsigned char* sm
     qb_tc_fence_after();
     cx.tmem = *reinterpret_cast<volatile uint32_t*>(smem + QB_TC_SLOT_OFF);
     cx.bar = qb_smem_u32(smem + QB_TC_BAR_OFF);
-    cx.phase = 0;
+    cx.abar = qb_smem_u32(smem + QB_TC_ABAR_OFF);
+    cx.phase = 0; cx.aphase = 0;
 }
 __device__ __forceinline__ void qb_tc_fini(const QbTcPlan& tp, const QbTcCtx& cx) {
     qb_tc_fence_before();
@@ -113,9 +125,10 @@ __device__ __forceinline__ void qb_tc_stage(const QbTcPlan& tp, unsigned char* s
     const int tid = threadIdx.x, nt = blockDim.x;
     const float fold = 2.8853900817779268f;
     {
+        // layer 0, units in pairs: float index ((j/2)*ni + q)*2 + (j&1); slot q == in_dim carries the bias
         const float s0 = tp.act0 == QB_ACT_TANH ? fold : 1.0f;
         for (int e = tid; e < tp.h0 * tp.ni; e += nt) {
-            const int j = e / tp.ni, q = e - j * tp.ni;
+            const int u = e & 1, q = (e >> 1) % tp.ni, j = ((e >> 1) / tp.ni) * 2 + u;
             float v = 0.0f;
             if (q < tp.in_dim) v = theta[tp.w0_off + j * tp.in_dim + q] * s0;
             else if (q == tp.in_dim && tp.b0_off >= 0) v = theta[tp.b0_off + j] * s0;
@@ -172,42 +185,163 @@ __device__ __forceinline__ void qb_tc_issue(const QbTcPlan& tp, const QbTcLayer&
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(cx.bar) : "memory");
 }
 
-template <int ACT> __device__ __forceinline__ float qb_tc_act(float z) {
-    if (ACT == QB_ACT_TANH) return qb_tanh_prescaled(z);
-    if (ACT == QB_ACT_RELU) return fmaxf(z, 0.0f);
-    return z;
+// tanh of four pre-activations that were already multiplied by 2*log2(e): tanh = 1 - 2/(1 + 2^z'), with ONE
+// reciprocal for the four denominators (the MUFU pipe, 16 results/clk/SM, is what bounds this kernel):
+// m = (da*db), r = 1/(m.x*m.y), 1/da = (r*m.y, r*m.x)*db ... .  z' is clamped at 30 (tanh(10.4) == 1.0f) so that the
+// product of four denominators stays finite; min.NaN keeps NaN pre-activations NaN.
+__device__ __forceinline__ float qb_min_nan(float a, float b) {
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float qb_ex2(float z) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z));
+    return e;
+}
+__device__ __forceinline__ void qb_tanh4_prescaled(float2& a, float2& b) {
+    const float2 one = make_float2(1.0f, 1.0f), m2 = make_float2(-2.0f, -2.0f);
+    float2 ea, eb;
+    ea.x = qb_ex2(qb_min_nan(a.x, 30.0f)); ea.y = qb_ex2(qb_min_nan(a.y, 30.0f));
+    eb.x = qb_ex2(qb_min_nan(b.x, 30.0f)); eb.y = qb_ex2(qb_min_nan(b.y, 30.0f));
+    const float2 da = __fadd2_rn(ea, one), db = __fadd2_rn(eb, one);
+    const float2 m = __fmul2_rn(da, db);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(m.x * m.y));
+    float2 rr;
+    rr.x = r * m.y; rr.y = r * m.x;                 // (1/m.x, 1/m.y)
+    const float2 ia = __fmul2_rn(rr, db), ib = __fmul2_rn(rr, da);
+    a = __ffma2_rn(ia, m2, one);
+    b = __ffma2_rn(ib, m2, one);
+}
+// Issue by a whole (convergent) warp with one elected lane, K/8 known at compile time: every descriptor is
+// base + constant, so the 3*K/8 MMAs go out back to back (a single thread doing address arithmetic between the
+// MMAs was the critical path of the tile loop: ~80 cycles per MMA).
+template <int KS>
+__device__ __forceinline__ void qb_tc_issue_ks(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t bhi, uint32_t blo,
+                                               uint32_t dhi, uint32_t idesc, uint32_t bar) {
+    uint32_t elected;
+    asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.b32 %0, 1, 0, p; }" : "=r"(elected) :: "memory");
+    if (elected) {
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+            for (int s = 0; s < KS; ++s) {
+                const uint32_t a = (pass == 0 ? a_lo : a_hi) + (uint32_t)s * 8u;
+                const uint32_t bl = (pass == 1 ? blo : bhi) + (uint32_t)s * 16u;       // +256 bytes, in 16-byte units
+                if (pass == 0 && s == 0)
+                    asm volatile("{ .reg .pred p; .reg .b64 dd; setp.ne.b32 p, 0, 0; mov.b64 dd, {%2, %3}; tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], dd, %4, p; }"
+                                 :: "r"(d), "r"(a), "r"(bl), "r"(dhi), "r"(idesc) : "memory");
+                else
+                    asm volatile("{ .reg .pred p; .reg .b64 dd; setp.eq.b32 p, 0, 0; mov.b64 dd, {%2, %3}; tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], dd, %4, p; }"
+                                 :: "r"(d), "r"(a), "r"(bl), "r"(dhi), "r"(idesc) : "memory");
+            }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+    }
+    __syncwarp();
+}
+// called by all lanes of warp 0
+__device__ __forceinline__ void qb_tc_issue_warp(const QbTcPlan& tp, const QbTcLayer& L, const QbTcCtx& cx, unsigned char* smem,
+                                                 uint32_t d_off) {
+    const uint32_t K = L.n_in, N = L.n_out;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t dhi = ((128u * (K >> 2)) >> 4) | (1u << 14);
+    const uint32_t bhi = ((qb_smem_u32(smem + L.bhi) >> 4) & 0x3FFFu) | ((128u >> 4) << 16);
+    const uint32_t blo = ((qb_smem_u32(smem + L.blo) >> 4) & 0x3FFFu) | ((128u >> 4) << 16);
+    const uint32_t d = cx.tmem + tp.d_col + d_off, a_hi = cx.tmem, a_lo = cx.tmem + tp.a_lo_col;
+    switch (K >> 3) {
+        case 2: qb_tc_issue_ks<2>(d, a_hi, a_lo, bhi, blo, dhi, idesc, cx.bar); break;
+        case 4: qb_tc_issue_ks<4>(d, a_hi, a_lo, bhi, blo, dhi, idesc, cx.bar); break;
+        case 6: qb_tc_issue_ks<6>(d, a_hi, a_lo, bhi, blo, dhi, idesc, cx.bar); break;
+        default: qb_tc_issue_ks<8>(d, a_hi, a_lo, bhi, blo, dhi, idesc, cx.bar); break;
+    }
 }
 
+__device__ __forceinline__ void qb_mbar_arrive(uint32_t bar) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" :: "r"(bar) : "memory");
+}
+// producer / consumer named barrier between the two warps that share a quarter of the tile's points
+__device__ __forceinline__ void qb_pair_arrive(int id) { asm volatile("bar.arrive %0, 64;" :: "r"(id) : "memory"); }
+__device__ __forceinline__ void qb_pair_sync(int id) { asm volatile("bar.sync %0, 64;" :: "r"(id) : "memory"); }
+
+template <int ACT> __device__ __forceinline__ void qb_tc_act4(float2& a, float2& b) {
+    if (ACT == QB_ACT_TANH) qb_tanh4_prescaled(a, b);
+    else if (ACT == QB_ACT_RELU) { a.x = fmaxf(a.x, 0.0f); a.y = fmaxf(a.y, 0.0f); b.x = fmaxf(b.x, 0.0f); b.y = fmaxf(b.y, 0.0f); }
+}
+
+// split 16 fp32 values into tf32 hi + remainder lo and write them to tensor memory (this thread's lane)
 __device__ __forceinline__ void qb_tc_split_store(uint32_t t_hi, uint32_t t_lo, const float (&h)[16]) {
     uint32_t hi[16], lo[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const float hh = qb_tf32_hi(h[i]);
-        hi[i] = __float_as_uint(hh);
-        lo[i] = __float_as_uint(h[i] - hh);
+    for (int i = 0; i < 16; i += 2) {
+        const float2 hh = make_float2(qb_tf32_hi(h[i]), qb_tf32_hi(h[i + 1]));
+        const float2 ll = __fadd2_rn(make_float2(h[i], h[i + 1]), make_float2(-hh.x, -hh.y));
+        hi[i] = __float_as_uint(hh.x); hi[i + 1] = __float_as_uint(hh.y);
+        lo[i] = __float_as_uint(ll.x); lo[i + 1] = __float_as_uint(ll.y);
     }
     qb_tmem_st16(t_hi, hi);
     qb_tmem_st16(t_lo, lo);
 }
 
-// layer 0 on the CUDA cores: h = act(W0 x + b0) for this thread's point, written as the first A operand
+// layer 0 on the CUDA cores for units c .. c+15 of this thread's point: h = act(W0 x + b0) (packed FFMA2, two units
+// per instruction; the bias rides in slot in_dim of the padded input, xr[in_dim] == 1)
+template <int NI, int ACT>
+__device__ __forceinline__ void qb_tc_l0_chunk(const QbTcPlan& tp, const float* F, int c, const float (&xr)[NI], float (&h)[16]) {
+    const float4* W = reinterpret_cast<const float4*>(F + tp.w0 + c * NI);     // pair p of the chunk: W[p*NI/2 + q/2]
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        float2 z0 = make_float2(0.0f, 0.0f), z1 = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int q = 0; q < NI; q += 2) {
+            const float4 wa = W[(2 * g) * (NI / 2) + q / 2], wb = W[(2 * g + 1) * (NI / 2) + q / 2];
+            z0 = __ffma2_rn(make_float2(wa.x, wa.y), make_float2(xr[q], xr[q]), z0);
+            z0 = __ffma2_rn(make_float2(wa.z, wa.w), make_float2(xr[q + 1], xr[q + 1]), z0);
+            z1 = __ffma2_rn(make_float2(wb.x, wb.y), make_float2(xr[q], xr[q]), z1);
+            z1 = __ffma2_rn(make_float2(wb.z, wb.w), make_float2(xr[q + 1], xr[q + 1]), z1);
+        }
+        qb_tc_act4<ACT>(z0, z1);
+        h[4 * g + 0] = z0.x; h[4 * g + 1] = z0.y; h[4 * g + 2] = z1.x; h[4 * g + 3] = z1.y;
+    }
+}
+
+// accumulator columns c .. c+15 of this thread's point -> h = act(D + bias)
+template <int ACT>
+__device__ __forceinline__ void qb_tc_epi_chunk(const float* bias, int c, const uint32_t (&v)[16], float (&h)[16]) {
+    const float4* B4 = reinterpret_cast<const float4*>(bias + c);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const float4 b = B4[g];
+        float2 z0 = __fadd2_rn(make_float2(__uint_as_float(v[4 * g + 0]), __uint_as_float(v[4 * g + 1])), make_float2(b.x, b.y));
+        float2 z1 = __fadd2_rn(make_float2(__uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])), make_float2(b.z, b.w));
+        qb_tc_act4<ACT>(z0, z1);
+        h[4 * g + 0] = z0.x; h[4 * g + 1] = z0.y; h[4 * g + 2] = z1.x; h[4 * g + 3] = z1.y;
+    }
+}
+
+// narrow output layer: yacc[o] (two partial sums each) += W_last[o][c .. c+15] . h
+template <int OD>
+__device__ __forceinline__ void qb_tc_dot_chunk(const QbTcPlan& tp, const float* F, int c, const float (&h)[16], float2 (&yacc)[OD]) {
+#pragma unroll
+    for (int o = 0; o < OD; ++o) {
+        if (o < tp.out_dim) {
+            const float4* w4 = reinterpret_cast<const float4*>(F + tp.wl + o * tp.kl + c);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const float4 w = w4[g];
+                yacc[o] = __ffma2_rn(make_float2(w.x, w.y), make_float2(h[4 * g + 0], h[4 * g + 1]), yacc[o]);
+                yacc[o] = __ffma2_rn(make_float2(w.z, w.w), make_float2(h[4 * g + 2], h[4 * g + 3]), yacc[o]);
+            }
+        }
+    }
+}
+
 template <int NI, int ACT>
 __device__ __forceinline__ void qb_tc_layer0(const QbTcPlan& tp, const float* F, uint32_t tl, const float (&xr)[NI]) {
-    const float4* W = reinterpret_cast<const float4*>(F + tp.w0);
 #pragma unroll 1
     for (int c = 0; c < tp.h0; c += 16) {
         float h[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            float z = 0.0f;
-#pragma unroll
-            for (int q4 = 0; q4 < NI / 4; ++q4) {
-                const float4 w = W[(c + i) * (NI / 4) + q4];
-                z = fmaf(w.x, xr[q4 * 4 + 0], z); z = fmaf(w.y, xr[q4 * 4 + 1], z);
-                z = fmaf(w.z, xr[q4 * 4 + 2], z); z = fmaf(w.w, xr[q4 * 4 + 3], z);
-            }
-            h[i] = qb_tc_act<ACT>(z);
-        }
+        qb_tc_l0_chunk<NI, ACT>(tp, F, c, xr, h);
         qb_tc_split_store(tl + c, tl + tp.a_lo_col + c, h);
     }
 }
@@ -215,58 +349,52 @@ __device__ __forceinline__ void qb_tc_layer0(const QbTcPlan& tp, const float* F,
 // hidden-layer epilogue: D -> +bias -> act -> next A operand
 template <int ACT>
 __device__ __forceinline__ void qb_tc_epi_mid(const QbTcPlan& tp, const QbTcLayer& L, const float* F, uint32_t tl) {
-    const float4* B4 = reinterpret_cast<const float4*>(F + L.bias);
 #pragma unroll 1
     for (int c = 0; c < L.n_out; c += 16) {
         uint32_t v[16];
         qb_tmem_ld16(tl + tp.d_col + c, v);
         qb_tmem_ld_wait16(v);
         float h[16];
-#pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) {
-            const float4 b = B4[(c >> 2) + i4];
-            h[i4 * 4 + 0] = qb_tc_act<ACT>(__uint_as_float(v[i4 * 4 + 0]) + b.x);
-            h[i4 * 4 + 1] = qb_tc_act<ACT>(__uint_as_float(v[i4 * 4 + 1]) + b.y);
-            h[i4 * 4 + 2] = qb_tc_act<ACT>(__uint_as_float(v[i4 * 4 + 2]) + b.z);
-            h[i4 * 4 + 3] = qb_tc_act<ACT>(__uint_as_float(v[i4 * 4 + 3]) + b.w);
-        }
+        qb_tc_epi_chunk<ACT>(F + L.bias, c, v, h);
         qb_tc_split_store(tl + c, tl + tp.a_lo_col + c, h);
     }
 }
 
-// last hidden layer's epilogue fused with the narrow output layer: yacc[o] += W_last[o][j] * act(D[j] + b[j])
+// last hidden layer's epilogue fused with the narrow output layer
 template <int ACT>
 __device__ __forceinline__ void qb_tc_epi_last(const QbTcPlan& tp, const QbTcLayer& L, const float* F, uint32_t tl,
-                                               float (&yacc)[4]) {
-    const float4* B4 = reinterpret_cast<const float4*>(F + L.bias);
-    const float* WL = F + tp.wl;
-    const int od = tp.out_dim, kl = tp.kl;
+                                               float2 (&yacc)[4]) {
 #pragma unroll 1
     for (int c = 0; c < L.n_out; c += 16) {
         uint32_t v[16];
         qb_tmem_ld16(tl + tp.d_col + c, v);
         qb_tmem_ld_wait16(v);
         float h[16];
+        qb_tc_epi_chunk<ACT>(F + L.bias, c, v, h);
+        qb_tc_dot_chunk<4>(tp, F, c, h, yacc);
+    }
+}
+
+// network output o from the finished dot product (bias, last activation, optional exp)
+__device__ __forceinline__ float qb_tc_out(const QbTcPlan& tp, const float* F, int o, float acc) {
+    float v = acc + F[tp.bl + o];
+    if (tp.act_last == QB_ACT_TANH) v = qb_tanh_prescaled(v);
+    else if (tp.act_last == QB_ACT_RELU) v = fmaxf(v, 0.0f);
+    if (tp.final_exp) v = expf(v);
+    return v;
+}
+__device__ __forceinline__ void qb_tc_finish_out(const QbTcPlan& tp, const float* F, const float2 (&yacc)[4], float (&yout)[4]) {
 #pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) {
-            const float4 b = B4[(c >> 2) + i4];
-            h[i4 * 4 + 0] = qb_tc_act<ACT>(__uint_as_float(v[i4 * 4 + 0]) + b.x);
-            h[i4 * 4 + 1] = qb_tc_act<ACT>(__uint_as_float(v[i4 * 4 + 1]) + b.y);
-            h[i4 * 4 + 2] = qb_tc_act<ACT>(__uint_as_float(v[i4 * 4 + 2]) + b.z);
-            h[i4 * 4 + 3] = qb_tc_act<ACT>(__uint_as_float(v[i4 * 4 + 3]) + b.w);
-        }
+    for (int o = 0; o < 4; ++o) yout[o] = o < tp.out_dim ? qb_tc_out(tp, F, o, yacc[o].x + yacc[o].y) : 0.0f;
+}
+
+template <int NI>
+__device__ __forceinline__ void qb_tc_load_x(const QbTcPlan& tp, const float* __restrict__ x, int64_t p, bool live, float (&xr)[NI]) {
 #pragma unroll
-        for (int o = 0; o < 4; ++o) {
-            if (o < od) {
-                const float4* w4 = reinterpret_cast<const float4*>(WL + o * kl + c);
-#pragma unroll
-                for (int i4 = 0; i4 < 4; ++i4) {
-                    const float4 w = w4[i4];
-                    yacc[o] = fmaf(w.x, h[i4 * 4 + 0], yacc[o]); yacc[o] = fmaf(w.y, h[i4 * 4 + 1], yacc[o]);
-                    yacc[o] = fmaf(w.z, h[i4 * 4 + 2], yacc[o]); yacc[o] = fmaf(w.w, h[i4 * 4 + 3], yacc[o]);
-                }
-            }
-        }
+    for (int q = 0; q < NI; ++q) {
+        float v = 0.0f;
+        if (q < tp.in_dim && live) v = __ldg(x + p * tp.in_dim + q);
+        xr[q] = (q == tp.in_dim) ? 1.0f : v;                       // slot in_dim: bias (selects, no indexed stores)
     }
 }
 
@@ -278,18 +406,15 @@ __device__ __forceinline__ void qb_tc_forward_tile(const QbTcPlan& tp, QbTcCtx& 
     const float* F = reinterpret_cast<const float*>(smem + tp.fl_base);
     const uint32_t tl = cx.tmem + ((uint32_t)((threadIdx.x >> 5) * 32) << 16);
     float xr[NI];
-#pragma unroll
-    for (int q = 0; q < NI; ++q) {
-        xr[q] = 0.0f;
-        if (q < tp.in_dim) { if (live) xr[q] = __ldg(x + p * tp.in_dim + q); }
-        else if (q == tp.in_dim) xr[q] = 1.0f;                     // bias slot
-    }
+    qb_tc_load_x<NI>(tp, x, p, live, xr);
     switch (tp.act0) {
         case QB_ACT_TANH: qb_tc_layer0<NI, QB_ACT_TANH>(tp, F, tl, xr); break;
         case QB_ACT_RELU: qb_tc_layer0<NI, QB_ACT_RELU>(tp, F, tl, xr); break;
         default: qb_tc_layer0<NI, QB_ACT_IDENTITY>(tp, F, tl, xr); break;
     }
-    float yacc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    float2 yacc[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) yacc[o] = make_float2(0.0f, 0.0f);
     const int last_tc = tp.n_layers - 2;
     for (int l = 1; l <= last_tc; ++l) {
         const QbTcLayer& L = tp.L[l];
@@ -318,17 +443,7 @@ __device__ __forceinline__ void qb_tc_forward_tile(const QbTcPlan& tp, QbTcCtx& 
             }
         }
     }
-#pragma unroll
-    for (int o = 0; o < 4; ++o) {
-        float v = 0.0f;
-        if (o < tp.out_dim) {
-            v = yacc[o] + F[tp.bl + o];
-            if (tp.act_last == QB_ACT_TANH) v = qb_tanh_prescaled(v);
-            else if (tp.act_last == QB_ACT_RELU) v = fmaxf(v, 0.0f);
-            if (tp.final_exp) v = expf(v);
-        }
-        yout[o] = v;
-    }
+    qb_tc_finish_out(tp, F, yacc, yout);
 }
 
 // sum of squared residuals over points [n0, n1) for the staged parameter vector (block-wide result)
@@ -353,11 +468,168 @@ __device__ __forceinline__ double qb_tc_eval_ni(const QbTcPlan& tp, QbTcCtx& cx,
     return qb_block_sum((double)ssq, reinterpret_cast<double*>(smem));
 }
 
+// Software-pipelined variant for networks with ONE tensor-core layer (in -> H -> H' -> out, H, H' <= 64, same
+// activation on both hidden layers), 256 threads: warps w and w+4 share the 32 points (tensor-memory lanes) of warp
+// quarter w and split the units / accumulator columns in chunks of 16 (even chunks: warps 0-3, odd chunks: warps
+// 4-7), so twice as many warps hide the MUFU / tcgen05.ld latencies for the same tensor-memory footprint.
+// Per tile: wait for the MMAs of tile t, compute layer 0 of tile t+1 straight into tensor memory, start the MMAs of
+// tile t+1 into the OTHER accumulator buffer (D is double-buffered), and only then read D(t) and do the tanh /
+// dot-product epilogue of tile t, which overlaps those MMAs; no register array lives across a wait.
+// The two partial dot products of a point meet through shared memory one tile later (ybuf, double-buffered).
+template <int NI, int ACT, int OD>
+__device__ __forceinline__ double qb_tc_eval_pipe(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem,
+                                                  const float* __restrict__ x, const float* __restrict__ y,
+                                                  int64_t n0, int64_t n1) {
+    const float* F = reinterpret_cast<const float*>(smem + tp.fl_base);
+    float* ybuf = reinterpret_cast<float*>(smem + tp.ybuf);          // [2][4][128]
+    const int half = threadIdx.x >> 7, pt = threadIdx.x & 127;
+    // named barriers of warps w and w+4: id 1+w for even tiles, 5+w for odd tiles (the producer may run one tile
+    // ahead of the consumer, never two: see the a_ready / mma_done chain below)
+    const int pair_id = 1 + ((threadIdx.x >> 5) & 3);
+    const uint32_t tl = cx.tmem + ((uint32_t)(((threadIdx.x >> 5) & 3) * 32) << 16);
+    const QbTcLayer& L = tp.L[1];
+    const int K = tp.h0, N = L.n_out, od = tp.out_dim;
+    const int64_t ntiles = (n1 - n0 + 127) / 128;
+    float ssq = 0.0f;
+    float xn[NI];
+    float yprev[OD], yvp[OD];
+#pragma unroll
+    for (int o = 0; o < OD; ++o) { yprev[o] = 0.0f; yvp[o] = 0.0f; }
+    bool livep = false;
+    __syncthreads();           // the previous evaluation's readers of ybuf / F are done (weights were restaged)
+    if (ntiles > 0) {
+        const int64_t p = n0 + pt;
+        qb_tc_load_x<NI>(tp, x, p, p < n1, xn);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int c = (2 * j + half) * 16;
+            if (c < K) {
+                float h[16];
+                qb_tc_l0_chunk<NI, ACT>(tp, F, c, xn, h);
+                qb_tc_split_store(tl + c, tl + tp.a_lo_col + c, h);
+            }
+        }
+        qb_tmem_st_wait();
+        qb_tc_fence_before();
+        qb_mbar_arrive(cx.abar);
+        if (threadIdx.x < 32) {
+            qb_mbar_wait(cx.abar, cx.aphase);
+            qb_tc_fence_after();
+            qb_tc_issue_warp(tp, L, cx, smem, 0u);
+        }
+        cx.aphase ^= 1u;
+        const int64_t p1 = p + 128;
+        qb_tc_load_x<NI>(tp, x, p1, p1 < n1, xn);
+    }
+    for (int64_t t = 0; t < ntiles; ++t) {
+        const bool more = t + 1 < ntiles;
+        const int64_t pc = n0 + t * 128 + pt;                        // this thread's point of tile t
+        float yv[OD];
+#pragma unroll
+        for (int o = 0; o < OD; ++o) yv[o] = 0.0f;
+        if (half == 0) {
+#pragma unroll
+            for (int o = 0; o < OD; ++o) if (o < od && pc < n1) yv[o] = __ldg(y + pc * od + o);
+        }
+        qb_mbar_wait(cx.bar, cx.phase);                              // MMAs of tile t complete: A is free, D[t&1] is ready
+        cx.phase ^= 1u;
+        qb_tc_fence_after();
+        // residual of tile t-1 (the partner warp published its partial sums one epilogue ago); these reads come
+        // before this thread's arrival below, which is what lets the partner reuse the slot two tiles later
+        if (half == 0 && t > 0) {
+            qb_pair_sync(pair_id + (int)((t - 1) & 1) * 4);
+            if (livep) {
+                const float* yb = ybuf + ((t - 1) & 1) * 512 + pt;
+#pragma unroll
+                for (int o = 0; o < OD; ++o)
+                    if (o < od) { const float r = yvp[o] - qb_tc_out(tp, F, o, yprev[o] + yb[o * 128]); ssq = fmaf(r, r, ssq); }
+            }
+        }
+        if (more) {
+            // layer 0 of tile t+1 straight into tensor memory (inputs were fetched one iteration ago), then fetch the
+            // inputs of tile t+2 and let warp 0 start the MMAs of tile t+1 into the other accumulator buffer
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int c = (2 * j + half) * 16;
+                if (c < K) {
+                    float h[16];
+                    qb_tc_l0_chunk<NI, ACT>(tp, F, c, xn, h);
+                    qb_tc_split_store(tl + c, tl + tp.a_lo_col + c, h);
+                }
+            }
+            const int64_t p2 = pc + 256;
+            qb_tc_load_x<NI>(tp, x, p2, p2 < n1, xn);
+            qb_tmem_st_wait();
+            qb_tc_fence_before();
+            qb_mbar_arrive(cx.abar);
+            if (threadIdx.x < 32) {
+                qb_mbar_wait(cx.abar, cx.aphase);
+                qb_tc_fence_after();
+                qb_tc_issue_warp(tp, L, cx, smem, (uint32_t)((t + 1) & 1) * (uint32_t)N);
+            }
+            cx.aphase ^= 1u;
+        }
+        // epilogue of tile t from D[t&1] (overlaps the MMAs of tile t+1, which write the other buffer)
+        float2 yacc[OD];
+#pragma unroll
+        for (int o = 0; o < OD; ++o) yacc[o] = make_float2(0.0f, 0.0f);
+        const uint32_t dcol = tp.d_col + (uint32_t)(t & 1) * (uint32_t)N;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int c = (2 * j + half) * 16;
+            if (c < N) {
+                uint32_t v[16];
+                qb_tmem_ld16(tl + dcol + c, v);
+                qb_tmem_ld_wait16(v);
+                float hh[16];
+                qb_tc_epi_chunk<ACT>(F + L.bias, c, v, hh);
+                qb_tc_dot_chunk<OD>(tp, F, c, hh, yacc);
+            }
+        }
+        if (half == 1) {
+            float* yb = ybuf + (t & 1) * 512 + pt;
+#pragma unroll
+            for (int o = 0; o < OD; ++o) if (o < od) yb[o * 128] = yacc[o].x + yacc[o].y;
+            qb_pair_arrive(pair_id + (int)(t & 1) * 4);
+        } else {
+#pragma unroll
+            for (int o = 0; o < OD; ++o) { yprev[o] = yacc[o].x + yacc[o].y; yvp[o] = yv[o]; }
+            livep = pc < n1;
+        }
+    }
+    if (half == 0 && ntiles > 0) {
+        qb_pair_sync(pair_id + (int)((ntiles - 1) & 1) * 4);
+        if (livep) {
+            const float* yb = ybuf + ((ntiles - 1) & 1) * 512 + pt;
+#pragma unroll
+            for (int o = 0; o < OD; ++o)
+                if (o < od) { const float r = yvp[o] - qb_tc_out(tp, F, o, yprev[o] + yb[o * 128]); ssq = fmaf(r, r, ssq); }
+        }
+    }
+    return qb_block_sum((double)ssq, reinterpret_cast<double*>(smem));
+}
+
+// Everything but the most common shape (<= 3 inputs, tanh, one tensor-core layer, one output) is compiled out of line: inlining
+// all variants into the chain kernels made them so large that the compiler stopped unrolling the chunk loops and put
+// the register arrays in local memory.
+__device__ __noinline__ double qb_tc_eval_other(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem,
+                                                const float* __restrict__ x, const float* __restrict__ y,
+                                                int64_t n0, int64_t n1) {
+    if (tp.pipe) {
+        if (tp.ni == 4 && tp.act0 == QB_ACT_TANH) return qb_tc_eval_pipe<4, QB_ACT_TANH, 4>(tp, cx, smem, x, y, n0, n1);
+        if (tp.ni == 4) return qb_tc_eval_pipe<4, QB_ACT_RELU, 4>(tp, cx, smem, x, y, n0, n1);
+        if (tp.act0 == QB_ACT_TANH) return qb_tc_eval_pipe<16, QB_ACT_TANH, 4>(tp, cx, smem, x, y, n0, n1);
+        return qb_tc_eval_pipe<16, QB_ACT_RELU, 4>(tp, cx, smem, x, y, n0, n1);
+    }
+    if (tp.ni == 4) return qb_tc_eval_ni<4>(tp, cx, smem, x, y, n0, n1);
+    return qb_tc_eval_ni<16>(tp, cx, smem, x, y, n0, n1);
+}
+
 __device__ __forceinline__ double qb_tc_eval(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem,
                                              const float* __restrict__ x, const float* __restrict__ y,
                                              int64_t n0, int64_t n1) {
-    if (tp.ni == 4) return qb_tc_eval_ni<4>(tp, cx, smem, x, y, n0, n1);
-    if (tp.ni == 8) return qb_tc_eval_ni<8>(tp, cx, smem, x, y, n0, n1);
-    return qb_tc_eval_ni<16>(tp, cx, smem, x, y, n0, n1);
+    if (tp.pipe && tp.ni == 4 && tp.act0 == QB_ACT_TANH && tp.out_dim == 1)
+        return qb_tc_eval_pipe<4, QB_ACT_TANH, 1>(tp, cx, smem, x, y, n0, n1);
+    return qb_tc_eval_other(tp, cx, smem, x, y, n0, n1);
 }
 #endif  // __CUDACC__
