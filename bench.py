@@ -364,6 +364,27 @@ def main():
                     frac=achieved / fma_peak, traffic=traffic,
                     note='FP32 CUDA-core FMA bound (not hbm/tensor): peak = live FMA micro-benchmark qb_fma_peak; '
                          'achieved = algorithmic GEMM flops (2 flop/MAC, SURVEY 8d) / CUDA-event time of the timed launches')
+    if spec['sampler'] == 'amcmc' and plan.get('tensor_core', 0):
+        # The hidden-layer GEMMs run on the tensor cores (tcgen05 kind::tf32, operands split hi/lo = 3 MMA passes for
+        # fp32-level accuracy).  Denominator: the measured dense bf16 rate (sustained figure, the kernel is timed inside a
+        # long step); TF32 runs at half of it and the 3 passes divide it by three again, so 1/6 of it is the ceiling of
+        # this algorithm on the tensor pipe.  What actually bounds the kernel is the tanh epilogue on the MUFU pipe
+        # (16 results/clk/SM): 1.25 MUFU operations per tanh (one ex2 each, one reciprocal shared by four).
+        peak_bf16, src = measured_bf16_peak()
+        sm_mhz = (clk or {}).get('sm_mhz') or 1965.0
+        n_tanh = N * sum(l.n_out for l in desc.layers[:-1])
+        mufu_ach = Kloc * args.steps * n_tanh * 1.25 / (ms_local * 1e-3)
+        mufu_peak = 16.0 * 148 * sm_mhz * 1e6
+        roofline = dict(bound='tensor', kernel='k_amcmc<float,1> (tcgen05.mma kind::tf32 x3 passes + MUFU tanh epilogue)',
+                        achieved=achieved / 1e12, peak=peak_bf16, unit='TFLOP/s', frac=achieved / 1e12 / peak_bf16,
+                        traffic=traffic, peak_source=src,
+                        tf32x3_peak=peak_bf16 / 6.0, frac_of_tf32x3_peak=achieved / 1e12 / (peak_bf16 / 6.0),
+                        fp32_core_peak=fma_peak / 1e12, x_fp32_core_peak=achieved / fma_peak,
+                        mufu=dict(achieved_gops=mufu_ach / 1e9, peak_gops=mufu_peak / 1e9, frac=mufu_ach / mufu_peak),
+                        note='achieved = algorithmic fp32 GEMM flops (2 flop/MAC, SURVEY 8d) / CUDA-event time; peak = measured '
+                             'dense bf16 TFLOP/s (%s); this kernel does 3 TF32 passes (ceiling = peak/6, frac_of_tf32x3_peak) '
+                             'and is bound by the MUFU pipe of the tanh epilogue (mufu.frac); x_fp32_core_peak compares '
+                             'with the live CUDA-core FMA peak that bounded the previous SIMT kernel' % src)
 
     # ---- end to end through the public API with host buffers
     e2e = None
@@ -385,6 +406,18 @@ def main():
     if world > 1:
         import torch.distributed as td
         td.destroy_process_group()
+
+
+def measured_bf16_peak():
+    """Dense bf16 TFLOP/s of this pool's B200s as measured by the driver (sustained figure); fallback per
+    B200_PROFILING.md when the file is absent."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d.get('bf16_tflops_sustained') or d['bf16_tflops']), 'of measured (MEASURED_PEAKS.json, sustained)'
+    except Exception:
+        return 1400.0, 'of fallback (1.4 PFLOP/s sustained)'
 
 
 def cpu_unit(spec):

@@ -221,7 +221,10 @@ int qb_vi_backward(int dtype, const void* mu, const void* rho, const void* eps, 
 int qb_fma_peak(int dtype, int variant, int64_t iters, double* flops_out_host, void* sink, void* stream);
 
 /* Launch-plan introspection for DESIGN.md / bench.py: fills out[0..7] =
- * {tile points TM, threads per block, dynamic smem bytes, N-splits S, blocks, inplace flag, 0, 0}. */
+ * {tile points TM, threads per block, dynamic smem bytes, N-splits S, blocks, inplace flag,
+ *  tensor-core path (0: CUDA-core kernel, 1: tcgen05 3xTF32, 2: same, software-pipelined), tensor-memory columns}.
+ * The tensor-core path serves the VALUE path (qb_logpost, qb_amcmc_run) of fp32 MLPs with <= 15 inputs, hidden
+ * widths that are multiples of 16 (<= 128), <= 4 outputs and no residual layers; QB_NO_TC=1 disables it. */
 int qb_plan_info(const qb_net_t* net, int dtype, int64_t K, int64_t N, int want_grad, int64_t* out);
 
 /* Number of kernel launches this library has enqueued since load (bench.py's gpu_launches). */

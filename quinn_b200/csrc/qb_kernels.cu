@@ -466,6 +466,12 @@ extern "C" int qb_plan_info(const qb_net_t* net, int dtype, int64_t K, int64_t N
     if (make_launch(net, dtype, want_grad != 0, K, N, false, &L)) return -1;
     out[0] = L.plan.TM; out[1] = L.plan.nthreads; out[2] = L.plan.smem_bytes; out[3] = L.S;
     out[4] = (int64_t)K * L.S; out[5] = L.plan.inplace; out[6] = 0; out[7] = 0;
+    QbTcPlan tp;
+    if (!want_grad && make_tc_plan(net, dtype, &tp)) {
+        // value path on the tensor cores: 128-point tiles, 128 or 256 threads, out[6] = 1 + pipelined flag,
+        // out[7] = tensor-memory columns per block
+        out[0] = 128; out[1] = tp.nthreads; out[2] = tp.smem_bytes; out[5] = 0; out[6] = 1 + tp.pipe; out[7] = tp.tmem_cols;
+    }
     return 0;
 }
 

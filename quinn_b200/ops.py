@@ -99,7 +99,8 @@ class Problem:
         out = (C.c_int64 * 8)()
         _lib.check(_lib.load().qb_plan_info(C.byref(self.cnet), self.qdt, K, self.n, 1 if want_grad else 0, out),
                    'qb_plan_info')
-        return dict(TM=out[0], threads=out[1], smem_bytes=out[2], splits=out[3], blocks=out[4], inplace=out[5])
+        return dict(TM=out[0], threads=out[1], smem_bytes=out[2], splits=out[3], blocks=out[4], inplace=out[5],
+                    tensor_core=int(out[6]), tmem_cols=int(out[7]))
 
     def theta(self, theta):
         t = as_device(theta, self.dtype, self.device)
