@@ -357,9 +357,13 @@ def main():
 
     value = units_per_step * args.steps / (ms * 1e-3)
     achieved = (Kloc if spec['sampler'] != 'predict' else spec['K'] * (xs.shape[0])) * args.steps * flop_per_unit / (ms_local * 1e-3)
-    # DRAM bytes per launch: from the ncu --set full capture profiles/r1_amcmc_r1d (653.0 MB for 4736 chain-steps of this
-    # kernel = 137.9 KB per chain-step: theta / proposal / Xm / var / pscale rows), scaled to this launch; null elsewhere
-    traffic = 137.9e3 * Kloc * args.steps if spec['sampler'] == 'amcmc' else None
+    # DRAM bytes per launch, scaled from ncu --set full captures (dram__bytes_read.sum + dram__bytes_write.sum): CUDA-core
+    # kernel profiles/r1_amcmc_r1d: 653.0 MB for 4736 chain-steps = 137.9 KB per chain-step; tensor-core kernel
+    # profiles/r1_amcmc_tc_r1f: 685.8 MB for 9472 chain-steps = 72.4 KB per chain-step (theta / proposal / Xm / var /
+    # pscale rows; the proposal row is re-read from L2 when the weights are staged); null for the other workloads
+    traffic = None
+    if spec['sampler'] == 'amcmc':
+        traffic = (72.4e3 if plan.get('tensor_core', 0) else 137.9e3) * Kloc * args.steps
     roofline = dict(bound='fp32', kernel=kernel_name, achieved=achieved / 1e12, peak=fma_peak / 1e12, unit='TFLOP/s',
                     frac=achieved / fma_peak, traffic=traffic,
                     note='FP32 CUDA-core FMA bound (not hbm/tensor): peak = live FMA micro-benchmark qb_fma_peak; '
