@@ -476,7 +476,9 @@ __device__ __forceinline__ double qb_tc_eval_ni(const QbTcPlan& tp, QbTcCtx& cx,
 // tile t+1 into the OTHER accumulator buffer (D is double-buffered), and only then read D(t) and do the tanh /
 // dot-product epilogue of tile t, which overlaps those MMAs; no register array lives across a wait.
 // The two partial dot products of a point meet through shared memory one tile later (ybuf, double-buffered).
-template <int NI, int ACT, int OD>
+// FULL: both hidden widths are 64, so every thread owns two full chunks and the chunk guards vanish (no branches
+// between the chunks: the compiler interleaves their independent dependency chains).
+template <int NI, int ACT, int OD, bool FULL>
 __device__ __forceinline__ double qb_tc_eval_pipe(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem,
                                                   const float* __restrict__ x, const float* __restrict__ y,
                                                   int64_t n0, int64_t n1) {
@@ -503,7 +505,7 @@ __device__ __forceinline__ double qb_tc_eval_pipe(const QbTcPlan& tp, QbTcCtx& c
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int c = (2 * j + half) * 16;
-            if (c < K) {
+            if (FULL || c < K) {
                 float h[16];
                 qb_tc_l0_chunk<NI, ACT>(tp, F, c, xn, h);
                 qb_tc_split_store(tl + c, tl + tp.a_lo_col + c, h);
@@ -551,7 +553,7 @@ __device__ __forceinline__ double qb_tc_eval_pipe(const QbTcPlan& tp, QbTcCtx& c
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int c = (2 * j + half) * 16;
-                if (c < K) {
+                if (FULL || c < K) {
                     float h[16];
                     qb_tc_l0_chunk<NI, ACT>(tp, F, c, xn, h);
                     qb_tc_split_store(tl + c, tl + tp.a_lo_col + c, h);
@@ -577,7 +579,7 @@ __device__ __forceinline__ double qb_tc_eval_pipe(const QbTcPlan& tp, QbTcCtx& c
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int c = (2 * j + half) * 16;
-            if (c < N) {
+            if (FULL || c < N) {
                 uint32_t v[16];
                 qb_tmem_ld16(tl + dcol + c, v);
                 qb_tmem_ld_wait16(v);
@@ -609,17 +611,17 @@ __device__ __forceinline__ double qb_tc_eval_pipe(const QbTcPlan& tp, QbTcCtx& c
     return qb_block_sum((double)ssq, reinterpret_cast<double*>(smem));
 }
 
-// Everything but the most common shape (<= 3 inputs, tanh, one tensor-core layer, one output) is compiled out of line: inlining
+// Everything but the most common shape (<= 3 inputs, tanh, one 64x64 tensor-core layer, one output) is compiled out of line: inlining
 // all variants into the chain kernels made them so large that the compiler stopped unrolling the chunk loops and put
 // the register arrays in local memory.
 __device__ __noinline__ double qb_tc_eval_other(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem,
                                                 const float* __restrict__ x, const float* __restrict__ y,
                                                 int64_t n0, int64_t n1) {
     if (tp.pipe) {
-        if (tp.ni == 4 && tp.act0 == QB_ACT_TANH) return qb_tc_eval_pipe<4, QB_ACT_TANH, 4>(tp, cx, smem, x, y, n0, n1);
-        if (tp.ni == 4) return qb_tc_eval_pipe<4, QB_ACT_RELU, 4>(tp, cx, smem, x, y, n0, n1);
-        if (tp.act0 == QB_ACT_TANH) return qb_tc_eval_pipe<16, QB_ACT_TANH, 4>(tp, cx, smem, x, y, n0, n1);
-        return qb_tc_eval_pipe<16, QB_ACT_RELU, 4>(tp, cx, smem, x, y, n0, n1);
+        if (tp.ni == 4 && tp.act0 == QB_ACT_TANH) return qb_tc_eval_pipe<4, QB_ACT_TANH, 4, false>(tp, cx, smem, x, y, n0, n1);
+        if (tp.ni == 4) return qb_tc_eval_pipe<4, QB_ACT_RELU, 4, false>(tp, cx, smem, x, y, n0, n1);
+        if (tp.act0 == QB_ACT_TANH) return qb_tc_eval_pipe<16, QB_ACT_TANH, 4, false>(tp, cx, smem, x, y, n0, n1);
+        return qb_tc_eval_pipe<16, QB_ACT_RELU, 4, false>(tp, cx, smem, x, y, n0, n1);
     }
     if (tp.ni == 4) return qb_tc_eval_ni<4>(tp, cx, smem, x, y, n0, n1);
     return qb_tc_eval_ni<16>(tp, cx, smem, x, y, n0, n1);
@@ -628,8 +630,8 @@ __device__ __noinline__ double qb_tc_eval_other(const QbTcPlan& tp, QbTcCtx& cx,
 __device__ __forceinline__ double qb_tc_eval(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem,
                                              const float* __restrict__ x, const float* __restrict__ y,
                                              int64_t n0, int64_t n1) {
-    if (tp.pipe && tp.ni == 4 && tp.act0 == QB_ACT_TANH && tp.out_dim == 1)
-        return qb_tc_eval_pipe<4, QB_ACT_TANH, 1>(tp, cx, smem, x, y, n0, n1);
+    if (tp.pipe && tp.ni == 4 && tp.act0 == QB_ACT_TANH && tp.out_dim == 1 && tp.h0 == 64 && tp.kl == 64)
+        return qb_tc_eval_pipe<4, QB_ACT_TANH, 1, true>(tp, cx, smem, x, y, n0, n1);
     return qb_tc_eval_other(tp, cx, smem, x, y, n0, n1);
 }
 #endif  // __CUDACC__
