@@ -100,7 +100,9 @@ def load(build_if_missing=True):
     if _lib is not None:
         return _lib
     path = lib_path()
-    if build_if_missing and not os.environ.get('QB_LIB') and _build.needs_build():
+    # build only when the library is absent: a stale-looking mtime must not trigger a multi-minute nvcc run inside
+    # every rank of a job (rebuild explicitly with `python -m quinn_b200.build` / __graft_entry__.build())
+    if build_if_missing and not os.environ.get('QB_LIB') and not os.path.exists(path):
         if os.path.exists('/usr/local/cuda/bin/nvcc') or os.environ.get('NVCC'):
             _build.build()
     if not os.path.exists(path):

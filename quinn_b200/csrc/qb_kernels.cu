@@ -281,18 +281,19 @@ static bool make_tc_plan(const qb_net_t* net, int dtype, QbTcPlan* tp) {
         if (l < nl - 1 && (S.n_out % 16 != 0 || S.n_out < 16 || S.n_out > 128)) return false;
         if (l >= 1 && l < nl - 1) { kmax = std::max(kmax, S.n_in); nmax = std::max(nmax, S.n_out); }
     }
-    const bool pipe = nl == 3 && kmax <= 64 && nmax <= 64 && net->layers[0].act == net->layers[1].act &&
+    const bool pipe = nl == 3 && net->layers[0].act == net->layers[1].act &&
                       (net->layers[0].act == QB_ACT_TANH || net->layers[0].act == QB_ACT_RELU) && !env_int("QB_NO_PIPE", 0);
+    const int grp = std::max(kmax, nmax) > 64 ? 4 : 2;       // column groups = warps per quarter of the tile
     const int cols = 2 * kmax + (pipe ? 2 : 1) * nmax;       // pipelined path: the accumulator is double-buffered
     if (cols > 512) return false;
     tp->n_layers = nl; tp->in_dim = net->in_dim; tp->out_dim = net->out_dim; tp->n_params = net->n_params;
-    tp->ni = net->in_dim < 4 ? 4 : 16;
+    tp->ni = (net->in_dim < 4 && !(pipe && grp == 4)) ? 4 : 16;
     tp->h0 = net->layers[0].n_out; tp->kl = net->layers[nl - 1].n_in;
     tp->act0 = net->layers[0].act; tp->act_last = net->layers[nl - 1].act; tp->final_exp = net->final_exp;
     tp->w0_off = net->layers[0].w_off; tp->b0_off = net->layers[0].b_off;
     tp->wl_off = net->layers[nl - 1].w_off; tp->bl_off = net->layers[nl - 1].b_off;
     tp->a_lo_col = kmax; tp->d_col = 2 * kmax;
-    tp->pipe = pipe ? 1 : 0;
+    tp->pipe = pipe ? grp : 0;
     tp->tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
     int off = QB_TC_HDR_BYTES;
     for (int l = 1; l < nl - 1; ++l) {
@@ -310,8 +311,8 @@ static bool make_tc_plan(const qb_net_t* net, int dtype, QbTcPlan* tp) {
     tp->bl = f; f += 4;
     long long bytes = (long long)off + (long long)f * 4;
     bytes = (bytes + 15) / 16 * 16;
-    tp->ybuf = (int)bytes; bytes += 2 * 4 * 128 * 4;
-    tp->nthreads = tp->pipe ? 256 : 128;
+    tp->ybuf = (int)bytes; bytes += 2 * 3 * 4 * 128 * 4;
+    tp->nthreads = tp->pipe ? 128 * tp->pipe : 128;
     if (bytes > QB_SMEM_MAX) return false;
     // tensor memory is 512 columns per SM: request enough shared memory that no more blocks than 512/tmem_cols
     // become resident (a further block would spin in tcgen05.alloc)
@@ -372,7 +373,7 @@ __global__ void __launch_bounds__(256, 2) k_logpost_grad(const __grid_constant__
 
 
 // kernel 1 on the tensor cores (fp32 eligible networks, see qb_tc.cuh)
-__global__ void __launch_bounds__(256, 2) k_logpost_tc(const __grid_constant__ QbTcPlan tp, const EvalArgs<float> a) {
+__global__ void __launch_bounds__(512, 1) k_logpost_tc(const __grid_constant__ QbTcPlan tp, const EvalArgs<float> a) {
     extern __shared__ __align__(128) unsigned char smem_tc[];
     QbTcCtx cx;
     qb_tc_init(tp, smem_tc, cx);
@@ -470,7 +471,7 @@ extern "C" int qb_plan_info(const qb_net_t* net, int dtype, int64_t K, int64_t N
     if (!want_grad && make_tc_plan(net, dtype, &tp)) {
         // value path on the tensor cores: 128-point tiles, 128 or 256 threads, out[6] = 1 + pipelined flag,
         // out[7] = tensor-memory columns per block
-        out[0] = 128; out[1] = tp.nthreads; out[2] = tp.smem_bytes; out[5] = 0; out[6] = 1 + tp.pipe; out[7] = tp.tmem_cols;
+        out[0] = 128; out[1] = tp.nthreads; out[2] = tp.smem_bytes; out[5] = 0; out[6] = tp.pipe ? 2 : 1; out[7] = tp.tmem_cols;
     }
     return 0;
 }
@@ -703,7 +704,7 @@ __device__ __noinline__ void qb_amcmc_post_cold(const ChainArgs<T>& c, const Amc
 
 // TC = 1 (fp32 only): the evaluation runs on the tensor cores (qb_tc.cuh), 128 or 256 threads, two blocks per SM.
 template <typename T, int TC>
-__global__ void __launch_bounds__(TC ? 256 : 512, TC ? 2 : 1)
+__global__ void __launch_bounds__(512, 1)
 k_amcmc(const __grid_constant__ QbPlan plan, const __grid_constant__ QbTcPlan tp, const __grid_constant__ ChainArgs<T> c,
         const __grid_constant__ AmcmcArgs<T> a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1086,6 +1087,25 @@ __global__ void k_moments(const T* out, long long M, long long n, T* mean, T* va
     if (var) var[i] = M > 1 ? m2 / (T)(M - 1) : T(NAN);
 }
 
+// kernel 4 on the tensor cores (member-parallel: block = member blockIdx.y x a chunk of consecutive tiles)
+__global__ void __launch_bounds__(512, 1) k_predict_tc(const __grid_constant__ QbTcPlan tp, const PredArgs<float> a) {
+    extern __shared__ __align__(128) unsigned char smem_tc[];
+    QbTcCtx cx;
+    qb_tc_init(tp, smem_tc, cx);
+    const long long m = blockIdx.y;
+    const long long n0 = (long long)blockIdx.x * a.tiles_per_block * 128, n1 = min(a.N, n0 + a.tiles_per_block * 128);
+    qb_tc_stage(tp, smem_tc, a.theta + m * tp.n_params);
+    __syncthreads();
+    qb_tc_predict(tp, cx, smem_tc, a.x, a.out + m * a.N * tp.out_dim, n0, n1);
+    qb_tc_fini(tp, cx);
+}
+template <typename T> static int launch_predict_tc(const QbTcPlan&, const PredArgs<T>&, dim3, cudaStream_t) { return qb_fail("tensor-core path is fp32 only"); }
+template <> int launch_predict_tc<float>(const QbTcPlan& tp, const PredArgs<float>& a, dim3 grid, cudaStream_t st) {
+    if (set_smem(k_predict_tc, tp.smem_bytes)) return -2;
+    k_predict_tc<<<grid, tp.nthreads, tp.smem_bytes, st>>>(tp, a);
+    return 0;
+}
+
 template <typename T>
 static int run_predict(const qb_net_t* net, int dtype, const void* theta, int64_t M, const void* x, int64_t N,
                        void* out, void* mean, void* var, cudaStream_t st) {
@@ -1101,6 +1121,24 @@ static int run_predict(const qb_net_t* net, int dtype, const void* theta, int64_
     PredArgs<T> a;
     a.theta = (const T*)theta; a.x = (const T*)x; a.M = M; a.N = N;
     a.out = (T*)out; a.mean = (T*)mean; a.var = (T*)var; a.fused = fused ? 1 : 0;
+    QbTcPlan tp;
+    if (!fused && out && M <= 65535 && make_tc_plan(net, dtype, &tp)) {
+        // tensor-core forward (qb_tc.cuh): 128-point tiles, weights staged once per block, >= 8 waves of blocks
+        const long long t128 = cdiv(N, 128);
+        long long ch = std::max<long long>(1, std::min<long long>(t128, cdiv((long long)QB_NUM_SMS * 2 * 8, M)));
+        a.tiles_per_block = cdiv(t128, ch);
+        ch = cdiv(t128, a.tiles_per_block);
+        if (launch_predict_tc<T>(tp, a, dim3((unsigned)ch, (unsigned)M), st)) return -2;
+        QB_CUDA(cudaGetLastError());
+        g_launches += 1;
+        if (want_mom) {
+            const long long n = N * P.out_dim;
+            k_moments<T><<<(unsigned)cdiv(n, 256), 256, 0, st>>>((const T*)out, M, n, (T*)mean, (T*)var);
+            QB_CUDA(cudaGetLastError());
+            g_launches += 1;
+        }
+        return 0;
+    }
     if (set_smem(k_predict<T>, P.smem_bytes)) return -2;
     long long chunks = tiles;
     a.tiles_per_block = 1;

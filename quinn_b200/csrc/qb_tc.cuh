@@ -29,7 +29,8 @@ struct QbTcPlan {
     int in_dim, ni, out_dim, n_params;  // ni: padded input width (4 or 16; slot in_dim carries the bias)
     int h0, kl;                         // width after layer 0; n_in of the last layer
     int act0, act_last, final_exp;
-    int pipe;                           // one tensor-core layer, widths <= 64: software-pipelined tile loop
+    int pipe;                           // one tensor-core layer: software-pipelined tile loop with 2 (widths <= 64) or 4
+                                        // (<= 128) column groups; 0: simple 128-thread loop
     int w0, wl, bl;                     // float indices: layer-0 rows [h0][ni], last-layer W [out][kl], last bias
     int w0_off, b0_off, wl_off, bl_off; // offsets in theta (b*_off < 0: no bias)
     int fl_base, ybuf;                  // byte offsets of the float area and of the partial-output exchange buffer
@@ -254,7 +255,11 @@ __device__ __forceinline__ void qb_tc_issue_warp(const QbTcPlan& tp, const QbTcL
         case 2: qb_tc_issue_ks<2>(d, a_hi, a_lo, bhi, blo, dhi, idesc, cx.bar); break;
         case 4: qb_tc_issue_ks<4>(d, a_hi, a_lo, bhi, blo, dhi, idesc, cx.bar); break;
         case 6: qb_tc_issue_ks<6>(d, a_hi, a_lo, bhi, blo, dhi, idesc, cx.bar); break;
-        default: qb_tc_issue_ks<8>(d, a_hi, a_lo, bhi, blo, dhi, idesc, cx.bar); break;
+        case 8: qb_tc_issue_ks<8>(d, a_hi, a_lo, bhi, blo, dhi, idesc, cx.bar); break;
+        case 10: qb_tc_issue_ks<10>(d, a_hi, a_lo, bhi, blo, dhi, idesc, cx.bar); break;
+        case 12: qb_tc_issue_ks<12>(d, a_hi, a_lo, bhi, blo, dhi, idesc, cx.bar); break;
+        case 14: qb_tc_issue_ks<14>(d, a_hi, a_lo, bhi, blo, dhi, idesc, cx.bar); break;
+        default: qb_tc_issue_ks<16>(d, a_hi, a_lo, bhi, blo, dhi, idesc, cx.bar); break;
     }
 }
 
@@ -468,43 +473,71 @@ __device__ __forceinline__ double qb_tc_eval_ni(const QbTcPlan& tp, QbTcCtx& cx,
     return qb_block_sum((double)ssq, reinterpret_cast<double*>(smem));
 }
 
-// Software-pipelined variant for networks with ONE tensor-core layer (in -> H -> H' -> out, H, H' <= 64, same
-// activation on both hidden layers), 256 threads: warps w and w+4 share the 32 points (tensor-memory lanes) of warp
-// quarter w and split the units / accumulator columns in chunks of 16 (even chunks: warps 0-3, odd chunks: warps
-// 4-7), so twice as many warps hide the MUFU / tcgen05.ld latencies for the same tensor-memory footprint.
+// Software-pipelined tile loop for networks with ONE tensor-core layer (in -> H -> H' -> out, same activation on both
+// hidden layers).  G = 2 (H, H' <= 64, 256 threads, two blocks per SM) or 4 (<= 128, 512 threads, one block per SM)
+// warps share each quarter of the tile's 128 points (tensor-memory lanes) and split the units / accumulator columns
+// in chunks of 16 (thread group g owns chunks g and G+g), so G times as many warps hide the MUFU / tcgen05.ld latencies
+// for the same tensor-memory footprint.
 // Per tile: wait for the MMAs of tile t, compute layer 0 of tile t+1 straight into tensor memory, start the MMAs of
 // tile t+1 into the OTHER accumulator buffer (D is double-buffered), and only then read D(t) and do the tanh /
 // dot-product epilogue of tile t, which overlaps those MMAs; no register array lives across a wait.
-// The two partial dot products of a point meet through shared memory one tile later (ybuf, double-buffered).
-// FULL: both hidden widths are 64, so every thread owns two full chunks and the chunk guards vanish (no branches
+// The G partial dot products of a point meet through shared memory one tile later (ybuf, double-buffered, named
+// producer / consumer barriers); group 0 finishes the point and hands the network output to the sink.
+// FULL: both hidden widths are 32*G, so every thread owns two full chunks and the chunk guards vanish (no branches
 // between the chunks: the compiler interleaves their independent dependency chains).
-template <int NI, int ACT, int OD, bool FULL>
-__device__ __forceinline__ double qb_tc_eval_pipe(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem,
-                                                  const float* __restrict__ x, const float* __restrict__ y,
-                                                  int64_t n0, int64_t n1) {
+struct QbSinkSsq {              // squared residuals against y (kernels 1 and 3)
+    const float* __restrict__ y; int od; float ssq;
+    template <int OD> __device__ __forceinline__ void prefetch(int64_t p, bool live, float (&s)[OD]) const {
+#pragma unroll
+        for (int o = 0; o < OD; ++o) { s[o] = 0.0f; if (o < od && live) s[o] = __ldg(y + p * od + o); }
+    }
+    template <int OD> __device__ __forceinline__ void consume(int64_t, bool live, const float (&s)[OD], const float (&yo)[OD]) {
+        if (live) {
+#pragma unroll
+            for (int o = 0; o < OD; ++o) if (o < od) { const float r = s[o] - yo[o]; ssq = fmaf(r, r, ssq); }
+        }
+    }
+};
+struct QbSinkStore {            // network outputs to out[p, o] (kernel 4)
+    float* __restrict__ out; int od;
+    template <int OD> __device__ __forceinline__ void prefetch(int64_t, bool, float (&s)[OD]) const {
+#pragma unroll
+        for (int o = 0; o < OD; ++o) s[o] = 0.0f;
+    }
+    template <int OD> __device__ __forceinline__ void consume(int64_t p, bool live, const float (&)[OD], const float (&yo)[OD]) {
+        if (live) {
+#pragma unroll
+            for (int o = 0; o < OD; ++o) if (o < od) out[p * od + o] = yo[o];
+        }
+    }
+};
+
+template <int NI, int ACT, int OD, bool FULL, int G, typename Sink>
+__device__ __forceinline__ void qb_tc_pipe_run(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem,
+                                               const float* __restrict__ x, int64_t n0, int64_t n1, Sink& sink) {
     const float* F = reinterpret_cast<const float*>(smem + tp.fl_base);
-    float* ybuf = reinterpret_cast<float*>(smem + tp.ybuf);          // [2][4][128]
-    const int half = threadIdx.x >> 7, pt = threadIdx.x & 127;
-    // named barriers of warps w and w+4: id 1+w for even tiles, 5+w for odd tiles (the producer may run one tile
+    float* ybuf = reinterpret_cast<float*>(smem + tp.ybuf);          // [2][3][4][128]
+    const int grp = threadIdx.x >> 7, pt = threadIdx.x & 127;
+    // named barriers of the G warps of a quarter: id 1+w for even tiles, 5+w for odd tiles (a producer may run one tile
     // ahead of the consumer, never two: see the a_ready / mma_done chain below)
     const int pair_id = 1 + ((threadIdx.x >> 5) & 3);
     const uint32_t tl = cx.tmem + ((uint32_t)(((threadIdx.x >> 5) & 3) * 32) << 16);
     const QbTcLayer& L = tp.L[1];
     const int K = tp.h0, N = L.n_out, od = tp.out_dim;
     const int64_t ntiles = (n1 - n0 + 127) / 128;
-    float ssq = 0.0f;
     float xn[NI];
-    float yprev[OD], yvp[OD];
+    float yprev[OD], sp[OD];
 #pragma unroll
-    for (int o = 0; o < OD; ++o) { yprev[o] = 0.0f; yvp[o] = 0.0f; }
+    for (int o = 0; o < OD; ++o) { yprev[o] = 0.0f; sp[o] = 0.0f; }
     bool livep = false;
+    int64_t pp = 0;
     __syncthreads();           // the previous evaluation's readers of ybuf / F are done (weights were restaged)
     if (ntiles > 0) {
         const int64_t p = n0 + pt;
         qb_tc_load_x<NI>(tp, x, p, p < n1, xn);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const int c = (2 * j + half) * 16;
+            const int c = (G * j + grp) * 16;
             if (FULL || c < K) {
                 float h[16];
                 qb_tc_l0_chunk<NI, ACT>(tp, F, c, xn, h);
@@ -526,33 +559,32 @@ __device__ __forceinline__ double qb_tc_eval_pipe(const QbTcPlan& tp, QbTcCtx& c
     for (int64_t t = 0; t < ntiles; ++t) {
         const bool more = t + 1 < ntiles;
         const int64_t pc = n0 + t * 128 + pt;                        // this thread's point of tile t
-        float yv[OD];
-#pragma unroll
-        for (int o = 0; o < OD; ++o) yv[o] = 0.0f;
-        if (half == 0) {
-#pragma unroll
-            for (int o = 0; o < OD; ++o) if (o < od && pc < n1) yv[o] = __ldg(y + pc * od + o);
-        }
+        float sv[OD];
+        if (grp == 0) sink.template prefetch<OD>(pc, pc < n1, sv);
         qb_mbar_wait(cx.bar, cx.phase);                              // MMAs of tile t complete: A is free, D[t&1] is ready
         cx.phase ^= 1u;
         qb_tc_fence_after();
-        // residual of tile t-1 (the partner warp published its partial sums one epilogue ago); these reads come
-        // before this thread's arrival below, which is what lets the partner reuse the slot two tiles later
-        if (half == 0 && t > 0) {
-            qb_pair_sync(pair_id + (int)((t - 1) & 1) * 4);
-            if (livep) {
-                const float* yb = ybuf + ((t - 1) & 1) * 512 + pt;
+        // finish tile t-1 (the partner warps published their partial sums one epilogue ago); these reads come before
+        // this thread's arrival below, which is what lets the partners reuse the slot two tiles later
+        if (grp == 0 && t > 0) {
+            asm volatile("bar.sync %0, %1;" :: "r"(pair_id + (int)((t - 1) & 1) * 4), "r"(32 * G) : "memory");
+            const float* yb = ybuf + ((t - 1) & 1) * 1536 + pt;
+            float yo[OD];
 #pragma unroll
-                for (int o = 0; o < OD; ++o)
-                    if (o < od) { const float r = yvp[o] - qb_tc_out(tp, F, o, yprev[o] + yb[o * 128]); ssq = fmaf(r, r, ssq); }
+            for (int o = 0; o < OD; ++o) {
+                float acc = yprev[o];
+#pragma unroll
+                for (int g = 1; g < G; ++g) acc += yb[((g - 1) * 4 + o) * 128];
+                yo[o] = o < od ? qb_tc_out(tp, F, o, acc) : 0.0f;
             }
+            sink.template consume<OD>(pp, livep, sp, yo);
         }
         if (more) {
             // layer 0 of tile t+1 straight into tensor memory (inputs were fetched one iteration ago), then fetch the
             // inputs of tile t+2 and let warp 0 start the MMAs of tile t+1 into the other accumulator buffer
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const int c = (2 * j + half) * 16;
+                const int c = (G * j + grp) * 16;
                 if (FULL || c < K) {
                     float h[16];
                     qb_tc_l0_chunk<NI, ACT>(tp, F, c, xn, h);
@@ -578,7 +610,7 @@ __device__ __forceinline__ double qb_tc_eval_pipe(const QbTcPlan& tp, QbTcCtx& c
         const uint32_t dcol = tp.d_col + (uint32_t)(t & 1) * (uint32_t)N;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const int c = (2 * j + half) * 16;
+            const int c = (G * j + grp) * 16;
             if (FULL || c < N) {
                 uint32_t v[16];
                 qb_tmem_ld16(tl + dcol + c, v);
@@ -588,27 +620,41 @@ __device__ __forceinline__ double qb_tc_eval_pipe(const QbTcPlan& tp, QbTcCtx& c
                 qb_tc_dot_chunk<OD>(tp, F, c, hh, yacc);
             }
         }
-        if (half == 1) {
-            float* yb = ybuf + (t & 1) * 512 + pt;
+        if (grp != 0) {
+            float* yb = ybuf + (t & 1) * 1536 + ((grp - 1) * 4) * 128 + pt;
 #pragma unroll
             for (int o = 0; o < OD; ++o) if (o < od) yb[o * 128] = yacc[o].x + yacc[o].y;
-            qb_pair_arrive(pair_id + (int)(t & 1) * 4);
+            asm volatile("bar.arrive %0, %1;" :: "r"(pair_id + (int)(t & 1) * 4), "r"(32 * G) : "memory");
         } else {
 #pragma unroll
-            for (int o = 0; o < OD; ++o) { yprev[o] = yacc[o].x + yacc[o].y; yvp[o] = yv[o]; }
+            for (int o = 0; o < OD; ++o) { yprev[o] = yacc[o].x + yacc[o].y; sp[o] = sv[o]; }
             livep = pc < n1;
+            pp = pc;
         }
     }
-    if (half == 0 && ntiles > 0) {
-        qb_pair_sync(pair_id + (int)((ntiles - 1) & 1) * 4);
-        if (livep) {
-            const float* yb = ybuf + ((ntiles - 1) & 1) * 512 + pt;
+    if (grp == 0 && ntiles > 0) {
+        asm volatile("bar.sync %0, %1;" :: "r"(pair_id + (int)((ntiles - 1) & 1) * 4), "r"(32 * G) : "memory");
+        const float* yb = ybuf + ((ntiles - 1) & 1) * 1536 + pt;
+        float yo[OD];
 #pragma unroll
-            for (int o = 0; o < OD; ++o)
-                if (o < od) { const float r = yvp[o] - qb_tc_out(tp, F, o, yprev[o] + yb[o * 128]); ssq = fmaf(r, r, ssq); }
+        for (int o = 0; o < OD; ++o) {
+            float acc = yprev[o];
+#pragma unroll
+            for (int g = 1; g < G; ++g) acc += yb[((g - 1) * 4 + o) * 128];
+            yo[o] = o < od ? qb_tc_out(tp, F, o, acc) : 0.0f;
         }
+        sink.template consume<OD>(pp, livep, sp, yo);
     }
-    return qb_block_sum((double)ssq, reinterpret_cast<double*>(smem));
+}
+
+template <int NI, int ACT, int OD, bool FULL, int G>
+__device__ __forceinline__ double qb_tc_eval_pipe(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem,
+                                                  const float* __restrict__ x, const float* __restrict__ y,
+                                                  int64_t n0, int64_t n1) {
+    QbSinkSsq sink;
+    sink.y = y; sink.od = tp.out_dim; sink.ssq = 0.0f;
+    qb_tc_pipe_run<NI, ACT, OD, FULL, G>(tp, cx, smem, x, n0, n1, sink);
+    return qb_block_sum((double)sink.ssq, reinterpret_cast<double*>(smem));
 }
 
 // Everything but the most common shape (<= 3 inputs, tanh, one 64x64 tensor-core layer, one output) is compiled out of line: inlining
@@ -617,11 +663,15 @@ __device__ __forceinline__ double qb_tc_eval_pipe(const QbTcPlan& tp, QbTcCtx& c
 __device__ __noinline__ double qb_tc_eval_other(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem,
                                                 const float* __restrict__ x, const float* __restrict__ y,
                                                 int64_t n0, int64_t n1) {
+    if (tp.pipe == 4) {
+        if (tp.act0 == QB_ACT_TANH) return qb_tc_eval_pipe<16, QB_ACT_TANH, 4, false, 4>(tp, cx, smem, x, y, n0, n1);
+        return qb_tc_eval_pipe<16, QB_ACT_RELU, 4, false, 4>(tp, cx, smem, x, y, n0, n1);
+    }
     if (tp.pipe) {
-        if (tp.ni == 4 && tp.act0 == QB_ACT_TANH) return qb_tc_eval_pipe<4, QB_ACT_TANH, 4, false>(tp, cx, smem, x, y, n0, n1);
-        if (tp.ni == 4) return qb_tc_eval_pipe<4, QB_ACT_RELU, 4, false>(tp, cx, smem, x, y, n0, n1);
-        if (tp.act0 == QB_ACT_TANH) return qb_tc_eval_pipe<16, QB_ACT_TANH, 4, false>(tp, cx, smem, x, y, n0, n1);
-        return qb_tc_eval_pipe<16, QB_ACT_RELU, 4, false>(tp, cx, smem, x, y, n0, n1);
+        if (tp.ni == 4 && tp.act0 == QB_ACT_TANH) return qb_tc_eval_pipe<4, QB_ACT_TANH, 4, false, 2>(tp, cx, smem, x, y, n0, n1);
+        if (tp.ni == 4) return qb_tc_eval_pipe<4, QB_ACT_RELU, 4, false, 2>(tp, cx, smem, x, y, n0, n1);
+        if (tp.act0 == QB_ACT_TANH) return qb_tc_eval_pipe<16, QB_ACT_TANH, 4, false, 2>(tp, cx, smem, x, y, n0, n1);
+        return qb_tc_eval_pipe<16, QB_ACT_RELU, 4, false, 2>(tp, cx, smem, x, y, n0, n1);
     }
     if (tp.ni == 4) return qb_tc_eval_ni<4>(tp, cx, smem, x, y, n0, n1);
     return qb_tc_eval_ni<16>(tp, cx, smem, x, y, n0, n1);
@@ -630,8 +680,32 @@ __device__ __noinline__ double qb_tc_eval_other(const QbTcPlan& tp, QbTcCtx& cx,
 __device__ __forceinline__ double qb_tc_eval(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem,
                                              const float* __restrict__ x, const float* __restrict__ y,
                                              int64_t n0, int64_t n1) {
-    if (tp.pipe && tp.ni == 4 && tp.act0 == QB_ACT_TANH && tp.out_dim == 1 && tp.h0 == 64 && tp.kl == 64)
-        return qb_tc_eval_pipe<4, QB_ACT_TANH, 1, true>(tp, cx, smem, x, y, n0, n1);
+    if (tp.pipe == 2 && tp.ni == 4 && tp.act0 == QB_ACT_TANH && tp.out_dim == 1 && tp.h0 == 64 && tp.kl == 64)
+        return qb_tc_eval_pipe<4, QB_ACT_TANH, 1, true, 2>(tp, cx, smem, x, y, n0, n1);
     return qb_tc_eval_other(tp, cx, smem, x, y, n0, n1);
+}
+
+// kernel 4 on the tensor cores: network outputs of points [n0, n1) for the staged parameter vector -> out[p, o]
+__device__ __forceinline__ void qb_tc_predict(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem,
+                                              const float* __restrict__ x, float* __restrict__ out, int64_t n0, int64_t n1) {
+    QbSinkStore sink;
+    sink.out = out; sink.od = tp.out_dim;
+    if (tp.pipe == 4) {
+        if (tp.act0 == QB_ACT_TANH) qb_tc_pipe_run<16, QB_ACT_TANH, 4, false, 4>(tp, cx, smem, x, n0, n1, sink);
+        else qb_tc_pipe_run<16, QB_ACT_RELU, 4, false, 4>(tp, cx, smem, x, n0, n1, sink);
+    } else if (tp.pipe) {
+        if (tp.ni == 4 && tp.act0 == QB_ACT_TANH) qb_tc_pipe_run<4, QB_ACT_TANH, 4, false, 2>(tp, cx, smem, x, n0, n1, sink);
+        else if (tp.ni == 4) qb_tc_pipe_run<4, QB_ACT_RELU, 4, false, 2>(tp, cx, smem, x, n0, n1, sink);
+        else if (tp.act0 == QB_ACT_TANH) qb_tc_pipe_run<16, QB_ACT_TANH, 4, false, 2>(tp, cx, smem, x, n0, n1, sink);
+        else qb_tc_pipe_run<16, QB_ACT_RELU, 4, false, 2>(tp, cx, smem, x, n0, n1, sink);
+    } else {
+        for (int64_t p0 = n0; p0 < n1; p0 += 128) {
+            const int64_t p = p0 + threadIdx.x;
+            float yo[4];
+            if (tp.ni == 4) qb_tc_forward_tile<4>(tp, cx, smem, x, p, p < n1, yo);
+            else qb_tc_forward_tile<16>(tp, cx, smem, x, p, p < n1, yo);
+            if (p < n1) for (int o = 0; o < tp.out_dim; ++o) out[p * tp.out_dim + o] = yo[o];
+        }
+    }
 }
 #endif  // __CUDACC__
