@@ -513,8 +513,8 @@ struct QbSinkStore {            // network outputs to out[p, o] (kernel 4)
 };
 
 template <int NI, int ACT, int OD, bool FULL, int G, typename Sink>
-__device__ __forceinline__ void qb_tc_pipe_run(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem,
-                                               const float* __restrict__ x, int64_t n0, int64_t n1, Sink& sink) {
+__device__ __forceinline__ Sink qb_tc_pipe_run(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem,
+                                               const float* __restrict__ x, int64_t n0, int64_t n1, Sink sink) {
     const float* F = reinterpret_cast<const float*>(smem + tp.fl_base);
     float* ybuf = reinterpret_cast<float*>(smem + tp.ybuf);          // [2][3][4][128]
     const int grp = threadIdx.x >> 7, pt = threadIdx.x & 127;
@@ -524,17 +524,15 @@ __device__ __forceinline__ void qb_tc_pipe_run(const QbTcPlan& tp, QbTcCtx& cx, 
     const uint32_t tl = cx.tmem + ((uint32_t)(((threadIdx.x >> 5) & 3) * 32) << 16);
     const QbTcLayer& L = tp.L[1];
     const int K = tp.h0, N = L.n_out, od = tp.out_dim;
-    const int64_t ntiles = (n1 - n0 + 127) / 128;
+    const int ntiles = (int)((n1 - n0 + 127) / 128);   // tile counters are 32-bit: this loop is register-bound
+    const int64_t pbase = n0 + pt;                     // this thread's point of tile 0
     float xn[NI];
     float yprev[OD], sp[OD];
 #pragma unroll
     for (int o = 0; o < OD; ++o) { yprev[o] = 0.0f; sp[o] = 0.0f; }
-    bool livep = false;
-    int64_t pp = 0;
     __syncthreads();           // the previous evaluation's readers of ybuf / F are done (weights were restaged)
     if (ntiles > 0) {
-        const int64_t p = n0 + pt;
-        qb_tc_load_x<NI>(tp, x, p, p < n1, xn);
+        qb_tc_load_x<NI>(tp, x, pbase, pbase < n1, xn);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int c = (G * j + grp) * 16;
@@ -553,12 +551,10 @@ __device__ __forceinline__ void qb_tc_pipe_run(const QbTcPlan& tp, QbTcCtx& cx, 
             qb_tc_issue_warp(tp, L, cx, smem, 0u);
         }
         cx.aphase ^= 1u;
-        const int64_t p1 = p + 128;
-        qb_tc_load_x<NI>(tp, x, p1, p1 < n1, xn);
     }
-    for (int64_t t = 0; t < ntiles; ++t) {
+    for (int t = 0; t < ntiles; ++t) {
         const bool more = t + 1 < ntiles;
-        const int64_t pc = n0 + t * 128 + pt;                        // this thread's point of tile t
+        const int64_t pc = pbase + (int64_t)t * 128;                 // this thread's point of tile t
         float sv[OD];
         if (grp == 0) sink.template prefetch<OD>(pc, pc < n1, sv);
         qb_mbar_wait(cx.bar, cx.phase);                              // MMAs of tile t complete: A is free, D[t&1] is ready
@@ -577,11 +573,12 @@ __device__ __forceinline__ void qb_tc_pipe_run(const QbTcPlan& tp, QbTcCtx& cx, 
                 for (int g = 1; g < G; ++g) acc += yb[((g - 1) * 4 + o) * 128];
                 yo[o] = o < od ? qb_tc_out(tp, F, o, acc) : 0.0f;
             }
-            sink.template consume<OD>(pp, livep, sp, yo);
+            sink.template consume<OD>(pc - 128, pc - 128 < n1, sp, yo);
         }
         if (more) {
-            // layer 0 of tile t+1 straight into tensor memory (inputs were fetched one iteration ago), then fetch the
-            // inputs of tile t+2 and let warp 0 start the MMAs of tile t+1 into the other accumulator buffer
+            // layer 0 of tile t+1 straight into tensor memory, then let warp 0 start the MMAs of tile t+1 into the other
+            // accumulator buffer (x is L1/L2-resident and shared by every chain: no prefetch registers are spent on it)
+            qb_tc_load_x<NI>(tp, x, pc + 128, pc + 128 < n1, xn);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int c = (G * j + grp) * 16;
@@ -591,8 +588,6 @@ __device__ __forceinline__ void qb_tc_pipe_run(const QbTcPlan& tp, QbTcCtx& cx, 
                     qb_tc_split_store(tl + c, tl + tp.a_lo_col + c, h);
                 }
             }
-            const int64_t p2 = pc + 256;
-            qb_tc_load_x<NI>(tp, x, p2, p2 < n1, xn);
             qb_tmem_st_wait();
             qb_tc_fence_before();
             qb_mbar_arrive(cx.abar);
@@ -628,8 +623,6 @@ __device__ __forceinline__ void qb_tc_pipe_run(const QbTcPlan& tp, QbTcCtx& cx, 
         } else {
 #pragma unroll
             for (int o = 0; o < OD; ++o) { yprev[o] = yacc[o].x + yacc[o].y; sp[o] = sv[o]; }
-            livep = pc < n1;
-            pp = pc;
         }
     }
     if (grp == 0 && ntiles > 0) {
@@ -643,8 +636,10 @@ __device__ __forceinline__ void qb_tc_pipe_run(const QbTcPlan& tp, QbTcCtx& cx, 
             for (int g = 1; g < G; ++g) acc += yb[((g - 1) * 4 + o) * 128];
             yo[o] = o < od ? qb_tc_out(tp, F, o, acc) : 0.0f;
         }
-        sink.template consume<OD>(pp, livep, sp, yo);
+        const int64_t pl = pbase + (int64_t)(ntiles - 1) * 128;
+        sink.template consume<OD>(pl, pl < n1, sp, yo);
     }
+    return sink;
 }
 
 template <int NI, int ACT, int OD, bool FULL, int G>
@@ -653,8 +648,8 @@ __device__ __forceinline__ double qb_tc_eval_pipe(const QbTcPlan& tp, QbTcCtx& c
                                                   int64_t n0, int64_t n1) {
     QbSinkSsq sink;
     sink.y = y; sink.od = tp.out_dim; sink.ssq = 0.0f;
-    qb_tc_pipe_run<NI, ACT, OD, FULL, G>(tp, cx, smem, x, n0, n1, sink);
-    return qb_block_sum((double)sink.ssq, reinterpret_cast<double*>(smem));
+    const QbSinkSsq done = qb_tc_pipe_run<NI, ACT, OD, FULL, G>(tp, cx, smem, x, n0, n1, sink);
+    return qb_block_sum((double)done.ssq, reinterpret_cast<double*>(smem));
 }
 
 // Everything but the most common shape (<= 3 inputs, tanh, one 64x64 tensor-core layer, one output) is compiled out of line: inlining
@@ -682,7 +677,10 @@ __device__ __forceinline__ double qb_tc_eval(const QbTcPlan& tp, QbTcCtx& cx, un
                                              int64_t n0, int64_t n1) {
     if (tp.pipe == 2 && tp.ni == 4 && tp.act0 == QB_ACT_TANH && tp.out_dim == 1 && tp.h0 == 64 && tp.kl == 64)
         return qb_tc_eval_pipe<4, QB_ACT_TANH, 1, true, 2>(tp, cx, smem, x, y, n0, n1);
-    return qb_tc_eval_other(tp, cx, smem, x, y, n0, n1);
+    QbTcCtx c2 = cx;            // only this copy has its address taken (keeps cx itself in registers)
+    const double r = qb_tc_eval_other(tp, c2, smem, x, y, n0, n1);
+    cx = c2;
+    return r;
 }
 
 // kernel 4 on the tensor cores: network outputs of points [n0, n1) for the staged parameter vector -> out[p, o]
