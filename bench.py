@@ -298,7 +298,10 @@ def main():
         advance = lambda n: [ops.predict(desc, th, xs, dtype=dt, device=dev, want_out=False, want_moments=True, cnet=cnet) for _ in range(n)]  # noqa: E731
         flop_per_unit, kernel_name = 2.0 * S, 'k_predict<float>'
         units_per_step = spec['K'] * N
-        plan = {}
+        import ctypes as _C
+        _pi = (_C.c_int64 * 8)()
+        lib.qb_plan_info(_C.byref(cnet), _lib.QB_F32, spec['K'], xs.shape[0], 0, _pi)
+        plan = dict(TM=_pi[0], threads=_pi[1], smem_bytes=_pi[2], tensor_core=int(_pi[6]), tmem_cols=int(_pi[7]))
     else:   # vi
         prob = ops.Problem(desc, x, y, 1.0, dtype=dt, device=dev)
         mu = torch.as_tensor(theta_init(spec, P, 0, 1)[0], device=dev)
@@ -368,7 +371,7 @@ def main():
                     frac=achieved / fma_peak, traffic=traffic,
                     note='FP32 CUDA-core FMA bound (not hbm/tensor): peak = live FMA micro-benchmark qb_fma_peak; '
                          'achieved = algorithmic GEMM flops (2 flop/MAC, SURVEY 8d) / CUDA-event time of the timed launches')
-    if spec['sampler'] == 'amcmc' and plan.get('tensor_core', 0):
+    if spec['sampler'] in ('amcmc', 'predict') and plan.get('tensor_core', 0):
         # The hidden-layer GEMMs run on the tensor cores (tcgen05 kind::tf32, operands split hi/lo = 3 MMA passes for
         # fp32-level accuracy).  Denominator: the measured dense bf16 rate (sustained figure, the kernel is timed inside a
         # long step); TF32 runs at half of it and the 3 passes divide it by three again, so 1/6 of it is the ceiling of
@@ -377,9 +380,11 @@ def main():
         peak_bf16, src = measured_bf16_peak()
         sm_mhz = (clk or {}).get('sm_mhz') or 1965.0
         n_tanh = N * sum(l.n_out for l in desc.layers[:-1])
-        mufu_ach = Kloc * args.steps * n_tanh * 1.25 / (ms_local * 1e-3)
+        n_evals = Kloc if spec['sampler'] == 'amcmc' else spec['K'] * xs.shape[0] / N     # N-point sweeps per step
+        mufu_ach = n_evals * args.steps * n_tanh * 1.25 / (ms_local * 1e-3)
         mufu_peak = 16.0 * 148 * sm_mhz * 1e6
-        roofline = dict(bound='tensor', kernel='k_amcmc<float,1> (tcgen05.mma kind::tf32 x3 passes + MUFU tanh epilogue)',
+        roofline = dict(bound='tensor', kernel=('k_amcmc<float,1>' if spec['sampler'] == 'amcmc' else 'k_predict_tc') +
+                        ' (tcgen05.mma kind::tf32 x3 passes + MUFU tanh epilogue)',
                         achieved=achieved / 1e12, peak=peak_bf16, unit='TFLOP/s', frac=achieved / 1e12 / peak_bf16,
                         traffic=traffic, peak_source=src,
                         tf32x3_peak=peak_bf16 / 6.0, frac_of_tf32x3_peak=achieved / 1e12 / (peak_bf16 / 6.0),

@@ -1,7 +1,7 @@
 """Tensor-core value path (quinn_b200/csrc/qb_tc.cuh: tcgen05.mma kind::tf32, operands split hi/lo) against the oracle
 and against the CUDA-core kernel it replaces: eligible architectures of every shape class (pipelined one-hidden-GEMM
 nets, deeper nets, 128-wide nets, several outputs, missing biases, relu / identity, exp output), ragged and tiny N,
-N-splits for few chains, saturation, NaN propagation, and fused AMCMC chains (replay and Philox)."""
+N-splits for few chains, saturation, NaN propagation, fused AMCMC chains (replay and Philox) and the predictive kernel."""
 import os
 
 import numpy as np
@@ -241,3 +241,43 @@ def test_tc_amcmc_philox_self_consistent_and_matches_simt_statistics():
     assert (a1 != a2).mean() < 0.01                 # decisions differ only at fp32-noise ties
     assert abs(a1.mean() - a2.mean()) < 0.01
     assert 0.02 < a1.mean() < 0.98
+
+
+@pytest.mark.parametrize('case', [0, 4, 6, 7, 9, 10, 12])
+def test_tc_predict_matches_oracle(case):
+    """Kernel 4 on the tensor cores (member-parallel forward + k_moments): outputs, mean and variance (ddof=1,
+    quinn.py:95-100) against the oracle, for pipelined (2 and 4 column groups) and deeper nets, ragged N."""
+    from quinn_b200 import ops
+    widths, acts, N, K = SHAPES[case]
+    rs = np.random.RandomState(900 + case)
+    layers, P = make_net(widths, acts)
+    final = 'exp' if case == 6 else None
+    desc = netdesc_from_layers(layers, P, final_exp=final == 'exp')
+    M = K + 2
+    N = N + 37
+    x = rs.rand(N, widths[0]) * 2 - 1
+    th = 0.5 * rs.randn(M, P)
+    out, mean, var = ops.predict(desc, th, x, dtype=torch.float32, want_out=True, want_moments=True)
+    ref = qo.predict_ens(layers, th, x, final=final)
+    scale = max(1.0, np.abs(ref).max())
+    np.testing.assert_allclose(out.double().cpu().numpy(), ref, rtol=2e-5, atol=2e-5 * scale)
+    np.testing.assert_allclose(mean.double().cpu().numpy(), ref.mean(0), rtol=2e-5, atol=2e-5 * scale)
+    np.testing.assert_allclose(var.double().cpu().numpy(), ref.var(0, ddof=1), rtol=1e-3, atol=1e-5 * scale * scale)
+    with no_tc():
+        out2, _, _ = ops.predict(desc, th, x, dtype=torch.float32, want_out=True, want_moments=False)
+    np.testing.assert_allclose(out.cpu().numpy(), out2.cpu().numpy(), rtol=2e-5, atol=2e-5 * scale)
+
+
+def test_tc_predict_moments_only_large():
+    """Moments without an output array (scratch path of ops.predict): 32 members x 20000 points of the config-3 net."""
+    from quinn_b200 import ops
+    rs = np.random.RandomState(33)
+    layers, P = make_net([10, 128, 128, 1], ['tanh', 'tanh', 'identity'])
+    desc = netdesc_from_layers(layers, P)
+    x = rs.rand(20000, 10)
+    th = rs.randn(32, P) / np.sqrt(128.0)
+    _, mean, var = ops.predict(desc, th, x, dtype=torch.float32, want_out=False, want_moments=True)
+    idx = rs.choice(20000, 200, replace=False)
+    ref = qo.predict_ens(layers, th, x[idx])
+    np.testing.assert_allclose(mean.double().cpu().numpy()[idx], ref.mean(0), rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(var.double().cpu().numpy()[idx], ref.var(0, ddof=1), rtol=1e-3, atol=1e-8)
