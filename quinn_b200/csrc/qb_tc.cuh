@@ -161,31 +161,6 @@ __device__ __forceinline__ void qb_tc_stage(const QbTcPlan& tp, unsigned char* s
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// one elected thread: D = A_lo*Bhi^T + A_hi*Blo^T + A_hi*Bhi^T, then commit to the mbarrier
-__device__ __forceinline__ void qb_tc_issue(const QbTcPlan& tp, const QbTcLayer& L, const QbTcCtx& cx, unsigned char* smem) {
-    const uint32_t K = L.n_in, N = L.n_out;
-    // instruction descriptor: D fp32, A and B tf32, both K-major, N>>3 at bit 17, M=128 (>>4) at bit 24
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t sbo = 128u * (K >> 2);
-    const uint64_t dfix = ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
-    const uint32_t bhi = qb_smem_u32(smem + L.bhi), blo = qb_smem_u32(smem + L.blo);
-    const uint32_t d = cx.tmem + tp.d_col;
-    uint32_t acc = 0;
-#pragma unroll 1
-    for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t a = cx.tmem + (pass == 0 ? tp.a_lo_col : 0);
-        const uint32_t b = pass == 1 ? blo : bhi;
-#pragma unroll 4
-        for (uint32_t s = 0; s < K / 8; ++s) {
-            const uint64_t desc = dfix | (uint64_t)(((b + s * 256u) >> 4) & 0x3FFFu);
-            asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p; }"
-                         :: "r"(d), "r"(a + s * 8u), "l"(desc), "r"(idesc), "r"(acc) : "memory");
-            acc = 1;
-        }
-    }
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(cx.bar) : "memory");
-}
-
 // tanh of four pre-activations that were already multiplied by 2*log2(e): tanh = 1 - 2/(1 + 2^z'), with ONE
 // reciprocal for the four denominators (the MUFU pipe, 16 results/clk/SM, is what bounds this kernel):
 // m = (da*db), r = 1/(m.x*m.y), 1/da = (r*m.y, r*m.x)*db ... .  z' is clamped at 30 (tanh(10.4) == 1.0f) so that the
@@ -215,6 +190,7 @@ __device__ __forceinline__ void qb_tanh4_prescaled(float2& a, float2& b) {
     a = __ffma2_rn(ia, m2, one);
     b = __ffma2_rn(ib, m2, one);
 }
+// D = A_lo*Bhi^T + A_hi*Blo^T + A_hi*Bhi^T, then commit to the mbarrier.
 // Issue by a whole (convergent) warp with one elected lane, K/8 known at compile time: every descriptor is
 // base + constant, so the 3*K/8 MMAs go out back to back (a single thread doing address arithmetic between the
 // MMAs was the critical path of the tile loop: ~80 cycles per MMA).
@@ -427,9 +403,9 @@ __device__ __forceinline__ void qb_tc_forward_tile(const QbTcPlan& tp, QbTcCtx& 
         qb_tmem_st_wait();
         qb_tc_fence_before();
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (threadIdx.x < 32) {
             qb_tc_fence_after();
-            qb_tc_issue(tp, L, cx, smem);
+            qb_tc_issue_warp(tp, L, cx, smem, 0u);
         }
         qb_mbar_wait(cx.bar, cx.phase);
         cx.phase ^= 1u;
