@@ -288,6 +288,7 @@ static bool make_tc_plan(const qb_net_t* net, int dtype, QbTcPlan* tp) {
     if (cols > 512) return false;
     tp->n_layers = nl; tp->in_dim = net->in_dim; tp->out_dim = net->out_dim; tp->n_params = net->n_params;
     tp->ni = (net->in_dim < 4 && !(pipe && grp == 4)) ? 4 : 16;
+    if (pipe && grp == 4 && net->in_dim <= 11 && net->layers[0].act == QB_ACT_TANH) tp->ni = 12;   // config 3: 10 inputs + bias
     tp->h0 = net->layers[0].n_out; tp->kl = net->layers[nl - 1].n_in;
     tp->act0 = net->layers[0].act; tp->act_last = net->layers[nl - 1].act; tp->final_exp = net->final_exp;
     tp->w0_off = net->layers[0].w_off; tp->b0_off = net->layers[0].b_off;
@@ -373,6 +374,7 @@ __global__ void __launch_bounds__(256, 2) k_logpost_grad(const __grid_constant__
 
 
 // kernel 1 on the tensor cores (fp32 eligible networks, see qb_tc.cuh)
+template <bool HOT>
 __global__ void __launch_bounds__(512, 1) k_logpost_tc(const __grid_constant__ QbTcPlan tp, const EvalArgs<float> a) {
     extern __shared__ __align__(128) unsigned char smem_tc[];
     QbTcCtx cx;
@@ -381,15 +383,20 @@ __global__ void __launch_bounds__(512, 1) k_logpost_tc(const __grid_constant__ Q
     const long long n0 = s * a.pps, n1 = min(a.N, n0 + a.pps);
     qb_tc_stage(tp, smem_tc, a.theta + k * tp.n_params);
     __syncthreads();
-    const double ssq = qb_tc_eval(tp, cx, smem_tc, a.x, a.y, n0, n1);
+    const double ssq = qb_tc_eval<HOT>(tp, cx, smem_tc, a.x, a.y, n0, n1);
     if (threadIdx.x == 0) a.part[k * a.S + s] = ssq;
     qb_tc_fini(tp, cx);
 }
 
 template <typename T> static int launch_logpost_tc(const QbTcPlan&, const EvalArgs<T>&, dim3, cudaStream_t) { return qb_fail("tensor-core path is fp32 only"); }
 template <> int launch_logpost_tc<float>(const QbTcPlan& tp, const EvalArgs<float>& a, dim3 grid, cudaStream_t st) {
-    if (set_smem(k_logpost_tc, tp.smem_bytes)) return -2;
-    k_logpost_tc<<<grid, tp.nthreads, tp.smem_bytes, st>>>(tp, a);
+    if (qb_tc_is_hot(tp)) {
+        if (set_smem(k_logpost_tc<true>, tp.smem_bytes)) return -2;
+        k_logpost_tc<true><<<grid, tp.nthreads, tp.smem_bytes, st>>>(tp, a);
+    } else {
+        if (set_smem(k_logpost_tc<false>, tp.smem_bytes)) return -2;
+        k_logpost_tc<false><<<grid, tp.nthreads, tp.smem_bytes, st>>>(tp, a);
+    }
     return 0;
 }
 
@@ -702,7 +709,8 @@ __device__ __noinline__ void qb_amcmc_post_cold(const ChainArgs<T>& c, const Amc
     qb_amcmc_post<T>(c, a, P, k, s, ssq, red, st);
 }
 
-// TC = 1 (fp32 only): the evaluation runs on the tensor cores (qb_tc.cuh), 128 or 256 threads, two blocks per SM.
+// TC = 1 / 2 (fp32 only): the evaluation runs on the tensor cores (qb_tc.cuh); 1 = the config-5 shape only (hot loop
+// fully inlined), 2 = every other eligible shape.
 template <typename T, int TC>
 __global__ void __launch_bounds__(512, 1)
 k_amcmc(const __grid_constant__ QbPlan plan, const __grid_constant__ QbTcPlan tp, const __grid_constant__ ChainArgs<T> c,
@@ -742,7 +750,7 @@ k_amcmc(const __grid_constant__ QbPlan plan, const __grid_constant__ QbTcPlan tp
         if constexpr (TC) {
             qb_tc_stage(tp, smem_raw, evalp);
             __syncthreads();
-            ssq = qb_tc_eval(tp, cx, smem_raw, c.x, c.y, 0, c.N);
+            ssq = qb_tc_eval<TC == 1>(tp, cx, smem_raw, c.x, c.y, 0, c.N);
         } else {
             ssq = qb_eval_value<T>(plan, S, evalp, c.x, c.y, 0, c.N, true);
         }
@@ -758,8 +766,13 @@ template <typename T> static int launch_amcmc_tc(const QbPlan&, const QbTcPlan&,
 }
 template <> int launch_amcmc_tc<float>(const QbPlan& plan, const QbTcPlan& tp, const ChainArgs<float>& c, const AmcmcArgs<float>& a,
                                        long long K, cudaStream_t st) {
-    if (set_smem(k_amcmc<float, 1>, tp.smem_bytes)) return -2;
-    k_amcmc<float, 1><<<(unsigned)K, tp.nthreads, tp.smem_bytes, st>>>(plan, tp, c, a);
+    if (qb_tc_is_hot(tp)) {
+        if (set_smem(k_amcmc<float, 1>, tp.smem_bytes)) return -2;
+        k_amcmc<float, 1><<<(unsigned)K, tp.nthreads, tp.smem_bytes, st>>>(plan, tp, c, a);
+    } else {
+        if (set_smem(k_amcmc<float, 2>, tp.smem_bytes)) return -2;
+        k_amcmc<float, 2><<<(unsigned)K, tp.nthreads, tp.smem_bytes, st>>>(plan, tp, c, a);
+    }
     return 0;
 }
 

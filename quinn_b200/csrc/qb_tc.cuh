@@ -26,7 +26,7 @@ struct QbTcLayer {
 };
 struct QbTcPlan {
     int n_layers;                       // layers 1 .. n_layers-2 run on the tensor cores
-    int in_dim, ni, out_dim, n_params;  // ni: padded input width (4 or 16; slot in_dim carries the bias)
+    int in_dim, ni, out_dim, n_params;  // ni: padded input width (4, 12 or 16; slot in_dim carries the bias)
     int h0, kl;                         // width after layer 0; n_in of the last layer
     int act0, act_last, final_exp;
     int pipe;                           // one tensor-core layer: software-pipelined tile loop with 2 (widths <= 64) or 4
@@ -635,7 +635,10 @@ __device__ __noinline__ double qb_tc_eval_other(const QbTcPlan& tp, QbTcCtx& cx,
                                                 const float* __restrict__ x, const float* __restrict__ y,
                                                 int64_t n0, int64_t n1) {
     if (tp.pipe == 4) {
-        if (tp.act0 == QB_ACT_TANH) return qb_tc_eval_pipe<16, QB_ACT_TANH, 4, false, 4>(tp, cx, smem, x, y, n0, n1);
+        if (tp.act0 == QB_ACT_TANH) {
+            if (tp.ni == 12) return qb_tc_eval_pipe<12, QB_ACT_TANH, 4, false, 4>(tp, cx, smem, x, y, n0, n1);
+            return qb_tc_eval_pipe<16, QB_ACT_TANH, 4, false, 4>(tp, cx, smem, x, y, n0, n1);
+        }
         return qb_tc_eval_pipe<16, QB_ACT_RELU, 4, false, 4>(tp, cx, smem, x, y, n0, n1);
     }
     if (tp.pipe) {
@@ -648,15 +651,26 @@ __device__ __noinline__ double qb_tc_eval_other(const QbTcPlan& tp, QbTcCtx& cx,
     return qb_tc_eval_ni<16>(tp, cx, smem, x, y, n0, n1);
 }
 
+// The chain kernel and kernel 1 exist in two instantiations: HOT contains only the config-5 shape (<= 3 inputs, tanh,
+// one 64x64 tensor-core layer, one output), fully inlined; the general one calls qb_tc_eval_other.  Keeping them apart
+// stops unrelated variants from disturbing the register allocation of the hot loop (it sits exactly at 128 registers:
+// every perturbation showed up as spills and -3..10 %).
+__host__ __device__ __forceinline__ bool qb_tc_is_hot(const QbTcPlan& tp) {
+    return tp.pipe == 2 && tp.ni == 4 && tp.act0 == QB_ACT_TANH && tp.out_dim == 1 && tp.h0 == 64 && tp.kl == 64 &&
+           tp.L[1].n_out == 64;
+}
+template <bool HOT>
 __device__ __forceinline__ double qb_tc_eval(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem,
                                              const float* __restrict__ x, const float* __restrict__ y,
                                              int64_t n0, int64_t n1) {
-    if (tp.pipe == 2 && tp.ni == 4 && tp.act0 == QB_ACT_TANH && tp.out_dim == 1 && tp.h0 == 64 && tp.kl == 64)
+    if constexpr (HOT) {
         return qb_tc_eval_pipe<4, QB_ACT_TANH, 1, true, 2>(tp, cx, smem, x, y, n0, n1);
-    QbTcCtx c2 = cx;            // only this copy has its address taken (keeps cx itself in registers)
-    const double r = qb_tc_eval_other(tp, c2, smem, x, y, n0, n1);
-    cx = c2;
-    return r;
+    } else {
+        QbTcCtx c2 = cx;            // only this copy has its address taken (keeps cx itself in registers)
+        const double r = qb_tc_eval_other(tp, c2, smem, x, y, n0, n1);
+        cx = c2;
+        return r;
+    }
 }
 
 // kernel 4 on the tensor cores: network outputs of points [n0, n1) for the staged parameter vector -> out[p, o]
@@ -665,7 +679,8 @@ __device__ __forceinline__ void qb_tc_predict(const QbTcPlan& tp, QbTcCtx& cx, u
     QbSinkStore sink;
     sink.out = out; sink.od = tp.out_dim;
     if (tp.pipe == 4) {
-        if (tp.act0 == QB_ACT_TANH) qb_tc_pipe_run<16, QB_ACT_TANH, 4, false, 4>(tp, cx, smem, x, n0, n1, sink);
+        if (tp.act0 == QB_ACT_TANH && tp.ni == 12) qb_tc_pipe_run<12, QB_ACT_TANH, 4, false, 4>(tp, cx, smem, x, n0, n1, sink);
+        else if (tp.act0 == QB_ACT_TANH) qb_tc_pipe_run<16, QB_ACT_TANH, 4, false, 4>(tp, cx, smem, x, n0, n1, sink);
         else qb_tc_pipe_run<16, QB_ACT_RELU, 4, false, 4>(tp, cx, smem, x, n0, n1, sink);
     } else if (tp.pipe) {
         if (tp.ni == 4 && tp.act0 == QB_ACT_TANH) qb_tc_pipe_run<4, QB_ACT_TANH, 4, false, 2>(tp, cx, smem, x, n0, n1, sink);
