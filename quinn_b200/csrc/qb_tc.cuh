@@ -579,16 +579,32 @@ __device__ __forceinline__ Sink qb_tc_pipe_run(const QbTcPlan& tp, QbTcCtx& cx, 
 #pragma unroll
         for (int o = 0; o < OD; ++o) yacc[o] = make_float2(0.0f, 0.0f);
         const uint32_t dcol = tp.d_col + (uint32_t)(t & 1) * (uint32_t)N;
+        if constexpr (FULL) {
+            // both accumulator chunks are requested before either is processed (the hot instantiation has the registers)
+            uint32_t v[2][16];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int c = (G * j + grp) * 16;
-            if (FULL || c < N) {
-                uint32_t v[16];
-                qb_tmem_ld16(tl + dcol + c, v);
-                qb_tmem_ld_wait16(v);
+            for (int j = 0; j < 2; ++j) qb_tmem_ld16(tl + dcol + (G * j + grp) * 16, v[j]);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) qb_tmem_ld_wait16(v[j]);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int c = (G * j + grp) * 16;
                 float hh[16];
-                qb_tc_epi_chunk<ACT>(F + L.bias, c, v, hh);
+                qb_tc_epi_chunk<ACT>(F + L.bias, c, v[j], hh);
                 qb_tc_dot_chunk<OD>(tp, F, c, hh, yacc);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int c = (G * j + grp) * 16;
+                if (c < N) {
+                    uint32_t v[16];
+                    qb_tmem_ld16(tl + dcol + c, v);
+                    qb_tmem_ld_wait16(v);
+                    float hh[16];
+                    qb_tc_epi_chunk<ACT>(F + L.bias, c, v, hh);
+                    qb_tc_dot_chunk<OD>(tp, F, c, hh, yacc);
+                }
             }
         }
         if (grp != 0) {
