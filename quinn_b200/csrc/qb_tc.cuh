@@ -2,19 +2,22 @@
 // ("3xTF32": a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, products accumulated in fp32 in tensor memory), which keeps
 // fp32-level accuracy (relative error of a product ~2^-21) while the 64x64 hidden-layer GEMMs leave the CUDA cores.
 //
-// One thread block = one warpgroup of 128 threads = one tile of 128 data points; thread t owns point t:
-//   layer 0 (n_in <= 15):  CUDA cores, thread-per-point; tanh; the result is split into hi/lo and written with
-//                          tcgen05.st to tensor memory as the A operand (lane = point, column = unit);
+// One tile = 128 data points = the 128 lanes of tensor memory; a thread works on one point (lane) and, in the pipelined
+// variants, on a subset of the units / accumulator columns:
+//   layer 0 (n_in <= 15):  CUDA cores; tanh; the result is split into hi/lo and written with tcgen05.st to tensor
+//                          memory as the A operand (lane = point, column = unit);
 //   hidden layers 1..L-2:  D[128 x n_out] = A[128 x n_in] * W^T, A from tensor memory, W (hi and lo) staged once per
 //                          parameter vector in shared memory in the K-major no-swizzle canonical layout (W is stored
-//                          (n_out, n_in) row-major in theta = already K-major).  One elected thread issues
-//                          3 * n_in/8 MMAs and a tcgen05.commit to an mbarrier; everybody waits on the mbarrier, reads
-//                          D back with tcgen05.ld, adds the bias, applies the activation and either writes the next
-//                          A operand or, for the last hidden layer, feeds
-//   last layer (n_out<=4): a per-thread dot product with weights broadcast from shared memory, then the residual.
+//                          (n_out, n_in) row-major in theta = already K-major).  One elected lane of a convergent warp
+//                          issues the 3 * n_in/8 MMAs back to back and a tcgen05.commit to an mbarrier; everybody waits
+//                          on the mbarrier, reads D back with tcgen05.ld, adds the bias, applies the activation and
+//                          either writes the next A operand or, for the last hidden layer, feeds
+//   last layer (n_out<=4): a per-thread dot product with weights broadcast from shared memory, then the residual
+//                          (kernels 1, 3) or the store of the network output (kernel 4).
 // Tensor-memory columns: [0,Kmax) A_hi, [Kmax,2Kmax) A_lo, [2Kmax, 2Kmax+Nmax) D (pipelined path: a second D buffer
-// follows).
-// The tensor pipe of one block overlaps with the CUDA-core phases of the other block(s) resident on the SM.
+// follows).  Two code paths: qb_tc_pipe_run (one hidden GEMM, 256 or 512 threads, mbarrier pipeline) and
+// qb_tc_forward_tile (any eligible depth, 128 threads, one block barrier per layer).
+// The tensor pipe of one block overlaps with the CUDA-core phases of the other block resident on the SM.
 #pragma once
 #include <stdint.h>
 #include "qb_plan.h"
@@ -41,9 +44,9 @@ struct QbTcPlan {
 };
 
 #ifdef __CUDACC__
-// shared-memory header: [0,320) reduction scratch, mbarriers, tensor-memory base, MMA descriptor table (<= 48 entries)
-enum { QB_TC_RED_BYTES = 320, QB_TC_BAR_OFF = 320, QB_TC_SLOT_OFF = 328, QB_TC_ABAR_OFF = 336, QB_TC_DTAB_OFF = 384,
-       QB_TC_HDR_BYTES = 768 };
+// shared-memory header: [0,320) reduction scratch, two mbarriers, tensor-memory base
+enum { QB_TC_RED_BYTES = 320, QB_TC_BAR_OFF = 320, QB_TC_SLOT_OFF = 328, QB_TC_ABAR_OFF = 336,
+       QB_TC_HDR_BYTES = 384 };
 
 struct QbTcCtx { uint32_t tmem, bar, phase, abar, aphase; };
 
@@ -242,9 +245,6 @@ __device__ __forceinline__ void qb_tc_issue_warp(const QbTcPlan& tp, const QbTcL
 __device__ __forceinline__ void qb_mbar_arrive(uint32_t bar) {
     asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" :: "r"(bar) : "memory");
 }
-// producer / consumer named barrier between the two warps that share a quarter of the tile's points
-__device__ __forceinline__ void qb_pair_arrive(int id) { asm volatile("bar.arrive %0, 64;" :: "r"(id) : "memory"); }
-__device__ __forceinline__ void qb_pair_sync(int id) { asm volatile("bar.sync %0, 64;" :: "r"(id) : "memory"); }
 
 template <int ACT> __device__ __forceinline__ void qb_tc_act4(float2& a, float2& b) {
     if (ACT == QB_ACT_TANH) qb_tanh4_prescaled(a, b);
