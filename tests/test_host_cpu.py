@@ -111,3 +111,35 @@ def test_nn_vi_num_batches_formula():
     # nn_vi.py:97-100
     f = lambda ntrn, bs: ntrn if bs == 1 else (ntrn + 1) // bs      # noqa: E731
     assert f(100, 1) == 100 and f(100, 100) == 1 and f(100, 32) == 3 and f(13, 13) == 1
+
+
+def test_tensor_core_plan_selection_is_host_logic():
+    """qb_plan_info reports which value-path kernel a call will take (include/quinn_b200.h): tcgen05 for eligible fp32
+    MLPs (config 5: 256 threads / 256 tensor-memory columns; config 3: 512 / 512), CUDA cores for fp64 and for
+    ineligible shapes, and for everything when QB_NO_TC=1."""
+    import os
+    from quinn_b200 import _lib
+    from golden_util import netdesc_from_spec
+    lib = _lib.load()
+    out = (ctypes.c_int64 * 8)()
+
+    def info(name, dtype, K=1000, N=10000, grad=0):
+        net = netdesc_from_spec(NET_CASES[name]).to_c()
+        assert lib.qb_plan_info(ctypes.byref(net), dtype, K, N, grad, out) == 0
+        return list(out)
+
+    c5 = info('mlp_c5', _lib.QB_F32)
+    assert c5[0] == 128 and c5[1] == 256 and c5[6] == 2 and c5[7] == 256 and 76 * 1024 < c5[2] <= 227 * 1024
+    c3 = info('mlp_c3', _lib.QB_F32)
+    assert c3[1] == 512 and c3[6] == 2 and c3[7] == 512
+    c2 = info('mlp_c2', _lib.QB_F32)
+    assert c2[6] == 2 and c2[7] == 128
+    assert info('mlp_c5', _lib.QB_F64)[6] == 0                  # fp64 stays on the CUDA cores
+    assert info('mlp_c5', _lib.QB_F32, grad=1)[6] == 0          # gradients too
+    assert info('rnet_c1', _lib.QB_F32)[6] == 0                 # residual nets are not eligible
+    assert info('mlp_tanh_o2', _lib.QB_F32)[6] == 0             # hidden widths 8, 6: not multiples of 16
+    os.environ['QB_NO_TC'] = '1'
+    try:
+        assert info('mlp_c5', _lib.QB_F32)[6] == 0
+    finally:
+        del os.environ['QB_NO_TC']
