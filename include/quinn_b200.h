@@ -94,6 +94,29 @@ int qb_logpost_grad(const qb_net_t* net, int dtype, const void* theta, int64_t K
                     const qb_lik_t* lik, double* lp, void* grad, void* workspace, size_t workspace_bytes,
                     void* stream);
 
+/* ---- Batched ensemble training --------------------------------------------
+ * NN_Ens.fit (quinn/solvers/nn_ens.py:51-69) trains nens members one after the other, each with
+ * Learner.fit -> nnfit (quinn/ens/learner.py:59-73, quinn/nns/nnfit.py:125-166: minibatch loop, torch Adam, best
+ * model by validation loss).  Here all members advance together: kernels 1 / 2 with per-member data, a flat Adam
+ * update and a masked row copy for the best-model bookkeeping. */
+
+/* Kernels 1 / 2 where member k sees x + k*x_stride and y + k*y_stride (strides in ELEMENTS, 0 = shared by all
+ * members): every member has its own subset (dfrac) or minibatch of data->n points.  grad may be NULL (value only).
+ * Workspace as qb_eval_workspace_bytes(net, dtype, K, data->n, grad != NULL). */
+int qb_logpost_members(const qb_net_t* net, int dtype, const void* theta, int64_t K, const qb_data_t* data,
+                       int64_t x_stride, int64_t y_stride, const qb_lik_t* lik, double* lp, void* grad,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* torch.optim.Adam step (nnfit.py:92-93 `optim.Adam(params, lr=lrate, weight_decay=wd)`) on flat arrays of n
+ * elements: g = grad*grad_scale + wd*theta; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+ * theta -= lr/(1-b1^step) * m / (sqrt(v)/sqrt(1-b2^step) + eps).  step counts from 1. */
+int qb_adam_step(int dtype, void* theta, const void* grad, void* m, void* v, int64_t n, double lr, double beta1,
+                 double beta2, double eps, double wd, int64_t step, double grad_scale, void* stream);
+
+/* dst[k,:] = src[k,:] for the rows with mask[k] != 0 (best-model tracking of nnfit.py:147-152, per member). */
+int qb_copy_rows_where(int dtype, void* dst, const void* src, const unsigned char* mask, int64_t K, int64_t P,
+                       void* stream);
+
 /* ---- Kernel 3: fused chain steps (propose + evaluate + accept) ------------------------------
  * Replaces the loop body of MCMCBase.run (quinn/mcmc/mcmc.py:65-85) together with
  * AMCMC.sampler (admcmc.py:38-74), HMC.sampler (hmc.py:27-70), MALA.sampler (mala.py:24-53).

@@ -70,6 +70,11 @@ SYMBOLS = {
                              _P, _P, C.c_size_t, _P]),
     'qb_logpost_grad': (C.c_int, [C.POINTER(qb_net_t), C.c_int, _P, C.c_int64, C.POINTER(qb_data_t),
                                   C.POINTER(qb_lik_t), _P, _P, _P, C.c_size_t, _P]),
+    'qb_logpost_members': (C.c_int, [C.POINTER(qb_net_t), C.c_int, _P, C.c_int64, C.POINTER(qb_data_t), C.c_int64, C.c_int64,
+                                     C.POINTER(qb_lik_t), _P, _P, _P, C.c_size_t, _P]),
+    'qb_adam_step': (C.c_int, [C.c_int, _P, _P, _P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
+                               C.c_double, C.c_int64, C.c_double, _P]),
+    'qb_copy_rows_where': (C.c_int, [C.c_int, _P, _P, _P, C.c_int64, C.c_int64, _P]),
     'qb_amcmc_run': (C.c_int, [C.POINTER(qb_net_t), C.c_int, C.POINTER(qb_data_t), C.POINTER(qb_lik_t),
                                C.POINTER(qb_chain_t), C.POINTER(qb_amcmc_t), C.POINTER(qb_rng_t),
                                C.POINTER(qb_record_t), C.c_int64, C.c_int64, C.c_int, _P, _P]),

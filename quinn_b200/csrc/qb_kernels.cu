@@ -343,6 +343,7 @@ static QbLikDev lik_dev(const qb_lik_t* lik) {
 // =================================================================================================
 template <typename T> struct EvalArgs {
     const T* theta; const T* x; const T* y;
+    long long xs, ys;          // per-member data strides in elements (0: x, y shared by all members)
     long long K, N; int S; long long pps;
     double* part;   // [K,S]
     T* grad;        // [K,P] (S == 1) or nullptr
@@ -357,7 +358,7 @@ __global__ void __launch_bounds__(512, 1) k_logpost(const __grid_constant__ QbPl
     const QbSmem S = qb_carve<T>(P, smem_raw);
     const long long k = blockIdx.x, s = blockIdx.y;
     const long long n0 = s * a.pps, n1 = min(a.N, n0 + a.pps);
-    const double ssq = qb_eval_value<T>(P, S, a.theta + k * P.n_params, a.x, a.y, n0, n1, true);
+    const double ssq = qb_eval_value<T>(P, S, a.theta + k * P.n_params, a.x + k * a.xs, a.y + k * a.ys, n0, n1, true);
     if (threadIdx.x == 0) a.part[k * a.S + s] = ssq;
 }
 
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(256, 2) k_logpost_grad(const __grid_constant__
     const long long k = blockIdx.x, s = blockIdx.y;
     const long long n0 = s * a.pps, n1 = min(a.N, n0 + a.pps);
     T* g = (a.S == 1) ? a.grad + k * P.n_params : a.gpart + (k * a.S + s) * P.n_params;
-    const double ssq = qb_eval_value_grad<T>(P, S, a.theta + k * P.n_params, a.x, a.y, n0, n1, a.lk.inv_sigma2, g);
+    const double ssq = qb_eval_value_grad<T>(P, S, a.theta + k * P.n_params, a.x + k * a.xs, a.y + k * a.ys, n0, n1, a.lk.inv_sigma2, g);
     if (threadIdx.x == 0) a.part[k * a.S + s] = ssq;
 }
 
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(512, 1) k_logpost_tc(const __grid_constant__ Q
     const long long n0 = s * a.pps, n1 = min(a.N, n0 + a.pps);
     qb_tc_stage(tp, smem_tc, a.theta + k * tp.n_params);
     __syncthreads();
-    const double ssq = qb_tc_eval<HOT>(tp, cx, smem_tc, a.x, a.y, n0, n1);
+    const double ssq = qb_tc_eval<HOT>(tp, cx, smem_tc, a.x + k * a.xs, a.y + k * a.ys, n0, n1);
     if (threadIdx.x == 0) a.part[k * a.S + s] = ssq;
     qb_tc_fini(tp, cx);
 }
@@ -427,7 +428,8 @@ __global__ void __launch_bounds__(128) k_finalize(const EvalArgs<T> a, int P, in
 
 template <typename T>
 static int run_eval(const qb_net_t* net, int dtype, const void* theta, int64_t K, const qb_data_t* data,
-                    const qb_lik_t* lik, double* lp, void* grad, void* ws, size_t ws_bytes, cudaStream_t st) {
+                    const qb_lik_t* lik, double* lp, void* grad, void* ws, size_t ws_bytes, cudaStream_t st,
+                    int64_t x_stride = 0, int64_t y_stride = 0) {
     const bool want_grad = grad != nullptr;
     QbLaunch L;
     if (make_launch(net, dtype, want_grad, K, data->n, false, &L)) return -1;
@@ -435,6 +437,7 @@ static int run_eval(const qb_net_t* net, int dtype, const void* theta, int64_t K
     if (ws_bytes < need || (need && !ws)) return qb_fail("workspace too small%s (need %lld bytes)", "", (long long)need);
     EvalArgs<T> a;
     a.theta = (const T*)theta; a.x = (const T*)data->x; a.y = (const T*)data->y;
+    a.xs = x_stride; a.ys = y_stride;
     a.K = K; a.N = data->n; a.S = L.S; a.pps = L.pts_per_split;
     a.part = (double*)ws;
     a.grad = (T*)grad;
@@ -495,6 +498,60 @@ extern "C" int qb_logpost_grad(const qb_net_t* net, int dtype, const void* theta
     if (!theta || !data || !lik || !lp || !grad) return qb_fail("NULL argument to qb_logpost_grad");
     if (dtype == QB_F64) return run_eval<double>(net, dtype, theta, K, data, lik, lp, grad, ws, ws_bytes, (cudaStream_t)stream);
     return run_eval<float>(net, dtype, theta, K, data, lik, lp, grad, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+/* Kernels 1 / 2 with per-member data (batched ensemble training: every member sees its own subset / minibatch). */
+extern "C" int qb_logpost_members(const qb_net_t* net, int dtype, const void* theta, int64_t K, const qb_data_t* data,
+                                  int64_t x_stride, int64_t y_stride, const qb_lik_t* lik, double* lp, void* grad,
+                                  void* ws, size_t ws_bytes, void* stream) {
+    if (!theta || !data || !lik || !lp) return qb_fail("NULL argument to qb_logpost_members");
+    if (x_stride < 0 || y_stride < 0) return qb_fail("negative data stride");
+    if (dtype == QB_F64) return run_eval<double>(net, dtype, theta, K, data, lik, lp, grad, ws, ws_bytes, (cudaStream_t)stream, x_stride, y_stride);
+    return run_eval<float>(net, dtype, theta, K, data, lik, lp, grad, ws, ws_bytes, (cudaStream_t)stream, x_stride, y_stride);
+}
+
+// Adam (torch.optim.Adam semantics, quinn/nns/nnfit.py:92-93) on a flat array: g = grad*grad_scale + wd*theta
+template <typename T>
+__global__ void k_adam(T* th, const T* g, T* m, T* v, long long n, double lr, double b1, double b2, double eps, double wd,
+                       double bc1, double bc2s, double gscale) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double t = (double)th[i];
+    const double gi = (double)g[i] * gscale + wd * t;
+    const double mi = b1 * (double)m[i] + (1.0 - b1) * gi;
+    const double vi = b2 * (double)v[i] + (1.0 - b2) * gi * gi;
+    m[i] = (T)mi; v[i] = (T)vi;
+    th[i] = (T)(t - (lr / bc1) * mi / (sqrt(vi) / bc2s + eps));
+}
+extern "C" int qb_adam_step(int dtype, void* theta, const void* grad, void* m, void* v, int64_t n, double lr, double beta1,
+                            double beta2, double eps, double wd, int64_t step, double grad_scale, void* stream) {
+    if (!theta || !grad || !m || !v || n < 1 || step < 1) return qb_fail("bad argument to qb_adam_step");
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2s = sqrt(1.0 - pow(beta2, (double)step));
+    const unsigned blocks = (unsigned)cdiv(n, 256);
+    if (dtype == QB_F64) k_adam<double><<<blocks, 256, 0, (cudaStream_t)stream>>>((double*)theta, (const double*)grad, (double*)m, (double*)v, n, lr, beta1, beta2, eps, wd, bc1, bc2s, grad_scale);
+    else k_adam<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((float*)theta, (const float*)grad, (float*)m, (float*)v, n, lr, beta1, beta2, eps, wd, bc1, bc2s, grad_scale);
+    QB_CUDA(cudaGetLastError());
+    g_launches += 1;
+    return 0;
+}
+
+// best-model tracking: dst[k,:] = src[k,:] where mask[k] != 0
+template <typename T>
+__global__ void k_copy_rows_where(T* dst, const T* src, const unsigned char* mask, long long P) {
+    const long long k = blockIdx.y;
+    if (!mask[k]) return;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) dst[k * P + i] = src[k * P + i];
+}
+extern "C" int qb_copy_rows_where(int dtype, void* dst, const void* src, const unsigned char* mask, int64_t K, int64_t P,
+                                  void* stream) {
+    if (!dst || !src || !mask || K < 1 || P < 1 || K > 65535) return qb_fail("bad argument to qb_copy_rows_where");
+    dim3 grid((unsigned)cdiv(P, 256), (unsigned)K);
+    if (dtype == QB_F64) k_copy_rows_where<double><<<grid, 256, 0, (cudaStream_t)stream>>>((double*)dst, (const double*)src, mask, P);
+    else k_copy_rows_where<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)dst, (const float*)src, mask, P);
+    QB_CUDA(cudaGetLastError());
+    g_launches += 1;
+    return 0;
 }
 
 // =================================================================================================

@@ -154,3 +154,15 @@ def _from_rnet(m, offs):
 def flatten_module(module) -> np.ndarray:
     """p_flatten (nnwrap.py:64-79) as a float64 numpy vector."""
     return np.concatenate([p.detach().cpu().double().numpy().ravel() for p in module.parameters()])
+
+
+def unflatten_module(module, flat) -> None:
+    """p_unflatten (nnwrap.py:81-106): fill the module's parameters, in parameters() order, from a flat vector."""
+    s = 0
+    flat = np.asarray(flat)
+    for p in module.parameters():
+        n = p.numel()
+        p.data = torch.as_tensor(flat[s:s + n], dtype=p.dtype, device=p.device).view(p.shape).clone()
+        s += n
+    if s != flat.size:
+        raise ValueError(f'flat vector has {flat.size} entries, the module {s} parameters')

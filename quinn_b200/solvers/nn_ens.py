@@ -1,11 +1,12 @@
-"""NN_Ens: deep ensemble with the reference's interface (quinn/solvers/nn_ens.py:9-127).  Training the
-members stays a host-side torch loop (section 8f rank 1); every predictive call is one kernel-4 launch
-over the stacked member weights."""
+"""NN_Ens: deep ensemble with the reference's interface (quinn/solvers/nn_ens.py:9-127).  The default MSE / Adam
+training runs for all members at once on the device (quinn_b200/ens/batched.py, section 8f rank 1), other nnfit
+options fall back to the member-by-member torch loop; every predictive call is one kernel-4 launch over the stacked
+member weights."""
 import numpy as np
 import torch
 
 from ..ens.learner import Learner
-from ..netdesc import netdesc_from_module, flatten_module
+from ..netdesc import netdesc_from_module, flatten_module, unflatten_module
 from .quinn import QUiNNBase
 
 
@@ -22,13 +23,57 @@ class NN_Ens(QUiNNBase):
             print(f"==========  Learner {i + 1}/{self.nens}  ============")
             learner.print_params(names_only=names_only)
 
+    # nnfit options the batched device trainer reproduces (quinn/nns/nnfit.py:15-21); anything else -> member by member
+    _BATCHED_OK = {'val', 'loss_fn', 'wd', 'optimizer', 'lrate', 'nepochs', 'batch_size', 'freq_out', 'freq_plot',
+                   'lhist_suffix', 'gradcheck', 'scheduler_lr', 'lmbd', 'loss_xy'}
+
+    def _can_batch(self, kwargs):
+        import os
+        if os.environ.get('QB_ENS_SEQUENTIAL') or not torch.cuda.is_available():
+            return False
+        if set(kwargs) - self._BATCHED_OK:
+            return False
+        if kwargs.get('loss_fn', 'mse') != 'mse' or kwargs.get('optimizer', 'adam') != 'adam':
+            return False
+        if kwargs.get('loss_xy') is not None or kwargs.get('lmbd') is not None or kwargs.get('scheduler_lr') is not None:
+            return False
+        if kwargs.get('gradcheck', False) or int(len(self.learners)) > 65535:
+            return False
+        if any(callable(getattr(l.nnmodel, 'fit', None)) for l in self.learners):
+            return False
+        try:
+            netdesc_from_module(self.learners[0].nnmodel)
+        except NotImplementedError:
+            return False
+        return True
+
     def fit(self, xtrn, ytrn, **kwargs):
-        for jens, learner in enumerate(self.learners):
-            print(f"======== Fitting Learner {jens + 1}/{self.nens} =======")
-            ntrn = ytrn.shape[0]
-            ind = np.random.permutation(ntrn)[:int(ntrn * self.dfrac)]
-            kwargs['lhist_suffix'] = f'_e{jens}'
-            learner.fit(xtrn[ind], ytrn[ind], **kwargs)
+        """Same call as the reference (nn_ens.py:51-69).  When the options are the default MSE / Adam training, all
+        members are trained TOGETHER on the device (quinn_b200/ens/batched.py): one kernel-2 launch per iteration for
+        the whole ensemble; the member subsets are drawn with the reference's np.random.permutation calls."""
+        ntrn = ytrn.shape[0]
+        if not self._can_batch(kwargs):
+            for jens, learner in enumerate(self.learners):
+                print(f"======== Fitting Learner {jens + 1}/{self.nens} =======")
+                ind = np.random.permutation(ntrn)[:int(ntrn * self.dfrac)]
+                kwargs['lhist_suffix'] = f'_e{jens}'
+                learner.fit(xtrn[ind], ytrn[ind], **kwargs)
+            return
+        import copy
+        from ..ens.batched import fit_members
+        print(f"======== Fitting {self.nens} learners together =======")
+        subsets = np.stack([np.random.permutation(ntrn)[:int(ntrn * self.dfrac)] for _ in range(self.nens)])
+        desc = netdesc_from_module(self.learners[0].nnmodel)
+        theta0 = np.stack([flatten_module(l.nnmodel) for l in self.learners])
+        res = fit_members(desc, theta0, np.asarray(xtrn), np.asarray(ytrn), subsets, val=kwargs.get('val'),
+                          nepochs=kwargs.get('nepochs', 5000), lrate=kwargs.get('lrate', 0.1), wd=kwargs.get('wd', 0.0),
+                          batch_size=kwargs.get('batch_size'), dtype=self.dtype, freq_out=kwargs.get('freq_out', 100))
+        best = res['best_theta'].double().cpu().numpy()
+        self.fit_info = {k: v.cpu().numpy() for k, v in res.items() if k in ('best_loss', 'best_epoch')}
+        for k, learner in enumerate(self.learners):
+            learner.best_model = copy.deepcopy(learner.nnmodel)
+            unflatten_module(learner.best_model, best[k])
+            learner.trained = True
 
     def member_thetas(self, order=None):
         """Flat weights of the trained members, (nens, P) float64, optionally re-ordered."""

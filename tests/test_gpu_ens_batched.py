@@ -1,0 +1,124 @@
+"""Batched ensemble training (quinn_b200/ens/batched.py) against the reference's procedure
+restated with torch on the CPU: per member an Adam loop over minibatches of its own subset with best-model tracking by
+the validation loss evaluated before each update (quinn/nns/nnfit.py:125-166, quinn/solvers/nn_ens.py:51-69)."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def torch_member_fit(net, x, y, val, nepochs, lrate, wd, batch_size, perms):
+    """nnfit's loop for ONE member (float64, CPU), minibatch orders given."""
+    net = copy.deepcopy(net).double()
+    x_, y_ = torch.as_tensor(x), torch.as_tensor(y)
+    xv_, yv_ = (x_, y_) if val is None else (torch.as_tensor(val[0]), torch.as_tensor(val[1]))
+    mse = torch.nn.MSELoss(reduction='mean')
+    opt = torch.optim.Adam(net.parameters(), lr=lrate, weight_decay=wd)
+    n = x.shape[0]
+    bs = n if batch_size is None or batch_size > n else batch_size
+    best_loss, best_model, best_epoch, hist = 1e100, copy.deepcopy(net), 0, []
+    for t in range(nepochs):
+        perm = torch.arange(n) if perms is None else torch.as_tensor(perms[t])
+        for i in range(0, n, bs):
+            idx = perm[i:i + bs]
+            loss = mse(net(x_[idx]), y_[idx])
+            with torch.no_grad():
+                crit = mse(net(xv_), yv_).item()
+            hist.append(crit)
+            if crit < best_loss:
+                best_loss, best_model, best_epoch = crit, copy.deepcopy(net), t
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+    flat = lambda m: np.concatenate([p.detach().numpy().ravel() for p in m.parameters()])     # noqa: E731
+    return flat(best_model), best_loss, best_epoch, flat(net), np.array(hist)
+
+
+@pytest.mark.parametrize('mode', ['full_own_val', 'full_shared_val', 'minibatch_own_val', 'minibatch_shared_val_wd'])
+def test_fit_members_matches_sequential_adam(mode):
+    from quinn_b200.ens.batched import fit_members
+    from quinn_b200.netdesc import netdesc_from_module, flatten_module
+    from quinn_b200.nns import MLP
+    rs = np.random.RandomState(5)
+    torch.manual_seed(5)
+    net = MLP(2, 2, (16, 16), activ='tanh').double()
+    N, K, nsub = 50, 3, 37
+    x = rs.rand(N, 2) * 2 - 1
+    y = np.stack([np.sin(2 * x.sum(1)), x[:, 0] * x[:, 1]], axis=1) + 0.01 * rs.randn(N, 2)
+    subsets = np.stack([rs.permutation(N)[:nsub] for _ in range(K)])
+    val = None if 'own_val' in mode else (rs.rand(20, 2) * 2 - 1, rs.randn(20, 2))
+    mini = mode.startswith('minibatch')
+    nepochs = 25 if mini else 120
+    bs = 10 if mini else None
+    wd = 1e-3 if mode.endswith('wd') else 0.0
+    perms = np.stack([[rs.permutation(nsub) for _ in range(nepochs)] for _ in range(K)]) if mini else None
+    # members start from different weights here (the solver starts them equal; this is the stronger test)
+    th0 = np.stack([flatten_module(net) + 0.05 * rs.randn(sum(p.numel() for p in net.parameters())) for _ in range(K)])
+    desc = netdesc_from_module(net)
+    res = fit_members(desc, th0, x, y, subsets, val=val, nepochs=nepochs, lrate=0.02, wd=wd, batch_size=bs, perms=perms,
+                      dtype=torch.float64, verbose=False)
+    from quinn_b200.netdesc import unflatten_module
+    for k in range(K):
+        nk = copy.deepcopy(net)
+        unflatten_module(nk, th0[k])
+        bt, bl, be, ft, hist = torch_member_fit(nk, x[subsets[k]], y[subsets[k]], val, nepochs, 0.02, wd, bs,
+                                                None if perms is None else perms[k])
+        np.testing.assert_allclose(res['history'][:, k].cpu().numpy(), hist, rtol=1e-7, atol=1e-12)
+        np.testing.assert_allclose(res['theta'][k].cpu().numpy(), ft, rtol=1e-6, atol=1e-8)
+        assert abs(res['best_loss'][k].item() - bl) <= 1e-8 * bl
+        assert int(res['best_epoch'][k].item()) == be
+        np.testing.assert_allclose(res['best_theta'][k].cpu().numpy(), bt, rtol=1e-6, atol=1e-8)
+
+
+def test_nn_ens_fit_batched_equals_member_by_member():
+    """NN_Ens.fit with the default MSE / Adam options takes the batched device path; with QB_ENS_SEQUENTIAL=1 it trains
+    member by member with torch (nnfit).  Same np.random subsets -> same trained members (full batch)."""
+    from quinn_b200.nns import MLP
+    from quinn_b200.solvers import NN_Ens
+    rs = np.random.RandomState(3)
+    x = rs.rand(40, 2) * 2 - 1
+    y = np.sin(3 * x[:, :1]) * x[:, 1:]
+    xt = rs.rand(11, 2) * 2 - 1
+    preds = {}
+    for seq in ('', '1'):
+        if seq:
+            os.environ['QB_ENS_SEQUENTIAL'] = '1'
+        try:
+            np.random.seed(21)
+            torch.manual_seed(21)
+            net = MLP(2, 1, (16, 16), activ='tanh')
+            ens = NN_Ens(net, nens=3, dfrac=0.75)
+            ens.fit(x, y, nepochs=60, lrate=0.01, freq_out=1000)
+            preds[seq] = np.stack([l.predict(xt) for l in ens.learners])
+        finally:
+            os.environ.pop('QB_ENS_SEQUENTIAL', None)
+    assert preds[''].shape == (3, 11, 1)
+    assert np.abs(preds[''][0] - preds[''][1]).max() > 1e-6           # members differ (different subsets)
+    np.testing.assert_allclose(preds[''], preds['1'], rtol=1e-6, atol=1e-8)
+
+
+def test_fit_members_fp32_large_ensemble_trains():
+    """256 members of the config-3 net shape (smaller data): the loss of every member goes down; fp32 evaluates the
+    validation loss on the tensor-core kernel."""
+    from quinn_b200.ens.batched import fit_members
+    from golden_util import netdesc_from_layers
+    from oracle import quinn_oracle as qo
+    rs = np.random.RandomState(8)
+    layers, P = qo.mlp_layers(10, 1, (32, 32), True, 'tanh')
+    desc = netdesc_from_layers(layers, P)
+    N, K = 512, 256
+    x = rs.rand(N, 10)
+    y = np.sin(x.sum(1, keepdims=True))
+    th0 = rs.uniform(-0.3, 0.3, size=(K, P))
+    subsets = np.stack([rs.permutation(N)[:400] for _ in range(K)])
+    res = fit_members(desc, th0, x, y, subsets, val=(x, y), nepochs=40, lrate=0.01, dtype=torch.float32, verbose=False)
+    h = res['history'].cpu().numpy()
+    assert h.shape == (40, K) and np.isfinite(h).all()
+    assert (h[-1] <= h[0]).all() and h[-1].mean() < 0.3 * h[0].mean()
+    k = 17
+    ref = np.mean((qo.forward(layers, res['best_theta'][k].double().cpu().numpy(), x) - y) ** 2)
+    assert abs(res['best_loss'][k].item() - ref) <= 1e-3 * ref
