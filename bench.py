@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the posterior-sampling hot path (contract: task statement "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c5h|c2|c3|c4] [--impl native|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c5h|c2|c3|c4|c3fit] [--impl native|reference]
 
 Default workload = BASELINE.json configs[4] / north_star target ("c5"): AMCMC, 10^5 chains TOTAL (sharded
 over the N GPUs: strong scaling), MLP 3->64->64->1 (P=4481), N=10^4 synthetic points, fp32.  A "step" is one
@@ -57,6 +57,10 @@ def workload_spec(name):
     if name == 'c4':
         return dict(name='c4', d=10, hls=(128, 128), N=100_000, K=128, sigma=0.05, sampler='vi',
                     desc='VI ELBO value+grad, 128 MC weight samples, MLP 10-128-128-1 tanh, N=1e5 Sine data')
+    if name == 'c3fit':
+        return dict(name='c3fit', d=10, hls=(128, 128), N=10_000, K=256, sigma=0.05, sampler='ensfit', dfrac=0.8,
+                    desc='NN_Ens training (SURVEY 8f rank 1): 256 members trained together, MLP 10-128-128-1 tanh, N=1e4 Sine data, '
+                         'dfrac=0.8, full-batch Adam epochs with best-model tracking')
     raise SystemExit(f'unknown workload {name}')
 
 
@@ -198,6 +202,26 @@ def cpu_baseline(spec, budget_s=18.0):
         step = (spec['L'] + 1) * t_g + t_v          # hmc.py: L+1 gradients + 1 value per step
         return dict(value=1.0 / step, unit='chain-steps/s', cores=cores, kind='port',
                     sample=f'1 chain of {spec["K"]}: {(spec["L"] + 1)} grads ({t_g * 1e3:.2f} ms) + 1 value ({t_v * 1e3:.2f} ms) per step')
+    if spec['sampler'] == 'ensfit':
+        # the reference's procedure for ONE member (nnfit.py:125-166): torch Adam on the MSE, full batch, validation loss
+        # on the member's own data before each update; members are trained one after the other (nn_ens.py:56-66)
+        from quinn_b200.nns import MLP
+        net = MLP(spec['d'], 1, spec['hls'], activ='tanh').double()
+        nsub = int(spec['N'] * spec['dfrac'])
+        xt, yt = torch.as_tensor(x[:nsub]), torch.as_tensor(y[:nsub])
+        opt = torch.optim.Adam(net.parameters(), lr=0.01)
+        mse = torch.nn.MSELoss(reduction='mean')
+
+        def epoch():
+            loss = mse(net(xt), yt)
+            with torch.no_grad():
+                mse(net(xt), yt).item()
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+        t_e = rate(epoch, 10.0)
+        return dict(value=1.0 / t_e, unit='member-epochs/s', cores=cores, kind='port',
+                    sample=f'1 member of {spec["K"]}: full-batch Adam epoch on {nsub} points ({t_e * 1e3:.2f} ms), members sequential')
     # vi: value+grad per MC sample
     t_g = rate(lambda: port.logpostgrad(th, x, ylist, spec['sigma']), 10.0)
     return dict(value=1.0 / t_g, unit='MC-sample evals/s', cores=cores, kind='port',
@@ -227,7 +251,7 @@ def run_reference_arm(args, spec):
 
 def metric_name(spec):
     return {'amcmc': 'MCMC chain-steps/sec', 'hmc': 'MCMC chain-steps/sec', 'predict': 'predictive member-points/sec',
-            'vi': 'VI MC-sample evals/sec'}[spec['sampler']]
+            'vi': 'VI MC-sample evals/sec', 'ensfit': 'ensemble-training member-epochs/sec'}[spec['sampler']]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -302,6 +326,26 @@ def main():
         _pi = (_C.c_int64 * 8)()
         lib.qb_plan_info(_C.byref(cnet), _lib.QB_F32, spec['K'], xs.shape[0], 0, _pi)
         plan = dict(TM=_pi[0], threads=_pi[1], smem_bytes=_pi[2], tensor_core=int(_pi[6]), tmem_cols=int(_pi[7]))
+    elif spec['sampler'] == 'ensfit':
+        # members are sharded over ranks; every member has its own dfrac subset (nn_ens.py:62-63); one step = one
+        # full-batch epoch of every member: kernel 2 with per-member data + best-model copy + Adam
+        from quinn_b200.ens.batched import MemberTrainer
+        nsub = int(N * spec['dfrac'])
+        rs_s = np.random.RandomState(99)
+        subsets = np.stack([rs_s.permutation(N)[:nsub] for _ in range(spec['K'])])[lo:hi]
+        trainer = MemberTrainer(desc, theta_init(spec, P, lo, hi), x, y, subsets, val=None, lrate=0.01, dtype=dt, device=dev)
+        epoch_no = [0]
+
+        def advance(n):
+            for _ in range(n):
+                trainer.epoch(epoch_no[0])
+                epoch_no[0] += 1
+        F_fit = 6.0 * nsub * S - 2.0 * nsub * desc.layers[0].n_in * desc.layers[0].n_out
+        flop_per_unit, kernel_name = F_fit, 'k_logpost_grad<float>'
+        units_per_step = spec['K']
+        _pi = (__import__('ctypes').c_int64 * 8)()
+        lib.qb_plan_info(__import__('ctypes').byref(desc.to_c()), _lib.QB_F32, Kloc, nsub, 1, _pi)
+        plan = dict(TM=_pi[0], threads=_pi[1], smem_bytes=_pi[2], splits=_pi[3], blocks=_pi[4], tensor_core=int(_pi[6]))
     else:   # vi
         prob = ops.Problem(desc, x, y, 1.0, dtype=dt, device=dev)
         mu = torch.as_tensor(theta_init(spec, P, 0, 1)[0], device=dev)
@@ -430,7 +474,8 @@ def measured_bf16_peak():
 
 
 def cpu_unit(spec):
-    return {'amcmc': 'chain-steps/s', 'hmc': 'chain-steps/s', 'predict': 'member-points/s', 'vi': 'MC-sample evals/s'}[spec['sampler']]
+    return {'amcmc': 'chain-steps/s', 'hmc': 'chain-steps/s', 'predict': 'member-points/s', 'vi': 'MC-sample evals/s',
+            'ensfit': 'member-epochs/s'}[spec['sampler']]
 
 
 def run_e2e(spec, desc, x, y, th0_host, lo, args, dev, world):
@@ -461,6 +506,28 @@ def run_e2e(spec, desc, x, y, th0_host, lo, args, dev, world):
         d2h = (2 * Kl * P * 4 + Kl * P * 4 + Kl * (2 * (steps + 1) * 8 + steps + 16)) / steps     # chain[K,2,P], MAP, scalars
         return dict(value=spec['K'] * steps / dtm, unit='chain-steps/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                     api='AMCMC/HMC.run(nmcmc=steps, param_ini=host[K,P]) -> host result dict (chain, mapparams, logpost, alphas, accrate); 4 shards pipelined on 2 streams when the states exceed 256 MB')
+    if spec['sampler'] == 'ensfit':
+        from quinn_b200.nns import MLP
+        from quinn_b200.solvers import NN_Ens
+        Kl = th0_host.shape[0]
+        net = MLP(spec['d'], 1, spec['hls'], activ='tanh')
+
+        def once():
+            np.random.seed(4)
+            ens = NN_Ens(net, nens=Kl, dfrac=spec['dfrac'], dtype=torch.float32)
+            ens.fit(x, y, nepochs=steps, lrate=0.01, freq_out=0)              # host data in, trained torch modules out
+            torch.cuda.synchronize()
+            return ens
+        once()
+        dist.barrier()
+        t0 = time.perf_counter()
+        once()
+        dist.barrier()
+        dtm = dist.max_over_ranks(time.perf_counter() - t0)
+        return dict(value=spec['K'] * steps / dtm, unit='member-epochs/s', h2d_bytes_per_step=(x.size + y.size + Kl * P) * 4 / steps,
+                    d2h_bytes_per_step=Kl * P * 4 / steps,
+                    api='NN_Ens(net, nens, dfrac).fit(x, y, nepochs=steps) from host arrays -> trained member modules '
+                        '(includes building the K learners and unflattening the best parameters)')
     if spec['sampler'] == 'predict':
         plo, phi = dist.shard_range(spec['N'], *dist.env_rank_world()[:2])
         xh = torch.from_numpy(np.ascontiguousarray(x[plo:phi], dtype=np.float32)).pin_memory()

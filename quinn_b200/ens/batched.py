@@ -58,6 +58,80 @@ class _MemberEval:
         return -(2.0 * self.lp + n * LOG_2PI) / (n * self.desc.out_dim)
 
 
+class MemberTrainer:
+    """State of a batched ensemble fit; `epoch(t, perm_t)` advances every member by one epoch (all its minibatches)."""
+
+    def __init__(self, desc, theta0, xtrn, ytrn, subsets, val=None, lrate=0.1, wd=0.0, batch_size=None,
+                 dtype=torch.float64, device='cuda'):
+        if not torch.cuda.is_available():
+            raise RuntimeError('batched ensemble training needs a CUDA device (there is no CPU fallback)')
+        self.device = device = torch.device(device)
+        self.desc, self.dtype, self.lrate, self.wd = desc, dtype, float(lrate), float(wd)
+        self.lib = _lib.load()
+        subsets = torch.as_tensor(np.asarray(subsets), dtype=torch.long, device=device)
+        self.K, self.nsub = K, nsub = subsets.shape
+        self.P = P = desc.n_params
+        th0 = as_device(theta0, dtype, device)
+        self.theta = (th0[None, :].repeat(K, 1) if th0.dim() == 1 else th0.clone()).contiguous()
+        if self.theta.shape != (K, P):
+            raise ValueError(f'theta0 must be [P] or [K,P] with K={K}, P={P}')
+        x_all = as_device(xtrn, dtype, device)
+        y_all = as_device(np.asarray(ytrn).reshape(len(ytrn), -1), dtype, device)
+        self.xs = x_all[subsets].contiguous()             # [K, nsub, d]: every member's own training subset
+        self.ys = y_all[subsets].contiguous()
+        self.own_val = val is None
+        if val is None:
+            self.xv, self.yv = self.xs, self.ys
+        else:
+            self.xv = as_device(np.asarray(val[0]), dtype, device).contiguous()
+            self.yv = as_device(np.asarray(val[1]).reshape(len(val[1]), -1), dtype, device).contiguous()
+        if batch_size is None or batch_size > nsub:
+            batch_size = nsub
+        self.batch_size = int(batch_size)
+        self.full_batch = self.batch_size == nsub
+        self.ev = _MemberEval(desc, K, dtype, device)
+        self.qdt = qb_dtype(dtype)
+        self.m = torch.zeros_like(self.theta)
+        self.v = torch.zeros_like(self.theta)
+        self.best_theta = self.theta.clone()
+        self.best_loss = torch.full((K,), 1.0e100, dtype=torch.float64, device=device)
+        self.best_epoch = torch.zeros(K, dtype=torch.long, device=device)
+        self.karange = torch.arange(K, device=device)[:, None]
+        self.step = 0
+        self.last_crit = None
+
+    def epoch(self, t, perm_t=None, history=None):
+        ev, K, P, lib = self.ev, self.K, self.P, self.lib
+        for i in range(0, self.nsub, self.batch_size):
+            if self.full_batch:
+                xb, yb = self.xs, self.ys
+            else:
+                idx = perm_t[:, i:i + self.batch_size]                # [K, b] positions inside each member's subset
+                xb = self.xs[self.karange, idx].contiguous()
+                yb = self.ys[self.karange, idx].contiguous()
+            loss_trn = ev(self.theta, xb, yb, True)                   # fills ev.grad = d lp / d theta
+            nb = xb.shape[1]
+            if self.own_val and self.full_batch:
+                crit = loss_trn                                       # validation data == the minibatch
+            else:
+                crit = ev(self.theta, self.xv, self.yv, False)
+            better = crit < self.best_loss                            # before the update (nnfit.py:143-152)
+            mask = better.to(torch.uint8)
+            with torch.cuda.device(self.device):
+                _lib.check(lib.qb_copy_rows_where(self.qdt, _ptr(self.best_theta), _ptr(self.theta), _ptr(mask), K, P,
+                                                  _stream()), 'qb_copy_rows_where')
+            self.best_loss = torch.where(better, crit, self.best_loss)
+            self.best_epoch = torch.where(better, torch.full_like(self.best_epoch, t), self.best_epoch)
+            if history is not None:
+                history.append(crit.clone())
+            self.last_crit = crit
+            self.step += 1
+            with torch.cuda.device(self.device):
+                _lib.check(lib.qb_adam_step(self.qdt, _ptr(self.theta), _ptr(ev.grad), _ptr(self.m), _ptr(self.v), K * P,
+                                            self.lrate, 0.9, 0.999, 1e-8, self.wd, self.step,
+                                            -2.0 / (nb * self.desc.out_dim), _stream()), 'qb_adam_step')
+
+
 def fit_members(desc, theta0, xtrn, ytrn, subsets, val=None, nepochs=5000, lrate=0.1, wd=0.0, batch_size=None,
                 perms=None, dtype=torch.float64, device='cuda', freq_out=100, verbose=True):
     """Train K members together.  theta0: [K,P] (or [P], replicated); subsets: [K, nsub] integer rows of xtrn that
@@ -65,82 +139,25 @@ def fit_members(desc, theta0, xtrn, ytrn, subsets, val=None, nepochs=5000, lrate
     all members; perms: optional [K, nepochs, nsub] minibatch orders (otherwise drawn with torch.randperm in the
     reference's member-major order when that array is small, else epoch by epoch).
     Returns dict(best_theta [K,P], best_loss [K], best_epoch [K], theta [K,P], history [niter, K] of validation MSE)."""
-    if not torch.cuda.is_available():
-        raise RuntimeError('batched ensemble training needs a CUDA device (there is no CPU fallback)')
-    device = torch.device(device)
-    lib = _lib.load()
-    subsets = torch.as_tensor(np.asarray(subsets), dtype=torch.long, device=device)
-    K, nsub = subsets.shape
-    P = desc.n_params
-    th0 = as_device(theta0, dtype, device)
-    theta = (th0[None, :].repeat(K, 1) if th0.dim() == 1 else th0.clone()).contiguous()
-    if theta.shape != (K, P):
-        raise ValueError(f'theta0 must be [P] or [K,P] with K={K}, P={P}')
-    x_all = as_device(xtrn, dtype, device)
-    y_all = as_device(np.asarray(ytrn).reshape(len(ytrn), -1), dtype, device)
-    xs = x_all[subsets].contiguous()                  # [K, nsub, d]: every member's own training subset
-    ys = y_all[subsets].contiguous()
-    if val is None:
-        xv, yv = xs, ys
-    else:
-        xv = as_device(np.asarray(val[0]), dtype, device).contiguous()
-        yv = as_device(np.asarray(val[1]).reshape(len(val[1]), -1), dtype, device).contiguous()
-    if batch_size is None or batch_size > nsub:
-        batch_size = nsub
-    full_batch = batch_size == nsub
-    starts = list(range(0, nsub, batch_size))
+    tr = MemberTrainer(desc, theta0, xtrn, ytrn, subsets, val=val, lrate=lrate, wd=wd, batch_size=batch_size, dtype=dtype,
+                       device=device)
+    K, nsub, device = tr.K, tr.nsub, tr.device
     if perms is not None:
         perms = torch.as_tensor(np.asarray(perms), dtype=torch.long, device=device)
-    elif not full_batch and K * nepochs * nsub <= 5 * 10 ** 7:
+    elif not tr.full_batch and K * nepochs * nsub <= 5 * 10 ** 7:
         # the reference's order of torch.randperm calls: all epochs of member 0, then member 1, ... (nn_ens.py:56-66)
         perms = torch.stack([torch.stack([torch.randperm(nsub) for _ in range(nepochs)]) for _ in range(K)]).to(device)
-    ev = _MemberEval(desc, K, dtype, device)
-    qdt = qb_dtype(dtype)
-    m = torch.zeros_like(theta)
-    v = torch.zeros_like(theta)
-    best_theta = theta.clone()
-    best_loss = torch.full((K,), 1.0e100, dtype=torch.float64, device=device)
-    best_epoch = torch.zeros(K, dtype=torch.long, device=device)
     history = []
-    karange = torch.arange(K, device=device)[:, None]
-    step = 0
     for t in range(nepochs):
-        if full_batch:
+        if tr.full_batch:
             perm_t = None
         elif perms is not None:
             perm_t = perms[:, t]
         else:
             perm_t = torch.stack([torch.randperm(nsub) for _ in range(K)]).to(device)
-        for i in starts:
-            if full_batch:
-                xb, yb = xs, ys
-            else:
-                idx = perm_t[:, i:i + batch_size]                     # [K, b] positions inside each member's subset
-                xb = xs[karange, idx].contiguous()
-                yb = ys[karange, idx].contiguous()
-            loss_trn = ev(theta, xb, yb, True)                        # fills ev.grad = d lp / d theta
-            nb = xb.shape[1]
-            if val is None and full_batch:
-                crit = loss_trn                                       # validation data == the minibatch
-            else:
-                grad_keep = ev.grad
-                crit = ev(theta, xv, yv, False).clone()
-                assert ev.grad is grad_keep
-            better = crit < best_loss                                 # before the update (nnfit.py:143-152)
-            mask = better.to(torch.uint8)
-            with torch.cuda.device(device):
-                _lib.check(lib.qb_copy_rows_where(qdt, _ptr(best_theta), _ptr(theta), _ptr(mask), K, P, _stream()),
-                           'qb_copy_rows_where')
-            best_loss = torch.where(better, crit, best_loss)
-            best_epoch = torch.where(better, torch.full_like(best_epoch, t), best_epoch)
-            history.append(crit.clone())
-            step += 1
-            with torch.cuda.device(device):
-                _lib.check(lib.qb_adam_step(qdt, _ptr(theta), _ptr(ev.grad), _ptr(m), _ptr(v), K * P, float(lrate), 0.9,
-                                            0.999, 1e-8, float(wd), step, -2.0 / (nb * desc.out_dim), _stream()),
-                           'qb_adam_step')
+        tr.epoch(t, perm_t, history)
         if verbose and freq_out and ((t + 1) % freq_out == 0 or t == 0 or t == nepochs - 1):
-            print(f'{t + 1:>10}{step:>10}   validation MSE: mean {history[-1].mean().item():.6f} '
-                  f'best {best_loss.mean().item():.6f}', flush=True)
-    return dict(best_theta=best_theta, best_loss=best_loss, best_epoch=best_epoch, theta=theta,
+            print(f'{t + 1:>10}{tr.step:>10}   validation MSE: mean {history[-1].mean().item():.6f} '
+                  f'best {tr.best_loss.mean().item():.6f}', flush=True)
+    return dict(best_theta=tr.best_theta, best_loss=tr.best_loss, best_epoch=tr.best_epoch, theta=tr.theta,
                 history=torch.stack(history) if history else torch.empty((0, K), device=device))

@@ -39,8 +39,11 @@ class NN_Ens(QUiNNBase):
             return False
         if kwargs.get('gradcheck', False) or int(len(self.learners)) > 65535:
             return False
-        if any(callable(getattr(l.nnmodel, 'fit', None)) for l in self.learners):
-            return False
+        from ..nns.nnbase import MLPBase
+        for l in self.learners:       # a model with its own training procedure keeps it (learner.py:66-70); MLPBase.fit IS nnfit
+            f = getattr(type(l.nnmodel), 'fit', None)
+            if f is not None and f is not MLPBase.fit:
+                return False
         try:
             netdesc_from_module(self.learners[0].nnmodel)
         except NotImplementedError:
@@ -52,6 +55,7 @@ class NN_Ens(QUiNNBase):
         members are trained TOGETHER on the device (quinn_b200/ens/batched.py): one kernel-2 launch per iteration for
         the whole ensemble; the member subsets are drawn with the reference's np.random.permutation calls."""
         ntrn = ytrn.shape[0]
+        self.batched_fit = False
         if not self._can_batch(kwargs):
             for jens, learner in enumerate(self.learners):
                 print(f"======== Fitting Learner {jens + 1}/{self.nens} =======")
@@ -70,6 +74,7 @@ class NN_Ens(QUiNNBase):
                           batch_size=kwargs.get('batch_size'), dtype=self.dtype, freq_out=kwargs.get('freq_out', 100))
         best = res['best_theta'].double().cpu().numpy()
         self.fit_info = {k: v.cpu().numpy() for k, v in res.items() if k in ('best_loss', 'best_epoch')}
+        self.batched_fit = True
         for k, learner in enumerate(self.learners):
             learner.best_model = copy.deepcopy(learner.nnmodel)
             unflatten_module(learner.best_model, best[k])

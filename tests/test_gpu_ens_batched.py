@@ -93,6 +93,7 @@ def test_nn_ens_fit_batched_equals_member_by_member():
             net = MLP(2, 1, (16, 16), activ='tanh')
             ens = NN_Ens(net, nens=3, dfrac=0.75)
             ens.fit(x, y, nepochs=60, lrate=0.01, freq_out=1000)
+            assert ens.batched_fit == (seq == '')
             preds[seq] = np.stack([l.predict(xt) for l in ens.learners])
         finally:
             os.environ.pop('QB_ENS_SEQUENTIAL', None)
