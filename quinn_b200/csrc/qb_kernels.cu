@@ -224,7 +224,7 @@ static int make_launch(const qb_net_t* net, int dtype, bool want_grad, long long
     int pick = -1, best_score = -1;
     bool wr_global = false;
     QbPlan tmp;
-    for (int g = 0; g < 2 && pick < 0; ++g) {
+    for (int g = (want_grad && env_int("QB_WR_GLOBAL", 0)) ? 1 : 0; g < 2 && pick < 0; ++g) {
         if (g == 1 && !want_grad) break;
         for (int c = 0; c < 4; ++c) {
             int TM = cands[c];

@@ -123,3 +123,37 @@ def test_fit_members_fp32_large_ensemble_trains():
     k = 17
     ref = np.mean((qo.forward(layers, res['best_theta'][k].double().cpu().numpy(), x) - y) ** 2)
     assert abs(res['best_loss'][k].item() - ref) <= 1e-3 * ref
+
+
+@pytest.mark.parametrize('dtype', [torch.float64, torch.float32])
+def test_adam_step_and_row_copy_kernels(dtype):
+    """qb_adam_step against torch.optim.Adam on a flat array (ragged length, weight decay, gradient scale) and
+    qb_copy_rows_where with all / some / no rows selected."""
+    import ctypes as C
+    from quinn_b200 import _lib
+    from quinn_b200.ops import _ptr, _stream, qb_dtype
+    lib = _lib.load()
+    torch.manual_seed(0)
+    n = 1000 + 37
+    th = torch.randn(n, dtype=dtype, device='cuda')
+    ref = th.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=0.03, weight_decay=0.01)
+    m, v = torch.zeros_like(th), torch.zeros_like(th)
+    for step in range(1, 6):
+        g = torch.randn(n, dtype=dtype, device='cuda')
+        _lib.check(lib.qb_adam_step(qb_dtype(dtype), _ptr(th), _ptr(g), _ptr(m), _ptr(v), n, 0.03, 0.9, 0.999, 1e-8, 0.01,
+                                    step, -0.5, _stream()), 'qb_adam_step')
+        ref.grad = -0.5 * g
+        opt.step()
+    tol = 1e-12 if dtype == torch.float64 else 2e-5
+    torch.testing.assert_close(th, ref.detach(), rtol=tol, atol=tol)
+    K, P = 5, 300 + 3
+    src = torch.randn(K, P, dtype=dtype, device='cuda')
+    for sel in ([1, 1, 1, 1, 1], [0, 1, 0, 0, 1], [0, 0, 0, 0, 0]):
+        dst = torch.zeros(K, P, dtype=dtype, device='cuda')
+        mask = torch.tensor(sel, dtype=torch.uint8, device='cuda')
+        _lib.check(lib.qb_copy_rows_where(qb_dtype(dtype), _ptr(dst), _ptr(src), _ptr(mask), K, P, _stream()), 'copy')
+        want = src * mask[:, None].to(dtype)
+        assert torch.equal(dst, want)
+    assert lib.qb_adam_step(qb_dtype(dtype), None, _ptr(th), _ptr(m), _ptr(v), n, 0.1, 0.9, 0.999, 1e-8, 0.0, 1, 1.0, None) != 0
+    assert b'qb_adam_step' in lib.qb_last_error()
