@@ -157,3 +157,27 @@ def test_adam_step_and_row_copy_kernels(dtype):
         assert torch.equal(dst, want)
     assert lib.qb_adam_step(qb_dtype(dtype), None, _ptr(th), _ptr(m), _ptr(v), n, 0.1, 0.9, 0.999, 1e-8, 0.0, 1, 1.0, None) != 0
     assert b'qb_adam_step' in lib.qb_last_error()
+
+
+def test_fit_members_rnet_shared_weights():
+    """RNet with Poly(0): one weight matrix is shared by all residual layers, so its gradient is a sum over layers
+    (kernel 2) and Adam sees it once in the flat vector, exactly like torch does."""
+    from quinn_b200.ens.batched import fit_members
+    from quinn_b200.netdesc import netdesc_from_module, flatten_module
+    from quinn_b200.nns import RNet, Poly
+    rs = np.random.RandomState(12)
+    torch.manual_seed(12)
+    net = RNet(3, 3, wp_function=Poly(0), indim=1, outdim=1, layer_pre=True, layer_post=True, biasorno=True,
+               nonlin=True, mlp=False, final_layer=None).double()
+    N, K, nsub, nepochs = 30, 2, 24, 80
+    x = rs.rand(N, 1) * 2 * np.pi - np.pi
+    y = np.sin(x) + 0.02 * rs.randn(N, 1)
+    subsets = np.stack([rs.permutation(N)[:nsub] for _ in range(K)])
+    th0 = flatten_module(net)
+    res = fit_members(netdesc_from_module(net), th0, x, y, subsets, nepochs=nepochs, lrate=0.02, dtype=torch.float64,
+                      verbose=False)
+    for k in range(K):
+        bt, bl, be, ft, hist = torch_member_fit(net, x[subsets[k]], y[subsets[k]], None, nepochs, 0.02, 0.0, None, None)
+        np.testing.assert_allclose(res['history'][:, k].cpu().numpy(), hist, rtol=1e-7, atol=1e-12)
+        np.testing.assert_allclose(res['theta'][k].cpu().numpy(), ft, rtol=1e-6, atol=1e-8)
+        assert int(res['best_epoch'][k].item()) == be
