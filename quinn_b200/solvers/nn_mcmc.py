@@ -104,8 +104,43 @@ class NN_MCMC(QUiNNBase):
             lp, g = ops.logpost_grad(self.device_logpost(self.lpinfo).problem, th)
             return -float(lp[0].item()), -g[0].double().cpu().numpy()
         rows = np.atleast_2d(param_ini)
+        if rows.shape[0] > self.map_batched_above:
+            return self._map_start_batched(rows)
         out = np.array([minimize(fg, r, jac=True, method='BFGS', options={'gtol': 1e-13}).x for r in rows])
         return out[0] if np.ndim(param_ini) == 1 else out
+
+    map_batched_above = 8          # more start points than this: one batched optimisation instead of K BFGS runs
+
+    def _map_start_batched(self, rows, nsteps=300, lrate=0.01):
+        """MAP pre-conditioning of MANY chains at once (the reference has one chain and BFGS with
+        finite differences, nn_mcmc.py:125-127): Adam ascent on log p(theta|D) for all K starts together - kernel 2,
+        qb_adam_step and qb_copy_rows_where, nothing leaves the device - returning the best state each chain visited."""
+        import ctypes as C
+        from .. import _lib
+        from ..ops import _ptr, _stream, qb_dtype
+        prob = self.device_logpost(self.lpinfo).problem
+        lib = _lib.load()
+        theta = prob.theta(rows).clone()
+        K, P = theta.shape
+        m, v, best = torch.zeros_like(theta), torch.zeros_like(theta), theta.clone()
+        best_lp = torch.full((K,), -float('inf'), dtype=torch.float64, device=theta.device)
+        lp = torch.empty(K, dtype=torch.float64, device=theta.device)
+        g = torch.empty_like(theta)
+        qdt = qb_dtype(prob.dtype)
+        for step in range(1, nsteps + 2):
+            ops.logpost_grad(prob, theta, lp, g)
+            better = lp > best_lp
+            mask = better.to(torch.uint8)
+            with torch.cuda.device(theta.device):
+                _lib.check(lib.qb_copy_rows_where(qdt, _ptr(best), _ptr(theta), _ptr(mask), K, P, _stream()), 'qb_copy_rows_where')
+            best_lp = torch.where(better, lp, best_lp)
+            if step > nsteps:
+                break
+            with torch.cuda.device(theta.device):
+                _lib.check(lib.qb_adam_step(qdt, _ptr(theta), _ptr(g), _ptr(m), _ptr(v), K * P, lrate, 0.9, 0.999, 1e-8, 0.0,
+                                            step, -1.0, _stream()), 'qb_adam_step')
+        self.map_start_logpost = best_lp.cpu().numpy()
+        return best.double().cpu().numpy()
 
     # ---- predictive (nn_mcmc.py:142-200)
     def get_best_model(self, param):

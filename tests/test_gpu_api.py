@@ -299,3 +299,25 @@ def test_sharded_host_pipeline_equals_single_launch():
         for k in ('chain', 'mapparams', 'maxpost', 'accrate', 'logpost', 'alphas', 'accepted'):
             np.testing.assert_array_equal(np.asarray(out[k], dtype=np.float64), np.asarray(ref[k], dtype=np.float64), err_msg=k)
         assert out['chain'].shape == (37, 4, P)
+
+
+def test_nn_mcmc_batched_map_start():
+    """zflag=True with many chains (extension): all start points are pre-conditioned together by Adam ascent on the
+    log-posterior (kernel 2 + qb_adam_step); every chain starts at least as high as its random draw."""
+    from quinn_b200.nns import MLP
+    from quinn_b200.solvers import NN_MCMC
+    np.random.seed(5)
+    torch.manual_seed(5)
+    net = MLP(2, 1, (16, 16), activ='tanh')
+    x = np.random.rand(60, 2) * 2 - 1
+    y = np.sin(2 * x[:, :1]) * x[:, 1:] + 0.05 * np.random.randn(60, 1)
+    uq = NN_MCMC(net, verbose=False)
+    np.random.seed(6)
+    start = np.random.rand(32, uq.pdim)                       # what fit() draws for param_ini (nn_mcmc.py:124)
+    np.random.seed(6)
+    uq.fit(x, y, zflag=True, datanoise=0.05, nmcmc=20, sampler='amcmc', sampler_params={'gamma': 0.1}, nchains=32, seed=1)
+    lp_start = uq.logpost(start, uq.lpinfo)
+    assert uq.map_start_logpost.shape == (32,) and np.isfinite(uq.map_start_logpost).all()
+    assert (uq.map_start_logpost >= lp_start).all() and uq.map_start_logpost.mean() > lp_start.mean() + 10.0
+    np.testing.assert_allclose(uq.mcmc_results['logpost'][:, 0], uq.map_start_logpost, rtol=1e-9)
+    assert uq.samples.shape == (32, 21, uq.pdim)
