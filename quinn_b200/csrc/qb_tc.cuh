@@ -44,11 +44,11 @@ struct QbTcPlan {
 };
 
 #ifdef __CUDACC__
-// shared-memory header: [0,320) reduction scratch, two mbarriers, tensor-memory base
+// shared-memory header: [0,320) reduction scratch, three mbarriers, tensor-memory base
 enum { QB_TC_RED_BYTES = 320, QB_TC_BAR_OFF = 320, QB_TC_SLOT_OFF = 328, QB_TC_ABAR_OFF = 336,
-       QB_TC_HDR_BYTES = 384 };
+       QB_TC_HBAR_OFF = 344, QB_TC_HDR_BYTES = 384 };
 
-struct QbTcCtx { uint32_t tmem, bar, phase, abar, aphase; };
+struct QbTcCtx { uint32_t tmem, bar, phase, abar, aphase, hbar, hphase; };
 
 __device__ __forceinline__ uint32_t qb_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -101,6 +101,7 @@ __device__ __forceinline__ void qb_tc_init(const QbTcPlan& tp, unsigned char* sm
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(qb_smem_u32(smem + QB_TC_BAR_OFF)), "r"(1u) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(qb_smem_u32(smem + QB_TC_ABAR_OFF)), "r"((uint32_t)blockDim.x) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(qb_smem_u32(smem + QB_TC_HBAR_OFF)), "r"(1u) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     qb_tc_fence_before();
@@ -109,7 +110,8 @@ __device__ __forceinline__ void qb_tc_init(const QbTcPlan& tp, unsigned char* sm
     cx.tmem = *reinterpret_cast<volatile uint32_t*>(smem + QB_TC_SLOT_OFF);
     cx.bar = qb_smem_u32(smem + QB_TC_BAR_OFF);
     cx.abar = qb_smem_u32(smem + QB_TC_ABAR_OFF);
-    cx.phase = 0; cx.aphase = 0;
+    cx.hbar = qb_smem_u32(smem + QB_TC_HBAR_OFF);
+    cx.phase = 0; cx.aphase = 0; cx.hphase = 0;
 }
 __device__ __forceinline__ void qb_tc_fini(const QbTcPlan& tp, const QbTcCtx& cx) {
     qb_tc_fence_before();
@@ -197,31 +199,41 @@ __device__ __forceinline__ void qb_tanh4_prescaled(float2& a, float2& b) {
 // Issue by a whole (convergent) warp with one elected lane, K/8 known at compile time: every descriptor is
 // base + constant, so the 3*K/8 MMAs go out back to back (a single thread doing address arithmetic between the
 // MMAs was the critical path of the tile loop: ~80 cycles per MMA).
-template <int KS>
+// HALF: the MMAs of the first half of K (all three passes) are committed to `hbar` on their own, so that the A columns
+// of that half can be refilled while the second half is still running.
+template <int KS, bool HALF = false>
 __device__ __forceinline__ void qb_tc_issue_ks(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t bhi, uint32_t blo,
-                                               uint32_t dhi, uint32_t idesc, uint32_t bar) {
+                                               uint32_t dhi, uint32_t idesc, uint32_t bar, uint32_t hbar = 0) {
     uint32_t elected;
     asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.b32 %0, 1, 0, p; }" : "=r"(elected) :: "memory");
     if (elected) {
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
+        for (int half = 0; half < (HALF ? 2 : 1); ++half) {
+            constexpr int S0 = 0, SN = HALF ? KS / 2 : KS;
 #pragma unroll
-            for (int s = 0; s < KS; ++s) {
-                const uint32_t a = (pass == 0 ? a_lo : a_hi) + (uint32_t)s * 8u;
-                const uint32_t bl = (pass == 1 ? blo : bhi) + (uint32_t)s * 16u;       // +256 bytes, in 16-byte units
-                if (pass == 0 && s == 0)
-                    asm volatile("{ .reg .pred p; .reg .b64 dd; setp.ne.b32 p, 0, 0; mov.b64 dd, {%2, %3}; tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], dd, %4, p; }"
-                                 :: "r"(d), "r"(a), "r"(bl), "r"(dhi), "r"(idesc) : "memory");
-                else
-                    asm volatile("{ .reg .pred p; .reg .b64 dd; setp.eq.b32 p, 0, 0; mov.b64 dd, {%2, %3}; tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], dd, %4, p; }"
-                                 :: "r"(d), "r"(a), "r"(bl), "r"(dhi), "r"(idesc) : "memory");
+            for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+                for (int ss = S0; ss < SN; ++ss) {
+                    const int s = ss + half * SN;
+                    const uint32_t a = (pass == 0 ? a_lo : a_hi) + (uint32_t)s * 8u;
+                    const uint32_t bl = (pass == 1 ? blo : bhi) + (uint32_t)s * 16u;   // +256 bytes, in 16-byte units
+                    if (half == 0 && pass == 0 && ss == 0)
+                        asm volatile("{ .reg .pred p; .reg .b64 dd; setp.ne.b32 p, 0, 0; mov.b64 dd, {%2, %3}; tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], dd, %4, p; }"
+                                     :: "r"(d), "r"(a), "r"(bl), "r"(dhi), "r"(idesc) : "memory");
+                    else
+                        asm volatile("{ .reg .pred p; .reg .b64 dd; setp.eq.b32 p, 0, 0; mov.b64 dd, {%2, %3}; tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], dd, %4, p; }"
+                                     :: "r"(d), "r"(a), "r"(bl), "r"(dhi), "r"(idesc) : "memory");
+                }
             }
+            if (HALF && half == 0)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(hbar) : "memory");
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
     }
     __syncwarp();
 }
 // called by all lanes of warp 0
+template <bool HALF = false>
 __device__ __forceinline__ void qb_tc_issue_warp(const QbTcPlan& tp, const QbTcLayer& L, const QbTcCtx& cx, unsigned char* smem,
                                                  uint32_t d_off) {
     const uint32_t K = L.n_in, N = L.n_out;
@@ -230,6 +242,10 @@ __device__ __forceinline__ void qb_tc_issue_warp(const QbTcPlan& tp, const QbTcL
     const uint32_t bhi = ((qb_smem_u32(smem + L.bhi) >> 4) & 0x3FFFu) | ((128u >> 4) << 16);
     const uint32_t blo = ((qb_smem_u32(smem + L.blo) >> 4) & 0x3FFFu) | ((128u >> 4) << 16);
     const uint32_t d = cx.tmem + tp.d_col + d_off, a_hi = cx.tmem, a_lo = cx.tmem + tp.a_lo_col;
+    if constexpr (HALF) {        // only used for K == 64 (the hot config-5 instantiation)
+        qb_tc_issue_ks<8, true>(d, a_hi, a_lo, bhi, blo, dhi, idesc, cx.bar, cx.hbar);
+        return;
+    }
     switch (K >> 3) {
         case 2: qb_tc_issue_ks<2>(d, a_hi, a_lo, bhi, blo, dhi, idesc, cx.bar); break;
         case 4: qb_tc_issue_ks<4>(d, a_hi, a_lo, bhi, blo, dhi, idesc, cx.bar); break;
@@ -500,6 +516,9 @@ __device__ __forceinline__ Sink qb_tc_pipe_run(const QbTcPlan& tp, QbTcCtx& cx, 
     const uint32_t tl = cx.tmem + ((uint32_t)(((threadIdx.x >> 5) & 3) * 32) << 16);
     const QbTcLayer& L = tp.L[1];
     const int K = tp.h0, N = L.n_out, od = tp.out_dim;
+    // HALFK (K = N = 64, two column groups): the MMAs of the first half of K are committed separately, so the first
+    // layer-0 chunk of tile t+1 (columns < 32) is written while the second half of tile t's MMAs is still running
+    constexpr bool HALFK = FULL && G == 2;
     const int ntiles = (int)((n1 - n0 + 127) / 128);   // tile counters are 32-bit: this loop is register-bound
     const int64_t pbase = n0 + pt;                     // this thread's point of tile 0
     float xn[NI];
@@ -524,7 +543,7 @@ __device__ __forceinline__ Sink qb_tc_pipe_run(const QbTcPlan& tp, QbTcCtx& cx, 
         if (threadIdx.x < 32) {
             qb_mbar_wait(cx.abar, cx.aphase);
             qb_tc_fence_after();
-            qb_tc_issue_warp(tp, L, cx, smem, 0u);
+            qb_tc_issue_warp<HALFK>(tp, L, cx, smem, 0u);
         }
         cx.aphase ^= 1u;
     }
@@ -533,6 +552,17 @@ __device__ __forceinline__ Sink qb_tc_pipe_run(const QbTcPlan& tp, QbTcCtx& cx, 
         const int64_t pc = pbase + (int64_t)t * 128;                 // this thread's point of tile t
         float sv[OD];
         if (grp == 0) sink.template prefetch<OD>(pc, pc < n1, sv);
+        if constexpr (HALFK) {
+            qb_mbar_wait(cx.hbar, cx.hphase);                        // first K-half of tile t done: A columns [0,32) are free
+            cx.hphase ^= 1u;
+            qb_tc_fence_after();
+            if (more) {
+                qb_tc_load_x<NI>(tp, x, pc + 128, pc + 128 < n1, xn);
+                float h[16];
+                qb_tc_l0_chunk<NI, ACT>(tp, F, grp * 16, xn, h);
+                qb_tc_split_store(tl + grp * 16, tl + tp.a_lo_col + grp * 16, h);
+            }
+        }
         qb_mbar_wait(cx.bar, cx.phase);                              // MMAs of tile t complete: A is free, D[t&1] is ready
         cx.phase ^= 1u;
         qb_tc_fence_after();
@@ -554,9 +584,9 @@ __device__ __forceinline__ Sink qb_tc_pipe_run(const QbTcPlan& tp, QbTcCtx& cx, 
         if (more) {
             // layer 0 of tile t+1 straight into tensor memory, then let warp 0 start the MMAs of tile t+1 into the other
             // accumulator buffer (x is L1/L2-resident and shared by every chain: no prefetch registers are spent on it)
-            qb_tc_load_x<NI>(tp, x, pc + 128, pc + 128 < n1, xn);
+            if constexpr (!HALFK) qb_tc_load_x<NI>(tp, x, pc + 128, pc + 128 < n1, xn);
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = HALFK ? 1 : 0; j < 2; ++j) {
                 const int c = (G * j + grp) * 16;
                 if (FULL || c < K) {
                     float h[16];
@@ -570,7 +600,7 @@ __device__ __forceinline__ Sink qb_tc_pipe_run(const QbTcPlan& tp, QbTcCtx& cx, 
             if (threadIdx.x < 32) {
                 qb_mbar_wait(cx.abar, cx.aphase);
                 qb_tc_fence_after();
-                qb_tc_issue_warp(tp, L, cx, smem, (uint32_t)((t + 1) & 1) * (uint32_t)N);
+                qb_tc_issue_warp<HALFK>(tp, L, cx, smem, (uint32_t)((t + 1) & 1) * (uint32_t)N);
             }
             cx.aphase ^= 1u;
         }
