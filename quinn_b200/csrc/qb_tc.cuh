@@ -233,7 +233,7 @@ __device__ __forceinline__ void qb_tc_issue_ks(uint32_t d, uint32_t a_hi, uint32
     __syncwarp();
 }
 // called by all lanes of warp 0
-template <bool HALF = false>
+template <bool HALF = false, int KSH = 8>
 __device__ __forceinline__ void qb_tc_issue_warp(const QbTcPlan& tp, const QbTcLayer& L, const QbTcCtx& cx, unsigned char* smem,
                                                  uint32_t d_off) {
     const uint32_t K = L.n_in, N = L.n_out;
@@ -242,8 +242,8 @@ __device__ __forceinline__ void qb_tc_issue_warp(const QbTcPlan& tp, const QbTcL
     const uint32_t bhi = ((qb_smem_u32(smem + L.bhi) >> 4) & 0x3FFFu) | ((128u >> 4) << 16);
     const uint32_t blo = ((qb_smem_u32(smem + L.blo) >> 4) & 0x3FFFu) | ((128u >> 4) << 16);
     const uint32_t d = cx.tmem + tp.d_col + d_off, a_hi = cx.tmem, a_lo = cx.tmem + tp.a_lo_col;
-    if constexpr (HALF) {        // only used for K == 64 (the hot config-5 instantiation)
-        qb_tc_issue_ks<8, true>(d, a_hi, a_lo, bhi, blo, dhi, idesc, cx.bar, cx.hbar);
+    if constexpr (HALF) {        // K == 8*KSH: 64 (two column groups) or 128 (four)
+        qb_tc_issue_ks<KSH, true>(d, a_hi, a_lo, bhi, blo, dhi, idesc, cx.bar, cx.hbar);
         return;
     }
     switch (K >> 3) {
@@ -504,7 +504,7 @@ struct QbSinkStore {            // network outputs to out[p, o] (kernel 4)
     }
 };
 
-template <int NI, int ACT, int OD, bool FULL, int G, typename Sink>
+template <int NI, int ACT, int OD, bool FULL, int G, typename Sink, bool HALFK_REQ = false>
 __device__ __forceinline__ Sink qb_tc_pipe_run(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem,
                                                const float* __restrict__ x, int64_t n0, int64_t n1, Sink sink) {
     const float* F = reinterpret_cast<const float*>(smem + tp.fl_base);
@@ -518,7 +518,7 @@ __device__ __forceinline__ Sink qb_tc_pipe_run(const QbTcPlan& tp, QbTcCtx& cx, 
     const int K = tp.h0, N = L.n_out, od = tp.out_dim;
     // HALFK (K = N = 64, two column groups): the MMAs of the first half of K are committed separately, so the first
     // layer-0 chunk of tile t+1 (columns < 32) is written while the second half of tile t's MMAs is still running
-    constexpr bool HALFK = FULL && G == 2;
+    constexpr bool HALFK = (FULL && G == 2) || HALFK_REQ;          // HALFK_REQ: the caller checked K == 32*G
     const int ntiles = (int)((n1 - n0 + 127) / 128);   // tile counters are 32-bit: this loop is register-bound
     const int64_t pbase = n0 + pt;                     // this thread's point of tile 0
     float xn[NI];
@@ -543,7 +543,7 @@ __device__ __forceinline__ Sink qb_tc_pipe_run(const QbTcPlan& tp, QbTcCtx& cx, 
         if (threadIdx.x < 32) {
             qb_mbar_wait(cx.abar, cx.aphase);
             qb_tc_fence_after();
-            qb_tc_issue_warp<HALFK>(tp, L, cx, smem, 0u);
+            qb_tc_issue_warp<HALFK, 4 * G>(tp, L, cx, smem, 0u);
         }
         cx.aphase ^= 1u;
     }
@@ -600,7 +600,7 @@ __device__ __forceinline__ Sink qb_tc_pipe_run(const QbTcPlan& tp, QbTcCtx& cx, 
             if (threadIdx.x < 32) {
                 qb_mbar_wait(cx.abar, cx.aphase);
                 qb_tc_fence_after();
-                qb_tc_issue_warp<HALFK>(tp, L, cx, smem, (uint32_t)((t + 1) & 1) * (uint32_t)N);
+                qb_tc_issue_warp<HALFK, 4 * G>(tp, L, cx, smem, (uint32_t)((t + 1) & 1) * (uint32_t)N);
             }
             cx.aphase ^= 1u;
         }
@@ -725,7 +725,9 @@ __device__ __forceinline__ void qb_tc_predict(const QbTcPlan& tp, QbTcCtx& cx, u
     QbSinkStore sink;
     sink.out = out; sink.od = tp.out_dim;
     if (tp.pipe == 4) {
-        if (tp.act0 == QB_ACT_TANH && tp.ni == 12) qb_tc_pipe_run<12, QB_ACT_TANH, 4, false, 4>(tp, cx, smem, x, n0, n1, sink);
+        if (tp.act0 == QB_ACT_TANH && tp.ni == 12 && tp.h0 == 128)      // config-3 shape: half-K commits
+            qb_tc_pipe_run<12, QB_ACT_TANH, 4, false, 4, QbSinkStore, true>(tp, cx, smem, x, n0, n1, sink);
+        else if (tp.act0 == QB_ACT_TANH && tp.ni == 12) qb_tc_pipe_run<12, QB_ACT_TANH, 4, false, 4>(tp, cx, smem, x, n0, n1, sink);
         else if (tp.act0 == QB_ACT_TANH) qb_tc_pipe_run<16, QB_ACT_TANH, 4, false, 4>(tp, cx, smem, x, n0, n1, sink);
         else qb_tc_pipe_run<16, QB_ACT_RELU, 4, false, 4>(tp, cx, smem, x, n0, n1, sink);
     } else if (tp.pipe) {
