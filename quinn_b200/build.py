@@ -1,44 +1,79 @@
-"""Build the CUDA library in-tree:  python -m quinn_b200.build
+"""Build the CUDA library in-tree:  python -m quinn_b200.build [--force] [-v]
 
-One translation unit, compiled for sm_100a only (-gencode arch=compute_100a,code=sm_100a).
-The resulting quinn_b200/lib/libquinn_b200.so is git-ignored but travels to the GPU box.
+Translation units under quinn_b200/csrc/*.cu are compiled for sm_100a only
+(-gencode arch=compute_100a,code=sm_100a -lineinfo), in parallel, and linked into
+quinn_b200/lib/libquinn_b200.so (git-ignored, but it travels to the GPU box).  A stamp file next to the
+library records the SHA-256 of every source; build() recompiles whenever the sources no longer match it.
 """
+import hashlib
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SRC = os.path.join(HERE, 'csrc', 'qb_kernels.cu')
-DEPS = [SRC, os.path.join(HERE, 'csrc', 'qb_device.cuh'), os.path.join(HERE, 'csrc', 'qb_tc.cuh'), os.path.join(HERE, 'csrc', 'qb_plan.h'),
-        os.path.join(ROOT, 'include', 'quinn_b200.h')]
+CSRC = os.path.join(HERE, 'csrc')
+UNITS = ['qb_kernels.cu', 'qb_grad_tc.cu']
+HEADERS = ['qb_device.cuh', 'qb_chain.cuh', 'qb_tc.cuh', 'qb_tcg.cuh', 'qb_grad_tc.h', 'qb_plan.h']
+DEPS = [os.path.join(CSRC, f) for f in UNITS + HEADERS] + [os.path.join(ROOT, 'include', 'quinn_b200.h')]
 OUT = os.path.join(HERE, 'lib', 'libquinn_b200.so')
+STAMP = OUT + '.srchash'
+OBJDIR = os.path.join(ROOT, 'build', 'obj')
+
+
+def source_hash():
+    h = hashlib.sha256()
+    for d in DEPS:
+        h.update(os.path.basename(d).encode())
+        with open(d, 'rb') as f:
+            h.update(f.read())
+    return h.hexdigest()
 
 
 def needs_build():
-    if not os.path.exists(OUT):
+    if not os.path.exists(OUT) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(OUT)
-    return any(os.path.getmtime(d) > t for d in DEPS)
+    with open(STAMP) as f:
+        return f.read().strip() != source_hash()
+
+
+def _nvcc():
+    return os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+
+
+def _compile(unit, verbose):
+    obj = os.path.join(OBJDIR, unit.replace('.cu', '.o'))
+    cmd = [_nvcc(), '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-c',
+           '-Xcompiler', '-fPIC', '-I', os.path.join(ROOT, 'include'), '-I', CSRC, '-o', obj, os.path.join(CSRC, unit)]
+    if verbose:
+        cmd[1:1] = ['-Xptxas', '-v']
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    return unit, obj, res
 
 
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-           '--shared', '-Xcompiler', '-fPIC', '-I', os.path.join(ROOT, 'include'), '-I', os.path.join(HERE, 'csrc'),
-           '-o', OUT, SRC]
-    if verbose:
-        cmd.insert(1, '-Xptxas')
-        cmd.insert(2, '-v')
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(OBJDIR, exist_ok=True)
+    with ThreadPoolExecutor(len(UNITS)) as ex:
+        results = list(ex.map(lambda u: _compile(u, verbose), UNITS))
+    objs = []
+    for unit, obj, res in results:
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError(f'nvcc failed compiling {unit}')
+        if verbose:
+            sys.stderr.write(res.stderr)
+        objs.append(obj)
+    res = subprocess.run([_nvcc(), '-gencode', 'arch=compute_100a,code=sm_100a', '--shared', '-o', OUT] + objs,
+                         capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError('nvcc failed building libquinn_b200.so')
-    if verbose:
-        sys.stderr.write(res.stderr)
+        raise RuntimeError('nvcc failed linking libquinn_b200.so')
+    with open(STAMP, 'w') as f:
+        f.write(source_hash() + '\n')
     return OUT
 
 

@@ -677,7 +677,7 @@ __device__ __forceinline__ double qb_tc_eval_pipe(const QbTcPlan& tp, QbTcCtx& c
 // Everything but the most common shape (<= 3 inputs, tanh, one 64x64 tensor-core layer, one output) is compiled out of line: inlining
 // all variants into the chain kernels made them so large that the compiler stopped unrolling the chunk loops and put
 // the register arrays in local memory.
-__device__ __noinline__ double qb_tc_eval_other(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem,
+static __device__ __noinline__ double qb_tc_eval_other(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem,
                                                 const float* __restrict__ x, const float* __restrict__ y,
                                                 int64_t n0, int64_t n1) {
     if (tp.pipe == 4) {
