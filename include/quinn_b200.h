@@ -75,7 +75,14 @@ typedef struct {
 } qb_data_t;
 
 const char* qb_last_error(void);
+
+/* ABI version: bumped with every change of a struct layout or a signature.  A binding must refuse a library whose
+ * qb_version() differs from the QB_ABI_VERSION it was written against (quinn_b200/_lib.py does), and can check its
+ * struct mirrors against qb_struct_sizes(): out[0..n) = sizeof of qb_layer_t, qb_net_t, qb_lik_t, qb_data_t, qb_chain_t,
+ * qb_rng_t, qb_record_t, qb_amcmc_t, qb_hmc_t (declaration order); returns how many sizes exist. */
+#define QB_ABI_VERSION 200
 int qb_version(void);
+int qb_struct_sizes(int64_t* out, int n);
 
 /* Bytes of scratch the evaluation entry points need for (net, dtype, K chains, N points). */
 size_t qb_eval_workspace_bytes(const qb_net_t* net, int dtype, int64_t K, int64_t N, int want_grad);
@@ -245,9 +252,12 @@ int qb_fma_peak(int dtype, int variant, int64_t iters, double* flops_out_host, v
 
 /* Launch-plan introspection for DESIGN.md / bench.py: fills out[0..7] =
  * {tile points TM, threads per block, dynamic smem bytes, N-splits S, blocks, inplace flag,
- *  tensor-core path (0: CUDA-core kernel, 1: tcgen05 3xTF32, 2: same, software-pipelined), tensor-memory columns}.
- * The tensor-core path serves the VALUE path (qb_logpost, qb_amcmc_run) of fp32 MLPs with <= 15 inputs, hidden
- * widths that are multiples of 16 (<= 128), <= 4 outputs and no residual layers; QB_NO_TC=1 disables it. */
+ *  tensor-core path (0: CUDA-core kernel, 1: tcgen05 3xTF32, 2: same, software-pipelined, 3: tcgen05 gradient kernel),
+ *  tensor-memory columns}.
+ * The tensor-core VALUE path (qb_logpost, qb_amcmc_run, qb_predict) serves fp32 MLPs with <= 15 inputs, hidden widths
+ * that are multiples of 16 (<= 128), <= 4 outputs and no residual layers; the tensor-core GRADIENT path
+ * (qb_logpost_grad, qb_logpost_members, qb_hmc_run) serves fp32 MLPs in(<= 7) -> H -> H -> 1 with H = 32 or 64 and
+ * tanh / relu hidden layers.  QB_NO_TC=1 disables both, QB_NO_TCG=1 only the gradient path. */
 int qb_plan_info(const qb_net_t* net, int dtype, int64_t K, int64_t N, int want_grad, int64_t* out);
 
 /* Number of kernel launches this library has enqueued since load (bench.py's gpu_launches). */

@@ -224,11 +224,15 @@ def amcmc_initial_propcov(theta0):
 
 
 def run_chain(logpost_fn, param_ini, nmcmc, sampler, draws, grad_fn=None,
-              epsilon=0.05, L=3, gamma=0.1, t0=100, tadapt=1000, cov_ini=None):
+              epsilon=0.05, L=3, gamma=0.1, t0=100, tadapt=1000, cov_ini=None, adapt_diag=True):
     """MCMCBase.run (mcmc.py:39-101) driven by recorded draws.
 
     sampler 'amcmc': draws['xi'][t] is the proposal increment the reference drew with
-      np.random.multivariate_normal at step t (admcmc.py:70);
+      np.random.multivariate_normal at step t (admcmc.py:70).  Alternatively draws['z0'][t], draws['z'][t] are
+      STANDARD normals and the increment is built here the way the many-chain kernels build it:
+      0.1*z0 + sqrt(0.09|theta0|)*z while the proposal covariance is the initial 0.01 + diag(0.09|theta0|)
+      (exactly that matrix: rank one plus diagonal), and sqrt(gamma*2.4^2/P*(diag(C)+1e-8))*z after an adaptation
+      when adapt_diag (the repo's DIAGONAL deviation from admcmc.py:59-67; '_pscale' is returned for it);
     sampler 'hmc' / 'mala': draws['p'][t] is the momentum np.random.randn(cdim)
       (hmc.py:43, mala.py:42);
     draws['u'][t] is np.random.random_sample() of mcmc.py:75.
@@ -250,7 +254,15 @@ def run_chain(logpost_fn, param_ini, nmcmc, sampler, draws, grad_fn=None,
                 propcov = cov_ini if cov_ini is not None else amcmc_initial_propcov(current)
             elif imcmc > t0 and imcmc % tadapt == 0:
                 propcov = (gamma * 2.4 ** 2 / cdim) * (cov + 10 ** (-8) * np.eye(cdim))
-            proposal = current + draws['xi'][imcmc]
+            if 'xi' in draws:
+                proposal = current + draws['xi'][imcmc]
+            else:
+                if imcmc == 0:
+                    pscale, kind = np.sqrt(0.09 * np.abs(current)), 0
+                elif adapt_diag and imcmc > t0 and imcmc % tadapt == 0:
+                    pscale, kind = np.sqrt((gamma * 2.4 ** 2 / cdim) * (np.diag(cov) + 1e-8)), 1
+                common = 0.1 * draws['z0'][imcmc] if kind == 0 else 0.0
+                proposal = current + (common + pscale * draws['z'][imcmc])
             K_cur = K_prop = 0.0
         elif sampler == 'hmc':                                    # hmc.py:43-68
             p = np.array(draws['p'][imcmc], dtype=np.float64)
@@ -294,6 +306,8 @@ def run_chain(logpost_fn, param_ini, nmcmc, sampler, draws, grad_fn=None,
                alphas=np.array(alphas), accepted=np.array(accepted, dtype=bool))
     if sampler == 'amcmc':
         res.update(_Xm=Xm, _cov=cov, _propcov=propcov)
+        if 'xi' not in draws:
+            res.update(_pscale=pscale, _kind=kind)
     return res
 
 

@@ -60,11 +60,15 @@ class qb_hmc_t(C.Structure):
                 ('mom', C.c_void_p), ('prop', C.c_void_p), ('grad_prop', C.c_void_p)]
 
 
+QB_ABI_VERSION = 200          # include/quinn_b200.h
+ABI_STRUCTS = (qb_layer_t, qb_net_t, qb_lik_t, qb_data_t, qb_chain_t, qb_rng_t, qb_record_t, qb_amcmc_t, qb_hmc_t)
+
 # every symbol include/quinn_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
     'qb_last_error': (C.c_char_p, []),
     'qb_version': (C.c_int, []),
+    'qb_struct_sizes': (C.c_int, [C.POINTER(C.c_int64), C.c_int]),
     'qb_eval_workspace_bytes': (C.c_size_t, [C.POINTER(qb_net_t), C.c_int, C.c_int64, C.c_int64, C.c_int]),
     'qb_logpost': (C.c_int, [C.POINTER(qb_net_t), C.c_int, _P, C.c_int64, C.POINTER(qb_data_t), C.POINTER(qb_lik_t),
                              _P, _P, C.c_size_t, _P]),
@@ -118,6 +122,15 @@ def load(build_if_missing=True):
         fn = getattr(lib, name)          # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
+    # ABI guard: a stale library with other struct layouts would be called with mismatched structs and corrupt memory
+    if lib.qb_version() != QB_ABI_VERSION:
+        raise RuntimeError(f'quinn_b200: {path} has ABI version {lib.qb_version()}, this binding expects {QB_ABI_VERSION}; '
+                           'rebuild with `python -m quinn_b200.build --force`')
+    sizes = (C.c_int64 * len(ABI_STRUCTS))()
+    n = lib.qb_struct_sizes(sizes, len(ABI_STRUCTS))
+    mine = [C.sizeof(t) for t in ABI_STRUCTS]
+    if n != len(ABI_STRUCTS) or list(sizes) != mine:
+        raise RuntimeError(f'quinn_b200: struct sizes of {path} {list(sizes)} differ from the ctypes mirrors {mine}')
     _lib = lib
     return lib
 

@@ -950,8 +950,12 @@ __device__ __forceinline__ uint4 qb_philox(uint4 c, uint2 k) {
 enum { QB_STREAM_INCR = 0, QB_STREAM_Z0 = 1, QB_STREAM_UNIF = 2, QB_STREAM_VI = 3 };
 
 __device__ __forceinline__ uint4 qb_rand4(uint64_t seed, int64_t chain, int64_t step, int stream, uint32_t idx4) {
-    uint2 key = make_uint2((uint32_t)seed ^ (uint32_t)chain, (uint32_t)(seed >> 32) ^ (uint32_t)((uint64_t)chain >> 32) ^ 0x5851F42Du);
-    uint4 ctr = make_uint4(idx4, (uint32_t)step, (uint32_t)((uint64_t)step >> 32), (uint32_t)stream);
+    // seed and chain live in DIFFERENT words (key = seed, counter = chain/step/index): two (seed, chain) pairs never share
+    // a stream, whatever their bits.  Injective for chain < 2^48, step < 2^40, stream < 256.
+    const uint64_t ch = (uint64_t)chain, sp = (uint64_t)step;
+    uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ 0x5851F42Du);
+    uint4 ctr = make_uint4(idx4, (uint32_t)sp, (uint32_t)ch,
+                           ((uint32_t)stream & 0xFFu) | (((uint32_t)(sp >> 32) & 0xFFu) << 8) | (((uint32_t)(ch >> 32) & 0xFFFFu) << 16));
     return qb_philox(ctr, key);
 }
 __device__ __forceinline__ double qb_u01(uint32_t a) { return ((double)a + 0.5) * 2.3283064365386963e-10; }

@@ -39,7 +39,15 @@ static int qb_fail(const char* fmt, const char* a = "", long long b = 0) {
     } while (0)
 
 extern "C" const char* qb_last_error(void) { return g_err; }
-extern "C" int qb_version(void) { return 100; }
+extern "C" int qb_version(void) { return QB_ABI_VERSION; }
+extern "C" int qb_struct_sizes(int64_t* out, int n) {
+    const int64_t sz[] = {(int64_t)sizeof(qb_layer_t), (int64_t)sizeof(qb_net_t), (int64_t)sizeof(qb_lik_t), (int64_t)sizeof(qb_data_t),
+                          (int64_t)sizeof(qb_chain_t), (int64_t)sizeof(qb_rng_t), (int64_t)sizeof(qb_record_t),
+                          (int64_t)sizeof(qb_amcmc_t), (int64_t)sizeof(qb_hmc_t)};
+    const int m = (int)(sizeof(sz) / sizeof(sz[0]));
+    for (int i = 0; i < n && i < m; ++i) out[i] = sz[i];
+    return m;
+}
 extern "C" int64_t qb_launch_count(void) { return (int64_t)g_launches.load(); }
 
 // =================================================================================================
@@ -54,7 +62,17 @@ static int env_int(const char* name, int dflt) {
 
 static const int QB_SMEM_MAX = 227 * 1024;
 static const int QB_SMEM_SM = 228 * 1024;    // shared memory per SM
-static const int QB_NUM_SMS = 148;
+// SM count of the current device (148 on B200), queried once per process
+static int qb_num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+        else n = 148;
+    }
+    return n;
+}
+#define QB_NUM_SMS (qb_num_sms())
 
 static int validate_net(const qb_net_t* net) {
     if (!net) return qb_fail("net is NULL");
@@ -551,15 +569,15 @@ extern "C" int qb_adam_step(int dtype, void* theta, const void* grad, void* m, v
 // best-model tracking: dst[k,:] = src[k,:] where mask[k] != 0
 template <typename T>
 __global__ void k_copy_rows_where(T* dst, const T* src, const unsigned char* mask, long long P) {
-    const long long k = blockIdx.y;
+    const long long k = blockIdx.x;          // rows on grid.x (2^31-1 blocks): K is not limited to 65535
     if (!mask[k]) return;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x;
     if (i < P) dst[k * P + i] = src[k * P + i];
 }
 extern "C" int qb_copy_rows_where(int dtype, void* dst, const void* src, const unsigned char* mask, int64_t K, int64_t P,
                                   void* stream) {
-    if (!dst || !src || !mask || K < 1 || P < 1 || K > 65535) return qb_fail("bad argument to qb_copy_rows_where");
-    dim3 grid((unsigned)cdiv(P, 256), (unsigned)K);
+    if (!dst || !src || !mask || K < 1 || P < 1 || cdiv(P, 256) > 65535) return qb_fail("bad argument to qb_copy_rows_where");
+    dim3 grid((unsigned)K, (unsigned)cdiv(P, 256));
     if (dtype == QB_F64) k_copy_rows_where<double><<<grid, 256, 0, (cudaStream_t)stream>>>((double*)dst, (const double*)src, mask, P);
     else k_copy_rows_where<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)dst, (const float*)src, mask, P);
     QB_CUDA(cudaGetLastError());
@@ -582,10 +600,15 @@ __device__ void qb_cholesky(const T* cov, T* Lf, int P, double fac, double jitte
             Lf[i * P + j] = (T)s;
         }
         __syncthreads();
-        const double d = sqrt((double)Lf[j * P + j]);
+        // In exact arithmetic the pivot is >= fac*jitter (the matrix is PSD + jitter*I); in floating point a rank-deficient
+        // covariance (fewer samples than parameters at the first adaptation) can round it to <= 0.  Such a direction has no
+        // variance beyond the jitter: clamp the pivot and zero the column instead of producing NaN proposals.
+        const double piv = (double)Lf[j * P + j], floor_ = fac * jitter;
+        const bool ok = piv > floor_;              // false for NaN too
+        const double d = sqrt(ok ? piv : floor_);
         __syncthreads();
         for (int i = j + threadIdx.x; i < P; i += blockDim.x)
-            Lf[i * P + j] = (i == j) ? (T)d : (T)((double)Lf[i * P + j] / d);
+            Lf[i * P + j] = (i == j) ? (T)d : (ok ? (T)((double)Lf[i * P + j] / d) : T(0));
         __syncthreads();
     }
 }
@@ -923,9 +946,9 @@ __global__ void __launch_bounds__(512, 1) k_predict(const __grid_constant__ QbPl
     if (!a.fused) {
         // member-parallel: this block owns member blockIdx.y and a chunk of consecutive tiles; the weights are
         // staged once and every warp (warp-synchronous plans) copies out its own points without a block barrier
-        const long long m = blockIdx.y;
+        const long long m = blockIdx.x;          // members on grid.x: M is not limited to 65535
         const long long ntiles = (a.N + TM - 1) / TM;
-        const long long t0 = (long long)blockIdx.x * a.tiles_per_block, t1 = min(ntiles, t0 + a.tiles_per_block);
+        const long long t0 = (long long)blockIdx.y * a.tiles_per_block, t1 = min(ntiles, t0 + a.tiles_per_block);
         qb_stage_weights<T>(P, sW, a.theta + m * P.n_params);
         __syncthreads();
         for (long long t = t0; t < t1; ++t) {
@@ -1024,8 +1047,8 @@ __global__ void __launch_bounds__(512, 1) k_predict_tc(const __grid_constant__ Q
     extern __shared__ __align__(128) unsigned char smem_tc[];
     QbTcCtx cx;
     qb_tc_init(tp, smem_tc, cx);
-    const long long m = blockIdx.y;
-    const long long n0 = (long long)blockIdx.x * a.tiles_per_block * 128, n1 = min(a.N, n0 + a.tiles_per_block * 128);
+    const long long m = blockIdx.x;
+    const long long n0 = (long long)blockIdx.y * a.tiles_per_block * 128, n1 = min(a.N, n0 + a.tiles_per_block * 128);
     qb_tc_stage(tp, smem_tc, a.theta + m * tp.n_params);
     __syncthreads();
     qb_tc_predict(tp, cx, smem_tc, a.x, a.out + m * a.N * tp.out_dim, n0, n1);
@@ -1049,18 +1072,17 @@ static int run_predict(const qb_net_t* net, int dtype, const void* theta, int64_
     const bool can_fuse = (long long)P.TM * P.out_dim <= 4LL * P.nthreads;
     bool fused = want_mom && can_fuse && !out;     // with an `out` buffer: member-parallel + k_moments (weights staged once)
     if (want_mom && !fused && !out) return qb_fail("moments without `out` need TM*out_dim <= 4*threads; pass an `out` buffer");
-    if (!fused && M > 65535) return qb_fail("member-parallel predictive supports M <= 65535; chunk the call");
     PredArgs<T> a;
     a.theta = (const T*)theta; a.x = (const T*)x; a.M = M; a.N = N;
     a.out = (T*)out; a.mean = (T*)mean; a.var = (T*)var; a.fused = fused ? 1 : 0;
     QbTcPlan tp;
-    if (!fused && out && M <= 65535 && make_tc_plan(net, dtype, &tp)) {
+    if (!fused && out && make_tc_plan(net, dtype, &tp)) {
         // tensor-core forward (qb_tc.cuh): 128-point tiles, weights staged once per block, >= 8 waves of blocks
         const long long t128 = cdiv(N, 128);
         long long ch = std::max<long long>(1, std::min<long long>(t128, cdiv((long long)QB_NUM_SMS * 2 * 8, M)));
         a.tiles_per_block = cdiv(t128, ch);
         ch = cdiv(t128, a.tiles_per_block);
-        if (launch_predict_tc<T>(tp, a, dim3((unsigned)ch, (unsigned)M), st)) return -2;
+        if (launch_predict_tc<T>(tp, a, dim3((unsigned)M, (unsigned)ch), st)) return -2;
         QB_CUDA(cudaGetLastError());
         g_launches += 1;
         if (want_mom) {
@@ -1079,7 +1101,7 @@ static int run_predict(const qb_net_t* net, int dtype, const void* theta, int64_
         a.tiles_per_block = cdiv(tiles, chunks);
         chunks = cdiv(tiles, a.tiles_per_block);
     }
-    dim3 grid((unsigned)chunks, fused ? 1u : (unsigned)M);
+    dim3 grid(fused ? (unsigned)chunks : (unsigned)M, fused ? 1u : (unsigned)chunks);
     k_predict<T><<<grid, P.nthreads, P.smem_bytes, st>>>(P, a);
     QB_CUDA(cudaGetLastError());
     g_launches += 1;

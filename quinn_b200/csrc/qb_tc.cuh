@@ -75,18 +75,20 @@ __device__ __forceinline__ void qb_tmem_st_wait() { asm volatile("tcgen05.wait::
 __device__ __forceinline__ void qb_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void qb_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// bounded wait: a lost arrival traps after ~2 s instead of hanging the GPU
+// bounded wait: a lost arrival traps after 20 s of wall-clock time (globaltimer, so that a context that is merely
+// preempted / time-sliced for a while does not trip it) instead of hanging the GPU
 __device__ __forceinline__ void qb_mbar_wait(uint32_t bar, uint32_t parity) {
-    long long t0 = 0;
+    unsigned long long t0 = 0;
     for (uint32_t it = 0;; ++it) {
         uint32_t ok;
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
         if (ok) return;
-        if ((it & 63u) == 63u) {
-            const long long now = clock64();
+        if ((it & 1023u) == 1023u) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000LL) __trap();
+            else if (now - t0 > 20000000000ULL) __trap();
         }
     }
 }

@@ -30,11 +30,18 @@ LOG_2PI = math.log(2.0 * math.pi)
 class _MemberEval:
     """qb_logpost_members on [K, n, d] / [K, n, o] (per-member) or [n, d] / [n, o] (shared) data."""
 
-    def __init__(self, desc, K, dtype, device):
+    def __init__(self, desc, K, dtype, device, logpost=None):
+        """logpost = None: MSE loss (from the sigma = 1 log-posterior); dict(sigma=, prior_sigma=, anchor=[K,P] tensor,
+        nfull=): the loss is NegLogPost itself (losses.py:186-206; nnfit's 'logpost' option, nnfit.py:64-65)."""
         self.desc, self.K, self.dtype, self.device = desc, K, dtype, device
         self.cnet = desc.to_c()
         self.qdt = qb_dtype(dtype)
-        self.lik = _lib.qb_lik_t(1.0, 0.0, 1.0, None, 0, 0)
+        self.logpost = logpost
+        if logpost is None:
+            self.lik = _lib.qb_lik_t(1.0, 0.0, 1.0, None, 0, 0)
+        else:
+            self.anchor = logpost['anchor']
+            self.lik = _lib.qb_lik_t(float(logpost['sigma']), float(logpost['prior_sigma']), 1.0, self.anchor.data_ptr(), 1, 0)
         self.lib = _lib.load()
         self.lp = torch.empty(K, dtype=torch.float64, device=device)
         self.grad = torch.empty((K, desc.n_params), dtype=dtype, device=device)
@@ -49,11 +56,15 @@ class _MemberEval:
         if self.ws is None or self.ws.numel() < need:
             self.ws = torch.empty(max(int(need), 256), dtype=torch.uint8, device=self.device)
         data = _lib.qb_data_t(_ptr(x), _ptr(y), n)
+        if self.logpost is not None:
+            self.lik.prior_scale = float(n) / float(self.logpost['nfull'])          # losses.py:204
         with torch.cuda.device(self.device):
             rc = self.lib.qb_logpost_members(C.byref(self.cnet), self.qdt, _ptr(theta), self.K, C.byref(data), xs, ys,
                                              C.byref(self.lik), _ptr(self.lp), _ptr(self.grad) if want_grad else None,
                                              _ptr(self.ws), self.ws.numel(), _stream())
         _lib.check(rc, 'qb_logpost_members')
+        if self.logpost is not None:
+            return -self.lp
         # MSE of every member from the sigma=1 log-posterior
         return -(2.0 * self.lp + n * LOG_2PI) / (n * self.desc.out_dim)
 
@@ -62,7 +73,7 @@ class MemberTrainer:
     """State of a batched ensemble fit; `epoch(t, perm_t)` advances every member by one epoch (all its minibatches)."""
 
     def __init__(self, desc, theta0, xtrn, ytrn, subsets, val=None, lrate=0.1, wd=0.0, batch_size=None,
-                 dtype=torch.float64, device='cuda'):
+                 dtype=torch.float64, device='cuda', logpost=None):
         if not torch.cuda.is_available():
             raise RuntimeError('batched ensemble training needs a CUDA device (there is no CPU fallback)')
         self.device = device = torch.device(device)
@@ -89,7 +100,13 @@ class MemberTrainer:
             batch_size = nsub
         self.batch_size = int(batch_size)
         self.full_batch = self.batch_size == nsub
-        self.ev = _MemberEval(desc, K, dtype, device)
+        if logpost is not None:
+            # NN_RMS (nn_rms.py:50-54): NegLogPost with a per-member anchor; fulldatasize = the member's subset size
+            logpost = dict(logpost, anchor=as_device(logpost['anchor'], dtype, device).contiguous(), nfull=nsub)
+            if logpost['anchor'].shape != (K, P):
+                raise ValueError('logpost anchor must be [K,P]')
+        self.ev = _MemberEval(desc, K, dtype, device, logpost)
+        self.grad_scale = None if logpost is None else -1.0
         self.qdt = qb_dtype(dtype)
         self.m = torch.zeros_like(self.theta)
         self.v = torch.zeros_like(self.theta)
@@ -129,18 +146,20 @@ class MemberTrainer:
             with torch.cuda.device(self.device):
                 _lib.check(lib.qb_adam_step(self.qdt, _ptr(self.theta), _ptr(ev.grad), _ptr(self.m), _ptr(self.v), K * P,
                                             self.lrate, 0.9, 0.999, 1e-8, self.wd, self.step,
-                                            -2.0 / (nb * self.desc.out_dim), _stream()), 'qb_adam_step')
+                                            self.grad_scale if self.grad_scale is not None else -2.0 / (nb * self.desc.out_dim),
+                                            _stream()), 'qb_adam_step')
 
 
 def fit_members(desc, theta0, xtrn, ytrn, subsets, val=None, nepochs=5000, lrate=0.1, wd=0.0, batch_size=None,
-                perms=None, dtype=torch.float64, device='cuda', freq_out=100, verbose=True):
+                perms=None, dtype=torch.float64, device='cuda', freq_out=100, verbose=True, logpost=None):
     """Train K members together.  theta0: [K,P] (or [P], replicated); subsets: [K, nsub] integer rows of xtrn that
     member k trains on (nn_ens.py:62-63); val: None (a member's own subset, nnfit.py:108-109) or (xval, yval) shared by
-    all members; perms: optional [K, nepochs, nsub] minibatch orders (otherwise drawn with torch.randperm in the
+    all members; logpost: None (MSE) or dict(sigma=, prior_sigma=, anchor=[K,P]) for nnfit's 'logpost' loss (NN_RMS);
+    perms: optional [K, nepochs, nsub] minibatch orders (otherwise drawn with torch.randperm in the
     reference's member-major order when that array is small, else epoch by epoch).
     Returns dict(best_theta [K,P], best_loss [K], best_epoch [K], theta [K,P], history [niter, K] of validation MSE)."""
     tr = MemberTrainer(desc, theta0, xtrn, ytrn, subsets, val=val, lrate=lrate, wd=wd, batch_size=batch_size, dtype=dtype,
-                       device=device)
+                       device=device, logpost=logpost)
     K, nsub, device = tr.K, tr.nsub, tr.device
     if perms is not None:
         perms = torch.as_tensor(np.asarray(perms), dtype=torch.long, device=device)

@@ -25,7 +25,7 @@ class AMCMC(MCMCBase):
                       "(deviation from admcmc.py:59; pass adapt='full' to force the dense recursion)")
         chol = None
         if self.cov_ini is not None:
-            chol = np.linalg.cholesky(np.asarray(self.cov_ini, dtype=np.float64))
+            chol = self._lower_factor(np.asarray(self.cov_ini, dtype=np.float64))
         self._adapt_used = adapt
         return ops.AmcmcState(st, gamma=self.gamma, t0=self.t0, tadapt=self.tadapt, adapt=adapt, chol_ini=chol)
 
@@ -42,6 +42,19 @@ class AMCMC(MCMCBase):
         if samp.chol is not None and int(samp.prop_kind[0].item()) == 2:
             Lf = samp.chol[0].double().cpu().numpy()
             self._propcov = Lf @ Lf.T
+
+    @staticmethod
+    def _lower_factor(cov):
+        """Lower-triangular L with L L^T = cov for a positive SEMI-definite cov: Cholesky when it exists, else the
+        eigen factor A = V sqrt(S) re-triangularised by a QR of A^T (A A^T = R^T R).  The reference accepts singular
+        cov_ini because np.random.multivariate_normal factors through an SVD (admcmc.py:70)."""
+        try:
+            return np.linalg.cholesky(cov)
+        except np.linalg.LinAlgError:
+            s, v = np.linalg.eigh(0.5 * (cov + cov.T))
+            a = v * np.sqrt(np.clip(s, 0.0, None))[None, :]
+            r = np.linalg.qr(a.T, mode='r')
+            return r.T
 
     @staticmethod
     def _factor(cov):

@@ -37,7 +37,7 @@ class NN_Ens(QUiNNBase):
             return False
         if kwargs.get('loss_xy') is not None or kwargs.get('lmbd') is not None or kwargs.get('scheduler_lr') is not None:
             return False
-        if kwargs.get('gradcheck', False) or int(len(self.learners)) > 65535:
+        if kwargs.get('gradcheck', False):
             return False
         from ..nns.nnbase import MLPBase
         for l in self.learners:       # a model with its own training procedure keeps it (learner.py:66-70); MLPBase.fit IS nnfit

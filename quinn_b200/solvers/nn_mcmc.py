@@ -110,14 +110,16 @@ class NN_MCMC(QUiNNBase):
         return out[0] if np.ndim(param_ini) == 1 else out
 
     map_batched_above = 8          # more start points than this: one batched optimisation instead of K BFGS runs
+    map_start_steps = 300          # Adam ascent steps of the batched MAP start
 
-    def _map_start_batched(self, rows, nsteps=300, lrate=0.01):
+    def _map_start_batched(self, rows, nsteps=None, lrate=0.01):
         """MAP pre-conditioning of MANY chains at once (the reference has one chain and BFGS with
         finite differences, nn_mcmc.py:125-127): Adam ascent on log p(theta|D) for all K starts together - kernel 2,
         qb_adam_step and qb_copy_rows_where, nothing leaves the device - returning the best state each chain visited."""
         import ctypes as C
         from .. import _lib
         from ..ops import _ptr, _stream, qb_dtype
+        nsteps = self.map_start_steps if nsteps is None else nsteps
         prob = self.device_logpost(self.lpinfo).problem
         lib = _lib.load()
         theta = prob.theta(rows).clone()

@@ -321,3 +321,33 @@ def test_nn_mcmc_batched_map_start():
     assert (uq.map_start_logpost >= lp_start).all() and uq.map_start_logpost.mean() > lp_start.mean() + 10.0
     np.testing.assert_allclose(uq.mcmc_results['logpost'][:, 0], uq.map_start_logpost, rtol=1e-9)
     assert uq.samples.shape == (32, 21, uq.pdim)
+
+
+def test_more_than_65535_chains_through_the_solver_api():
+    """The advertised scale is 1e5 chains: row-copy, member-parallel predictive and the chain kernels put chains on
+    gridDim.x, so K > 65535 works through NN_MCMC.fit(zflag=True) (batched MAP start), predict_MAP and predict_ens."""
+    from quinn_b200.nns import MLP
+    from quinn_b200.solvers import NN_MCMC
+    np.random.seed(8)
+    torch.manual_seed(8)
+    net = MLP(1, 1, (4,), activ='tanh')
+    x = np.random.rand(16, 1) * 2 - 1
+    y = np.sin(2 * x) + 0.05 * np.random.randn(16, 1)
+    uq = NN_MCMC(net, verbose=False, dtype=torch.float32)
+    uq.map_start_steps = 20
+    K = 70_000
+    res = uq.fit(x, y, zflag=True, datanoise=0.1, nmcmc=6, sampler='amcmc', sampler_params={'gamma': 0.1}, nchains=K, seed=2)
+    assert uq.samples.shape == (K, 7, uq.pdim) and np.isfinite(uq.samples).all()
+    assert uq.map_start_logpost.shape == (K,)
+    xt = np.linspace(-1, 1, 5)[:, None]
+    pm = uq.predict_MAP(xt)
+    assert pm.shape == (K, 5, 1) and np.isfinite(pm).all()
+    # spot check of the last chains (beyond 65535) against the oracle forward
+    from oracle import quinn_oracle as qo
+    layers, P = qo.mlp_layers(1, 1, (4,), True, 'tanh')
+    for k in (65_535, 65_536, K - 1):
+        ref = qo.forward(layers, np.asarray(uq.cmode[k], dtype=np.float64), xt)
+        np.testing.assert_allclose(pm[k], ref, rtol=1e-4, atol=1e-5)
+    pe = uq.predict_ens(xt, nens=2, nburn=2)
+    assert pe.shape == (2 * K, 5, 1) and np.isfinite(pe).all()
+    assert 0.0 < np.asarray(res['accrate']).mean() <= 1.0

@@ -181,3 +181,83 @@ def test_fit_members_rnet_shared_weights():
         np.testing.assert_allclose(res['history'][:, k].cpu().numpy(), hist, rtol=1e-7, atol=1e-12)
         np.testing.assert_allclose(res['theta'][k].cpu().numpy(), ft, rtol=1e-6, atol=1e-8)
         assert int(res['best_epoch'][k].item()) == be
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# golden fixtures produced by RUNNING THE REFERENCE (tests/golden/make_golden_r2.py): NN_Ens.fit / NN_RMS.fit
+# ------------------------------------------------------------------------------------------------------------------
+def _golden(name):
+    from golden_util import load
+    return load(name)
+
+
+@pytest.mark.parametrize('name', ['ensfit_full', 'ensfit_mini'])
+def test_fit_members_reproduces_the_reference_nn_ens_fit(name):
+    """The batched device trainer against what the reference's NN_Ens.fit produced (nn_ens.py:51-69 -> nnfit.py:125-166):
+    same member subsets and minibatch orders => same validation-loss history, best epoch, best and final weights."""
+    from quinn_b200.ens.batched import fit_members
+    from quinn_b200.netdesc import netdesc_from_module
+    from quinn_b200.nns import MLP
+    g = _golden(name + '.npz')
+    net = MLP(2, 2, (16, 16), activ='tanh').double()
+    desc = netdesc_from_module(net)
+    bs = int(g['batch_size'])
+    res = fit_members(desc, g['theta0'], g['x'], g['y'], g['subsets'], nepochs=int(g['nepochs']), lrate=float(g['lrate']),
+                      batch_size=None if bs < 0 else bs, perms=g['perms'], dtype=torch.float64, verbose=False)
+    hist = res['history'].cpu().numpy()                 # [niter, K] validation loss before every update
+    np.testing.assert_allclose(hist.T, g['history'][:, :, 3], rtol=1e-7, atol=1e-12)
+    np.testing.assert_allclose(res['best_loss'].cpu().numpy(), g['best_loss'], rtol=1e-8)
+    assert np.array_equal(res['best_epoch'].cpu().numpy(), g['best_epoch'])
+    np.testing.assert_allclose(res['best_theta'].cpu().numpy(), g['best_theta'], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(res['theta'].cpu().numpy(), g['final_theta'], rtol=1e-6, atol=1e-8)
+
+
+def test_nn_ens_fit_reproduces_the_reference_under_the_same_seeds():
+    """The solver call itself (full batch): np.random.seed / torch.manual_seed as in the generating script."""
+    from quinn_b200.nns import MLP
+    from quinn_b200.solvers import NN_Ens
+    from quinn_b200.netdesc import flatten_module, unflatten_module
+    g = _golden('ensfit_full.npz')
+    np.random.seed(21)
+    torch.manual_seed(21)
+    net = MLP(2, 2, (16, 16), activ='tanh')
+    unflatten_module(net, g['theta0'])                  # the reference's initial weights (its own torch init stream)
+    x, y = g['x'], g['y']
+    np.random.rand(50, 2), np.random.randn(50, 2)       # the data draws of the generating script come first
+    ens = NN_Ens(net, nens=int(g['nens']), dfrac=float(g['dfrac']))
+    ens.fit(x, y, nepochs=int(g['nepochs']), lrate=float(g['lrate']), batch_size=None, freq_out=10 ** 9, freq_plot=10 ** 9)
+    assert ens.batched_fit
+    best = np.stack([flatten_module(l.best_model) for l in ens.learners])
+    np.testing.assert_allclose(best, g['best_theta'], rtol=1e-6, atol=1e-8)
+
+
+def test_nn_rms_reproduces_the_reference_fit():
+    """NN_RMS (nn_rms.py:33-56) on the batched trainer: anchored NegLogPost loss, per-member anchors."""
+    from quinn_b200.ens.batched import fit_members
+    from quinn_b200.netdesc import netdesc_from_module, flatten_module, unflatten_module
+    from quinn_b200.nns import MLP
+    from quinn_b200.solvers import NN_RMS
+    g = _golden('rms_fit.npz')
+    net = MLP(2, 1, (12,), activ='tanh').double()
+    desc = netdesc_from_module(net)
+    anchors = g['anchors_raw'] * float(g['priorsigma'])
+    res = fit_members(desc, g['theta0'], g['x'], g['y'], g['subsets'], nepochs=int(g['nepochs']), lrate=float(g['lrate']),
+                      dtype=torch.float64, verbose=False,
+                      logpost=dict(sigma=float(g['datanoise']), prior_sigma=float(g['priorsigma']), anchor=anchors))
+    np.testing.assert_allclose(res['history'].cpu().numpy().T, g['history'][:, :, 3], rtol=1e-8)
+    assert np.array_equal(res['best_epoch'].cpu().numpy(), g['best_epoch'])
+    np.testing.assert_allclose(res['best_theta'].cpu().numpy(), g['best_theta'], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(res['theta'].cpu().numpy(), g['final_theta'], rtol=1e-6, atol=1e-8)
+    # the solver class under the generating script's seeds: same subsets, anchors and trained members
+    np.random.seed(22)
+    torch.manual_seed(22)
+    net2 = MLP(2, 1, (12,), activ='tanh')
+    unflatten_module(net2, g['theta0'])
+    np.random.rand(40, 2), np.random.randn(40, 1)
+    rms = NN_RMS(net2, nens=int(g['nens']), dfrac=float(g['dfrac']), datanoise=float(g['datanoise']), priorsigma=float(g['priorsigma']))
+    rms.fit(g['x'], g['y'], nepochs=int(g['nepochs']), lrate=float(g['lrate']), freq_out=10 ** 9, freq_plot=10 ** 9)
+    assert rms.batched_fit
+    np.testing.assert_allclose(rms.anchors, anchors, rtol=0, atol=0)
+    best = np.stack([flatten_module(l.best_model) for l in rms.learners])
+    np.testing.assert_allclose(best, g['best_theta'], rtol=1e-6, atol=1e-8)
+    assert rms.predict_ens(g['x'][:5]).shape == (3, 5, 1)

@@ -167,3 +167,43 @@ def test_degenerate_sizes_are_refused_or_handled():
     th_nan = np.zeros((2, desc.n_params))
     th_nan[1, 0] = np.nan                                        # NaN state: lp is NaN and every proposal from it rejects
     assert np.isnan(ops.logpost(p, th_nan)[1].item())
+
+
+@pytest.mark.parametrize('shape', ['c5_hot', 'c3_wide'])
+def test_tensor_core_value_path_against_the_oracle_at_bench_size(shape):
+    """Direct fp64-oracle comparison of the tensor-core value kernels at N >= 10^4: the 79-tile loop (odd count, ragged
+    last tile) of the half-K pipeline of the config-5 shape, and the 128-wide (4 column groups) pipe of the config-3/4
+    net at 80 tiles + 1 point, in the log-posterior kernel, the fused chain kernel and the predictive kernel."""
+    from quinn_b200 import ops
+    if shape == 'c5_hot':
+        d, hls, N, sigma, tscale = 3, (64, 64), 10_000, 0.05, None
+    else:
+        d, hls, N, sigma, tscale = 10, (128, 128), 10_241, 0.05, 0.1
+    rs = np.random.RandomState(len(shape))
+    layers, desc = _net(d, hls)
+    x = (rs.rand(N, d) * 2 * math.pi - math.pi).astype(np.float32).astype(np.float64)
+    y = (np.sin(x).sum(1, keepdims=True) + sigma * rs.randn(N, 1)).astype(np.float32).astype(np.float64)
+    K = 160
+    th = (rs.rand(K, desc.n_params) if tscale is None else tscale * rs.randn(K, desc.n_params)).astype(np.float32).astype(np.float64)
+    prob = ops.Problem(desc, x, y, sigma, dtype=torch.float32)
+    assert prob.plan_info(K)['tensor_core'] == 2
+    lp = ops.logpost(prob, th).cpu().numpy()
+    picks = (0, K // 2, K - 1)
+    refs = {k: qo.logpost(layers, th[k], x, y, sigma) for k in picks}
+    for k in picks:
+        assert abs(lp[k] - refs[k]) <= 1e-5 * abs(refs[k]), (k, lp[k], refs[k])
+    # fused chain kernel: the log-posterior it records for the initial state and for an accepted step
+    st = ops.ChainState(prob, th)
+    rec = ops.Recorder(st, 2, store_every=1)
+    ops.amcmc_run(st, ops.AmcmcState(st, gamma=0.01), 2, rec, seed=4)
+    lp0 = rec.logpost0.cpu().numpy()
+    for k in picks:
+        assert abs(lp0[k] - refs[k]) <= 1e-5 * abs(refs[k])
+        s1 = rec.samples[k, 1].double().cpu().numpy()
+        r1 = qo.logpost(layers, s1, x, y, sigma)
+        assert abs(rec.logpost[k, 1].item() - r1) <= 1e-5 * abs(r1)
+    # predictive kernel
+    out, _, _ = ops.predict(desc, th[:3], x, dtype=torch.float32)
+    for k in range(3):
+        ref = qo.forward(layers, th[k], x)
+        assert np.abs(out[k].double().cpu().numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())

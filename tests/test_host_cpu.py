@@ -22,7 +22,7 @@ def test_library_exports_every_header_symbol():
         assert hasattr(lib, n), f'{n} declared in include/quinn_b200.h but not exported'
     assert names == set(_lib.SYMBOLS), (names ^ set(_lib.SYMBOLS))
     lib = _lib.load()
-    assert lib.qb_version() >= 100
+    assert lib.qb_version() == _lib.QB_ABI_VERSION
     assert lib.qb_launch_count() >= 0
 
 
@@ -135,7 +135,17 @@ def test_tensor_core_plan_selection_is_host_logic():
     c2 = info('mlp_c2', _lib.QB_F32)
     assert c2[6] == 2 and c2[7] == 128
     assert info('mlp_c5', _lib.QB_F64)[6] == 0                  # fp64 stays on the CUDA cores
-    assert info('mlp_c5', _lib.QB_F32, grad=1)[6] == 0          # gradients too
+    g5 = info('mlp_c5', _lib.QB_F32, grad=1)                    # gradient path: tcgen05 kernel 2 (qb_tcg.cuh)
+    assert g5[6] == 3 and g5[1] == 512 and g5[7] == 512 and g5[2] <= 227 * 1024
+    g2 = info('mlp_c2', _lib.QB_F32, grad=1)
+    assert g2[6] == 3 and g2[1] == 256 and g2[7] == 256
+    assert info('mlp_c3', _lib.QB_F32, grad=1)[6] == 0          # 128-wide: operands exceed shared memory -> CUDA cores
+    assert info('mlp_c5', _lib.QB_F64, grad=1)[6] == 0
+    os.environ['QB_NO_TCG'] = '1'
+    try:
+        assert info('mlp_c5', _lib.QB_F32, grad=1)[6] == 0 and info('mlp_c5', _lib.QB_F32)[6] == 2
+    finally:
+        del os.environ['QB_NO_TCG']
     assert info('rnet_c1', _lib.QB_F32)[6] == 0                 # residual nets are not eligible
     assert info('mlp_tanh_o2', _lib.QB_F32)[6] == 0             # hidden widths 8, 6: not multiples of 16
     os.environ['QB_NO_TC'] = '1'
