@@ -269,53 +269,82 @@ __device__ __forceinline__ double qb_tcg_eval(const QbTcgPlan& tp, QbTcgCtx& cx,
     float ssq = 0.0f, dbl = 0.0f;
     __syncthreads();               // staged weights visible; the previous evaluation's readers are done
 
-    for (int t = 0; t < ntiles; ++t) {
-        const int64_t p = n0 + (int64_t)t * 128 + pt;
-        const bool live = p < n1;
-        unsigned char* xt = smem + tp.xt + (t & 1) * QB_TCG_XT_TILE;
-        // ---------------- L0
-        {
-            float xr[NI];
+    // Pipeline (two block-wide hand-overs per tile):
+    //   phase B(t): wait FWD(t) -> EPI1(t) -> [wait DW0(t-1)] store z1            -> issue BWD(t), DW1(t), DB1(t)
+    //   phase A(t): wait BWD(t) -> EPI0(t) and L0(t+1), results parked in tensor memory (the z and a0 OPERAND columns are
+    //               free once BWD(t) / FWD(t) are done) while DW1(t) / DB1(t) still read the shared-memory operands
+    //               -> wait DW1(t) -> copy z0(t) and a0(t+1) from tensor memory to shared memory -> issue FWD(t+1), DW0(t)
+    // so layer 0 of the next tile and the back-propagation epilogue overlap the weight-gradient MMAs.
+    // Inputs and target of a point are fetched one tile ahead (one block per SM in lock step: nothing else hides L2 latency).
+    float xn[NI], yn = 0.0f;
+    auto fetch = [&](int tt) {
+        const int64_t pp = n0 + (int64_t)tt * 128 + pt;
 #pragma unroll
-            for (int q = 0; q < NI; ++q) {
-                float v = 0.0f;
-                if (q < tp.in_dim && live) v = __ldg(x + p * tp.in_dim + q);
-                xr[q] = (q == tp.in_dim) ? 1.0f : v;
+        for (int q = 0; q < NI; ++q) xn[q] = (q < tp.in_dim && pp < n1) ? __ldg(x + pp * tp.in_dim + q) : 0.0f;
+        yn = pp < n1 ? __ldg(y + pp) : 0.0f;
+    };
+    // layer 0 of tile tt from the prefetched inputs: X^T rows (group 0) to shared memory, a0 to tensor memory
+    auto layer0 = [&](int tt) {
+        unsigned char* xt = smem + tp.xt + (tt & 1) * QB_TCG_XT_TILE;
+        float xr[NI];
+#pragma unroll
+        for (int q = 0; q < NI; ++q) xr[q] = (q == tp.in_dim) ? 1.0f : xn[q];
+        if (grp == 0) {
+            // X^T rows q = 0..7 (inputs, then the constant 1, then zeros), element (q, pt): chunk stride 144
+            float* xh = reinterpret_cast<float*>(xt + (pt >> 2) * 144u + (pt & 3u) * 4u);
+            float* xl = reinterpret_cast<float*>(xt + QB_TCG_XT_HALF + (pt >> 2) * 144u + (pt & 3u) * 4u);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float v = q < NI ? xr[q < NI ? q : 0] : 0.0f;
+                const float h = qb_tf32_hi(v);
+                xh[q * 4] = h;
+                xl[q * 4] = v - h;
             }
-            if (grp == 0) {
-                // X^T rows q = 0..7 (inputs, then the constant 1, then zeros), element (q, pt): chunk stride 144
-                float* xh = reinterpret_cast<float*>(xt + (pt >> 2) * 144u + (pt & 3u) * 4u);
-                float* xl = reinterpret_cast<float*>(xt + QB_TCG_XT_HALF + (pt >> 2) * 144u + (pt & 3u) * 4u);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float v = q < NI ? xr[q < NI ? q : 0] : 0.0f;
-                    const float h = qb_tf32_hi(v);
-                    xh[q * 4] = h;
-                    xl[q * 4] = v - h;
-                }
-            }
-            float h[16];
-            // same layer-0 code as the value path (QbTcPlan fields it reads: w0)
-            {
-                const float4* W = reinterpret_cast<const float4*>(F + tp.w0 + c * NI);
-#pragma unroll
-                for (int gq = 0; gq < 4; ++gq) {
-                    float2 z0 = make_float2(0.0f, 0.0f), z1 = make_float2(0.0f, 0.0f);
-#pragma unroll
-                    for (int q = 0; q < NI; q += 2) {
-                        const float4 wa = W[(2 * gq) * (NI / 2) + q / 2], wb = W[(2 * gq + 1) * (NI / 2) + q / 2];
-                        z0 = __ffma2_rn(make_float2(wa.x, wa.y), make_float2(xr[q], xr[q]), z0);
-                        z0 = __ffma2_rn(make_float2(wa.z, wa.w), make_float2(xr[q + 1], xr[q + 1]), z0);
-                        z1 = __ffma2_rn(make_float2(wb.x, wb.y), make_float2(xr[q], xr[q]), z1);
-                        z1 = __ffma2_rn(make_float2(wb.z, wb.w), make_float2(xr[q + 1], xr[q + 1]), z1);
-                    }
-                    qb_tc_act4<ACT>(z0, z1);
-                    h[4 * gq + 0] = z0.x; h[4 * gq + 1] = z0.y; h[4 * gq + 2] = z1.x; h[4 * gq + 3] = z1.y;
-                }
-            }
-            qb_tc_split_store(tl + tp.c_a0hi + c, tl + tp.c_a0lo + c, h);
-            qb_tcg_store_mn(a0hi, a0lo, pt, c, (uint32_t)tp.a0_sbo, h);
         }
+        float h[16];
+        const float4* W = reinterpret_cast<const float4*>(F + tp.w0 + c * NI);
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+            float2 z0 = make_float2(0.0f, 0.0f), z1 = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int q = 0; q < NI; q += 2) {
+                const float4 wa = W[(2 * gq) * (NI / 2) + q / 2], wb = W[(2 * gq + 1) * (NI / 2) + q / 2];
+                z0 = __ffma2_rn(make_float2(wa.x, wa.y), make_float2(xr[q], xr[q]), z0);
+                z0 = __ffma2_rn(make_float2(wa.z, wa.w), make_float2(xr[q + 1], xr[q + 1]), z0);
+                z1 = __ffma2_rn(make_float2(wb.x, wb.y), make_float2(xr[q], xr[q]), z1);
+                z1 = __ffma2_rn(make_float2(wb.z, wb.w), make_float2(xr[q + 1], xr[q + 1]), z1);
+            }
+            qb_tc_act4<ACT>(z0, z1);
+            h[4 * gq + 0] = z0.x; h[4 * gq + 1] = z0.y; h[4 * gq + 2] = z1.x; h[4 * gq + 3] = z1.y;
+        }
+        qb_tc_split_store(tl + tp.c_a0hi + c, tl + tp.c_a0lo + c, h);
+    };
+    // this thread's 16-unit chunk, already split, from tensor memory columns (hi_col, lo_col) to an MN-major point buffer
+    auto park_to_smem = [&](uint32_t hi_col, uint32_t lo_col, unsigned char* bhi, unsigned char* blo, uint32_t sbo) {
+        uint32_t vh[16], vl[16];
+        qb_tmem_ld16(tl + hi_col + c, vh);
+        qb_tmem_ld16(tl + lo_col + c, vl);
+        qb_tmem_ld_wait16(vh);
+        qb_tmem_ld_wait16(vl);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int u0 = c + 8 * half;
+            const uint32_t off = qb_tcg_piece(pt, (uint32_t)u0 >> 5, ((uint32_t)u0 >> 3) & 3u, sbo);
+            uint4* ph = reinterpret_cast<uint4*>(bhi + off);
+            uint4* pl = reinterpret_cast<uint4*>(blo + off);
+            ph[0] = make_uint4(vh[8 * half + 0], vh[8 * half + 1], vh[8 * half + 2], vh[8 * half + 3]);
+            ph[1] = make_uint4(vh[8 * half + 4], vh[8 * half + 5], vh[8 * half + 6], vh[8 * half + 7]);
+            pl[0] = make_uint4(vl[8 * half + 0], vl[8 * half + 1], vl[8 * half + 2], vl[8 * half + 3]);
+            pl[1] = make_uint4(vl[8 * half + 4], vl[8 * half + 5], vl[8 * half + 6], vl[8 * half + 7]);
+        }
+    };
+
+    if (ntiles > 0) {
+        fetch(0);
+        layer0(0);
+        fetch(1);
+        qb_tmem_st_wait();
+        park_to_smem(tp.c_a0hi, tp.c_a0lo, a0hi, a0lo, (uint32_t)tp.a0_sbo);
         qb_tcg_publish(cx);
         if (warp == 0) {
             qb_mbar_wait(cx.abar, cx.ph & 1u);
@@ -325,13 +354,21 @@ __device__ __forceinline__ double qb_tcg_eval(const QbTcgPlan& tp, QbTcgCtx& cx,
             __syncwarp();
         }
         cx.ph ^= 1u;
-        // ---------------- EPI1
-        float yv = 0.0f;
-        if (live) yv = __ldg(y + p);
+    }
+    float yv = 0.0f;                                             // target of this thread's point of the current tile
+    {
+        const int64_t p0 = n0 + pt;
+        if (p0 < n1) yv = __ldg(y + p0);
+    }
+    for (int t = 0; t < ntiles; ++t) {
+        const int64_t p = n0 + (int64_t)t * 128 + pt;
+        const bool live = p < n1;
+        const bool more = t + 1 < ntiles;
+        // ---------------- phase B: EPI1(t)
         qb_tcg_wait(cx.barf, cx, 1);
-        float a1[16];
-        float dy;
         {
+            float a1[16];
+            float dy;
             uint32_t v[16];
             qb_tmem_ld16(tl + tp.c_d1 + c, v);
             qb_tmem_ld_wait16(v);
@@ -352,10 +389,7 @@ __device__ __forceinline__ double qb_tcg_eval(const QbTcgPlan& tp, QbTcgCtx& cx,
             const float r = live ? yv - yo : 0.0f;
             dy = r * is2;
             if (grp == 0) { ssq = fmaf(r, r, ssq); dbl += dy; }
-        }
-        {
             float z[16];
-            const float4* w4 = reinterpret_cast<const float4*>(F + tp.wl + c);
 #pragma unroll
             for (int gq = 0; gq < 4; ++gq) {
                 const float4 w = w4[gq];
@@ -367,7 +401,7 @@ __device__ __forceinline__ double qb_tcg_eval(const QbTcgPlan& tp, QbTcgCtx& cx,
                     dwl[4 * gq + e] = fmaf(dy, a, dwl[4 * gq + e]);
                 }
             }
-            if (t > 0) qb_tcg_wait(cx.barz, cx, 4);            // DW0 of the previous tile has finished reading the z buffer
+            if (t > 0) qb_tcg_wait(cx.barz, cx, 4);            // DW0(t-1) has finished reading the z buffer
             qb_tc_split_store(tl + tp.c_zhi + c, tl + tp.c_zlo + c, z);
             qb_tcg_store_mn(zhi, zlo, pt, c, (uint32_t)tp.z_sbo, z);
         }
@@ -379,7 +413,7 @@ __device__ __forceinline__ double qb_tcg_eval(const QbTcgPlan& tp, QbTcgCtx& cx,
                 qb_tcg_issue_ts<KS>(cx.tmem + tp.c_d0, cx.tmem + tp.c_zhi, cx.tmem + tp.c_zlo, w1thi_lo, w1tlo_lo, w_hi, id_fwd, cx.barb);
                 const uint32_t acc0 = t > 0 ? 1u : 0u;
                 qb_tcg_issue_ss(cx.tmem + tp.c_dw1, zhi_lo, zlo_lo, z_hi, z_step, a0hi_lo, a0lo_lo, a0_hi, a0_step, id_dw1, acc0);
-                const uint32_t xs = qb_smem_u32(xt);
+                const uint32_t xs = qb_smem_u32(smem + tp.xt + (t & 1) * QB_TCG_XT_TILE);
                 qb_tcg_issue_ss(cx.tmem + tp.c_db1, zhi_lo, zlo_lo, z_hi, z_step, qb_desc_lo(xs, 144u),
                                 qb_desc_lo(xs + QB_TCG_XT_HALF, 144u), x_hi, 18u, id_dx, acc0);
                 qb_tcg_commit(cx.barw);
@@ -387,7 +421,7 @@ __device__ __forceinline__ double qb_tcg_eval(const QbTcgPlan& tp, QbTcgCtx& cx,
             __syncwarp();
         }
         cx.ph ^= 1u;
-        // ---------------- EPI0
+        // ---------------- phase A: EPI0(t) and L0(t+1), parked in tensor memory while DW1(t) / DB1(t) run
         qb_tcg_wait(cx.barb, cx, 2);
         {
             float z[16];
@@ -403,15 +437,25 @@ __device__ __forceinline__ double qb_tcg_eval(const QbTcgPlan& tp, QbTcgCtx& cx,
                 const float a = __uint_as_float(ah[e]) + __uint_as_float(al[e]);
                 z[e] = __uint_as_float(v[e]) * qb_tcg_dact<ACT>(a);
             }
-            qb_tcg_wait(cx.barw, cx, 3);                       // DW1 / DB1 have finished reading the z and a0 buffers
-            qb_tcg_store_mn(zhi, zlo, pt, c, (uint32_t)tp.z_sbo, z);
+            qb_tc_split_store(tl + tp.c_zhi + c, tl + tp.c_zlo + c, z);      // BWD(t) is done: the z operand columns are free
         }
+        if (more) {
+            yv = yn;
+            layer0(t + 1);                                       // FWD(t) is done and a0(t) was consumed above
+            fetch(t + 2);
+        }
+        qb_tmem_st_wait();
+        qb_tcg_wait(cx.barw, cx, 3);                             // DW1 / DB1 have finished reading the z and a0 buffers
+        park_to_smem(tp.c_zhi, tp.c_zlo, zhi, zlo, (uint32_t)tp.z_sbo);
+        if (more) park_to_smem(tp.c_a0hi, tp.c_a0lo, a0hi, a0lo, (uint32_t)tp.a0_sbo);
         qb_tcg_publish(cx);
         if (warp == 0) {
             qb_mbar_wait(cx.abar, cx.ph & 1u);
             qb_tc_fence_after();
             if (qb_elect()) {
-                const uint32_t xs = qb_smem_u32(xt);
+                if (more)
+                    qb_tcg_issue_ts<KS>(cx.tmem + tp.c_d1, cx.tmem + tp.c_a0hi, cx.tmem + tp.c_a0lo, w1hi_lo, w1lo_lo, w_hi, id_fwd, cx.barf);
+                const uint32_t xs = qb_smem_u32(smem + tp.xt + (t & 1) * QB_TCG_XT_TILE);
                 qb_tcg_issue_ss(cx.tmem + tp.c_dw0, zhi_lo, zlo_lo, z_hi, z_step, qb_desc_lo(xs, 144u),
                                 qb_desc_lo(xs + QB_TCG_XT_HALF, 144u), x_hi, 18u, id_dx, t > 0 ? 1u : 0u);
                 qb_tcg_commit(cx.barz);
