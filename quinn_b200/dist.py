@@ -99,3 +99,63 @@ def max_over_ranks(value):
 def barrier():
     if td.is_available() and td.is_initialized() and td.get_world_size() > 1:
         td.barrier()
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# running diagnostics of a sharded chain run (north_star: "NCCL ... only to gather samples and reduce cross-chain
+# diagnostics (R-hat, predictive mean and variance)")
+# --------------------------------------------------------------------------------------------------------------------
+class RunningDiagnostics:
+    """Per-segment cross-chain diagnostics, reduced over all ranks on a SIDE stream so that the chain kernels of the next
+    segment are not held up: the Gelman-Rubin R-hat of the log-posterior over the segment and the mean acceptance rate.
+    Use as the `on_segment` hook of MCMCBase.run (quinn_b200/mcmc/mcmc.py); `finish()` returns the history."""
+
+    def __init__(self, device=None):
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device) if (device is not None and torch.device(device).type == 'cuda') else None
+        self.rows = []
+        self._prev_acc = None
+
+    def __call__(self, state, rec, t_end):
+        lp, acc = rec.logpost, rec.accepted
+        n = lp.shape[1]
+        if self.stream is None:
+            self._reduce(lp, acc, n, t_end)
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(lp.device))
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ev)
+            self._reduce(lp, acc, n, t_end)
+
+    def _reduce(self, lp, acc, n, t_end):
+        if n >= 2:
+            r = rhat(lp.mean(1), lp.var(1, unbiased=True), n)
+        else:
+            r = torch.full((1,), float('nan'), dtype=torch.float64, device=lp.device)
+        s = torch.stack([acc.double().sum(), torch.tensor(float(acc.numel()), dtype=torch.float64, device=lp.device)])
+        _allreduce(s)
+        self.rows.append((int(t_end), r.reshape(-1)[:1], s))
+
+    def finish(self):
+        if self.stream is not None:
+            self.stream.synchronize()
+        return [dict(step=t, rhat_logpost=float(r[0].item()), accept_rate=float((s[0] / s[1]).item())) for t, r, s in self.rows]
+
+
+def allreduce_sum_(t):
+    """In-place SUM over ranks (no-op for a single process); returns t."""
+    return _allreduce(t)
+
+
+def broadcast_from_rank0(t):
+    if td.is_available() and td.is_initialized() and td.get_world_size() > 1:
+        td.broadcast(t, src=0)
+    return t
+
+
+def world():
+    """(rank, world_size) of the initialised process group, (0, 1) otherwise."""
+    if td.is_available() and td.is_initialized():
+        return td.get_rank(), td.get_world_size()
+    return 0, 1

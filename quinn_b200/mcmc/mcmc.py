@@ -21,6 +21,23 @@ from .. import ops
 
 
 _SIDE_STREAMS = {}
+_PINNED = {}          # result buffers of the host-pipelined path, reused from one run() to the next
+
+
+def _pinned_results(K, nstored, P, nmcmc, dtype):
+    """Pinned host buffers for the result dict of a (K, nmcmc) run.  Allocating GBs of page-locked memory costs more than
+    the chain kernel of a short run, so the buffers of the latest shape are kept (results returned to the caller are
+    numpy views of them: a following run() with the same shape overwrites them, pass copy_results=True to run() to keep
+    independent arrays)."""
+    key = (K, nstored, P, nmcmc, dtype)
+    if key not in _PINNED:
+        _PINNED.clear()
+        pin = lambda *shape, dtype: torch.empty(shape, dtype=dtype, pin_memory=True)      # noqa: E731
+        _PINNED[key] = dict(chain=pin(K, nstored, P, dtype=dtype), mapparams=pin(K, P, dtype=dtype),
+                            maxpost=pin(K, dtype=torch.float64), accrate=pin(K, dtype=torch.float64),
+                            logpost=pin(K, nmcmc + 1, dtype=torch.float64), alphas=pin(K, nmcmc + 1, dtype=torch.float64),
+                            accepted=pin(K, nmcmc, dtype=torch.uint8))
+    return _PINNED[key]
 
 
 def _side_streams(device):
@@ -47,6 +64,33 @@ class DeviceLogPost:
         return g[0].double().cpu().numpy() if np.ndim(theta) == 1 else g
 
 
+class ShardedDataLogPost:
+    """Log-posterior of data that is SHARDED over the ranks (north_star: "allreduce of log-likelihood partial sums when N
+    exceeds one GPU"): every rank evaluates kernels 1 / 2 on its slice for all chains; the Gaussian log-likelihood and
+    its constants are sums over points (losses.py:197-200), so the all-reduced SUM of the per-rank values is the
+    full-data log-posterior, bit-identical on every rank.  A batched callable for the generic sampler path (propose /
+    accept run redundantly on every rank from the same seed)."""
+    batched = True
+
+    def __init__(self, problem_local, n_total):
+        self.problem, self.n_total = problem_local, int(n_total)
+
+    def __call__(self, theta, **_):
+        from .. import dist
+        th = theta if torch.is_tensor(theta) else torch.as_tensor(np.atleast_2d(np.asarray(theta, dtype=np.float64)))
+        lp = ops.logpost(self.problem, th.to(self.problem.device)).clone()
+        return dist.allreduce_sum_(lp)
+
+    def grad(self, theta, **_):
+        from .. import dist
+        th = theta if torch.is_tensor(theta) else torch.as_tensor(np.atleast_2d(np.asarray(theta, dtype=np.float64)))
+        _, g = ops.logpost_grad(self.problem, th.to(self.problem.device))
+        return dist.allreduce_sum_(g.double().clone())
+
+
+ShardedDataLogPost.grad.batched = True          # the generic driver looks for this flag on the callable it was given
+
+
 class MCMCBase(object):
     def __init__(self):
         self.logPost = None
@@ -68,13 +112,15 @@ class MCMCBase(object):
 
     # ------------------------------------------------------------------ public driver
     def run(self, nmcmc, param_ini, *, seed=None, store_every=1, replay=None, chain_offset=0, verbose=True,
-            keep_on_device=False):
+            keep_on_device=False, copy_results=False, segment_every=None, on_segment=None):
         """nmcmc steps for every row of param_ini.
 
         Extensions (keyword-only): ``seed`` Philox seed (default: drawn from np.random so np.random.seed
         controls it), ``store_every`` thinning of the returned chain, ``replay=dict(incr=[M,(K,)P],
         unif=[M,(K)])`` to consume recorded draws instead of Philox, ``chain_offset`` global index of the
-        first chain (multi-GPU sharding), ``keep_on_device`` return CUDA tensors.
+        first chain (multi-GPU sharding), ``keep_on_device`` return CUDA tensors, ``copy_results`` detach the returned
+        arrays of the host-pipelined path from its reusable pinned buffers, ``segment_every`` / ``on_segment(state, recorder,
+        t_end)`` one kernel launch per that many steps with a hook after each (running diagnostics on a side stream).
         """
         assert self.logPost is not None
         if not torch.is_tensor(param_ini):          # tensors (e.g. pinned host memory) are passed through untouched
@@ -84,17 +130,18 @@ class MCMCBase(object):
         if seed is None:
             seed = int(np.random.randint(1, 2 ** 31 - 1))
         if self._device_lp is not None:
-            nsh = self._auto_shards(theta0, replay, keep_on_device)
+            nsh = 1 if on_segment is not None else self._auto_shards(theta0, replay, keep_on_device)
             if nsh != 1:
                 return self._run_fused_sharded(int(nmcmc), theta0, int(seed), int(store_every), int(chain_offset), verbose,
-                                               max(nsh, 1))
-            res = self._run_fused(int(nmcmc), theta0, int(seed), int(store_every), replay, int(chain_offset), verbose)
+                                               max(nsh, 1), copy_results)
+            res = self._run_fused(int(nmcmc), theta0, int(seed), int(store_every), replay, int(chain_offset), verbose,
+                                  segment_every, on_segment)
         else:
             res = self._run_generic(int(nmcmc), theta0, int(seed), int(store_every), verbose)
         return self._finish(res, single, keep_on_device)
 
     # ------------------------------------------------------------------ fused path (kernel 3)
-    def _run_fused(self, nmcmc, theta0, seed, store_every, replay, chain_offset, verbose):
+    def _run_fused(self, nmcmc, theta0, seed, store_every, replay, chain_offset, verbose, segment_every=None, on_segment=None):
         prob = self._device_lp.problem
         st = ops.ChainState(prob, theta0)
         K, P = st.K, st.P
@@ -105,6 +152,8 @@ class MCMCBase(object):
             unif = ops.as_device(np.asarray(replay['unif']).reshape(nmcmc, K), torch.float64, prob.device)
         nseg = 10 if (verbose and nmcmc >= 10) else 1
         bounds = [int(round(i * nmcmc / nseg)) for i in range(nseg + 1)]
+        if segment_every:           # one launch per `segment_every` steps (running diagnostics hook, multi-GPU driver)
+            bounds = list(range(0, nmcmc, int(segment_every))) + [nmcmc]
         if store_every > 1:          # segment boundaries must fall on stored steps
             bounds = sorted(set([0, nmcmc] + [b - b % store_every for b in bounds[1:-1]]))
         recs = []
@@ -118,6 +167,8 @@ class MCMCBase(object):
                 kw.update(incr=incr[a:b].contiguous(), unif=unif[a:b].contiguous())
             self._device_advance(st, samp, b - a, rec, kw)
             recs.append(rec)
+            if on_segment is not None:
+                on_segment(st, rec, b)          # must only ENQUEUE work (side stream); rec stays alive until the run returns
             if verbose:
                 acc = st.naccept.double().mean().item() / b
                 print('%d / %d completed, acceptance rate %lg' % (b, nmcmc, acc))
@@ -142,19 +193,16 @@ class MCMCBase(object):
         nbytes = theta0.shape[0] * theta0.shape[1] * prob.x.element_size()
         if not on_host or nbytes < 8 * 2 ** 20:
             return 1
-        # >= 8 MB of states: results go straight into pinned host buffers (path below); >= 256 MB: 4 pipelined shards
-        return 4 if (nbytes >= 256 * 2 ** 20 and theta0.shape[0] >= 8) else -1
+        # >= 8 MB of states: results go straight into pinned host buffers (path below); >= 256 MB: 8 pipelined shards (only
+        # the download of the last shard, 1/8 of the results, is not hidden behind a kernel)
+        return 8 if (nbytes >= 256 * 2 ** 20 and theta0.shape[0] >= 16) else -1
 
-    def _run_fused_sharded(self, nmcmc, theta0, seed, store_every, chain_offset, verbose, nsh):
+    def _run_fused_sharded(self, nmcmc, theta0, seed, store_every, chain_offset, verbose, nsh, copy_results=False):
         prob = self._device_lp.problem
         th = theta0 if torch.is_tensor(theta0) else torch.from_numpy(np.ascontiguousarray(theta0))
         K, P = th.shape
         nstored = 1 + (nmcmc // store_every if store_every > 0 else 0)
-        pin = lambda *shape, dtype: torch.empty(shape, dtype=dtype, pin_memory=True)      # noqa: E731
-        host = dict(chain=pin(K, nstored, P, dtype=prob.dtype), mapparams=pin(K, P, dtype=prob.dtype),
-                    maxpost=pin(K, dtype=torch.float64), accrate=pin(K, dtype=torch.float64),
-                    logpost=pin(K, nmcmc + 1, dtype=torch.float64), alphas=pin(K, nmcmc + 1, dtype=torch.float64),
-                    accepted=pin(K, nmcmc, dtype=torch.uint8))
+        host = _pinned_results(K, nstored, P, nmcmc, prob.dtype)
         main = torch.cuda.current_stream(prob.device)
         streams = _side_streams(prob.device)
         from ..dist import shard_range
@@ -175,7 +223,7 @@ class MCMCBase(object):
             s.synchronize()
         if verbose:
             print('%d / %d completed, acceptance rate %lg' % (nmcmc, nmcmc, host['accrate'].mean().item()))
-        out = {k: v.numpy() for k, v in host.items()}          # chain / mapparams stay in the compute dtype
+        out = {k: (v.numpy().copy() if copy_results else v.numpy()) for k, v in host.items()}   # chain / mapparams stay in the compute dtype
         out['accepted'] = out['accepted'].astype(bool)
         return out
 

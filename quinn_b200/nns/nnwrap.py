@@ -78,8 +78,17 @@ class NNWrap:
                 'quinn_b200.NNWrap evaluates losses in fused CUDA kernels and only knows NegLogPost '
                 '(the loss every sampler uses, SURVEY.md section 2 row 3); other loss modules have no GPU path here')
         inputs, targets = np.asarray(inputs, dtype=np.float64), np.asarray(targets, dtype=np.float64)
-        key = (id(loss_fn), inputs.shape, targets.shape, float(inputs.sum()), float(targets.sum()),
-               float(loss_fn.sigma), loss_fn.fulldatasize, id(loss_fn.priorparams))
+        # content key: data bytes, likelihood and prior values (equal-shape / equal-sum data no longer collide, in-place
+        # edits of the loss module or of the anchor are seen)
+        import hashlib
+        hsh = hashlib.blake2b(np.ascontiguousarray(inputs).tobytes(), digest_size=16)
+        hsh.update(np.ascontiguousarray(targets).tobytes())
+        pp0 = loss_fn.priorparams
+        if pp0 is not None:
+            hsh.update(np.ascontiguousarray(np.asarray(pp0['anchor'].detach().cpu() if hasattr(pp0['anchor'], 'detach') else pp0['anchor'],
+                                                       dtype=np.float64)).tobytes())
+        key = (inputs.shape, targets.shape, hsh.hexdigest(), float(loss_fn.sigma), loss_fn.fulldatasize,
+               None if pp0 is None else float(pp0['sigma']))
         if key != self._prob_key:
             pp = loss_fn.priorparams
             self._prob = ops.Problem(self.desc(), inputs, targets, float(loss_fn.sigma), dtype=_dtype_of(self.nnmodel),

@@ -40,14 +40,19 @@ class NN_MCMC(QUiNNBase):
         """GPU-resident log-posterior for this lpinfo dict (built once, unlike nn_mcmc.py:55-66)."""
         if lpinfo['ltype'] != 'classical':
             raise ValueError('Likelihood type is not recognized.')
-        key = id(lpinfo)
+        # keyed by CONTENT (data bytes, shapes, sigma): mutating lpinfo in place, which is legal in the reference (it rebuilds
+        # everything per call), gives a new key; calling fit() again with the same data reuses the resident copy
+        import hashlib
+        xd = np.ascontiguousarray(np.asarray(lpinfo['xd'], dtype=np.float64))
+        yd = np.ascontiguousarray(np.asarray(lpinfo['yd'], dtype=np.float64))
+        hsh = hashlib.blake2b(xd.tobytes(), digest_size=16)
+        hsh.update(yd.tobytes())
+        key = (xd.shape, yd.shape, float(lpinfo['lparams']['sigma']), str(self.dtype), str(self.device), hsh.hexdigest())
         h = self._problems.get(key)
         if h is None:
-            prob = ops.Problem(self.desc, np.asarray(lpinfo['xd']), np.asarray(lpinfo['yd']),
-                               lpinfo['lparams']['sigma'], dtype=self.dtype, device=self.device)
+            prob = ops.Problem(self.desc, xd, yd, lpinfo['lparams']['sigma'], dtype=self.dtype, device=self.device)
             h = DeviceLogPost(prob)
             self._problems = {key: h}
-            self._problems_ref = lpinfo      # keep the dict alive so its id stays unique
         return h
 
     def logpost(self, modelpars, lpinfo):
@@ -64,14 +69,30 @@ class NN_MCMC(QUiNNBase):
         return g[0] if modelpars.ndim == 1 else g
 
     def fit(self, xtrn, ytrn, zflag=True, datanoise=0.05, nmcmc=6000, param_ini=None, sampler='amcmc',
-            sampler_params=None, *, nchains=None, seed=None, store_every=1, replay=None, chain_offset=0):
+            sampler_params=None, *, nchains=None, seed=None, store_every=1, replay=None, chain_offset=0,
+            distributed=False, diag_every=None, gather=True, data_sharded=False):
         """Sample the posterior of the flat parameters (nn_mcmc.py:100-139).
 
         Extensions (keyword-only): ``nchains`` / a (K,P) ``param_ini`` run K chains at once (``samples``
         becomes (K, M+1, P)); ``seed``, ``store_every``, ``replay``, ``chain_offset`` are passed to the sampler.
         With ``zflag`` the start point is refined by BFGS on -logpost using the analytic gradient of kernel 2
-        (the reference uses finite differences, nn_mcmc.py:126)."""
+        (the reference uses finite differences, nn_mcmc.py:126).
+
+        Multi-GPU (one process per GPU under torchrun, ``quinn_b200.dist.init()`` or an initialised process group):
+        ``distributed=True`` shards the K chains over the ranks (block partition, Philox keyed by the global chain index, so
+        the chains are the ones a single process would run), reduces the R-hat of the log-posterior and the acceptance
+        rate over all ranks every ``diag_every`` steps (default: the sampler's ``tadapt`` or nmcmc/10) on a side stream
+        (``self.diagnostics``), and, with ``gather``, collects the result dict on rank 0 (other ranks keep their shard).
+        ``data_sharded=True``: every rank passes ITS slice of the data and all chains; each step's log-posterior
+        (and gradient) is the all-reduced sum of the per-rank partial sums (the N-sharded mode for data that exceed one
+        GPU; propose / accept run redundantly and identically on every rank)."""
         assert xtrn.shape[0] == ytrn.shape[0]
+        if data_sharded:
+            return self._fit_data_sharded(xtrn, ytrn, datanoise, nmcmc, param_ini, sampler, sampler_params, nchains, seed,
+                                          store_every)
+        if distributed:
+            return self._fit_distributed(xtrn, ytrn, zflag, datanoise, nmcmc, param_ini, sampler, sampler_params, nchains,
+                                         seed, store_every, chain_offset, diag_every, gather)
         self.lpinfo = {'model': nn_p, 'xd': xtrn, 'yd': [y for y in ytrn], 'ltype': 'classical',
                        'lparams': {'sigma': datanoise}}
         if param_ini is None:
@@ -93,6 +114,105 @@ class NN_MCMC(QUiNNBase):
             raise ValueError(f"sampler {sampler!r} is not one of 'amcmc', 'hmc', 'mala'")
         res = mymcmc.run(param_ini=param_ini, nmcmc=nmcmc, seed=seed, store_every=store_every, replay=replay,
                          chain_offset=chain_offset, verbose=self.verbose)
+        self.sampler_obj, self.mcmc_results = mymcmc, res
+        self.samples, self.cmode = res['chain'], res['mapparams']
+        return res
+
+    # ---- multi-GPU drivers ------------------------------------------------------------------------------------------
+    def _make_sampler(self, sampler, sampler_params):
+        sampler_params = {} if sampler_params is None else sampler_params
+        if sampler == 'amcmc':
+            m = AMCMC(**sampler_params)
+            m.setLogPost(self.logpost, None, lpinfo=self.lpinfo)
+        elif sampler == 'hmc':
+            m = HMC(**sampler_params)
+            m.setLogPost(self.logpost, self.logpostgrad, lpinfo=self.lpinfo)
+        elif sampler == 'mala':
+            m = MALA(**sampler_params)
+            m.setLogPost(self.logpost, self.logpostgrad, lpinfo=self.lpinfo)
+        else:
+            raise ValueError(f"sampler {sampler!r} is not one of 'amcmc', 'hmc', 'mala'")
+        return m
+
+    def _fit_distributed(self, xtrn, ytrn, zflag, datanoise, nmcmc, param_ini, sampler, sampler_params, nchains, seed,
+                         store_every, chain_offset, diag_every, gather):
+        """Chains sharded over the ranks; diagnostics reduced on a side stream; results gathered on rank 0."""
+        from .. import dist
+        rank, world = dist.world()
+        self.lpinfo = {'model': nn_p, 'xd': xtrn, 'yd': [y for y in ytrn], 'ltype': 'classical', 'lparams': {'sigma': datanoise}}
+        dev = torch.device(self.device)
+        # every rank must use the same start points and the same Philox seed: rank 0's are broadcast
+        if param_ini is None:
+            K = 1 if nchains is None else int(nchains)
+            p0 = torch.as_tensor(np.random.rand(K, self.pdim), dtype=torch.float64)
+        else:
+            p0 = torch.as_tensor(np.atleast_2d(np.asarray(param_ini, dtype=np.float64)))
+        sd = torch.tensor([int(seed) if seed is not None else int(np.random.randint(1, 2 ** 31 - 1))], dtype=torch.int64)
+        if world > 1:
+            on = dev if dev.type == 'cuda' else torch.device('cpu')
+            p0 = dist.broadcast_from_rank0(p0.to(on)).cpu()
+            sd = dist.broadcast_from_rank0(sd.to(on)).cpu()
+        K = p0.shape[0]
+        lo, hi = dist.shard_range(K, rank, world)
+        mine = p0[lo:hi].numpy()
+        if zflag:
+            mine = np.atleast_2d(self._map_start(mine))
+        mymcmc = self._make_sampler(sampler, sampler_params)
+        every = int(diag_every or getattr(mymcmc, 'tadapt', 0) or max(1, nmcmc // 10))
+        every = max(1, min(every, nmcmc))
+        diag = dist.RunningDiagnostics(dev)
+        res = mymcmc.run(param_ini=mine, nmcmc=nmcmc, seed=int(sd.item()), store_every=store_every,
+                         chain_offset=chain_offset + lo, verbose=False, keep_on_device=True, segment_every=every, on_segment=diag)
+        self.diagnostics = diag.finish()
+        if self.verbose and rank == 0:
+            for row in self.diagnostics:
+                print('%d / %d completed, acceptance rate %lg, R-hat(logpost) %lg' % (row['step'], nmcmc, row['accept_rate'], row['rhat_logpost']))
+        self.sampler_obj = mymcmc
+        self.shard = (lo, hi)
+        out = {}
+        for k, v in res.items():
+            if k == 'state':
+                continue
+            full = dist.gather_to_rank0(v.contiguous()) if (gather and world > 1) else v
+            if full is None:            # not rank 0: keep the local shard
+                full = v
+            out[k] = full.cpu().numpy().astype(bool) if full.dtype in (torch.uint8, torch.bool) else full.cpu().numpy()
+        self.mcmc_results = out
+        self.samples, self.cmode = out['chain'], out['mapparams']
+        return out
+
+    def predict_moments_distributed(self, x, nens=10, nburn=1000):
+        """Posterior-predictive mean / variance (ddof=1) over the thinned samples of ALL ranks' chains (quinn.py:85-99 with
+        the thinning rule of nn_mcmc.py:194-196 applied to every chain): per-rank sums of y and y^2, one all-reduce each.
+        Call after fit(distributed=True, gather=False); every rank returns the same arrays."""
+        from .. import dist
+        thetas = self._thinned(nens, nburn)
+        dev = torch.device(self.device)
+        out, _, _ = ops.predict(self.desc, thetas, np.asarray(x), dtype=self.dtype, device=dev)
+        y = out.double()
+        mean, var = dist.reduce_predictive_moments(y.sum(0), (y * y).sum(0), y.shape[0])
+        return mean.cpu().numpy(), var.cpu().numpy()
+
+    def _fit_data_sharded(self, xtrn, ytrn, datanoise, nmcmc, param_ini, sampler, sampler_params, nchains, seed, store_every):
+        """N-sharded mode: this rank holds a slice of the data; log-posteriors / gradients are all-reduced partial sums."""
+        from .. import dist
+        from ..mcmc.mcmc import ShardedDataLogPost
+        rank, world = dist.world()
+        dev = torch.device(self.device)
+        n_local = torch.tensor([float(xtrn.shape[0])], dtype=torch.float64, device=dev)
+        n_total = int(dist.allreduce_sum_(n_local.clone()).item())
+        prob = ops.Problem(self.desc, np.asarray(xtrn), np.asarray(ytrn), datanoise, dtype=self.dtype, device=dev)
+        slp = ShardedDataLogPost(prob, n_total)
+        if param_ini is None:
+            K = 1 if nchains is None else int(nchains)
+            param_ini = np.random.rand(K, self.pdim)
+        p0 = torch.as_tensor(np.atleast_2d(np.asarray(param_ini, dtype=np.float64)), device=dev)
+        sd = torch.tensor([int(seed) if seed is not None else int(np.random.randint(1, 2 ** 31 - 1))], dtype=torch.int64, device=dev)
+        p0, sd = dist.broadcast_from_rank0(p0), dist.broadcast_from_rank0(sd)
+        sampler_params = {} if sampler_params is None else sampler_params
+        mymcmc = {'amcmc': AMCMC, 'hmc': HMC, 'mala': MALA}[sampler](**sampler_params)
+        mymcmc.setLogPost(slp, slp.grad if sampler != 'amcmc' else None)
+        res = mymcmc.run(param_ini=p0.cpu().numpy(), nmcmc=nmcmc, seed=int(sd.item()), store_every=store_every, verbose=False)
         self.sampler_obj, self.mcmc_results = mymcmc, res
         self.samples, self.cmode = res['chain'], res['mapparams']
         return res
