@@ -30,6 +30,7 @@ extern "C" {
 #endif
 
 #define QB_MAX_LAYERS 16
+#define QB_MAX_TERMS 6
 
 enum { QB_F32 = 0, QB_F64 = 1 };
 enum { QB_ACT_IDENTITY = 0, QB_ACT_TANH = 1, QB_ACT_RELU = 2 };
@@ -37,13 +38,18 @@ enum { QB_ACT_IDENTITY = 0, QB_ACT_TANH = 1, QB_ACT_RELU = 2 };
 /* One Linear(+activation) step.  res_step == 0: h <- act(W h + b)   (quinn/nns/mlp.py:59-86).
  * res_step != 0: h <- h + res_step * act(W h + b)                   (quinn/nns/rnet.py:150-158).
  * Several layers may name the same w_off/b_off (RNet with Poly(0), rnet.py:344-347). */
+/* n_terms >= 2: weights that are a polynomial in the depth variable (RNet with Lin / Quad / Cubic / Poly(n),
+ * quinn/nns/rnet.py:244-347):  W = sum_m coef[m] * theta[w_off + m*w_stride ...], b likewise with b_stride; coef[m] = t^m
+ * of the residual step.  Gradients are scattered back to every term (chain rule).  n_terms 0 or 1: plain layer. */
 typedef struct {
     int32_t n_in, n_out;
     int32_t w_off;          /* offset of W (n_out x n_in row-major) in the flat parameter vector */
     int32_t b_off;          /* offset of the bias, or -1 */
     int32_t act;            /* QB_ACT_* */
-    int32_t reserved;
+    int32_t n_terms;
     double  res_step;
+    int32_t w_stride, b_stride;
+    double  coef[QB_MAX_TERMS];
 } qb_layer_t;
 
 /* The network the kernels evaluate: MLP.forward (mlp.py:92-101) / RNet.forward (rnet.py:124-164). */
@@ -80,7 +86,7 @@ const char* qb_last_error(void);
  * qb_version() differs from the QB_ABI_VERSION it was written against (quinn_b200/_lib.py does), and can check its
  * struct mirrors against qb_struct_sizes(): out[0..n) = sizeof of qb_layer_t, qb_net_t, qb_lik_t, qb_data_t, qb_chain_t,
  * qb_rng_t, qb_record_t, qb_amcmc_t, qb_hmc_t (declaration order); returns how many sizes exist. */
-#define QB_ABI_VERSION 200
+#define QB_ABI_VERSION 201
 int qb_version(void);
 int qb_struct_sizes(int64_t* out, int n);
 
@@ -259,6 +265,27 @@ int qb_fma_peak(int dtype, int variant, int64_t iters, double* flops_out_host, v
  * (qb_logpost_grad, qb_logpost_members, qb_hmc_run) serves fp32 MLPs in(<= 7) -> H -> H -> 1 with H = 32 or 64 and
  * tanh / relu hidden layers.  QB_NO_TC=1 disables both, QB_NO_TCG=1 only the gradient path. */
 int qb_plan_info(const qb_net_t* net, int dtype, int64_t K, int64_t N, int want_grad, int64_t* out);
+
+/* ---- device-side post-processing of chains / ensembles -------------------------------------
+ * None of these has a counterpart kernel in the reference; they replace host numpy on arrays that should not leave
+ * the device: the (M, N*, o) predictive array of QUiNNBase.predict_ens (quinn/solvers/quinn.py:51-70) and the per-step
+ * records of MCMCBase.run (quinn/mcmc/mcmc.py:92-99). */
+
+/* mean[k], var[k] (ddof = 1) of the rows of x[K, n] (doubles): per-chain moments of a monitored scalar, the inputs of the
+ * Gelman-Rubin R-hat (quinn_b200/dist.py: rhat). */
+int qb_row_moments(const double* x, int64_t K, int64_t n, double* mean, double* var, void* stream);
+
+/* Effective sample size of every row of x[K, n]: n / tau with tau = -1 + 2 sum_m (rho_2m + rho_2m+1) over Geyer's initial
+ * positive sequence (autocorrelations up to max_lag, <= 0: n - 1).  tau may be NULL. */
+int qb_ess(const double* x, int64_t K, int64_t n, int64_t max_lag, double* ess, double* tau, void* stream);
+
+/* out[p] = mean_k g[k,p]^2 (double).  With g = per-point loss gradients (qb_logpost_members, one point per member) this is
+ * the diagonal Fisher of NNWrap.calc_hess_diag (quinn/nns/nnwrap.py:204-229). */
+int qb_colsq_mean(int dtype, const void* g, int64_t K, int64_t P, double* out, void* stream);
+
+/* out[iq, i] = quantile q[iq] of y[:, i] over the leading (member) axis of y[M, n], numpy's default linear interpolation:
+ * the quantiles of get_stats (quinn/utils/stats.py:8-32: 0.25, 0.5, 0.75).  q: host array of nq <= 8 values in [0, 1]. */
+int qb_quantiles(int dtype, const void* y, int64_t M, int64_t n, const double* q_host, int nq, void* out, void* stream);
 
 /* Number of kernel launches this library has enqueued since load (bench.py's gpu_launches). */
 int64_t qb_launch_count(void);

@@ -63,11 +63,14 @@ def mlp_layers(indim, outdim, hls, biasorno=True, activ='tanh'):
 
 
 def rnet_layers(rdim, nlayers, indim, outdim, biasorno=True, nonlin=True, mlp=False,
-                layer_pre=True, layer_post=True, shared=True):
+                layer_pre=True, layer_post=True, shared=True, poly_order=None):
     """Layer list of quinn.nns.rnet.RNet (rnet.py:90-111 order, :124-164 forward).
 
     ``shared=True`` is wp_function=Poly(0) (one ww_0/bb_0 used by all nlayers+1
     residual steps, rnet.py:344-347); ``shared=False`` is NonPar(nlayers+1).
+    ``poly_order=n`` is wp_function=Poly(n) (Lin = 1, Quad = 2, Cubic = 3; rnet.py:244-347): residual step i uses
+    W = sum_m ww_m * t_i^m with t_i = i/(nlayers+1), same for the bias; the layer dict then carries
+    ``terms = [(t_i^m, ww_m offset, bb_m offset), ...]``.
     Parameter order: weight_pre, bias_pre, weight_post, bias_post, ww_*, bb_*.
     """
     act = 'tanh' if nonlin else 'identity'
@@ -80,6 +83,8 @@ def rnet_layers(rdim, nlayers, indim, outdim, biasorno=True, nonlin=True, mlp=Fa
         post = (off, off + outdim * rdim)
         off += outdim * rdim + outdim
     npar = 1 if shared else nlayers + 1
+    if poly_order is not None:
+        npar = poly_order + 1
     ww = []
     for _ in range(npar):
         ww.append(off)
@@ -94,12 +99,34 @@ def rnet_layers(rdim, nlayers, indim, outdim, biasorno=True, nonlin=True, mlp=Fa
     if layer_pre:
         layers.append(dict(n_in=indim, n_out=rdim, w_off=pre[0], b_off=pre[1], act=act, res_step=0.0))
     for i in range(nlayers + 1):
+        if poly_order is not None:
+            t = step * i
+            layers.append(dict(n_in=rdim, n_out=rdim, w_off=ww[0], b_off=(bb[0] if biasorno else -1), act=act,
+                               res_step=(0.0 if mlp else step),
+                               terms=[(t ** m, ww[m], bb[m] if biasorno else -1) for m in range(npar)]))
+            continue
         ip = 0 if shared else int((step * i) * npar)      # rnet.py:377 NonPar index rule
         layers.append(dict(n_in=rdim, n_out=rdim, w_off=ww[ip], b_off=(bb[ip] if biasorno else -1),
                            act=act, res_step=(0.0 if mlp else step)))
     if layer_post:
         layers.append(dict(n_in=rdim, n_out=outdim, w_off=post[0], b_off=post[1], act='identity', res_step=0.0))
     return layers, off
+
+
+def _layer_wb(L, theta):
+    """Weight matrix and bias of a layer; polynomial-in-depth layers (rnet.py:344-347) sum their terms in the reference's
+    order: val = 0.0; val += pars[m] * t**m."""
+    nw = L['n_in'] * L['n_out']
+    if 'terms' not in L:
+        W = theta[L['w_off']:L['w_off'] + nw].reshape(L['n_out'], L['n_in'])
+        b = theta[L['b_off']:L['b_off'] + L['n_out']] if L['b_off'] >= 0 else None
+        return W, b
+    W, b = 0.0, (0.0 if L['b_off'] >= 0 else None)
+    for c, wo, bo in L['terms']:
+        W = W + theta[wo:wo + nw].reshape(L['n_out'], L['n_in']) * c
+        if b is not None:
+            b = b + theta[bo:bo + L['n_out']] * c
+    return W, b
 
 
 def _act(name, z):
@@ -132,10 +159,10 @@ def forward(layers, theta, x, final=None, keep=False):
     h = np.asarray(x, dtype=np.float64)
     cache = []
     for L in layers:
-        W = theta[L['w_off']:L['w_off'] + L['n_in'] * L['n_out']].reshape(L['n_out'], L['n_in'])
+        W, b = _layer_wb(L, theta)
         z = h @ W.T
-        if L['b_off'] >= 0:
-            z = z + theta[L['b_off']:L['b_off'] + L['n_out']]
+        if b is not None:
+            z = z + b
         a = _act(L['act'], z)
         hin = h
         h = hin + L['res_step'] * a if L['res_step'] != 0.0 else a
@@ -187,12 +214,14 @@ def logpost_grad(layers, theta, x, y, sigma, fulldatasize=None, prior=None, fina
     if final == 'exp':
         da = da * out
     for L, (hin, z, a) in zip(reversed(layers), reversed(cache)):
-        W = theta[L['w_off']:L['w_off'] + L['n_in'] * L['n_out']].reshape(L['n_out'], L['n_in'])
+        W, _ = _layer_wb(L, theta)
         scale = L['res_step'] if L['res_step'] != 0.0 else 1.0
         dz = scale * da * _dact(L['act'], z, a)
-        g[L['w_off']:L['w_off'] + L['n_in'] * L['n_out']] += (dz.T @ hin).ravel()
-        if L['b_off'] >= 0:
-            g[L['b_off']:L['b_off'] + L['n_out']] += dz.sum(axis=0)
+        dW, db = (dz.T @ hin).ravel(), dz.sum(axis=0)
+        for c, wo, bo in L.get('terms', [(1.0, L['w_off'], L['b_off'])]):       # chain rule through W = sum_m c_m ww_m
+            g[wo:wo + L['n_in'] * L['n_out']] += c * dW
+            if bo >= 0:
+                g[bo:bo + L['n_out']] += c * db
         dprev = dz @ W
         da = dprev + da if L['res_step'] != 0.0 else dprev
     if prior is not None:
@@ -200,6 +229,24 @@ def logpost_grad(layers, theta, x, y, sigma, fulldatasize=None, prior=None, fina
         lp -= n * neg_log_prior(theta, prior['sigma'], anchor) / fulldatasize
         g -= (n / fulldatasize) * (theta - anchor) / prior['sigma'] ** 2
     return lp, g
+
+
+def diag_fisher(layers, theta, x, y, sigma, fulldatasize=None, prior=None, final=None):
+    """Diagonal of NNWrap.calc_hess_diag (nnwrap.py:204-229): the mean over data points of the squared gradient of the
+    loss evaluated on ONE point at a time.  For a single point the reference hands NegLogPost a 1-D prediction of
+    length o, so ``len(predictions)`` is o there (losses.py:199-204): the prior enters each point's loss with weight
+    o / fulldatasize."""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    acc = np.zeros(np.asarray(theta).size)
+    o = y.shape[1]
+    for i in range(x.shape[0]):
+        _, g = logpost_grad(layers, theta, x[i:i + 1], y[i:i + 1], sigma, final=final)
+        g = -g                                   # gradient of the loss (minus log-posterior)
+        if prior is not None:
+            g = g + (o / fulldatasize) * (np.asarray(theta, dtype=np.float64) - np.asarray(prior['anchor'], dtype=np.float64)) / prior['sigma'] ** 2
+        acc += g * g
+    return acc / x.shape[0]
 
 
 # ----------------------------------------------------------------------------

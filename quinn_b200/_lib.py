@@ -15,9 +15,13 @@ QB_RNG_PHILOX, QB_RNG_REPLAY = 0, 1
 QB_ADAPT_NONE, QB_ADAPT_DIAG, QB_ADAPT_FULL = 0, 1, 2
 
 
+QB_MAX_TERMS = 6
+
+
 class qb_layer_t(C.Structure):
     _fields_ = [('n_in', C.c_int32), ('n_out', C.c_int32), ('w_off', C.c_int32), ('b_off', C.c_int32),
-                ('act', C.c_int32), ('reserved', C.c_int32), ('res_step', C.c_double)]
+                ('act', C.c_int32), ('n_terms', C.c_int32), ('res_step', C.c_double),
+                ('w_stride', C.c_int32), ('b_stride', C.c_int32), ('coef', C.c_double * QB_MAX_TERMS)]
 
 
 class qb_net_t(C.Structure):
@@ -60,7 +64,7 @@ class qb_hmc_t(C.Structure):
                 ('mom', C.c_void_p), ('prop', C.c_void_p), ('grad_prop', C.c_void_p)]
 
 
-QB_ABI_VERSION = 200          # include/quinn_b200.h
+QB_ABI_VERSION = 201          # include/quinn_b200.h
 ABI_STRUCTS = (qb_layer_t, qb_net_t, qb_lik_t, qb_data_t, qb_chain_t, qb_rng_t, qb_record_t, qb_amcmc_t, qb_hmc_t)
 
 # every symbol include/quinn_b200.h declares: name -> (restype, argtypes)
@@ -93,6 +97,10 @@ SYMBOLS = {
     'qb_fma_peak': (C.c_int, [C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_double), _P, _P]),
     'qb_plan_info': (C.c_int, [C.POINTER(qb_net_t), C.c_int, C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_int64)]),
     'qb_launch_count': (C.c_int64, []),
+    'qb_row_moments': (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P]),
+    'qb_ess': (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P]),
+    'qb_colsq_mean': (C.c_int, [C.c_int, _P, C.c_int64, C.c_int64, _P, _P]),
+    'qb_quantiles': (C.c_int, [C.c_int, _P, C.c_int64, C.c_int64, C.POINTER(C.c_double), C.c_int, _P, _P]),
 }
 
 _lib = None

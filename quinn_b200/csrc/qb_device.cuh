@@ -15,6 +15,11 @@
 #define QB_STR_(x) #x
 #define QB_PRAGMA_UNROLL(n) _Pragma(QB_STR_(unroll n))
 
+__device__ __forceinline__ float qb_mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double qb_mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float qb_add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double qb_add_rn(double a, double b) { return __dadd_rn(a, b); }
+
 // --------------------------------------------------------------------------------------------
 // per-dtype tile constants and 128-bit vector access
 // --------------------------------------------------------------------------------------------
@@ -146,6 +151,16 @@ __device__ __forceinline__ double qb_block_sum(double v, double* red /* >= 33 do
 // --------------------------------------------------------------------------------------------
 // weight staging: flat theta (global) -> Wt / Wr / bias (shared), once per parameter vector
 // --------------------------------------------------------------------------------------------
+// One weight / bias entry of a layer.  Polynomial-in-depth layers (rnet.py:344-347) sum their terms in the reference's
+// order, val = 0; val += pars[m] * t^m, with separate multiply and add (no FMA contraction) so that fp64 reproduces it.
+template <typename T>
+__device__ __forceinline__ T qb_layer_param(const QbLayerPlan& L, const T* __restrict__ theta, int off, int stride) {
+    if (L.n_terms <= 1) return theta[off];
+    T v = T(0);
+    for (int m = 0; m < L.n_terms; ++m) v = qb_add_rn(v, qb_mul_rn(theta[off + m * stride], (T)L.coef[m]));
+    return v;
+}
+
 template <typename T>
 __device__ void qb_stage_weights(const QbPlan& P, T* sW, const T* theta) {
     constexpr int TU = VT<T>::TU;
@@ -164,12 +179,12 @@ __device__ void qb_stage_weights(const QbPlan& P, T* sW, const T* theta) {
         for (int idx = tid; idx < nwt; idx += nt) {
             const int i = idx / L.n_out_pad, col = idx - i * L.n_out_pad;
             const int j = gemm ? qb_col_to_unit<T>(col, UG) : col;
-            Wt[idx] = (j < L.n_out) ? theta[L.w_off + j * L.n_in + i] * fold : T(0);
+            Wt[idx] = (j < L.n_out) ? qb_layer_param<T>(L, theta, L.w_off + j * L.n_in + i, L.w_stride) * fold : T(0);
         }
         T* bs = sW + L.bias_off;
         for (int col = tid; col < L.n_out_pad; col += nt) {
             const int j = gemm ? qb_col_to_unit<T>(col, UG) : col;
-            bs[col] = (j < L.n_out && L.b_off >= 0) ? theta[L.b_off + j] * fold : T(0);
+            bs[col] = (j < L.n_out && L.b_off >= 0) ? qb_layer_param<T>(L, theta, L.b_off + j, L.b_stride) * fold : T(0);
         }
         if (L.wr_off >= 0) {
             const int UGI = L.n_in_pad / TU;
@@ -178,7 +193,7 @@ __device__ void qb_stage_weights(const QbPlan& P, T* sW, const T* theta) {
             for (int idx = tid; idx < nwr; idx += nt) {
                 const int j = idx / L.n_in_pad, col = idx - j * L.n_in_pad;
                 const int i = qb_col_to_unit<T>(col, UGI);
-                Wr[idx] = (i < L.n_in) ? theta[L.w_off + j * L.n_in + i] : T(0);
+                Wr[idx] = (i < L.n_in) ? qb_layer_param<T>(L, theta, L.w_off + j * L.n_in + i, L.w_stride) : T(0);
             }
         }
     }
@@ -725,7 +740,15 @@ __device__ void qb_dw_accumulate(const QbLayerPlan& L, const T* R, int lda, int 
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
                         const int i = ig + IG * b;
-                        if (i < L.n_in) g[L.w_off + j * L.n_in + i] = gold[a][b] + acc[a][b];
+                        if (i < L.n_in) {
+                            const int e = L.w_off + j * L.n_in + i;
+                            if (L.n_terms <= 1) g[e] = gold[a][b] + acc[a][b];
+                            else {
+                                // chain rule through W = sum_m coef[m] * ww_m: every term receives coef[m] * dW
+                                g[e] = gold[a][b] + (T)L.coef[0] * acc[a][b];
+                                for (int m = 1; m < L.n_terms; ++m) g[e + m * L.w_stride] += (T)L.coef[m] * acc[a][b];
+                            }
+                        }
                     }
                 }
             }
@@ -751,7 +774,10 @@ __device__ void qb_dw_accumulate(const QbLayerPlan& L, const T* R, int lda, int 
             }
             sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
             sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-            if (q == 0 && j < L.n_out) g[L.b_off + j] += sacc;
+            if (q == 0 && j < L.n_out) {
+                if (L.n_terms <= 1) g[L.b_off + j] += sacc;
+                else for (int m = 0; m < L.n_terms; ++m) g[L.b_off + j + m * L.b_stride] += (T)L.coef[m] * sacc;
+            }
         }
     }
 }

@@ -26,6 +26,7 @@ bool qb_tcg_make_plan(const qb_net_t* net, int dtype, QbTcgPlan* tp) {
     const qb_layer_t& L1 = net->layers[1];
     const qb_layer_t& L2 = net->layers[2];
     if (L0.res_step != 0.0 || L1.res_step != 0.0 || L2.res_step != 0.0) return false;
+    if (L0.n_terms > 1 || L1.n_terms > 1 || L2.n_terms > 1) return false;
     const int H = L0.n_out;
     if (L1.n_out != H || (H != 32 && H != 64)) return false;
     if (L0.act != L1.act || (L0.act != QB_ACT_TANH && L0.act != QB_ACT_RELU) || L2.act != QB_ACT_IDENTITY) return false;

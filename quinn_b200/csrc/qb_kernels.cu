@@ -39,6 +39,9 @@ static int qb_fail(const char* fmt, const char* a = "", long long b = 0) {
     } while (0)
 
 extern "C" const char* qb_last_error(void) { return g_err; }
+// used by the other translation units of the library (qb_post.cu)
+void qb_internal_set_error(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
+void qb_internal_count_launches(int n) { g_launches += n; }
 extern "C" int qb_version(void) { return QB_ABI_VERSION; }
 extern "C" int qb_struct_sizes(int64_t* out, int n) {
     const int64_t sz[] = {(int64_t)sizeof(qb_layer_t), (int64_t)sizeof(qb_net_t), (int64_t)sizeof(qb_lik_t), (int64_t)sizeof(qb_data_t),
@@ -86,6 +89,13 @@ static int validate_net(const qb_net_t* net) {
         if (L.res_step != 0.0 && L.n_in != L.n_out) return qb_fail("layer %s%lld: residual layer must be square", "", l);
         if (L.w_off < 0 || L.w_off + L.n_in * L.n_out > net->n_params) return qb_fail("layer %s%lld: weight offset out of range", "", l);
         if (L.b_off >= 0 && L.b_off + L.n_out > net->n_params) return qb_fail("layer %s%lld: bias offset out of range", "", l);
+        if (L.n_terms < 0 || L.n_terms > QB_MAX_TERMS) return qb_fail("layer %s%lld: n_terms out of range", "", l);
+        if (L.n_terms > 1) {
+            const long long lastw = (long long)L.w_off + (long long)(L.n_terms - 1) * L.w_stride;
+            const long long lastb = (long long)L.b_off + (long long)(L.n_terms - 1) * L.b_stride;
+            if (L.w_stride < 0 || lastw + (long long)L.n_in * L.n_out > net->n_params) return qb_fail("layer %s%lld: polynomial weight terms out of range", "", l);
+            if (L.b_off >= 0 && (L.b_stride < 0 || lastb + L.n_out > net->n_params)) return qb_fail("layer %s%lld: polynomial bias terms out of range", "", l);
+        }
         width = L.n_out;
     }
     if (width != net->out_dim) return qb_fail("out_dim does not match the last layer");
@@ -114,6 +124,8 @@ static long long plan_for_tm(const qb_net_t* net, int dtype, bool want_grad, int
         QbLayerPlan& L = P->L[l];
         L.n_in = S.n_in; L.n_out = S.n_out; L.n_in_pad = rup(S.n_in, TU); L.n_out_pad = rup(S.n_out, TU);
         L.w_off = S.w_off; L.b_off = S.b_off; L.act = S.act; L.res_step = S.res_step; L.has_res = S.res_step != 0.0;
+        L.n_terms = S.n_terms > 1 ? S.n_terms : 0; L.w_stride = S.w_stride; L.b_stride = S.b_stride;
+        for (int m = 0; m < QB_MAX_TERMS; ++m) L.coef[m] = S.coef[m];
         if (L.has_res) P->has_res = 1;
         const int UG = L.n_out_pad / TU;
         L.ug_shift = L.ugi_shift = L.ig_shift = -1;
@@ -132,7 +144,10 @@ static long long plan_for_tm(const qb_net_t* net, int dtype, bool want_grad, int
         int dup = -1;
         for (int m = 0; m < l; ++m) {
             const qb_layer_t& Sm = net->layers[m];
-            if (Sm.w_off == S.w_off && Sm.b_off == S.b_off && Sm.n_in == S.n_in && Sm.n_out == S.n_out &&
+            bool same_terms = (Sm.n_terms > 1 ? Sm.n_terms : 0) == (S.n_terms > 1 ? S.n_terms : 0);
+            if (same_terms && S.n_terms > 1)
+                for (int q = 0; q < S.n_terms; ++q) same_terms = same_terms && Sm.coef[q] == S.coef[q];
+            if (same_terms && Sm.w_off == S.w_off && Sm.b_off == S.b_off && Sm.n_in == S.n_in && Sm.n_out == S.n_out &&
                 (Sm.act == QB_ACT_TANH) == (S.act == QB_ACT_TANH) &&      // fp32 tanh layers stage W * 2log2(e)
                 P->L[m].mode == L.mode && (P->L[m].wr_off >= 0) == (want_grad && l > 0 && !wr_global)) { dup = m; break; }
         }
@@ -244,8 +259,10 @@ static int make_launch(const qb_net_t* net, int dtype, bool want_grad, long long
     int pick = -1, best_score = -1;
     bool wr_global = false;
     QbPlan tmp;
+    bool any_poly = false;
+    for (int l = 0; l < net->n_layers; ++l) any_poly = any_poly || net->layers[l].n_terms > 1;
     for (int g = (want_grad && env_int("QB_WR_GLOBAL", 0)) ? 1 : 0; g < 2 && pick < 0; ++g) {
-        if (g == 1 && !want_grad) break;
+        if (g == 1 && (!want_grad || any_poly)) break;      // the global-W fallback reads theta directly: no polynomial terms
         for (int c = 0; c < 4; ++c) {
             int TM = cands[c];
             if (forced) TM = forced;
@@ -297,7 +314,7 @@ static bool make_tc_plan(const qb_net_t* net, int dtype, QbTcPlan* tp) {
     int kmax = 0, nmax = 0;
     for (int l = 0; l < nl; ++l) {
         const qb_layer_t& S = net->layers[l];
-        if (S.res_step != 0.0) return false;
+        if (S.res_step != 0.0 || S.n_terms > 1) return false;
         if (l < nl - 1 && (S.n_out % 16 != 0 || S.n_out < 16 || S.n_out > 128)) return false;
         if (l >= 1 && l < nl - 1) { kmax = std::max(kmax, S.n_in); nmax = std::max(nmax, S.n_out); }
     }

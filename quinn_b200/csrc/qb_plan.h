@@ -25,6 +25,8 @@ struct QbLayerPlan {
     int has_res, ug_shift;        // ug_shift: log2(n_out_pad/TU) if that is a power of two, else -1
     int ugi_shift, ig_shift, c_shift, pad2_;   // same for n_in_pad/TU, ceil(n_in/4), dw_chunks
     double res_step;
+    int n_terms, w_stride, b_stride, pad3_;   // polynomial-in-depth weights (qb_layer_t): W = sum_m coef[m]*theta[w_off + m*w_stride ..]
+    double coef[QB_MAX_TERMS];
 };
 
 struct QbPlan {

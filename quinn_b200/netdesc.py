@@ -3,7 +3,7 @@
 The descriptor pins the flat parameter contract of the reference (quinn/nns/nnwrap.py:64-106):
 ``nnmodel.parameters()`` order, each tensor flattened C-order, Linear weights (n_out, n_in) row-major.
 Supported modules are the ones on the hot path: ``MLP`` (mlp.py:59-86),
-``RNet`` with Poly(0) / NonPar weight parameterisation (rnet.py:124-164), ``torch.nn.Linear`` and plain
+``RNet`` with Poly(n) / Lin / Quad / Cubic / NonPar weight parameterisation (rnet.py:124-164, 244-377), ``torch.nn.Linear`` and plain
 ``torch.nn.Sequential`` stacks of Linear / Tanh / ReLU / Identity.  Anything else (batch norm, dropout,
 higher-order Poly, 'sin') raises -- there is no slow path.
 """
@@ -26,6 +26,7 @@ class Layer:
     b_off: int = -1
     act: str = 'identity'
     res_step: float = 0.0
+    terms: list = None      # polynomial-in-depth weights (rnet.py:244-347): [(coef, w_off_m, b_off_m), ...]; W = sum coef*ww_m
 
 
 @dataclass
@@ -46,12 +47,28 @@ class NetDesc:
             c = net.layers[i]
             c.n_in, c.n_out, c.w_off, c.b_off = L.n_in, L.n_out, L.w_off, L.b_off
             c.act, c.res_step = _ACT[L.act], float(L.res_step)
+            if L.terms:
+                if len(L.terms) > _lib.QB_MAX_TERMS:
+                    raise NotImplementedError(f'at most {_lib.QB_MAX_TERMS} polynomial terms per layer')
+                ws = (L.terms[1][1] - L.terms[0][1]) if len(L.terms) > 1 else 0
+                bs = (L.terms[1][2] - L.terms[0][2]) if (len(L.terms) > 1 and L.b_off >= 0) else 0
+                for m, (_, wo, bo) in enumerate(L.terms):
+                    if wo != L.w_off + m * ws or (L.b_off >= 0 and bo != L.b_off + m * bs):
+                        raise ValueError('polynomial terms must be equally spaced tensors starting at w_off / b_off')
+                c.n_terms, c.w_stride, c.b_stride = len(L.terms), ws, bs
+                for m, t in enumerate(L.terms):
+                    c.coef[m] = float(t[0])
         return net
 
     def as_oracle_layers(self):
         """Same description in the dict form oracle/quinn_oracle.py takes (tests only)."""
-        return [dict(n_in=L.n_in, n_out=L.n_out, w_off=L.w_off, b_off=L.b_off, act=L.act, res_step=L.res_step)
-                for L in self.layers]
+        out = []
+        for L in self.layers:
+            d = dict(n_in=L.n_in, n_out=L.n_out, w_off=L.w_off, b_off=L.b_off, act=L.act, res_step=L.res_step)
+            if L.terms:
+                d['terms'] = list(L.terms)
+            out.append(d)
+        return out
 
     def macs_per_point(self):
         """S of SURVEY.md section 8: sum of n_in*n_out over the executed layers."""
@@ -129,10 +146,15 @@ def _from_rnet(m, offs):
     """RNet.forward (rnet.py:124-164): pre layer (with activation), nlayers+1 residual steps, post layer."""
     wp = m.wp_function
     kind = type(wp).__name__
+    poly = False
     if kind == 'Poly' and wp.npar == 1:
         pick = lambda i: 0                                   # noqa: E731  (Poly(0): pars[0]*t**0)
     elif kind == 'NonPar':
         pick = lambda i: int((m.step_size * i) * wp.npar)    # noqa: E731  (rnet.py:377)
+    elif kind in ('Poly', 'Lin', 'Quad', 'Cubic') and wp.npar <= _lib.QB_MAX_TERMS:
+        # polynomial in the depth variable t_i = i/(nlayers+1) (rnet.py:244-347): the kernels stage W_i = sum_m t_i^m ww_m
+        # and scatter dW_i back to every term (chain rule)
+        poly, pick = True, (lambda i: 0)                     # noqa: E731
     else:
         raise NotImplementedError(f'RNet weight parameterisation {kind}(npar={wp.npar}) is outside the fused path '
                                   '(SURVEY.md section 8f rank 4)')
@@ -144,8 +166,12 @@ def _from_rnet(m, offs):
         layers.append(Layer(m.indim, m.rdim, offs['weight_pre'], offs['bias_pre'], act, 0.0))
     for i in range(m.nlayers + 1):
         ip = pick(i)
+        terms = None
+        if poly:
+            t = m.step_size * i
+            terms = [(t ** k, offs[f'ww_{k}'], offs[f'bb_{k}'] if m.biasorno else -1) for k in range(wp.npar)]
         layers.append(Layer(m.rdim, m.rdim, offs[f'ww_{ip}'], offs[f'bb_{ip}'] if m.biasorno else -1, act,
-                            0.0 if m.mlp else float(m.step_size)))
+                            0.0 if m.mlp else float(m.step_size), terms=terms))
     if m.layer_post:
         layers.append(Layer(m.rdim, m.outdim, offs['weight_post'], offs['bias_post'], 'identity', 0.0))
     return layers, m.final_layer == 'exp'

@@ -113,6 +113,43 @@ class NNWrap:
         return -g[0].double().cpu().numpy()
 
 
+    # ---- diagonal Fisher (the by-product of kernel 2 that NN_Laplace uses)
+    def calc_fisher_diag(self, weights, loss_fn, inputs, targets, chunk=65536):
+        """Diagonal of calc_hess_diag as a vector: mean over the data points of the squared gradient of the loss
+        evaluated on one point at a time (nnwrap.py:204-229).  Kernel 2 runs with one data point per "member"
+        (qb_logpost_members: member i sees x[i], y[i]; all members share theta), qb_colsq_mean reduces the squares."""
+        import ctypes as C
+        from .. import _lib, post
+        from ..ops import _ptr, _stream
+        prob = self._problem(loss_fn, inputs, targets)
+        self.p_unflatten(weights)
+        N, P, o = prob.n, prob.desc.n_params, prob.desc.out_dim
+        theta = prob.theta(np.asarray(weights, dtype=np.float64))
+        lik = _lib.qb_lik_t(prob.clik.sigma, prob.clik.prior_sigma, 0.0, prob.clik.prior_anchor, 0, 0)
+        if loss_fn.priorparams is not None:
+            lik.prior_scale = float(o) / float(loss_fn.fulldatasize)      # a single point: len(predictions) == o (losses.py:199-204)
+        lib = _lib.load()
+        acc = torch.zeros(P, dtype=torch.float64, device=prob.device)
+        for lo in range(0, N, chunk):
+            n = min(chunk, N - lo)
+            th = theta.expand(n, P).contiguous()
+            lp = torch.empty(n, dtype=torch.float64, device=prob.device)
+            g = torch.empty((n, P), dtype=prob.dtype, device=prob.device)
+            need = lib.qb_eval_workspace_bytes(C.byref(prob.cnet), prob.qdt, n, 1, 1)
+            ws = torch.empty(max(int(need), 256), dtype=torch.uint8, device=prob.device)
+            data = _lib.qb_data_t(prob.x[lo:lo + n].data_ptr(), prob.y[lo:lo + n].data_ptr(), 1)
+            with torch.cuda.device(prob.device):
+                _lib.check(lib.qb_logpost_members(C.byref(prob.cnet), prob.qdt, _ptr(th), n, C.byref(data), prob.desc.in_dim, o,
+                                                  C.byref(lik), _ptr(lp), _ptr(g), _ptr(ws), ws.numel(), _stream()),
+                           'qb_logpost_members')
+            acc += post.fisher_diag(g) * (n / float(N))
+        return acc.cpu().numpy()
+
+    def calc_hess_diag(self, weights, loss_fn, inputs, targets):
+        """The reference's return value: a (P, P) matrix with the diagonal Fisher on its diagonal (nnwrap.py:229)."""
+        return np.diag(self.calc_fisher_diag(weights, loss_fn, inputs, targets))
+
+
 def nnwrapper(x, nnmodel):
     return device_forward(nnmodel, x)
 

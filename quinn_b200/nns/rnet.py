@@ -1,6 +1,5 @@
 """ResNet with the reference's constructor and parameter order (quinn/nns/rnet.py:39-164).
-Only Poly(0) (shared weights) and NonPar are on the fused path; the other LayerFcn families are
-section 8f rank 4."""
+Poly(n) (Poly(0) = shared weights, Lin, Quad, Cubic) and NonPar weight parameterisations are all on the fused path."""
 import math
 
 import torch
@@ -25,6 +24,27 @@ class Poly(LayerFcn):
     def __call__(self, pars, t):
         assert len(pars) == self.npar
         return sum(p * t ** i for i, p in enumerate(pars))
+
+
+class Lin(Poly):
+    """pars[0] + pars[1] t (rnet.py:244-264)."""
+
+    def __init__(self):
+        super().__init__(1)
+
+
+class Quad(Poly):
+    """pars[0] + pars[1] t + pars[2] t^2 (rnet.py:267-288)."""
+
+    def __init__(self):
+        super().__init__(2)
+
+
+class Cubic(Poly):
+    """pars[0] + ... + pars[3] t^3 (rnet.py:290-311)."""
+
+    def __init__(self):
+        super().__init__(3)
 
 
 class NonPar(LayerFcn):

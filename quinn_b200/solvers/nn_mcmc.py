@@ -70,7 +70,7 @@ class NN_MCMC(QUiNNBase):
 
     def fit(self, xtrn, ytrn, zflag=True, datanoise=0.05, nmcmc=6000, param_ini=None, sampler='amcmc',
             sampler_params=None, *, nchains=None, seed=None, store_every=1, replay=None, chain_offset=0,
-            distributed=False, diag_every=None, gather=True, data_sharded=False):
+            distributed=False, diag_every=None, gather=True, data_sharded=False, keep_on_device=False):
         """Sample the posterior of the flat parameters (nn_mcmc.py:100-139).
 
         Extensions (keyword-only): ``nchains`` / a (K,P) ``param_ini`` run K chains at once (``samples``
@@ -83,6 +83,8 @@ class NN_MCMC(QUiNNBase):
         the chains are the ones a single process would run), reduces the R-hat of the log-posterior and the acceptance
         rate over all ranks every ``diag_every`` steps (default: the sampler's ``tadapt`` or nmcmc/10) on a side stream
         (``self.diagnostics``), and, with ``gather``, collects the result dict on rank 0 (other ranks keep their shard).
+        ``keep_on_device=True`` leaves the result dict (and ``self.samples``) as CUDA tensors: predict_ens / predict_mom_sample
+        / predict_stats then thin and evaluate the chain without a host round trip.
         ``data_sharded=True``: every rank passes ITS slice of the data and all chains; each step's log-posterior
         (and gradient) is the all-reduced sum of the per-rank partial sums (the N-sharded mode for data that exceed one
         GPU; propose / accept run redundantly and identically on every rank)."""
@@ -113,7 +115,7 @@ class NN_MCMC(QUiNNBase):
         else:
             raise ValueError(f"sampler {sampler!r} is not one of 'amcmc', 'hmc', 'mala'")
         res = mymcmc.run(param_ini=param_ini, nmcmc=nmcmc, seed=seed, store_every=store_every, replay=replay,
-                         chain_offset=chain_offset, verbose=self.verbose)
+                         chain_offset=chain_offset, verbose=self.verbose, keep_on_device=keep_on_device)
         self.sampler_obj, self.mcmc_results = mymcmc, res
         self.samples, self.cmode = res['chain'], res['mapparams']
         return res
@@ -271,12 +273,13 @@ class NN_MCMC(QUiNNBase):
         return copy.deepcopy(nnw.nnmodel)
 
     def _forward(self, thetas, x):
-        out, _, _ = ops.predict(self.desc, np.asarray(thetas, dtype=np.float64), np.asarray(x), dtype=self.dtype,
-                                device=self.device)
+        if not torch.is_tensor(thetas):                  # CUDA tensors (keep_on_device) are passed through untouched
+            thetas = np.asarray(thetas, dtype=np.float64)
+        out, _, _ = ops.predict(self.desc, thetas, np.asarray(x), dtype=self.dtype, device=self.device)
         return out.double().cpu().numpy()
 
     def predict_MAP(self, x):
-        cm = np.asarray(self.cmode)
+        cm = self.cmode if torch.is_tensor(self.cmode) else np.asarray(self.cmode)
         return self._forward(cm, x)[0] if cm.ndim == 1 else self._forward(cm, x)
 
     def predict_sample(self, x, param):
@@ -285,10 +288,22 @@ class NN_MCMC(QUiNNBase):
     def _thinned(self, nens, nburn):
         """Rows samples[nburn + j*nevery], nevery = int((M'-nburn)/nens) (nn_mcmc.py:194-196); for a
         multi-chain run the same rows of every chain, chain-major."""
-        s = np.asarray(self.samples)
+        s = self.samples if torch.is_tensor(self.samples) else np.asarray(self.samples)      # device chains stay on the device
         nevery = int((s.shape[-2] - nburn) / nens)
         rows = [nburn + j * nevery for j in range(nens)]
         return s[..., rows, :].reshape(-1, s.shape[-1])
+
+    def diagnose(self, max_lag=0):
+        """Cross-chain diagnostics of the last fit computed on the device (qb_post.cu): R-hat of the log-posterior over the
+        second half of the run and the effective sample size of the log-posterior per chain (extensions: the reference has
+        neither)."""
+        from .. import post
+        lp = torch.as_tensor(self.mcmc_results['logpost'])
+        lp = lp[None, :] if lp.dim() == 1 else lp
+        half = lp[:, lp.shape[1] // 2:]
+        r = post.rhat(half) if half.shape[0] > 1 else torch.full((1,), float('nan'))
+        e = post.ess(half, max_lag)
+        return dict(rhat_logpost=float(r.reshape(-1)[0].item()), ess_logpost=e.cpu().numpy(), nsteps=int(half.shape[1]))
 
     def predict_ens(self, x, nens=10, nburn=1000):
         return self._forward(self._thinned(nens, nburn), x)

@@ -41,6 +41,18 @@ class QUiNNBase:
     def predict(self, x):
         return self.predict_mom_sample(x)[0]
 
+    def predict_stats(self, x, nsam=1000, qt=True):
+        """get_stats (quinn/utils/stats.py:8-32) of nsam sampled predictions without the (M, N, o) array visiting the host:
+        (median, q50-q25, q75-q50) when qt, else (mean, std, std); kernel 4 + the quantile / moment kernels of qb_post.cu."""
+        from .. import post
+        ens = self._ens_thetas(nsam)
+        if ens is None:
+            y = torch.as_tensor(self.predict_ens(x, nens=nsam)).cuda()
+        else:
+            desc, thetas, dtype = ens
+            y, _, _ = ops.predict(desc, thetas, np.asarray(x), dtype=dtype)
+        return tuple(t.double().cpu().numpy() for t in post.get_stats(y, qt))
+
     def predict_mom_sample(self, x, msc=0, nsam=1000):
         """mean / variance (ddof=1) / covariance of nsam sampled predictions (quinn.py:75-104).
 

@@ -26,6 +26,13 @@ NET_CASES = {
     'rnet_nonpar':  dict(kind='rnet', rdim=4, nlayers=2, indim=2, outdim=2, bias=True, nonlin=True, mlp=False, shared=False, N=11, sigma=0.2, seed=108, ntheta=4, tscale=0.7),
     'rnet_mlpmode': dict(kind='rnet', rdim=5, nlayers=1, indim=2, outdim=1, bias=False, nonlin=True, mlp=True, shared=False, N=12, sigma=0.2, seed=109, ntheta=4, tscale=0.7),
 }
+# round 2: polynomial-in-depth RNet weights (rnet.py:244-347); fixtures from tests/golden/make_golden_r2.py
+NET_CASES_R2 = {
+    'rnet_lin':   dict(kind='rnet', rdim=4, nlayers=2, indim=2, outdim=1, bias=True, nonlin=True, mlp=False, poly=1, N=15, sigma=0.2, seed=201, ntheta=4, tscale=0.6),
+    'rnet_quad':  dict(kind='rnet', rdim=3, nlayers=3, indim=1, outdim=2, bias=True, nonlin=True, mlp=False, poly=2, N=12, sigma=0.1, seed=202, ntheta=4, tscale=0.6),
+    'rnet_cubic': dict(kind='rnet', rdim=5, nlayers=4, indim=2, outdim=1, bias=False, nonlin=True, mlp=True, poly=3, N=14, sigma=0.3, seed=203, ntheta=3, tscale=0.5),
+    'rnet_poly4': dict(kind='rnet', rdim=3, nlayers=5, indim=1, outdim=1, bias=True, nonlin=False, mlp=False, poly=4, N=10, sigma=0.2, seed=204, ntheta=3, tscale=0.5),
+}
 
 
 def make_inputs(spec):
@@ -46,7 +53,7 @@ def oracle_layers(spec):
     if spec['kind'] == 'mlp':
         return qo.mlp_layers(spec['indim'], spec['outdim'], spec['hls'], spec['bias'], spec['activ'])
     return qo.rnet_layers(spec['rdim'], spec['nlayers'], spec['indim'], spec['outdim'], biasorno=spec['bias'],
-                          nonlin=spec['nonlin'], mlp=spec['mlp'], shared=spec['shared'])
+                          nonlin=spec['nonlin'], mlp=spec['mlp'], shared=spec.get('shared', True), poly_order=spec.get('poly'))
 
 
 def load(name):
@@ -62,5 +69,5 @@ def netdesc_from_spec(spec):
 
 def netdesc_from_layers(layers, P, final_exp=False):
     from quinn_b200.netdesc import NetDesc, Layer
-    ls = [Layer(L['n_in'], L['n_out'], L['w_off'], L['b_off'], L['act'], L['res_step']) for L in layers]
+    ls = [Layer(L['n_in'], L['n_out'], L['w_off'], L['b_off'], L['act'], L['res_step'], terms=L.get('terms')) for L in layers]
     return NetDesc(ls[0].n_in, ls[-1].n_out, P, ls, final_exp)

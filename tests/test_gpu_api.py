@@ -351,3 +351,30 @@ def test_more_than_65535_chains_through_the_solver_api():
     pe = uq.predict_ens(xt, nens=2, nburn=2)
     assert pe.shape == (2 * K, 5, 1) and np.isfinite(pe).all()
     assert 0.0 < np.asarray(res['accrate']).mean() <= 1.0
+
+
+def test_batched_map_start_against_per_chain_bfgs():
+    """the batched MAP pre-conditioning (Adam ascent on kernel 2 for all starts at once) against what
+    the reference's zflag=True does per chain (scipy BFGS on -logpost, nn_mcmc.py:125-127; here with the analytic
+    gradient): from the same random starts it recovers most of the log-posterior improvement BFGS finds."""
+    from quinn_b200.nns import MLP
+    from quinn_b200.solvers import NN_MCMC
+    np.random.seed(11)
+    torch.manual_seed(11)
+    net = MLP(1, 1, (6,), activ='tanh')
+    x = np.random.rand(30, 1) * 2 - 1
+    y = np.sin(3 * x) + 0.05 * np.random.randn(30, 1)
+    uq = NN_MCMC(net, verbose=False)
+    uq.lpinfo = {'model': None, 'xd': x, 'yd': [yy for yy in y], 'ltype': 'classical', 'lparams': {'sigma': 0.1}}
+    starts = np.random.rand(12, uq.pdim)
+    lp0 = uq.logpost(starts, uq.lpinfo)
+    uq.map_batched_above = 10 ** 9
+    bfgs = uq._map_start(starts)                                  # one BFGS run per start
+    lp_bfgs = uq.logpost(bfgs, uq.lpinfo)
+    uq.map_batched_above, uq.map_start_steps = 8, 3000
+    batched = uq._map_start(starts)                               # all starts together
+    lp_b = uq.logpost(batched, uq.lpinfo)
+    assert (lp_b >= lp0).all() and (lp_bfgs >= lp0 - 1e-9).all()
+    gain_b, gain_bfgs = lp_b - lp0, lp_bfgs - lp0
+    assert np.median(gain_b) >= 0.9 * np.median(gain_bfgs), (np.median(gain_b), np.median(gain_bfgs))
+    assert (gain_b >= 0.5 * gain_bfgs).mean() >= 0.75

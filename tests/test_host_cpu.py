@@ -28,8 +28,8 @@ def test_library_exports_every_header_symbol():
 
 def test_struct_sizes_match_the_header():
     from quinn_b200 import _lib
-    assert ctypes.sizeof(_lib.qb_layer_t) == 32
-    assert ctypes.sizeof(_lib.qb_net_t) == 32 + 16 * 32
+    assert ctypes.sizeof(_lib.qb_layer_t) == 88
+    assert ctypes.sizeof(_lib.qb_net_t) == 32 + 16 * 88
     assert ctypes.sizeof(_lib.qb_data_t) == 24
     assert ctypes.sizeof(_lib.qb_lik_t) == 40
 

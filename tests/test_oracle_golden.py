@@ -3,15 +3,15 @@
 import numpy as np
 import pytest
 
-from golden_util import NET_CASES, make_inputs, make_thetas, oracle_layers, load
+from golden_util import NET_CASES, NET_CASES_R2, make_inputs, make_thetas, oracle_layers, load
 from oracle import quinn_oracle as qo
 
 RTOL = 1e-12
 
 
-@pytest.mark.parametrize('name', list(NET_CASES))
+@pytest.mark.parametrize('name', list(NET_CASES) + list(NET_CASES_R2))
 def test_logpost_and_grad_match_reference(name):
-    spec = NET_CASES[name]
+    spec = NET_CASES[name] if name in NET_CASES else NET_CASES_R2[name]
     g = load(f'logpost_{name}.npz')
     layers, P = oracle_layers(spec)
     assert P == int(g['pdim'])
@@ -144,3 +144,25 @@ def test_torch_port_matches_golden():
         assert abs(lp - g['lp'][0]) <= 1e-12 * abs(g['lp'][0])
         gr = port.logpostgrad(th[0], x, [r for r in y], spec['sigma'])
         assert np.abs(gr - g['grad'][0]).max() <= 1e-11 * np.abs(g['grad'][0]).max()
+
+
+def test_diag_fisher_matches_reference():
+    """oracle.diag_fisher against NNWrap.calc_hess_diag (nnwrap.py:204-229) recorded from the reference."""
+    g = load('hessdiag_mlp.npz')
+    layers, P = qo.mlp_layers(2, 1, (6, 5), True, 'tanh')
+    f0 = qo.diag_fisher(layers, g['theta'], g['x'], g['y'], float(g['sigma']))
+    np.testing.assert_allclose(f0, g['fisher_noprior'], rtol=1e-10)
+    f1 = qo.diag_fisher(layers, g['theta'], g['x'], g['y'], float(g['sigma']), fulldatasize=int(g['nfull']),
+                        prior=dict(sigma=float(g['sigma_prior']), anchor=g['anchor']))
+    np.testing.assert_allclose(f1, g['fisher_prior'], rtol=1e-10)
+
+
+def test_philox_known_answers():
+    """oracle/philox.py (the counter-based streams of the chain kernels) against the published Philox4x32-10 vectors."""
+    from oracle import philox
+    assert [int(v) for v in philox.philox4x32_10((0, 0, 0, 0), (0, 0))] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert [int(v) for v in philox.philox4x32_10((0xffffffff,) * 4, (0xffffffff,) * 2)] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert [int(v) for v in philox.philox4x32_10((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0))] == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    z = philox.normals(5, 3, 7, philox.STREAM_INCR, 40001)
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1.0) < 0.02
