@@ -40,6 +40,9 @@ struct QbTcPlan {
     int nthreads;                       // 256 (pipelined) or 128
     int a_lo_col, d_col, tmem_cols;
     int smem_bytes;
+    int v3;                             // warp-specialised hot-shape path (qb_tc3.cuh): 288 threads, layouts below
+    int v3_w0, v3_w1, v3_x;             // byte offsets: W0 tf32 hi|lo, W1 fp16 hi|lo, x tiles [2][hi|lo]
+    int v3_c1;                          // float index of the accumulator scale of the hidden GEMM
     QbTcLayer L[QB_MAX_LAYERS];
 };
 
@@ -705,6 +708,11 @@ static __device__ __noinline__ double qb_tc_eval_other(const QbTcPlan& tp, QbTcC
 // every perturbation showed up as spills and -3..10 %).
 __host__ __device__ __forceinline__ bool qb_tc_is_hot(const QbTcPlan& tp) {
     return tp.pipe == 2 && tp.ni == 4 && tp.act0 == QB_ACT_TANH && tp.out_dim == 1 && tp.h0 == 64 && tp.kl == 64 &&
+           tp.L[1].n_out == 64;
+}
+// the shape the warp-specialised path (qb_tc3.cuh) covers
+__host__ __device__ __forceinline__ bool qb_tc_v3_shape(const QbTcPlan& tp) {
+    return tp.pipe == 2 && tp.in_dim <= 7 && tp.act0 == QB_ACT_TANH && tp.out_dim == 1 && tp.h0 == 64 && tp.kl == 64 &&
            tp.L[1].n_out == 64;
 }
 template <bool HOT>

@@ -1,0 +1,434 @@
+// Warp-specialised tensor-core value path for the hot shape (in <= 7 -> 64 -> 64 -> 1, tanh): kernels 1 and 3 at the
+// config-5 shape.  Same arithmetic contract as qb_tc.cuh (fp32-level accuracy through split operands), different
+// machine mapping:
+//   * 8 compute warps (256 threads: thread = one of the tile's 128 points x one half of the 64 columns) and ONE issue
+//     warp (warp 8) that never computes: it stages the x tile, issues every tcgen05.mma and commits them to mbarriers.
+//     No compute warp ever issues an MMA or waits for the other warps to arrive (the old loop spent 20 % of its stall
+//     samples there and ~1100 cycles per tile of warp 0 on the issue itself).
+//   * layer 0 runs on the tensor cores as well: D0[128 x 64] = X[128 x 8] * W0^T, kind::tf32, 3 passes, both operands in
+//     shared memory.  X = (x_0 .. x_{in-1}, 1, 0 ..): the bias rides in the K slot that holds 1.0.  The issue warp
+//     loads x two tiles ahead, splits it into tf32 hi + lo and writes the canonical K-major tile; the compute warps
+//     never touch x.
+//   * the hidden 64x64 GEMM runs as kind::f16 with fp16 hi + lo splits ("3 x FP16": a_hi*b_hi + a_lo*b_hi + a_hi*b_lo,
+//     fp32 accumulation): K = 16 per MMA instead of 8 (12 MMAs per tile instead of 24) and the A operand takes 64
+//     tensor-memory columns instead of 128.  fp16 has 11 significant bits like tf32; its narrow exponent is handled
+//     by exact power-of-two scaling: activations are produced as 2^14 * sigmoid (in (2^-16, 2^14]) and the weights
+//     are scaled per parameter vector so that max |w| lies in [2^13, 2^14): every lo part within 2^16 of the largest
+//     is a normal fp16 number, smaller ones carry an absolute error of 2^-25 in units of the scaled maximum.
+//   * tanh = 1 - 2 s with s = 1 / (1 + 2^z'): the affine part is folded into the NEXT layer's weights and bias at
+//     staging (W' = -2 W, b' = b + sum_k W_k), so the epilogues produce s only (2 packed FMAs per 4 activations less).
+// Tensor memory (256 columns per block, two blocks per SM): D0 [0,64) | A_hi [64,96) | -A_lo [96,128) | D1 x 2 [128,256).
+// Per tile t:   issue warp:     wait a_ready(t) -> MMA0(t+1) -> commit d0_full -> MMA1(t) -> commit d1_full -> stage X(t+2)
+//               compute warps:  EPI1(t-1) [D1 -> s -> dot with the output row]  then  EPI0(t+1) [D0 -> 2^14 s -> fp16
+//                               hi/lo -> A; the tensor-memory store waits for d1_full(t) = "A is free"] -> arrive a_ready(t+1)
+// so the MMAs of tile t run under EPI1(t-1) and the only block-wide rendezvous is the arrival count of a_ready.
+#pragma once
+#include "qb_tc.cuh"
+
+#ifdef __CUDACC__
+enum { QB3_D0F = 320, QB3_ARDY = 336, QB3_D1F = 344, QB3_D1FREE = 352,      // mbarriers in the shared-memory header
+       QB3_COL_AHI = 64, QB3_COL_ALO = 96, QB3_COL_D1 = 128, QB3_NCOMPUTE = 256 };
+
+// all threads; tensor-memory allocation (the mbarriers are (re)initialised by every evaluation)
+__device__ __forceinline__ void qb_tc3_init(const QbTcPlan& tp, unsigned char* smem, QbTcCtx& cx) {
+    if ((threadIdx.x >> 5) == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(qb_smem_u32(smem + QB_TC_SLOT_OFF)), "r"((uint32_t)tp.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x == 0) {
+        const uint32_t b = qb_smem_u32(smem);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB3_D0F), "r"(1u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB3_ARDY), "r"((uint32_t)QB3_NCOMPUTE) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB3_D1F), "r"(1u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB3_D1FREE), "r"((uint32_t)QB3_NCOMPUTE) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB3_D1FREE + 8), "r"((uint32_t)QB3_NCOMPUTE) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    qb_tc_fence_before();
+    __syncthreads();
+    qb_tc_fence_after();
+    cx.tmem = *reinterpret_cast<volatile uint32_t*>(smem + QB_TC_SLOT_OFF);
+    cx.bar = cx.abar = cx.hbar = 0; cx.phase = cx.aphase = cx.hphase = 0;
+}
+// thread 0, between two block barriers: every phase of the previous evaluation has completed, start again at parity 0
+__device__ __forceinline__ void qb_tc3_reset_barriers(unsigned char* smem) {
+    const uint32_t b = qb_smem_u32(smem);
+    const uint32_t off[5] = {QB3_D0F, QB3_ARDY, QB3_D1F, QB3_D1FREE, QB3_D1FREE + 8};
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"(b + off[i]) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + off[i]), "r"((i == 0 || i == 2) ? 1u : (uint32_t)QB3_NCOMPUTE) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t qb3_pack_f16(float lo_elem, float hi_elem) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
+}
+// (x0, x1) -> fp16 pair `hi` (round to nearest) and the fp16 pair of the NEGATED remainders hi - x (the mixed-precision
+// subtract takes the fp16 operand first; the sign is absorbed by a negated copy of the other operand's hi tile)
+__device__ __forceinline__ void qb3_split_f16(float x0, float x1, uint32_t& hi, uint32_t& nlo) {
+    hi = qb3_pack_f16(x0, x1);
+    float d0, d1;       // hi - x, exactly: one instruction per element
+    asm("{ .reg .b16 a, b; mov.b32 {a, b}, %2; sub.rn.f32.f16 %0, a, %3; sub.rn.f32.f16 %1, b, %4; }"
+        : "=f"(d0), "=f"(d1) : "r"(hi), "f"(x0), "f"(x1));
+    nlo = qb3_pack_f16(d0, d1);
+}
+
+// flat theta (global) -> shared operands of the three layers.  All threads of the block; ends with the async-proxy fence.
+//   W0  : tf32 hi / lo, [64 x 8] canonical K-major (k < in: weight, k == in: bias, else 0), times 2 log2 e
+//   W1  : fp16 hi / lo / -hi of -2 * 2 log2 e * 2^sW * W1 (the -2: tanh = 1 - 2 s), [64 x 64] canonical K-major
+//         (core matrix = 8 rows x 8 halves; LBO 128 B, SBO 1024 B); -hi multiplies the negated lo parts of A
+//   F[bias1 + j] = 2 log2 e * (b1_j + sum_k W1_jk);  F[c1] = 2^(-14 - sW)  (D1 is in units of 2^14 * 2^sW)
+//   F[wl + k] = -2 * sl * wl_k;  F[bl] = sl * (bl + sum_k wl_k)
+__device__ __forceinline__ void qb_tc3_stage(const QbTcPlan& tp, unsigned char* smem, const float* __restrict__ theta) {
+    float* F = reinterpret_cast<float*>(smem + tp.fl_base);
+    double* red = reinterpret_cast<double*>(smem);
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const float fold = 2.8853900817779268f;
+    const QbTcLayer& L = tp.L[1];
+    // ---- scale of W1: largest magnitude -> [2^13, 2^14)
+    float mx = 0.0f;
+    for (int e = tid; e < 64 * 64; e += nt) mx = fmaxf(mx, fabsf(theta[L.w_off + e]));
+    uint32_t mb = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
+    __syncthreads();                       // the previous evaluation's readers of F / red are done
+    if (lane == 0) reinterpret_cast<uint32_t*>(red)[wid] = mb;
+    __syncthreads();
+    mb = 0;
+    for (int w = 0; w < (nt + 31) >> 5; ++w) mb = max(mb, reinterpret_cast<const uint32_t*>(red)[w]);
+    int sW = 0;
+    {
+        const float m = __uint_as_float(mb) * fold;
+        if (m > 0.0f && m < 3.0e38f) sW = 13 - ilogbf(m);
+        sW = max(-60, min(60, sW));
+    }
+    const float wscale = -2.0f * fold * __uint_as_float((uint32_t)(127 + sW) << 23);
+    // ---- W0 (tf32 hi / lo): element (n, k) at float index ((n/8)*2 + k/4)*32 + (n%8)*4 + k%4
+    {
+        float* hi = reinterpret_cast<float*>(smem + tp.v3_w0);
+        float* lo = hi + 64 * 8;
+        for (int e = tid; e < 64 * 8; e += nt) {
+            const int n = e >> 3, k = e & 7;
+            float v = 0.0f;
+            if (k < tp.in_dim) v = theta[tp.w0_off + n * tp.in_dim + k] * fold;
+            else if (k == tp.in_dim && tp.b0_off >= 0) v = theta[tp.b0_off + n] * fold;
+            const float h = qb_tf32_hi(v);
+            const int idx = ((n >> 3) * 2 + (k >> 2)) * 32 + (n & 7) * 4 + (k & 3);
+            hi[idx] = h; lo[idx] = v - h;
+        }
+    }
+    // ---- W1 (fp16 hi / lo) and its row sums: warp w of the first eight takes rows w, w+8, ..; lane = a pair of columns
+    if (wid < 8) {
+        uint32_t* hi = reinterpret_cast<uint32_t*>(smem + tp.v3_w1);
+        uint32_t* lo = hi + 64 * 64 / 2;
+        uint32_t* nhi = lo + 64 * 64 / 2;
+        for (int n = wid; n < 64; n += 8) {
+            const int k = lane * 2;
+            const float w0 = theta[L.w_off + n * 64 + k], w1 = theta[L.w_off + n * 64 + k + 1];
+            uint32_t h2, l2;
+            qb3_split_f16(w0 * wscale, w1 * wscale, h2, l2);
+            const int idx = (((n >> 3) * 8 + (k >> 3)) * 64 + (n & 7) * 8 + (k & 7)) >> 1;      // 32-bit word index
+            hi[idx] = h2; lo[idx] = l2 ^ 0x80008000u; nhi[idx] = h2 ^ 0x80008000u;
+            double s = (double)w0 + (double)w1;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (lane == 0) F[L.bias + n] = (float)((double)fold * ((L.b_off >= 0 ? (double)theta[L.b_off + n] : 0.0) + s));
+        }
+    } else if (wid == 8) {
+        // ---- output row: -2 sl wl, bias sl (bl + sum wl)
+        const float sl = tp.act_last == QB_ACT_TANH ? fold : 1.0f;
+        const float a = theta[tp.wl_off + lane], b = theta[tp.wl_off + 32 + lane];
+        F[tp.wl + lane] = -2.0f * sl * a; F[tp.wl + 32 + lane] = -2.0f * sl * b;
+        double s = (double)a + (double)b;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) {
+            F[tp.bl] = (float)((double)sl * ((tp.bl_off >= 0 ? (double)theta[tp.bl_off] : 0.0) + s));
+            F[tp.v3_c1] = __uint_as_float((uint32_t)(127 - 14 - sW) << 23);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// 1 / (1 + 2^z) for four pre-activations with ONE reciprocal (see qb_tanh4_prescaled); SC: results times 2^14
+template <bool SC>
+__device__ __forceinline__ void qb3_sig4(float2& a, float2& b) {
+    float2 ea, eb;
+    ea.x = qb_ex2(qb_min_nan(a.x, 30.0f)); ea.y = qb_ex2(qb_min_nan(a.y, 30.0f));
+    eb.x = qb_ex2(qb_min_nan(b.x, 30.0f)); eb.y = qb_ex2(qb_min_nan(b.y, 30.0f));
+    float2 da, db;
+    if (SC) {
+        const float2 c = make_float2(6.103515625e-05f, 6.103515625e-05f);        // 2^-14
+        da = __ffma2_rn(ea, c, c); db = __ffma2_rn(eb, c, c);
+    } else {
+        const float2 one = make_float2(1.0f, 1.0f);
+        da = __fadd2_rn(ea, one); db = __fadd2_rn(eb, one);
+    }
+    const float2 m = __fmul2_rn(da, db);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(m.x * m.y));
+    float2 rr;
+    rr.x = r * m.y; rr.y = r * m.x;
+    a = __fmul2_rn(rr, db);
+    b = __fmul2_rn(rr, da);
+}
+
+// one tcgen05.mma (issued by the elected lane); ACC: accumulate into D
+template <bool ACC>
+__device__ __forceinline__ void qb3_mma_tf32_ss(uint32_t d, uint32_t a_lo32, uint32_t b_lo32, uint32_t dhi, uint32_t idesc) {
+    asm volatile("{ .reg .pred p; .reg .b64 da, db; setp.ne.b32 p, %5, 0; mov.b64 da, {%1, %3}; mov.b64 db, {%2, %3};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p; }"
+                 :: "r"(d), "r"(a_lo32), "r"(b_lo32), "r"(dhi), "r"(idesc), "n"(ACC ? 1 : 0) : "memory");
+}
+template <bool ACC>
+__device__ __forceinline__ void qb3_mma_f16_ts(uint32_t d, uint32_t a_tmem, uint32_t b_lo32, uint32_t dhi, uint32_t idesc) {
+    asm volatile("{ .reg .pred p; .reg .b64 db; setp.ne.b32 p, %5, 0; mov.b64 db, {%2, %3};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p; }"
+                 :: "r"(d), "r"(a_tmem), "r"(b_lo32), "r"(dhi), "r"(idesc), "n"(ACC ? 1 : 0) : "memory");
+}
+__device__ __forceinline__ void qb3_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool qb3_elect() {
+    uint32_t e;
+    asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.b32 %0, 1, 0, p; }" : "=r"(e) :: "memory");
+    return e != 0;
+}
+
+// The issue warp's view of an x tile: lane l owns points 4l .. 4l+3
+template <int IN>          // IN: upper bound of the input width (3 or 7)
+struct Qb3X {
+    float v[4][IN];
+    int in_dim;
+    __device__ __forceinline__ void load(const float* __restrict__ x, int64_t p0, int64_t n1, int lane) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t p = p0 + lane * 4 + i;
+#pragma unroll
+            for (int q = 0; q < IN; ++q) v[i][q] = (p < n1 && q < in_dim) ? __ldg(x + p * in_dim + q) : 0.0f;
+        }
+    }
+    // canonical K-major tile [128 x 8]: element (m, k) at float index ((m/8)*2 + k/4)*32 + (m%8)*4 + k%4
+    __device__ __forceinline__ void store(float* hi, float* lo, int lane) const {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = lane * 4 + i;
+            float w[8], h[8], l[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                w[q] = q < IN ? v[i][q < IN ? q : 0] : 0.0f;
+                if (q == in_dim) w[q] = 1.0f;                    // the bias slot
+                h[q] = qb_tf32_hi(w[q]); l[q] = w[q] - h[q];
+            }
+            const int idx = ((m >> 3) * 2) * 32 + (m & 7) * 4;
+            *reinterpret_cast<float4*>(hi + idx) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(hi + idx + 32) = make_float4(h[4], h[5], h[6], h[7]);
+            *reinterpret_cast<float4*>(lo + idx) = make_float4(l[0], l[1], l[2], l[3]);
+            *reinterpret_cast<float4*>(lo + idx + 32) = make_float4(l[4], l[5], l[6], l[7]);
+        }
+    }
+};
+
+// sum of squared residuals over points [n0, n1) for the staged parameter vector (block-wide result); every thread of
+// the 288-thread block calls it
+template <int IN>
+__device__ __forceinline__ double qb_tc3_eval(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem,
+                                              const float* __restrict__ x, const float* __restrict__ y,
+                                              int64_t n0, int64_t n1) {
+    const float* F = reinterpret_cast<const float*>(smem + tp.fl_base);
+    const uint32_t sb = qb_smem_u32(smem);
+    const uint32_t bar_d0f = sb + QB3_D0F, bar_ardy = sb + QB3_ARDY, bar_d1f = sb + QB3_D1F, bar_d1free = sb + QB3_D1FREE;
+    const int T = (int)((n1 - n0 + 127) / 128);
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();                               // staging complete; nobody is still inside the previous evaluation
+    if (threadIdx.x == 0) qb_tc3_reset_barriers(smem);
+    __syncthreads();
+    float ssq = 0.0f;
+    if (T > 0 && wid == 8) {
+        // ================================ issue warp ================================
+        float* xb = reinterpret_cast<float*>(smem + tp.v3_x);         // [2][hi 1024 | lo 1024] floats
+        const uint32_t dhi8 = ((128u * 2u) >> 4) | (1u << 14);        // K = 8 tf32: SBO 256 B
+        const uint32_t dhi64 = (1024u >> 4) | (1u << 14);             // K = 64 fp16: SBO 1024 B
+        const uint32_t lbo = (128u >> 4) << 16;
+        const uint32_t w0hi = ((qb_smem_u32(smem + tp.v3_w0) >> 4) & 0x3FFFu) | lbo, w0lo = w0hi + (64u * 8u * 4u >> 4);
+        const uint32_t w1hi = ((qb_smem_u32(smem + tp.v3_w1) >> 4) & 0x3FFFu) | lbo, w1lo = w1hi + (64u * 64u * 2u >> 4),
+                       w1nhi = w1lo + (64u * 64u * 2u >> 4);
+        const uint32_t xd = ((qb_smem_u32(xb) >> 4) & 0x3FFFu) | lbo;  // + 512 (16-byte units) per buffer, + 256 for lo
+        const uint32_t id_tf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t id_f16 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t d0 = cx.tmem, a_hi = cx.tmem + QB3_COL_AHI, a_lo = cx.tmem + QB3_COL_ALO;
+        Qb3X<IN> X;
+        X.in_dim = tp.in_dim;
+        X.load(x, n0, n1, lane);
+        X.store(xb, xb + 1024, lane);
+        if (T > 1) X.load(x, n0 + 128, n1, lane);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (qb3_elect()) {
+            qb3_mma_tf32_ss<false>(d0, xd + 256u, w0hi, dhi8, id_tf32);
+            qb3_mma_tf32_ss<true>(d0, xd, w0lo, dhi8, id_tf32);
+            qb3_mma_tf32_ss<true>(d0, xd, w0hi, dhi8, id_tf32);
+            qb3_commit(bar_d0f);
+        }
+        __syncwarp();
+        if (T > 1) {
+            X.store(xb + 2048, xb + 3072, lane);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (T > 2) X.load(x, n0 + 256, n1, lane);
+        }
+#pragma unroll 1
+        for (int t = 0; t < T; ++t) {
+            qb_mbar_wait(bar_ardy, (uint32_t)t & 1u);                                 // A(t) written, D0 read
+            if (t >= 2) qb_mbar_wait(bar_d1free + (uint32_t)(t & 1) * 8u, (uint32_t)((t >> 1) - 1) & 1u);
+            qb_tc_fence_after();
+            __syncwarp();
+            if (qb3_elect()) {
+                if (t + 1 < T) {
+                    const uint32_t xa = xd + (uint32_t)((t + 1) & 1) * 512u;
+                    qb3_mma_tf32_ss<false>(d0, xa + 256u, w0hi, dhi8, id_tf32);
+                    qb3_mma_tf32_ss<true>(d0, xa, w0lo, dhi8, id_tf32);
+                    qb3_mma_tf32_ss<true>(d0, xa, w0hi, dhi8, id_tf32);
+                    qb3_commit(bar_d0f);
+                }
+                const uint32_t d1 = cx.tmem + QB3_COL_D1 + (uint32_t)(t & 1) * 64u;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    if (s == 0) qb3_mma_f16_ts<false>(d1, a_lo, w1nhi, dhi64, id_f16);
+                    else qb3_mma_f16_ts<true>(d1, a_lo + 8u * s, w1nhi + 16u * s, dhi64, id_f16);
+                }
+#pragma unroll
+                for (int s = 0; s < 4; ++s) qb3_mma_f16_ts<true>(d1, a_hi + 8u * s, w1lo + 16u * s, dhi64, id_f16);
+#pragma unroll
+                for (int s = 0; s < 4; ++s) qb3_mma_f16_ts<true>(d1, a_hi + 8u * s, w1hi + 16u * s, dhi64, id_f16);
+                qb3_commit(bar_d1f);
+            }
+            __syncwarp();
+            if (t + 2 < T) {
+                // MMA0(t) has completed (the compute warps waited for it before they arrived on a_ready(t))
+                float* b = xb + (t & 1) * 2048;
+                X.store(b, b + 1024, lane);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (t + 3 < T) X.load(x, n0 + (int64_t)(t + 3) * 128, n1, lane);
+            }
+        }
+    } else if (T > 0) {
+        // ================================ compute warps ================================
+        const int g = threadIdx.x >> 7, pt = threadIdx.x & 127;
+        const uint32_t tl = cx.tmem + ((uint32_t)((wid & 3) * 32) << 16);
+        float* ybuf = reinterpret_cast<float*>(smem + tp.ybuf);           // [4][128] partial outputs of group 1
+        const float c1 = F[tp.v3_c1];
+        const float4* B4 = reinterpret_cast<const float4*>(F + tp.L[1].bias + 32 * g);
+        const float4* W4 = reinterpret_cast<const float4*>(F + tp.wl + 32 * g);
+        const int64_t pbase = n0 + pt;
+        float own0 = 0.0f, own1 = 0.0f, yt0 = 0.0f, yt1 = 0.0f;          // group 0: own partial sum / target of tiles t-1, t-2
+
+        // EPI0(u): D0 -> 2^14 * s -> fp16 hi / lo -> A.  `afree`: wait for d1_full(u - 1) before the stores.
+        auto epi0 = [&](int u) {
+            qb_mbar_wait(bar_d0f, (uint32_t)u & 1u);
+            qb_tc_fence_after();
+            uint32_t v[2][16];
+            qb_tmem_ld16(tl + 32 * g, v[0]);
+            qb_tmem_ld16(tl + 32 * g + 16, v[1]);
+            qb_tmem_ld_wait16(v[0]);
+            qb_tmem_ld_wait16(v[1]);
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float2 a = make_float2(__uint_as_float(v[j][4 * q + 0]), __uint_as_float(v[j][4 * q + 1]));
+                    float2 b = make_float2(__uint_as_float(v[j][4 * q + 2]), __uint_as_float(v[j][4 * q + 3]));
+                    qb3_sig4<true>(a, b);
+                    qb3_split_f16(a.x, a.y, hi[8 * j + 2 * q], lo[8 * j + 2 * q]);
+                    qb3_split_f16(b.x, b.y, hi[8 * j + 2 * q + 1], lo[8 * j + 2 * q + 1]);
+                }
+            }
+            if (u > 0) {
+                qb_mbar_wait(bar_d1f, (uint32_t)(u - 1) & 1u);           // MMA1(u-1) complete: A is free, D1[(u-1)&1] is ready
+                qb_tc_fence_after();
+            }
+            qb_tmem_st16(tl + QB3_COL_AHI + 16 * g, hi);
+            qb_tmem_st16(tl + QB3_COL_ALO + 16 * g, lo);
+            qb_tmem_st_wait();
+            qb_tc_fence_before();
+            qb_mbar_arrive(bar_ardy);
+        };
+        // EPI1(u): D1[u&1] -> s -> partial dot product with the output row
+        auto epi1 = [&](int u) -> float {
+            uint32_t v[2][16];
+            const uint32_t dcol = QB3_COL_D1 + (uint32_t)(u & 1) * 64u + 32u * g;
+            qb_tmem_ld16(tl + dcol, v[0]);
+            qb_tmem_ld16(tl + dcol + 16, v[1]);
+            qb_tmem_ld_wait16(v[0]);
+            qb_tmem_ld_wait16(v[1]);
+            qb_tc_fence_before();
+            qb_mbar_arrive(bar_d1free + (uint32_t)(u & 1) * 8u);         // the accumulator is in registers
+            float2 acc = make_float2(0.0f, 0.0f);
+            const float2 c2 = make_float2(c1, c1);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 bb = B4[4 * j + q], ww = W4[4 * j + q];
+                    float2 a = __ffma2_rn(make_float2(__uint_as_float(v[j][4 * q + 0]), __uint_as_float(v[j][4 * q + 1])), c2, make_float2(bb.x, bb.y));
+                    float2 b = __ffma2_rn(make_float2(__uint_as_float(v[j][4 * q + 2]), __uint_as_float(v[j][4 * q + 3])), c2, make_float2(bb.z, bb.w));
+                    qb3_sig4<false>(a, b);
+                    acc = __ffma2_rn(a, make_float2(ww.x, ww.y), acc);
+                    acc = __ffma2_rn(b, make_float2(ww.z, ww.w), acc);
+                }
+            }
+            return acc.x + acc.y;
+        };
+        // group 0: residual of tile u (own partial sum + the partner's from ybuf)
+        auto finish = [&](int u, float own, float yt) {
+            const int64_t p = pbase + (int64_t)u * 128;
+            const float yo = qb_tc_out(tp, F, 0, own + ybuf[(u & 3) * 128 + pt]);
+            if (p < n1) { const float r = yt - yo; ssq = fmaf(r, r, ssq); }
+        };
+
+        epi0(0);
+#pragma unroll 1
+        for (int t = 0; t < T; ++t) {
+            if (t >= 1) {
+                // tile t-1 (d1_full(t-1) was waited for in EPI0(t)); the partner's partial sum of tile t-3 became visible
+                // with d1_full(t-1) at the latest (it arrived on a_ready(t-1) after writing it)
+                const int u = t - 1;
+                float ytn = 0.0f;
+                if (g == 0) { const int64_t p = pbase + (int64_t)u * 128; if (p < n1) ytn = __ldg(y + p); }
+                const float part = epi1(u);
+                if (g == 0) {
+                    if (u >= 2) finish(u - 2, own1, yt1);
+                    own1 = own0; yt1 = yt0; own0 = part; yt0 = ytn;
+                } else {
+                    ybuf[(u & 3) * 128 + pt] = part;
+                }
+            }
+            if (t + 1 < T) epi0(t + 1);
+            else { qb_mbar_wait(bar_d1f, (uint32_t)t & 1u); qb_tc_fence_after(); }
+        }
+        {
+            const int u = T - 1;
+            float ytn = 0.0f;
+            if (g == 0) { const int64_t p = pbase + (int64_t)u * 128; if (p < n1) ytn = __ldg(y + p); }
+            const float part = epi1(u);
+            if (g != 0) ybuf[(u & 3) * 128 + pt] = part;
+            asm volatile("bar.sync 1, 256;" ::: "memory");               // the compute warps only
+            if (g == 0) {
+                if (u >= 2) finish(u - 2, own1, yt1);
+                if (u >= 1) finish(u - 1, own0, yt0);
+                finish(u, part, ytn);
+            }
+        }
+    }
+    return qb_block_sum((double)ssq, reinterpret_cast<double*>(smem));
+}
+__device__ __forceinline__ double qb_tc3_eval_any(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem,
+                                                  const float* __restrict__ x, const float* __restrict__ y,
+                                                  int64_t n0, int64_t n1) {
+    if (tp.in_dim <= 3) return qb_tc3_eval<3>(tp, cx, smem, x, y, n0, n1);
+    return qb_tc3_eval<7>(tp, cx, smem, x, y, n0, n1);
+}
+#endif  // __CUDACC__
