@@ -14,6 +14,7 @@ template <typename T> struct EvalArgs {
     T* gpart;       // [K,S,P] (S > 1)
     double* lp;
     QbLikDev lk;
+    const T* xsplit;           // hot-shape tensor-core path: x as ready-made operand tiles (qb_value_tc3.cu), or nullptr
 };
 
 template <typename T> __device__ __forceinline__ T qb_mul(T a, T b);

@@ -12,7 +12,7 @@
 #include "qb_device.cuh"
 #include "qb_chain.cuh"
 #include "qb_tc.cuh"
-#include "qb_tc3.cuh"
+#include "qb_value_tc3.h"
 #include "qb_grad_tc.h"
 
 #ifndef QB_LB_T
@@ -307,7 +307,9 @@ static int make_launch(const qb_net_t* net, int dtype, bool want_grad, long long
 
 // Tensor-core (tcgen05 3xTF32) plan for the value path; returns false when the network is not eligible:
 // fp32, >= 3 layers, no residual layers, n_in <= 15, hidden widths multiples of 16 (<= 128), <= 4 outputs.
-static bool make_tc_plan(const qb_net_t* net, int dtype, QbTcPlan* tp, bool allow_v3 = false) {
+// allow_v3: 1 = the caller can run the warp-specialised hot-shape kernels (qb_value_tc3.cu); 2 = and wants room for the
+// chain state (3 P floats) in shared memory
+static bool make_tc_plan(const qb_net_t* net, int dtype, QbTcPlan* tp, int allow_v3 = 0) {
     memset(tp, 0, sizeof(*tp));
     if (dtype != QB_F32 || env_int("QB_NO_TC", 0)) return false;
     const int nl = net->n_layers;
@@ -358,18 +360,22 @@ static bool make_tc_plan(const qb_net_t* net, int dtype, QbTcPlan* tp, bool allo
     const int max_blocks = 512 / tp->tmem_cols;
     const long long floor_bytes = QB_SMEM_SM / (max_blocks + 1) + 1;
     tp->smem_bytes = (int)std::min<long long>(QB_SMEM_MAX, std::max(bytes, floor_bytes));
-    if (allow_v3 && qb_tc_v3_shape(*tp) && !env_int("QB_NO_V3", 0)) {
+    if (allow_v3 && qb_tc_v3_shape(*tp) && net->layers[1].act == QB_ACT_TANH && !env_int("QB_NO_V3", 0)) {
         // warp-specialised path (qb_tc3.cuh): 8 compute warps + 1 issue warp, 256 tensor-memory columns, own layout
         tp->v3 = 1; tp->nthreads = 288; tp->tmem_cols = 256;
         int o = QB_TC_HDR_BYTES;
         tp->v3_w1 = o; o += 3 * 64 * 64 * 2;
         tp->v3_w0 = o; o += 2 * 64 * 8 * 4;
-        tp->v3_x = o; o += 2 * 2 * 128 * 8 * 4;
+        tp->v3_x = o; o += 3 * 2 * 128 * 8 * 4;
         tp->fl_base = o;
         tp->L[1].bias = 0; tp->wl = 64; tp->bl = 128; tp->v3_c1 = 132;
         o += 136 * 4;
         tp->ybuf = o; o += 4 * 128 * 4;
+        tp->v3_xbar = o; o += 32;
+        tp->v3_state = o;
+        if (allow_v3 == 2) o += 3 * ((net->n_params + 3) / 4 * 4) * 4;
         tp->smem_bytes = (int)std::max<long long>(o, QB_SMEM_SM / 3 + 1);
+        if (tp->smem_bytes > (QB_SMEM_SM - 2048) / 2) return make_tc_plan(net, dtype, tp, 0);     // two blocks per SM must fit
     }
     return true;
 }
@@ -415,35 +421,26 @@ __global__ void __launch_bounds__(256, 2) k_logpost_grad(const __grid_constant__
 
 
 // kernel 1 on the tensor cores (fp32 eligible networks, see qb_tc.cuh)
-template <bool V3>
-__global__ void __launch_bounds__(V3 ? 288 : 512, V3 ? 2 : 1) k_logpost_tc(const __grid_constant__ QbTcPlan tp, const EvalArgs<float> a) {
+__global__ void __launch_bounds__(512, 1) k_logpost_tc(const __grid_constant__ QbTcPlan tp, const EvalArgs<float> a) {
     extern __shared__ __align__(128) unsigned char smem_tc[];
     QbTcCtx cx;
+    qb_tc_init(tp, smem_tc, cx);
     const long long k = blockIdx.x, s = blockIdx.y;
     const long long n0 = s * a.pps, n1 = min(a.N, n0 + a.pps);
-    double ssq;
-    if constexpr (V3) {
-        qb_tc3_init(tp, smem_tc, cx);
-        qb_tc3_stage(tp, smem_tc, a.theta + k * tp.n_params);
-        ssq = qb_tc3_eval_any(tp, cx, smem_tc, a.x + k * a.xs, a.y + k * a.ys, n0, n1);
-    } else {
-        qb_tc_init(tp, smem_tc, cx);
-        qb_tc_stage(tp, smem_tc, a.theta + k * tp.n_params);
-        __syncthreads();
-        ssq = qb_tc_eval<false>(tp, cx, smem_tc, a.x + k * a.xs, a.y + k * a.ys, n0, n1);
-    }
+    qb_tc_stage(tp, smem_tc, a.theta + k * tp.n_params);
+    __syncthreads();
+    const double ssq = qb_tc_eval<false>(tp, cx, smem_tc, a.x + k * a.xs, a.y + k * a.ys, n0, n1);
     if (threadIdx.x == 0) a.part[k * a.S + s] = ssq;
     qb_tc_fini(tp, cx);
 }
 
 template <typename T> static int launch_logpost_tc(const QbTcPlan&, const EvalArgs<T>&, dim3, cudaStream_t) { return qb_fail("tensor-core path is fp32 only"); }
 template <> int launch_logpost_tc<float>(const QbTcPlan& tp, const EvalArgs<float>& a, dim3 grid, cudaStream_t st) {
-    if (tp.v3) {
-        if (set_smem(k_logpost_tc<true>, tp.smem_bytes)) return -2;
-        k_logpost_tc<true><<<grid, tp.nthreads, tp.smem_bytes, st>>>(tp, a);
+    if (tp.v3) {                  // hot shape: warp-specialised kernel (qb_value_tc3.cu)
+        QB_CUDA(qb_tc3_launch_logpost(tp, a, grid, st));
     } else {
-        if (set_smem(k_logpost_tc<false>, tp.smem_bytes)) return -2;
-        k_logpost_tc<false><<<grid, tp.nthreads, tp.smem_bytes, st>>>(tp, a);
+        if (set_smem(k_logpost_tc, tp.smem_bytes)) return -2;
+        k_logpost_tc<<<grid, tp.nthreads, tp.smem_bytes, st>>>(tp, a);
     }
     return 0;
 }
@@ -503,6 +500,7 @@ static int run_eval(const qb_net_t* net, int dtype, const void* theta, int64_t K
     const size_t part_bytes = ((size_t)K * L.S * sizeof(double) + 255) / 256 * 256;
     a.gpart = (L.S > 1 && want_grad) ? (T*)((char*)ws + part_bytes) : nullptr;
     a.lp = lp; a.lk = lik_dev(lik);
+    a.xsplit = nullptr;
     dim3 grid((unsigned)K, (unsigned)L.S);
     if (want_grad) {
         QbTcgPlan tg;
@@ -514,7 +512,9 @@ static int run_eval(const qb_net_t* net, int dtype, const void* theta, int64_t K
         }
     } else {
         QbTcPlan tp;
-        if (make_tc_plan(net, dtype, &tp, true)) {
+        if (make_tc_plan(net, dtype, &tp, 1)) {
+            // hot shape with shared data: x goes to the kernel as ready-made operand tiles at the end of the workspace
+            if (tp.v3 && x_stride == 0) a.xsplit = (const T*)((char*)ws + need - qb_tc3_xsplit_bytes(data->n));
             if (launch_logpost_tc<T>(tp, a, grid, st)) return -2;
         } else {
             if (set_smem(k_logpost<T>, L.plan.smem_bytes)) return -2;
@@ -533,6 +533,8 @@ extern "C" size_t qb_eval_workspace_bytes(const qb_net_t* net, int dtype, int64_
     if (make_launch(net, dtype, want_grad != 0, K, N, false, &L)) return 0;
     size_t b = ((size_t)K * L.S * sizeof(double) + 255) / 256 * 256;
     if (want_grad && L.S > 1) b += (size_t)K * L.S * net->n_params * (dtype == QB_F64 ? 8 : 4);
+    QbTcPlan tp;
+    if (!want_grad && make_tc_plan(net, dtype, &tp, 1) && tp.v3) b = (b + 255) / 256 * 256 + qb_tc3_xsplit_bytes(N);
     return b;
 }
 
@@ -547,7 +549,7 @@ extern "C" int qb_plan_info(const qb_net_t* net, int dtype, int64_t K, int64_t N
         out[0] = 128; out[1] = tg.nthreads; out[2] = tg.smem_bytes; out[5] = 0; out[6] = 3; out[7] = tg.tmem_cols;
     }
     QbTcPlan tp;
-    if (!want_grad && make_tc_plan(net, dtype, &tp, true)) {
+    if (!want_grad && make_tc_plan(net, dtype, &tp, 1)) {
         // value path on the tensor cores: 128-point tiles, 128 or 256 threads, out[6] = 1 + pipelined flag,
         // out[7] = tensor-memory columns per block
         out[0] = 128; out[1] = tp.nthreads; out[2] = tp.smem_bytes; out[5] = 0; out[6] = tp.pipe ? 2 : 1; out[7] = tp.tmem_cols;
@@ -778,10 +780,10 @@ __device__ __noinline__ void qb_amcmc_post_cold(const ChainArgs<T>& c, const Amc
     qb_amcmc_post<T>(c, a, P, k, s, ssq, red, st);
 }
 
-// TC = 1 / 2 (fp32 only): the evaluation runs on the tensor cores (qb_tc.cuh); 1 = the config-5 shape only (hot loop
-// fully inlined), 2 = every other eligible shape.
+// TC = 2 (fp32 only): the evaluation runs on the tensor cores (qb_tc.cuh); the config-5 shape has its own kernel
+// (qb_value_tc3.cu).
 template <typename T, int TC>
-__global__ void __launch_bounds__(TC == 1 ? 288 : 512, TC == 1 ? 2 : 1)
+__global__ void __launch_bounds__(512, 1)
 k_amcmc(const __grid_constant__ QbPlan plan, const __grid_constant__ QbTcPlan tp, const __grid_constant__ ChainArgs<T> c,
         const __grid_constant__ AmcmcArgs<T> a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -790,8 +792,7 @@ k_amcmc(const __grid_constant__ QbPlan plan, const __grid_constant__ QbTcPlan tp
     if constexpr (TC) {
         S.red = reinterpret_cast<double*>(smem_raw); S.w = nullptr;
         S.act = smem_raw + tp.fl_base;       // never used as scratch: full-covariance proposals take the SIMT kernel
-        if constexpr (TC == 1) qb_tc3_init(tp, smem_raw, cx);
-        else qb_tc_init(tp, smem_raw, cx);
+        qb_tc_init(tp, smem_raw, cx);
     } else {
         S = qb_carve<T>(plan, smem_raw);
     }
@@ -817,10 +818,7 @@ k_amcmc(const __grid_constant__ QbPlan plan, const __grid_constant__ QbTcPlan tp
         }
         // ---- evaluate + accept
         double ssq;
-        if constexpr (TC == 1) {
-            qb_tc3_stage(tp, smem_raw, evalp);
-            ssq = qb_tc3_eval_any(tp, cx, smem_raw, c.x, c.y, 0, c.N);
-        } else if constexpr (TC == 2) {
+        if constexpr (TC == 2) {
             qb_tc_stage(tp, smem_raw, evalp);
             __syncthreads();
             ssq = qb_tc_eval<false>(tp, cx, smem_raw, c.x, c.y, 0, c.N);
@@ -839,9 +837,8 @@ template <typename T> static int launch_amcmc_tc(const QbPlan&, const QbTcPlan&,
 }
 template <> int launch_amcmc_tc<float>(const QbPlan& plan, const QbTcPlan& tp, const ChainArgs<float>& c, const AmcmcArgs<float>& a,
                                        long long K, cudaStream_t st) {
-    if (tp.v3) {
-        if (set_smem(k_amcmc<float, 1>, tp.smem_bytes)) return -2;
-        k_amcmc<float, 1><<<(unsigned)K, tp.nthreads, tp.smem_bytes, st>>>(plan, tp, c, a);
+    if (tp.v3) {                  // hot shape: warp-specialised kernel with the chain state in shared memory (qb_value_tc3.cu)
+        QB_CUDA(qb_tc3_launch_amcmc(tp, c, a, K, st));
     } else {
         if (set_smem(k_amcmc<float, 2>, tp.smem_bytes)) return -2;
         k_amcmc<float, 2><<<(unsigned)K, tp.nthreads, tp.smem_bytes, st>>>(plan, tp, c, a);
@@ -912,7 +909,7 @@ static int run_amcmc(const qb_net_t* net, int dtype, const qb_data_t* data, cons
     if (am->adapt == QB_ADAPT_FULL && !a.chol) return qb_fail("full adaptation needs chol");
     if (!a.pscale || !a.prop_kind || !a.prop) return qb_fail("amcmc needs pscale, prop_kind and scratch");
     QbTcPlan tp;
-    const bool tc = am->adapt != QB_ADAPT_FULL && !am->chol_ini && make_tc_plan(net, dtype, &tp, true);
+    const bool tc = am->adapt != QB_ADAPT_FULL && !am->chol_ini && make_tc_plan(net, dtype, &tp, 2);
     if (tc) {
         if (launch_amcmc_tc<T>(L.plan, tp, c, a, ch->K, st)) return -2;
     } else {

@@ -43,6 +43,8 @@ struct QbTcPlan {
     int v3;                             // warp-specialised hot-shape path (qb_tc3.cuh): 288 threads, layouts below
     int v3_w0, v3_w1, v3_x;             // byte offsets: W0 tf32 hi|lo, W1 fp16 hi|lo, x tiles [2][hi|lo]
     int v3_c1;                          // float index of the accumulator scale of the hidden GEMM
+    int v3_xbar;                        // byte offset of the three x_full mbarriers
+    int v3_state;                       // byte offset of the chain state kept in shared memory (chain kernel): cur | prop | scale
     QbTcLayer L[QB_MAX_LAYERS];
 };
 
@@ -84,8 +86,8 @@ __device__ __forceinline__ void qb_mbar_wait(uint32_t bar, uint32_t parity) {
     unsigned long long t0 = 0;
     for (uint32_t it = 0;; ++it) {
         uint32_t ok;
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.b32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");       // suspend-time hint: 20 us
         if (ok) return;
         if ((it & 1023u) == 1023u) {
             unsigned long long now;

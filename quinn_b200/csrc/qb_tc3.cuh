@@ -17,17 +17,34 @@
 //     is a normal fp16 number, smaller ones carry an absolute error of 2^-25 in units of the scaled maximum.
 //   * tanh = 1 - 2 s with s = 1 / (1 + 2^z'): the affine part is folded into the NEXT layer's weights and bias at
 //     staging (W' = -2 W, b' = b + sum_k W_k), so the epilogues produce s only (2 packed FMAs per 4 activations less).
-// Tensor memory (256 columns per block, two blocks per SM): D0 [0,64) | A_hi [64,96) | -A_lo [96,128) | D1 x 2 [128,256).
-// Per tile t:   issue warp:     wait a_ready(t) -> MMA0(t+1) -> commit d0_full -> MMA1(t) -> commit d1_full -> stage X(t+2)
-//               compute warps:  EPI1(t-1) [D1 -> s -> dot with the output row]  then  EPI0(t+1) [D0 -> 2^14 s -> fp16
-//                               hi/lo -> A; the tensor-memory store waits for d1_full(t) = "A is free"] -> arrive a_ready(t+1)
-// so the MMAs of tile t run under EPI1(t-1) and the only block-wide rendezvous is the arrival count of a_ready.
+// Tensor memory (256 columns per block, two blocks per SM): D0 x 2 [0,128) | A_hi [128,160) | -A_lo [160,192) | D1 [192,256).
+// Per tile t:   issue warp:     wait a_ready(t) -> MMA0(t+2) into D0[t&1] -> commit d0_full -> wait d1_free(t-1) -> MMA1(t)
+//                               -> commit d1_full -> stage X(t+3)
+//               compute warps:  EPI1(t-1) [D1 -> registers -> arrive d1_free -> s -> dot with the output row]  then
+//                               EPI0(t+1) [D0[(t+1)&1] -> 2^14 s -> fp16 hi/lo; wait d1_full(t) = "A is free" -> A]
+//                               -> arrive a_ready(t+1)
+// Layer 0 runs two tiles ahead (D0 is double-buffered), so d0_full is never waited for in steady state; between a
+// warp's arrival on a_ready(t) and its need for d1_full(t) lies almost a whole tile of its own work (EPI1(t-1) and the
+// arithmetic of EPI0(t+1)), which is the slack that absorbs the skew between the eight compute warps and the
+// ~800 cycles from the last arrival to the commit of MMA1(t).  D1 needs no second buffer: its reader copies it to
+// registers first thing and releases it at once.
 #pragma once
 #include "qb_tc.cuh"
 
 #ifdef __CUDACC__
-enum { QB3_D0F = 320, QB3_ARDY = 336, QB3_D1F = 344, QB3_D1FREE = 352,      // mbarriers in the shared-memory header
-       QB3_COL_AHI = 64, QB3_COL_ALO = 96, QB3_COL_D1 = 128, QB3_NCOMPUTE = 256 };
+// Development aid (-DQB3_TRACE, scripts/tc3_trace.py): SM-clock stamps of the phases of every compute warp.
+#ifdef QB3_TRACE
+enum { QB3_TR_BLOCKS = 296, QB3_TR_TILES = 80, QB3_TR_EV = 8 };
+__device__ unsigned int qb3_trace_buf[QB3_TR_BLOCKS * 9 * QB3_TR_TILES * QB3_TR_EV];
+__device__ unsigned int qb3_trace_sm[QB3_TR_BLOCKS];
+#define QB3_STAMP(tile, ev) do { if ((threadIdx.x & 31) == 0 && blockIdx.x < QB3_TR_BLOCKS && blockIdx.y == 0 && (tile) < QB3_TR_TILES) \
+    qb3_trace_buf[((blockIdx.x * 9 + (threadIdx.x >> 5)) * QB3_TR_TILES + (tile)) * QB3_TR_EV + (ev)] = (unsigned int)clock64(); } while (0)
+#else
+#define QB3_STAMP(tile, ev) do { } while (0)
+#endif
+enum { QB3_D0F = 320, QB3_ARDY = 336, QB3_D1F = 344, QB3_D1FREE = 352, QB3_D0F1 = 360,   // mbarriers in the shared-memory header
+       // (d0_full exists once per D0 buffer: layer 0 runs two tiles ahead and a parity wait must never fall two phases behind)
+       QB3_COL_AHI = 128, QB3_COL_ALO = 160, QB3_COL_D1 = 192, QB3_NCOMPUTE = 256 };
 
 // all threads; tensor-memory allocation (the mbarriers are (re)initialised by every evaluation)
 __device__ __forceinline__ void qb_tc3_init(const QbTcPlan& tp, unsigned char* smem, QbTcCtx& cx) {
@@ -42,7 +59,9 @@ __device__ __forceinline__ void qb_tc3_init(const QbTcPlan& tp, unsigned char* s
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB3_ARDY), "r"((uint32_t)QB3_NCOMPUTE) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB3_D1F), "r"(1u) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB3_D1FREE), "r"((uint32_t)QB3_NCOMPUTE) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB3_D1FREE + 8), "r"((uint32_t)QB3_NCOMPUTE) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB3_D0F1), "r"(1u) : "memory");
+        for (int i = 0; i < 3; ++i)          // x_full[3]: initialised once, their phases run across evaluations
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + (uint32_t)tp.v3_xbar + 8u * i), "r"(1u) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     qb_tc_fence_before();
@@ -54,11 +73,11 @@ __device__ __forceinline__ void qb_tc3_init(const QbTcPlan& tp, unsigned char* s
 // thread 0, between two block barriers: every phase of the previous evaluation has completed, start again at parity 0
 __device__ __forceinline__ void qb_tc3_reset_barriers(unsigned char* smem) {
     const uint32_t b = qb_smem_u32(smem);
-    const uint32_t off[5] = {QB3_D0F, QB3_ARDY, QB3_D1F, QB3_D1FREE, QB3_D1FREE + 8};
+    const uint32_t off[5] = {QB3_D0F, QB3_ARDY, QB3_D1F, QB3_D1FREE, QB3_D0F1};
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
         asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"(b + off[i]) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + off[i]), "r"((i == 0 || i == 2) ? 1u : (uint32_t)QB3_NCOMPUTE) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + off[i]), "r"((i == 0 || i == 2 || i == 4) ? 1u : (uint32_t)QB3_NCOMPUTE) : "memory");
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -83,7 +102,7 @@ __device__ __forceinline__ void qb3_split_f16(float x0, float x1, uint32_t& hi, 
 //   W1  : fp16 hi / lo / -hi of -2 * 2 log2 e * 2^sW * W1 (the -2: tanh = 1 - 2 s), [64 x 64] canonical K-major
 //         (core matrix = 8 rows x 8 halves; LBO 128 B, SBO 1024 B); -hi multiplies the negated lo parts of A
 //   F[bias1 + j] = 2 log2 e * (b1_j + sum_k W1_jk);  F[c1] = 2^(-14 - sW)  (D1 is in units of 2^14 * 2^sW)
-//   F[wl + k] = -2 * sl * wl_k;  F[bl] = sl * (bl + sum_k wl_k)
+//   F[wl + k] = -2 * 2^-14 * sl * wl_k (the epilogue produces 2^14 s);  F[bl] = sl * (bl + sum_k wl_k)
 __device__ __forceinline__ void qb_tc3_stage(const QbTcPlan& tp, unsigned char* smem, const float* __restrict__ theta) {
     float* F = reinterpret_cast<float*>(smem + tp.fl_base);
     double* red = reinterpret_cast<double*>(smem);
@@ -141,7 +160,7 @@ __device__ __forceinline__ void qb_tc3_stage(const QbTcPlan& tp, unsigned char* 
         // ---- output row: -2 sl wl, bias sl (bl + sum wl)
         const float sl = tp.act_last == QB_ACT_TANH ? fold : 1.0f;
         const float a = theta[tp.wl_off + lane], b = theta[tp.wl_off + 32 + lane];
-        F[tp.wl + lane] = -2.0f * sl * a; F[tp.wl + 32 + lane] = -2.0f * sl * b;
+        F[tp.wl + lane] = -1.220703125e-04f * sl * a; F[tp.wl + 32 + lane] = -1.220703125e-04f * sl * b;     // -2 * 2^-14
         double s = (double)a + (double)b;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
@@ -153,27 +172,29 @@ __device__ __forceinline__ void qb_tc3_stage(const QbTcPlan& tp, unsigned char* 
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// 1 / (1 + 2^z) for four pre-activations with ONE reciprocal (see qb_tanh4_prescaled); SC: results times 2^14
-template <bool SC>
-__device__ __forceinline__ void qb3_sig4(float2& a, float2& b) {
-    float2 ea, eb;
-    ea.x = qb_ex2(qb_min_nan(a.x, 30.0f)); ea.y = qb_ex2(qb_min_nan(a.y, 30.0f));
-    eb.x = qb_ex2(qb_min_nan(b.x, 30.0f)); eb.y = qb_ex2(qb_min_nan(b.y, 30.0f));
-    float2 da, db;
-    if (SC) {
-        const float2 c = make_float2(6.103515625e-05f, 6.103515625e-05f);        // 2^-14
-        da = __ffma2_rn(ea, c, c); db = __ffma2_rn(eb, c, c);
-    } else {
-        const float2 one = make_float2(1.0f, 1.0f);
-        da = __fadd2_rn(ea, one); db = __fadd2_rn(eb, one);
+// 2^14 / (1 + 2^z) for EIGHT pre-activations with ONE reciprocal (the MUFU pipe, 16 results/clk/SM, is the first
+// bound of this kernel: 9 MUFU operations per 8 activations).  d_i = 2^-14 (1 + 2^min(z_i, 26)) lies in [2^-14, 2^12], so
+// the product of eight stays inside the fp32 range; 1/d_i comes out of a product tree of the other seven times the
+// reciprocal of the whole product: 12 multiplies (8 of them packed) for 8 values, the same count as two groups of four.
+// The clamp at 26 is exact for tanh: 1 - 2/(1 + 2^26) rounds to 1.0f.  min.NaN keeps NaN pre-activations NaN.
+__device__ __forceinline__ void qb3_sig8(float2 (&v)[4]) {
+    const float2 c = make_float2(6.103515625e-05f, 6.103515625e-05f);        // 2^-14
+    float2 d[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 e;
+        e.x = qb_ex2(qb_min_nan(v[i].x, 26.0f)); e.y = qb_ex2(qb_min_nan(v[i].y, 26.0f));
+        d[i] = __ffma2_rn(e, c, c);
     }
-    const float2 m = __fmul2_rn(da, db);
+    const float2 p01 = __fmul2_rn(d[0], d[1]), p23 = __fmul2_rn(d[2], d[3]);
+    const float2 q = __fmul2_rn(p01, p23);
     float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(m.x * m.y));
-    float2 rr;
-    rr.x = r * m.y; rr.y = r * m.x;
-    a = __fmul2_rn(rr, db);
-    b = __fmul2_rn(rr, da);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(q.x * q.y));
+    float2 rq;
+    rq.x = r * q.y; rq.y = r * q.x;                       // (1/q.x, 1/q.y)
+    const float2 i01 = __fmul2_rn(rq, p23), i23 = __fmul2_rn(rq, p01);      // 1/p01, 1/p23
+    v[0] = __fmul2_rn(i01, d[1]); v[1] = __fmul2_rn(i01, d[0]);
+    v[2] = __fmul2_rn(i23, d[3]); v[3] = __fmul2_rn(i23, d[2]);
 }
 
 // one tcgen05.mma (issued by the elected lane); ACC: accumulate into D
@@ -219,8 +240,8 @@ struct Qb3X {
             float w[8], h[8], l[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                w[q] = q < IN ? v[i][q < IN ? q : 0] : 0.0f;
-                if (q == in_dim) w[q] = 1.0f;                    // the bias slot
+                const float xv = q < IN ? v[i][q < IN ? q : 0] : 0.0f;
+                w[q] = (q == in_dim) ? 1.0f : xv;                // the bias slot (a select: no indexed store)
                 h[q] = qb_tf32_hi(w[q]); l[q] = w[q] - h[q];
             }
             const int idx = ((m >> 3) * 2) * 32 + (m & 7) * 4;
@@ -233,11 +254,12 @@ struct Qb3X {
 };
 
 // sum of squared residuals over points [n0, n1) for the staged parameter vector (block-wide result); every thread of
-// the 288-thread block calls it
-template <int IN>
+// the 288-thread block calls it.  PRESTAGE (chain kernel: same x, n0, n1 in every call): the issue warp leaves the first
+// three x tiles of the NEXT evaluation in the ring when it is done, so an evaluation does not start with global loads.
+template <int IN, bool PRESTAGE>
 __device__ __forceinline__ double qb_tc3_eval(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem,
                                               const float* __restrict__ x, const float* __restrict__ y,
-                                              int64_t n0, int64_t n1) {
+                                              int64_t n0, int64_t n1, const float* __restrict__ xs) {
     const float* F = reinterpret_cast<const float*>(smem + tp.fl_base);
     const uint32_t sb = qb_smem_u32(smem);
     const uint32_t bar_d0f = sb + QB3_D0F, bar_ardy = sb + QB3_ARDY, bar_d1f = sb + QB3_D1F, bar_d1free = sb + QB3_D1FREE;
@@ -249,7 +271,7 @@ __device__ __forceinline__ double qb_tc3_eval(const QbTcPlan& tp, QbTcCtx& cx, u
     float ssq = 0.0f;
     if (T > 0 && wid == 8) {
         // ================================ issue warp ================================
-        float* xb = reinterpret_cast<float*>(smem + tp.v3_x);         // [2][hi 1024 | lo 1024] floats
+        float* xb = reinterpret_cast<float*>(smem + tp.v3_x);         // [3][hi 1024 | lo 1024] floats
         const uint32_t dhi8 = ((128u * 2u) >> 4) | (1u << 14);        // K = 8 tf32: SBO 256 B
         const uint32_t dhi64 = (1024u >> 4) | (1u << 14);             // K = 64 fp16: SBO 1024 B
         const uint32_t lbo = (128u >> 4) << 16;
@@ -260,40 +282,69 @@ __device__ __forceinline__ double qb_tc3_eval(const QbTcPlan& tp, QbTcCtx& cx, u
         const uint32_t id_tf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
         const uint32_t id_f16 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
         const uint32_t d0 = cx.tmem, a_hi = cx.tmem + QB3_COL_AHI, a_lo = cx.tmem + QB3_COL_ALO;
+        // x tiles come either as ready-made operand images from global memory (xs: tile u = 8 KB, tf32 hi | lo in the
+        // canonical layout, written once per launch by k_tc3_xsplit; one bulk copy per tile, completion on x_full[u % 3]) or,
+        // without such a buffer, are loaded, split and laid out by this warp (Qb3X)
+        const bool bulk = xs != nullptr;
+        const uint32_t bar_x = sb + (uint32_t)tp.v3_xbar;
+        uint32_t xpar = cx.hphase;                 // parities of x_full[0..2] (they are never re-initialised)
+        auto xcopy = [&](int u) {                  // one lane: start the bulk copy of tile u into ring slot u % 3
+            const uint32_t bar = bar_x + (uint32_t)(u % 3) * 8u, dst = qb_smem_u32(xb) + (uint32_t)(u % 3) * 8192u;
+            const float* src = xs + (int64_t)u * 2048;
+            asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" :: "r"(bar), "r"(8192u) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(dst), "l"(src), "r"(8192u), "r"(bar) : "memory");
+        };
+        auto xwait = [&](int u) {                  // all lanes: tile u has landed
+            const int sl = u % 3;
+            qb_mbar_wait(bar_x + (uint32_t)sl * 8u, (xpar >> sl) & 1u);
+            xpar ^= 1u << sl;
+        };
         Qb3X<IN> X;
         X.in_dim = tp.in_dim;
-        X.load(x, n0, n1, lane);
-        X.store(xb, xb + 1024, lane);
-        if (T > 1) X.load(x, n0 + 128, n1, lane);
+        auto mma0 = [&](int u) {           // layer 0 of tile u: x buffer u % 3 -> D0[u & 1]
+            const uint32_t xa = xd + (uint32_t)(u % 3) * 512u, d = d0 + (uint32_t)(u & 1) * 64u;
+            qb3_mma_tf32_ss<false>(d, xa + 256u, w0hi, dhi8, id_tf32);
+            qb3_mma_tf32_ss<true>(d, xa, w0lo, dhi8, id_tf32);
+            qb3_mma_tf32_ss<true>(d, xa, w0hi, dhi8, id_tf32);
+            qb3_commit((u & 1) ? sb + QB3_D0F1 : bar_d0f);
+        };
+        // x tiles 0 .. 2 staged up front (unless the previous evaluation left them), layer 0 of tiles 0 and 1 started
+        if (!(PRESTAGE && cx.phase)) {
+            if (bulk) {
+                if (lane == 0) for (int u = 0; u < 3 && u < T; ++u) xcopy(u);
+            } else {
+#pragma unroll 1
+                for (int u = 0; u < 3 && u < T; ++u) {
+                    X.load(x, n0 + (int64_t)u * 128, n1, lane);
+                    X.store(xb + u * 2048, xb + u * 2048 + 1024, lane);
+                }
+            }
+        }
+        if (bulk) { xwait(0); if (T > 1) xwait(1); }
+        else if (T > 3) X.load(x, n0 + 3 * 128, n1, lane);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (qb3_elect()) {
-            qb3_mma_tf32_ss<false>(d0, xd + 256u, w0hi, dhi8, id_tf32);
-            qb3_mma_tf32_ss<true>(d0, xd, w0lo, dhi8, id_tf32);
-            qb3_mma_tf32_ss<true>(d0, xd, w0hi, dhi8, id_tf32);
-            qb3_commit(bar_d0f);
+            mma0(0);
+            if (T > 1) mma0(1);
         }
         __syncwarp();
-        if (T > 1) {
-            X.store(xb + 2048, xb + 3072, lane);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            if (T > 2) X.load(x, n0 + 256, n1, lane);
-        }
 #pragma unroll 1
         for (int t = 0; t < T; ++t) {
-            qb_mbar_wait(bar_ardy, (uint32_t)t & 1u);                                 // A(t) written, D0 read
-            if (t >= 2) qb_mbar_wait(bar_d1free + (uint32_t)(t & 1) * 8u, (uint32_t)((t >> 1) - 1) & 1u);
+            if (bulk && t + 2 < T) xwait(t + 2);                                      // long since landed
+            qb_mbar_wait(bar_ardy, (uint32_t)t & 1u);                                 // A(t) written, D0[t&1] read
+            QB3_STAMP(t, 0);
             qb_tc_fence_after();
             __syncwarp();
+            if (t + 2 < T && qb3_elect()) mma0(t + 2);
+            __syncwarp();
+            QB3_STAMP(t, 1);
+            if (t >= 1) { qb_mbar_wait(bar_d1free, (uint32_t)(t - 1) & 1u); qb_tc_fence_after(); }   // EPI1(t-1) holds D1 in registers
+            __syncwarp();
+            QB3_STAMP(t, 2);
             if (qb3_elect()) {
-                if (t + 1 < T) {
-                    const uint32_t xa = xd + (uint32_t)((t + 1) & 1) * 512u;
-                    qb3_mma_tf32_ss<false>(d0, xa + 256u, w0hi, dhi8, id_tf32);
-                    qb3_mma_tf32_ss<true>(d0, xa, w0lo, dhi8, id_tf32);
-                    qb3_mma_tf32_ss<true>(d0, xa, w0hi, dhi8, id_tf32);
-                    qb3_commit(bar_d0f);
-                }
-                const uint32_t d1 = cx.tmem + QB3_COL_D1 + (uint32_t)(t & 1) * 64u;
+                const uint32_t d1 = cx.tmem + QB3_COL_D1;
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
                     if (s == 0) qb3_mma_f16_ts<false>(d1, a_lo, w1nhi, dhi64, id_f16);
@@ -306,14 +357,34 @@ __device__ __forceinline__ double qb_tc3_eval(const QbTcPlan& tp, QbTcCtx& cx, u
                 qb3_commit(bar_d1f);
             }
             __syncwarp();
-            if (t + 2 < T) {
-                // MMA0(t) has completed (the compute warps waited for it before they arrived on a_ready(t))
-                float* b = xb + (t & 1) * 2048;
-                X.store(b, b + 1024, lane);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                if (t + 3 < T) X.load(x, n0 + (int64_t)(t + 3) * 128, n1, lane);
+            QB3_STAMP(t, 3);
+            if (t + 3 < T) {
+                // x buffer t % 3 was read by MMA0(t), which completed before the compute warps arrived on a_ready(t)
+                if (bulk) {
+                    if (lane == 0) xcopy(t + 3);
+                } else {
+                    float* b = xb + (t % 3) * 2048;
+                    X.store(b, b + 1024, lane);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    if (t + 4 < T) X.load(x, n0 + (int64_t)(t + 4) * 128, n1, lane);
+                }
             }
         }
+        if (PRESTAGE) {
+            // every MMA0 has completed (a_ready(T-1) was waited for): the ring is free
+            if (bulk) {
+                if (lane == 0) for (int u = 0; u < 3 && u < T; ++u) xcopy(u);
+            } else {
+#pragma unroll 1
+                for (int u = 0; u < 3 && u < T; ++u) {
+                    X.load(x, n0 + (int64_t)u * 128, n1, lane);
+                    X.store(xb + u * 2048, xb + u * 2048 + 1024, lane);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+            cx.phase = 1u;
+        }
+        cx.hphase = xpar;
     } else if (T > 0) {
         // ================================ compute warps ================================
         const int g = threadIdx.x >> 7, pt = threadIdx.x & 127;
@@ -327,59 +398,80 @@ __device__ __forceinline__ double qb_tc3_eval(const QbTcPlan& tp, QbTcCtx& cx, u
 
         // EPI0(u): D0 -> 2^14 * s -> fp16 hi / lo -> A.  `afree`: wait for d1_full(u - 1) before the stores.
         auto epi0 = [&](int u) {
-            qb_mbar_wait(bar_d0f, (uint32_t)u & 1u);
-            qb_tc_fence_after();
+            QB3_STAMP(u, 0);
+            // layer 0 of tiles u >= 2 was issued BEFORE MMA1(u-2), whose commit (d1_full(u-2), waited for in EPI0(u-1))
+            // covers every earlier tcgen05 operation of the issuing thread: only the first two tiles wait on d0_full
+            if (u < 2) {
+                qb_mbar_wait((u & 1) ? sb + QB3_D0F1 : bar_d0f, 0u);
+                qb_tc_fence_after();
+            }
             uint32_t v[2][16];
-            qb_tmem_ld16(tl + 32 * g, v[0]);
-            qb_tmem_ld16(tl + 32 * g + 16, v[1]);
+            qb_tmem_ld16(tl + 64 * (u & 1) + 32 * g, v[0]);
+            qb_tmem_ld16(tl + 64 * (u & 1) + 32 * g + 16, v[1]);
             qb_tmem_ld_wait16(v[0]);
             qb_tmem_ld_wait16(v[1]);
+            QB3_STAMP(u, 1);
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float2 a = make_float2(__uint_as_float(v[j][4 * q + 0]), __uint_as_float(v[j][4 * q + 1]));
-                    float2 b = make_float2(__uint_as_float(v[j][4 * q + 2]), __uint_as_float(v[j][4 * q + 3]));
-                    qb3_sig4<true>(a, b);
-                    qb3_split_f16(a.x, a.y, hi[8 * j + 2 * q], lo[8 * j + 2 * q]);
-                    qb3_split_f16(b.x, b.y, hi[8 * j + 2 * q + 1], lo[8 * j + 2 * q + 1]);
+                for (int q = 0; q < 2; ++q) {
+                    float2 a[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) a[i] = make_float2(__uint_as_float(v[j][8 * q + 2 * i]), __uint_as_float(v[j][8 * q + 2 * i + 1]));
+                    qb3_sig8(a);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) qb3_split_f16(a[i].x, a[i].y, hi[8 * j + 4 * q + i], lo[8 * j + 4 * q + i]);
                 }
             }
+            QB3_STAMP(u, 2);
             if (u > 0) {
-                qb_mbar_wait(bar_d1f, (uint32_t)(u - 1) & 1u);           // MMA1(u-1) complete: A is free, D1[(u-1)&1] is ready
+                qb_mbar_wait(bar_d1f, (uint32_t)(u - 1) & 1u);           // MMA1(u-1) complete: A is free, D1 is ready
                 qb_tc_fence_after();
             }
+            QB3_STAMP(u, 3);
             qb_tmem_st16(tl + QB3_COL_AHI + 16 * g, hi);
             qb_tmem_st16(tl + QB3_COL_ALO + 16 * g, lo);
             qb_tmem_st_wait();
             qb_tc_fence_before();
             qb_mbar_arrive(bar_ardy);
+            QB3_STAMP(u, 4);
         };
         // EPI1(u): D1[u&1] -> s -> partial dot product with the output row
         auto epi1 = [&](int u) -> float {
+            QB3_STAMP(u, 5);
             uint32_t v[2][16];
-            const uint32_t dcol = QB3_COL_D1 + (uint32_t)(u & 1) * 64u + 32u * g;
+            const uint32_t dcol = QB3_COL_D1 + 32u * g;
             qb_tmem_ld16(tl + dcol, v[0]);
             qb_tmem_ld16(tl + dcol + 16, v[1]);
             qb_tmem_ld_wait16(v[0]);
             qb_tmem_ld_wait16(v[1]);
             qb_tc_fence_before();
-            qb_mbar_arrive(bar_d1free + (uint32_t)(u & 1) * 8u);         // the accumulator is in registers
+            qb_mbar_arrive(bar_d1free);                                  // the accumulator is in registers
+            QB3_STAMP(u, 6);
             float2 acc = make_float2(0.0f, 0.0f);
             const float2 c2 = make_float2(c1, c1);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 bb = B4[4 * j + q], ww = W4[4 * j + q];
-                    float2 a = __ffma2_rn(make_float2(__uint_as_float(v[j][4 * q + 0]), __uint_as_float(v[j][4 * q + 1])), c2, make_float2(bb.x, bb.y));
-                    float2 b = __ffma2_rn(make_float2(__uint_as_float(v[j][4 * q + 2]), __uint_as_float(v[j][4 * q + 3])), c2, make_float2(bb.z, bb.w));
-                    qb3_sig4<false>(a, b);
-                    acc = __ffma2_rn(a, make_float2(ww.x, ww.y), acc);
-                    acc = __ffma2_rn(b, make_float2(ww.z, ww.w), acc);
+                for (int q = 0; q < 2; ++q) {
+                    float2 a[4];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const float4 bb = B4[4 * j + 2 * q + i];
+                        a[2 * i] = __ffma2_rn(make_float2(__uint_as_float(v[j][8 * q + 4 * i]), __uint_as_float(v[j][8 * q + 4 * i + 1])), c2, make_float2(bb.x, bb.y));
+                        a[2 * i + 1] = __ffma2_rn(make_float2(__uint_as_float(v[j][8 * q + 4 * i + 2]), __uint_as_float(v[j][8 * q + 4 * i + 3])), c2, make_float2(bb.z, bb.w));
+                    }
+                    qb3_sig8(a);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const float4 ww = W4[4 * j + 2 * q + i];
+                        acc = __ffma2_rn(a[2 * i], make_float2(ww.x, ww.y), acc);
+                        acc = __ffma2_rn(a[2 * i + 1], make_float2(ww.z, ww.w), acc);
+                    }
                 }
             }
+            QB3_STAMP(u, 7);
             return acc.x + acc.y;
         };
         // group 0: residual of tile u (own partial sum + the partner's from ybuf)
@@ -425,10 +517,11 @@ __device__ __forceinline__ double qb_tc3_eval(const QbTcPlan& tp, QbTcCtx& cx, u
     }
     return qb_block_sum((double)ssq, reinterpret_cast<double*>(smem));
 }
+template <bool PRESTAGE>
 __device__ __forceinline__ double qb_tc3_eval_any(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem,
                                                   const float* __restrict__ x, const float* __restrict__ y,
-                                                  int64_t n0, int64_t n1) {
-    if (tp.in_dim <= 3) return qb_tc3_eval<3>(tp, cx, smem, x, y, n0, n1);
-    return qb_tc3_eval<7>(tp, cx, smem, x, y, n0, n1);
+                                                  int64_t n0, int64_t n1, const float* __restrict__ xs) {
+    if (tp.in_dim <= 3) return qb_tc3_eval<3, PRESTAGE>(tp, cx, smem, x, y, n0, n1, xs);
+    return qb_tc3_eval<7, PRESTAGE>(tp, cx, smem, x, y, n0, n1, xs);
 }
 #endif  // __CUDACC__
