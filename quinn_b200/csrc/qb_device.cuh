@@ -992,12 +992,16 @@ __device__ __forceinline__ void qb_normal4(uint4 r, double (&z)[4]) {
     sincospi(2.0 * qb_u01(r.w), &s2, &c2);
     z[0] = r1 * c1; z[1] = r1 * s1; z[2] = r2 * c2; z[3] = r2 * s2;
 }
+// fp32 Box-Muller on the special-function unit: lg2 / sqrt / sin / cos approximations (absolute error of sin and cos
+// 2^-20.9 on (-pi, pi), which is where the angle is kept: cos(2 pi u) = -cos(2 pi u - pi)).  The fp64 version above is
+// the one the numpy Philox oracle replays; the fp32 draws only have to be the same in every fp32 kernel.
 __device__ __forceinline__ void qb_normal4(uint4 r, float (&z)[4]) {
     const float u1 = ((float)(r.x >> 8) + 0.5f) * 5.9604644775390625e-8f;
     const float u2 = ((float)(r.z >> 8) + 0.5f) * 5.9604644775390625e-8f;
-    const float r1 = sqrtf(-2.0f * __logf(u1)), r2 = sqrtf(-2.0f * __logf(u2));
-    float s1, c1, s2, c2;
-    sincospif(2.0f * ((float)(r.y >> 8) + 0.5f) * 5.9604644775390625e-8f, &s1, &c1);
-    sincospif(2.0f * ((float)(r.w >> 8) + 0.5f) * 5.9604644775390625e-8f, &s2, &c2);
-    z[0] = r1 * c1; z[1] = r1 * s1; z[2] = r2 * c2; z[3] = r2 * s2;
+    float r1, r2;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(-2.0f * __logf(u1)));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r2) : "f"(-2.0f * __logf(u2)));
+    const float a1 = ((float)(r.y >> 8) + 0.5f) * 3.7450702829239286e-7f - 3.14159265358979f;     // 2 pi 2^-24
+    const float a2 = ((float)(r.w >> 8) + 0.5f) * 3.7450702829239286e-7f - 3.14159265358979f;
+    z[0] = -r1 * __cosf(a1); z[1] = -r1 * __sinf(a1); z[2] = -r2 * __cosf(a2); z[3] = -r2 * __sinf(a2);
 }

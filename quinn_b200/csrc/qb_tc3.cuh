@@ -34,7 +34,7 @@
 #ifdef __CUDACC__
 // Development aid (-DQB3_TRACE, scripts/tc3_trace.py): SM-clock stamps of the phases of every compute warp.
 #ifdef QB3_TRACE
-enum { QB3_TR_BLOCKS = 296, QB3_TR_TILES = 80, QB3_TR_EV = 8 };
+enum { QB3_TR_BLOCKS = 296, QB3_TR_TILES = 82, QB3_TR_EV = 8 };
 __device__ unsigned int qb3_trace_buf[QB3_TR_BLOCKS * 9 * QB3_TR_TILES * QB3_TR_EV];
 __device__ unsigned int qb3_trace_sm[QB3_TR_BLOCKS];
 #define QB3_STAMP(tile, ev) do { if ((threadIdx.x & 31) == 0 && blockIdx.x < QB3_TR_BLOCKS && blockIdx.y == 0 && (tile) < QB3_TR_TILES) \
@@ -45,6 +45,20 @@ __device__ unsigned int qb3_trace_sm[QB3_TR_BLOCKS];
 enum { QB3_D0F = 320, QB3_ARDY = 336, QB3_D1F = 344, QB3_D1FREE = 352, QB3_D0F1 = 360,   // mbarriers in the shared-memory header
        // (d0_full exists once per D0 buffer: layer 0 runs two tiles ahead and a parity wait must never fall two phases behind)
        QB3_COL_AHI = 128, QB3_COL_ALO = 160, QB3_COL_D1 = 192, QB3_NCOMPUTE = 256 };
+
+// mbarrier wait of the tile loops: try_wait suspends the thread until the phase completes or the 20 us hint expires, so a
+// plain counted loop is a bounded wait (2^20 x 20 us, then trap) with no state beyond its counter -- the timer-based
+// loop of qb_mbar_wait, inlined or called, made ptxas shuffle the live register arrays around it
+__device__ __forceinline__ void qb3_wait(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
+    for (int it = 0; it < (1 << 20); ++it) {
+        uint32_t ok;
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.b32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
 
 // all threads; tensor-memory allocation (the mbarriers are (re)initialised by every evaluation)
 __device__ __forceinline__ void qb_tc3_init(const QbTcPlan& tp, unsigned char* smem, QbTcCtx& cx) {
@@ -103,15 +117,18 @@ __device__ __forceinline__ void qb3_split_f16(float x0, float x1, uint32_t& hi, 
 //         (core matrix = 8 rows x 8 halves; LBO 128 B, SBO 1024 B); -hi multiplies the negated lo parts of A
 //   F[bias1 + j] = 2 log2 e * (b1_j + sum_k W1_jk);  F[c1] = 2^(-14 - sW)  (D1 is in units of 2^14 * 2^sW)
 //   F[wl + k] = -2 * 2^-14 * sl * wl_k (the epilogue produces 2^14 s);  F[bl] = sl * (bl + sum_k wl_k)
-__device__ __forceinline__ void qb_tc3_stage(const QbTcPlan& tp, unsigned char* smem, const float* __restrict__ theta) {
+// wmax: this thread's share of max |W1| when the caller has already looked at every W1 entry (all threads pass >= 0,
+// block-uniformly), else < 0 and the entries are scanned here
+__device__ __forceinline__ void qb_tc3_stage(const QbTcPlan& tp, unsigned char* smem, const float* __restrict__ theta, float wmax) {
     float* F = reinterpret_cast<float*>(smem + tp.fl_base);
     double* red = reinterpret_cast<double*>(smem);
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
     const float fold = 2.8853900817779268f;
     const QbTcLayer& L = tp.L[1];
     // ---- scale of W1: largest magnitude -> [2^13, 2^14)
-    float mx = 0.0f;
-    for (int e = tid; e < 64 * 64; e += nt) mx = fmaxf(mx, fabsf(theta[L.w_off + e]));
+    float mx = fmaxf(wmax, 0.0f);
+    if (wmax < 0.0f)
+        for (int e = tid; e < 64 * 64; e += nt) mx = fmaxf(mx, fabsf(theta[L.w_off + e]));
     uint32_t mb = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
     __syncthreads();                       // the previous evaluation's readers of F / red are done
     if (lane == 0) reinterpret_cast<uint32_t*>(red)[wid] = mb;
@@ -151,10 +168,10 @@ __device__ __forceinline__ void qb_tc3_stage(const QbTcPlan& tp, unsigned char* 
             qb3_split_f16(w0 * wscale, w1 * wscale, h2, l2);
             const int idx = (((n >> 3) * 8 + (k >> 3)) * 64 + (n & 7) * 8 + (k & 7)) >> 1;      // 32-bit word index
             hi[idx] = h2; lo[idx] = l2 ^ 0x80008000u; nhi[idx] = h2 ^ 0x80008000u;
-            double s = (double)w0 + (double)w1;
+            float s = w0 + w1;                     // pairwise tree: the error stays below that of the GEMM's own fp32 sums
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-            if (lane == 0) F[L.bias + n] = (float)((double)fold * ((L.b_off >= 0 ? (double)theta[L.b_off + n] : 0.0) + s));
+            if (lane == 0) F[L.bias + n] = fold * ((L.b_off >= 0 ? theta[L.b_off + n] : 0.0f) + s);
         }
     } else if (wid == 8) {
         // ---- output row: -2 sl wl, bias sl (bl + sum wl)
@@ -170,6 +187,11 @@ __device__ __forceinline__ void qb_tc3_stage(const QbTcPlan& tp, unsigned char* 
         }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void qb_tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
 
 // 2^14 / (1 + 2^z) for EIGHT pre-activations with ONE reciprocal (the MUFU pipe, 16 results/clk/SM, is the first
@@ -297,7 +319,7 @@ __device__ __forceinline__ double qb_tc3_eval(const QbTcPlan& tp, QbTcCtx& cx, u
         };
         auto xwait = [&](int u) {                  // all lanes: tile u has landed
             const int sl = u % 3;
-            qb_mbar_wait(bar_x + (uint32_t)sl * 8u, (xpar >> sl) & 1u);
+            qb3_wait(bar_x + (uint32_t)sl * 8u, (xpar >> sl) & 1u);
             xpar ^= 1u << sl;
         };
         Qb3X<IN> X;
@@ -333,14 +355,14 @@ __device__ __forceinline__ double qb_tc3_eval(const QbTcPlan& tp, QbTcCtx& cx, u
 #pragma unroll 1
         for (int t = 0; t < T; ++t) {
             if (bulk && t + 2 < T) xwait(t + 2);                                      // long since landed
-            qb_mbar_wait(bar_ardy, (uint32_t)t & 1u);                                 // A(t) written, D0[t&1] read
+            qb3_wait(bar_ardy, (uint32_t)t & 1u);                                 // A(t) written, D0[t&1] read
             QB3_STAMP(t, 0);
             qb_tc_fence_after();
             __syncwarp();
             if (t + 2 < T && qb3_elect()) mma0(t + 2);
             __syncwarp();
             QB3_STAMP(t, 1);
-            if (t >= 1) { qb_mbar_wait(bar_d1free, (uint32_t)(t - 1) & 1u); qb_tc_fence_after(); }   // EPI1(t-1) holds D1 in registers
+            if (t >= 1) { qb3_wait(bar_d1free, (uint32_t)(t - 1) & 1u); qb_tc_fence_after(); }   // EPI1(t-1) holds D1 in registers
             __syncwarp();
             QB3_STAMP(t, 2);
             if (qb3_elect()) {
@@ -402,7 +424,7 @@ __device__ __forceinline__ double qb_tc3_eval(const QbTcPlan& tp, QbTcCtx& cx, u
             // layer 0 of tiles u >= 2 was issued BEFORE MMA1(u-2), whose commit (d1_full(u-2), waited for in EPI0(u-1))
             // covers every earlier tcgen05 operation of the issuing thread: only the first two tiles wait on d0_full
             if (u < 2) {
-                qb_mbar_wait((u & 1) ? sb + QB3_D0F1 : bar_d0f, 0u);
+                qb3_wait((u & 1) ? sb + QB3_D0F1 : bar_d0f, 0u);
                 qb_tc_fence_after();
             }
             uint32_t v[2][16];
@@ -411,7 +433,7 @@ __device__ __forceinline__ double qb_tc3_eval(const QbTcPlan& tp, QbTcCtx& cx, u
             qb_tmem_ld_wait16(v[0]);
             qb_tmem_ld_wait16(v[1]);
             QB3_STAMP(u, 1);
-            uint32_t hi[16], lo[16];
+            uint32_t hi[2][8], lo[2][8];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
 #pragma unroll
@@ -421,17 +443,20 @@ __device__ __forceinline__ double qb_tc3_eval(const QbTcPlan& tp, QbTcCtx& cx, u
                     for (int i = 0; i < 4; ++i) a[i] = make_float2(__uint_as_float(v[j][8 * q + 2 * i]), __uint_as_float(v[j][8 * q + 2 * i + 1]));
                     qb3_sig8(a);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) qb3_split_f16(a[i].x, a[i].y, hi[8 * j + 4 * q + i], lo[8 * j + 4 * q + i]);
+                    for (int i = 0; i < 4; ++i) qb3_split_f16(a[i].x, a[i].y, hi[j][4 * q + i], lo[j][4 * q + i]);
                 }
             }
             QB3_STAMP(u, 2);
             if (u > 0) {
-                qb_mbar_wait(bar_d1f, (uint32_t)(u - 1) & 1u);           // MMA1(u-1) complete: A is free, D1 is ready
+                qb3_wait(bar_d1f, (uint32_t)(u - 1) & 1u);           // MMA1(u-1) complete: A is free, D1 is ready
                 qb_tc_fence_after();
             }
             QB3_STAMP(u, 3);
-            qb_tmem_st16(tl + QB3_COL_AHI + 16 * g, hi);
-            qb_tmem_st16(tl + QB3_COL_ALO + 16 * g, lo);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                qb_tmem_st8(tl + QB3_COL_AHI + 16 * g + 8 * j, hi[j]);
+                qb_tmem_st8(tl + QB3_COL_ALO + 16 * g + 8 * j, lo[j]);
+            }
             qb_tmem_st_wait();
             qb_tc_fence_before();
             qb_mbar_arrive(bar_ardy);
@@ -499,7 +524,7 @@ __device__ __forceinline__ double qb_tc3_eval(const QbTcPlan& tp, QbTcCtx& cx, u
                 }
             }
             if (t + 1 < T) epi0(t + 1);
-            else { qb_mbar_wait(bar_d1f, (uint32_t)t & 1u); qb_tc_fence_after(); }
+            else { qb3_wait(bar_d1f, (uint32_t)t & 1u); qb_tc_fence_after(); }
         }
         {
             const int u = T - 1;

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(288, 2) k_logpost_tc3(const __grid_constant__ 
 #ifdef QB3_TRACE
     if (threadIdx.x == 0 && blockIdx.x < QB3_TR_BLOCKS && blockIdx.y == 0) { unsigned int id; asm("mov.u32 %0, %%smid;" : "=r"(id)); qb3_trace_sm[blockIdx.x] = id; }
 #endif
-    qb_tc3_stage(tp, smem_tc, a.theta + k * tp.n_params);
+    qb_tc3_stage(tp, smem_tc, a.theta + k * tp.n_params, -1.0f);
     const float* xs = a.xsplit ? a.xsplit + (n0 >> 7) * 2048 : nullptr;
     const double ssq = qb_tc3_eval_any<false>(tp, cx, smem_tc, a.x + k * a.xs, a.y + k * a.ys, n0, n1, xs);
     if (threadIdx.x == 0) a.part[k * a.S + s] = ssq;
@@ -81,7 +81,12 @@ k_amcmc_tc3(const __grid_constant__ QbTcPlan tp, const __grid_constant__ ChainAr
             const float* __restrict__ xs) {
     extern __shared__ __align__(128) unsigned char smem[];
     QbTcCtx cx;
+    QB3_STAMP(80, 0);
     qb_tc3_init(tp, smem, cx);
+    QB3_STAMP(80, 1);
+#ifdef QB3_TRACE
+    if (threadIdx.x == 0 && blockIdx.x < QB3_TR_BLOCKS) { unsigned int id; asm("mov.u32 %0, %%smid;" : "=r"(id)); qb3_trace_sm[blockIdx.x] = id; }
+#endif
     double* red = reinterpret_cast<double*>(smem);
     const long long k = blockIdx.x;
     const int P = tp.n_params, Pp = (P + 3) & ~3, tid = threadIdx.x, nt = blockDim.x;
@@ -102,9 +107,12 @@ k_amcmc_tc3(const __grid_constant__ QbTcPlan tp, const __grid_constant__ ChainAr
     if (!c.init_lp) { lp_cur = c.lp[k]; map_lp = c.map_lp[k]; na = c.naccept[k]; }
     int kind = a.prop_kind[k];
     __syncthreads();
+    QB3_STAMP(80, 2);
 
     for (long long s = c.init_lp ? -1 : 0; s < c.nsteps; ++s) {
         const float* evalp = cur_s;
+        float wmax = -1.0f;                        // largest |W1| entry of the proposal seen by this thread (< 0: not computed)
+        QB3_STAMP(81, 0);
         if (s >= 0) {
             // ---- running moments (admcmc.py:52-59), proposal scale (61-67), proposal (70): one pass, thread-owned elements
             const long long t = c.t_start + s;
@@ -119,44 +127,70 @@ k_amcmc_tc3(const __grid_constant__ QbTcPlan tp, const __grid_constant__ ChainAr
             float z0 = 0.0f;
             if (!replay && kind == 0) { float zz[4]; qb_normal4(qb_rand4(c.seed, chain, t, QB_STREAM_Z0, 0), zz); z0 = 0.1f * zz[0]; }
             const float* xi = replay ? c.incr + (s * c.K + k) * P : nullptr;
-            for (int i4 = tid; i4 * 4 < P; i4 += nt) {
-                float z[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                if (!replay) qb_normal4(qb_rand4(c.seed, chain, t, QB_STREAM_INCR, (uint32_t)i4), z);
+            // the thread's moments first: all global loads of the step are in flight together (one round trip, not one
+            // per element; the stores below could alias them, so the compiler would not hoist them on its own)
+            constexpr int JMAX = 5;                      // groups of 4 per thread: P <= 4 * 288 * 5
+            float xmv[JMAX][4], cvv[JMAX][4];
+            const bool ldm = track && !first, ldc = cov && (ldm || (!track && adapt_now));
+#pragma unroll
+            for (int j = 0; j < JMAX; ++j) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const int i = i4 * 4 + q;
-                    if (i < P) {
-                        const float cu = cur_s[i];
-                        float cv = 0.0f;
-                        if (track) {
-                            if (first) {
-                                xm[i] = cu;
-                                if (cov) cov[i] = 0.0f;
-                            } else {
-                                const float m = qb_add<float>(qb_mul<float>(tdf, xm[i]), cu) / td1;
-                                xm[i] = m;
-                                if (cov) {
-                                    const float d = cu - m;
-                                    cv = qb_add<float>(qb_mul<float>(rt, cov[i]), qb_mul<float>(st, qb_mul<float>(d, d)));
-                                    cov[i] = cv;
+                    const int i = (tid + j * nt) * 4 + q;
+                    xmv[j][q] = (ldm && i < P) ? xm[i] : 0.0f;
+                    cvv[j][q] = (ldc && i < P) ? cov[i] : 0.0f;
+                }
+            }
+            const int w1lo = tp.L[1].w_off, w1hi = w1lo + 64 * 64;
+            QB3_STAMP(81, 5);
+#pragma unroll
+            for (int j = 0; j < JMAX; ++j) {
+                const int i4 = tid + j * nt;
+                if (j == 1) QB3_STAMP(81, 6);
+                if (j == 2) QB3_STAMP(81, 7);
+                if (i4 * 4 < P) {
+                    float z[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                    if (!replay) qb_normal4(qb_rand4(c.seed, chain, t, QB_STREAM_INCR, (uint32_t)i4), z);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int i = i4 * 4 + q;
+                        if (i < P) {
+                            const float cu = cur_s[i];
+                            float cv = cvv[j][q];
+                            if (track) {
+                                if (first) {
+                                    xm[i] = cu;
+                                    if (cov) cov[i] = 0.0f;
+                                } else {
+                                    const float m = qb_add<float>(qb_mul<float>(tdf, xmv[j][q]), cu) / td1;
+                                    xm[i] = m;
+                                    if (cov) {
+                                        const float d = cu - m;
+                                        cv = qb_add<float>(qb_mul<float>(rt, cv), qb_mul<float>(st, qb_mul<float>(d, d)));
+                                        cov[i] = cv;
+                                    }
                                 }
                             }
-                        } else if (adapt_now && cov) {
-                            cv = cov[i];
+                            float ps = ps_s[i];
+                            if (first) { ps = (float)sqrt(0.09 * fabs((double)cu)); ps_s[i] = ps; }
+                            else if (adapt_now) { ps = (float)sqrt(fac * ((double)cv + 1e-8)); ps_s[i] = ps; }
+                            const float pr = replay ? qb_add<float>(cu, xi[i]) : cu + (z0 + ps * z[q]);
+                            prop_s[i] = pr;
+                            if (i >= w1lo && i < w1hi) wmax = fmaxf(wmax, fabsf(pr));
                         }
-                        float ps = ps_s[i];
-                        if (first) { ps = (float)sqrt(0.09 * fabs((double)cu)); ps_s[i] = ps; }
-                        else if (adapt_now) { ps = (float)sqrt(fac * ((double)cv + 1e-8)); ps_s[i] = ps; }
-                        prop_s[i] = replay ? qb_add<float>(cu, xi[i]) : cu + (z0 + ps * z[q]);
                     }
                 }
             }
+            wmax = fmaxf(wmax, 0.0f);             // every thread has looked at its share of W1
             evalp = prop_s;
         }
         // ---- evaluate
+        QB3_STAMP(81, 1);
         __syncthreads();                           // the proposal is complete in shared memory
-        qb_tc3_stage(tp, smem, evalp);
+        qb_tc3_stage(tp, smem, evalp, wmax);
+        QB3_STAMP(81, 2);
         const double ssq = qb_tc3_eval_chain(tp, cx, smem, c.x, c.y, c.N, xs);
+        QB3_STAMP(81, 3);
         double pss = 0.0;
         if (c.lk.has_prior) pss = qb_prior_ss<float>(c.lk, evalp, k, P, red);
         const double lp_prop = qb_lp_from(c.lk, ssq, c.N, pss, P);
@@ -199,10 +233,12 @@ k_amcmc_tc3(const __grid_constant__ QbTcPlan tp, const __grid_constant__ ChainAr
             }
         }
     }
+    QB3_STAMP(81, 4);
     qb_tc3_drain(tp, cx, smem, c.N, xs != nullptr);
     __syncthreads();
     for (int i = tid; i < P; i += nt) { curg[i] = cur_s[i]; psg[i] = ps_s[i]; }
     if (tid == 0) { c.lp[k] = lp_cur; c.map_lp[k] = map_lp; c.naccept[k] = na; a.prop_kind[k] = kind; }
+    QB3_STAMP(80, 3);
     qb_tc_fini(tp, cx);
 }
 

@@ -29,7 +29,7 @@ for _ in range(3):
     ops.logpost(prob, th, lp)
 torch.cuda.synchronize()
 lib = _lib.load()
-NB, NT, NE = 296, 80, 8
+NB, NT, NE = 296, 82, 8
 buf = np.zeros(NB * 9 * NT * NE, dtype=np.uint32)
 sm = np.zeros(NB, dtype=np.uint32)
 rc = lib.qb_tc3_trace_dump(buf.ctypes.data_as(C.c_void_p), sm.ctypes.data_as(C.c_void_p))
