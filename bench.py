@@ -549,7 +549,10 @@ def run_native(spec, args, steps, warmup, rank, world, local, headline):
         # half of it and the 3 passes divide it by three again, so 1/6 of it is the ceiling of this algorithm on the tensor pipe.
         peak_bf16, src = measured_bf16_peak()
         sm_mhz = (clk or {}).get('sm_mhz') or 1965.0
-        kname = {'amcmc': 'k_amcmc<float,1> (tcgen05.mma kind::tf32 x3 passes + MUFU tanh epilogue)',
+        v3 = spec['sampler'] == 'amcmc' and int(plan.get('threads', 0)) == 288      # warp-specialised hot-shape kernel
+        kname = {'amcmc': 'k_amcmc_tc3 (tcgen05.mma: layer 0 kind::tf32 x3 passes, hidden GEMM kind::f16 x3 passes with exact power-of-two '
+                          'scaling, issued by a dedicated warp; sigmoid epilogues on MUFU; chain state in shared memory)' if v3 else
+                          'k_amcmc<float,2> (tcgen05.mma kind::tf32 x3 passes + MUFU tanh epilogue)',
                  'predict': 'k_predict_tc (tcgen05.mma kind::tf32 x3 passes + MUFU tanh epilogue)',
                  'hmc': 'k_hmc_tc (forward, back-propagation and weight-gradient GEMMs on tcgen05.mma kind::tf32 x3 passes)'
                  }.get(spec['sampler'], 'k_logpost_grad_tc (tcgen05.mma kind::tf32 x3 passes)')
@@ -562,11 +565,19 @@ def run_native(spec, args, steps, warmup, rank, world, local, headline):
                              'dense bf16 TFLOP/s (%s); kind::tf32 runs at half of it (tf32_peak) and these kernels do 3 TF32 passes '
                              'per GEMM for fp32 accuracy (ceiling = peak/6, frac_of_tf32x3_peak); x_fp32_core_peak compares with the '
                              'live CUDA-core FMA peak that bounds the SIMT kernels' % src)
+        if v3:
+            # tensor-pipe ceiling of THIS algorithm: per point 3 x (8 x 64) tf32 MAC slots (layer 0, K padded to 8; tf32 = half the
+            # bf16 rate) + 3 x (64 x 64) f16 slots against S algorithmic MACs
+            slots = 2.0 * 3 * 8 * 64 + 3.0 * 64 * 64
+            roofline.update(algo_ceiling=peak_bf16 * S / slots, frac_of_algo_ceiling=achieved / 1e12 / (peak_bf16 * S / slots),
+                            algo_ceiling_note='peak x S / (bf16-equivalent MMA slots per point): layer 0 3 tf32 passes over K=8, '
+                                              'hidden layer 3 fp16 passes (hi*hi + lo*hi + hi*lo)')
         if spec['sampler'] in ('amcmc', 'predict'):
-            # what bounds the value kernels is the tanh epilogue on the MUFU pipe (16 results/clk/SM): 1.25 MUFU per tanh
+            # what bounds the value kernels is the sigmoid/tanh epilogue on the MUFU pipe (16 results/clk/SM): one ex2 per
+            # activation + one reciprocal shared by 8 (hot-shape kernel: 1.125 MUFU per activation) or by 4 (1.25)
             n_tanh = N * sum(l.n_out for l in desc.layers[:-1])
             n_evals = Kloc if spec['sampler'] == 'amcmc' else spec['K'] * xs.shape[0] / N     # N-point sweeps per step
-            mufu_ach = n_evals * steps * n_tanh * 1.25 / (ms_local * 1e-3)
+            mufu_ach = n_evals * steps * n_tanh * (1.125 if v3 else 1.25) / (ms_local * 1e-3)
             mufu_peak = 16.0 * 148 * sm_mhz * 1e6
             roofline['mufu'] = dict(achieved_gops=mufu_ach / 1e9, peak_gops=mufu_peak / 1e9, frac=mufu_ach / mufu_peak)
 
@@ -602,7 +613,7 @@ def measured_traffic(spec, tc, units):
     """DRAM bytes (read + write) of the dominant kernel for `units` chain-steps / member-points, from the committed
     `ncu --set full` capture of this build (profiles/r2_traffic.json: bytes per unit per kernel), or None."""
     path = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
-    key = {'amcmc': 'k_amcmc_tc' if tc else 'k_amcmc', 'hmc': 'k_hmc_tc' if tc else 'k_hmc',
+    key = {'amcmc': 'k_amcmc_tc3' if tc else 'k_amcmc', 'hmc': 'k_hmc_tc' if tc else 'k_hmc',
            'predict': 'k_predict_tc' if tc else 'k_predict'}.get(spec['sampler'])
     try:
         with open(path) as f:
