@@ -307,8 +307,8 @@ static int make_launch(const qb_net_t* net, int dtype, bool want_grad, long long
 
 // Tensor-core (tcgen05 3xTF32) plan for the value path; returns false when the network is not eligible:
 // fp32, >= 3 layers, no residual layers, n_in <= 15, hidden widths multiples of 16 (<= 128), <= 4 outputs.
-// allow_v3: 1 = the caller can run the warp-specialised hot-shape kernels (qb_value_tc3.cu); 2 = and wants room for the
-// chain state (3 P floats) in shared memory
+// allow_v3: 1 = the caller can run the warp-specialised kernels (qb_value_tc3.cu); 2 = the chain kernel (hidden width 64
+// only, with room for the chain state, 3 P floats, in shared memory); 3 = kernel 4
 static bool make_tc_plan(const qb_net_t* net, int dtype, QbTcPlan* tp, int allow_v3 = 0) {
     memset(tp, 0, sizeof(*tp));
     if (dtype != QB_F32 || env_int("QB_NO_TC", 0)) return false;
@@ -360,22 +360,25 @@ static bool make_tc_plan(const qb_net_t* net, int dtype, QbTcPlan* tp, int allow
     const int max_blocks = 512 / tp->tmem_cols;
     const long long floor_bytes = QB_SMEM_SM / (max_blocks + 1) + 1;
     tp->smem_bytes = (int)std::min<long long>(QB_SMEM_MAX, std::max(bytes, floor_bytes));
-    if (allow_v3 && qb_tc_v3_shape(*tp) && net->layers[1].act == QB_ACT_TANH && !env_int("QB_NO_V3", 0)) {
-        // warp-specialised path (qb_tc3.cuh): 8 compute warps + 1 issue warp, 256 tensor-memory columns, own layout
-        tp->v3 = 1; tp->nthreads = 288; tp->tmem_cols = 256;
+    const int v3h = allow_v3 ? qb_tc_v3_shape(*tp) : 0;
+    if (v3h && net->layers[1].act == QB_ACT_TANH && !env_int("QB_NO_V3", 0) && !(allow_v3 == 2 && v3h != 64)) {
+        // warp-specialised path (qb_tc3.cuh): 4 H/32 compute warps + 1 issue warp, 4 H tensor-memory columns, own layout
+        const int H = v3h, K0 = H == 64 ? 8 : 16, G = H / 32;
+        tp->v3 = H == 64 ? 1 : 2; tp->nthreads = 128 * G + 32; tp->tmem_cols = 4 * H;
         int o = QB_TC_HDR_BYTES;
-        tp->v3_w1 = o; o += 3 * 64 * 64 * 2;
-        tp->v3_w0 = o; o += 2 * 64 * 8 * 4;
-        tp->v3_x = o; o += 3 * 2 * 128 * 8 * 4;
+        tp->v3_w1 = o; o += 3 * H * H * 2;
+        tp->v3_w0 = o; o += 2 * H * K0 * 4;
+        tp->v3_x = o; o += 3 * 2 * 128 * K0 * 4;
         tp->fl_base = o;
-        tp->L[1].bias = 0; tp->wl = 64; tp->bl = 128; tp->v3_c1 = 132;
-        o += 136 * 4;
-        tp->ybuf = o; o += 4 * 128 * 4;
+        tp->L[1].bias = 0; tp->wl = H; tp->bl = 2 * H; tp->v3_c1 = 2 * H + 4;
+        o += (2 * H + 8) * 4;
+        tp->ybuf = o; o += 4 * (G - 1) * 128 * 4;
         tp->v3_xbar = o; o += 32;
         tp->v3_state = o;
         if (allow_v3 == 2) o += 3 * ((net->n_params + 3) / 4 * 4) * 4;
-        tp->smem_bytes = (int)std::max<long long>(o, QB_SMEM_SM / 3 + 1);
-        if (tp->smem_bytes > (QB_SMEM_SM - 2048) / 2) return make_tc_plan(net, dtype, tp, 0);     // two blocks per SM must fit
+        const int max_blocks3 = 512 / tp->tmem_cols;
+        tp->smem_bytes = (int)std::max<long long>(o, QB_SMEM_SM / (max_blocks3 + 1) + 1);
+        if (tp->smem_bytes > (QB_SMEM_SM - 1024 * max_blocks3) / max_blocks3) return make_tc_plan(net, dtype, tp, 0);     // the blocks must fit
     }
     return true;
 }
@@ -514,7 +517,7 @@ static int run_eval(const qb_net_t* net, int dtype, const void* theta, int64_t K
         QbTcPlan tp;
         if (make_tc_plan(net, dtype, &tp, 1)) {
             // hot shape with shared data: x goes to the kernel as ready-made operand tiles at the end of the workspace
-            if (tp.v3 && x_stride == 0) a.xsplit = (const T*)((char*)ws + need - qb_tc3_xsplit_bytes(data->n));
+            if (tp.v3 && x_stride == 0) a.xsplit = (const T*)((char*)ws + need - qb_tc3_xsplit_bytes(data->n, tp.v3 == 1 ? 8 : 16));
             if (launch_logpost_tc<T>(tp, a, grid, st)) return -2;
         } else {
             if (set_smem(k_logpost<T>, L.plan.smem_bytes)) return -2;
@@ -534,7 +537,7 @@ extern "C" size_t qb_eval_workspace_bytes(const qb_net_t* net, int dtype, int64_
     size_t b = ((size_t)K * L.S * sizeof(double) + 255) / 256 * 256;
     if (want_grad && L.S > 1) b += (size_t)K * L.S * net->n_params * (dtype == QB_F64 ? 8 : 4);
     QbTcPlan tp;
-    if (!want_grad && make_tc_plan(net, dtype, &tp, 1) && tp.v3) b = (b + 255) / 256 * 256 + qb_tc3_xsplit_bytes(N);
+    if (!want_grad && make_tc_plan(net, dtype, &tp, 1) && tp.v3) b = (b + 255) / 256 * 256 + qb_tc3_xsplit_bytes(N, tp.v3 == 1 ? 8 : 16);
     return b;
 }
 
@@ -1095,6 +1098,10 @@ __global__ void __launch_bounds__(512, 1) k_predict_tc(const __grid_constant__ Q
 }
 template <typename T> static int launch_predict_tc(const QbTcPlan&, const PredArgs<T>&, dim3, cudaStream_t) { return qb_fail("tensor-core path is fp32 only"); }
 template <> int launch_predict_tc<float>(const QbTcPlan& tp, const PredArgs<float>& a, dim3 grid, cudaStream_t st) {
+    if (tp.v3) {                  // 64- / 128-wide tanh nets with one output: warp-specialised kernel (qb_value_tc3.cu)
+        QB_CUDA(qb_tc3_launch_predict(tp, a.theta, a.x, a.N, a.out, a.tiles_per_block, grid, st));
+        return 0;
+    }
     if (set_smem(k_predict_tc, tp.smem_bytes)) return -2;
     k_predict_tc<<<grid, tp.nthreads, tp.smem_bytes, st>>>(tp, a);
     return 0;
@@ -1115,8 +1122,8 @@ static int run_predict(const qb_net_t* net, int dtype, const void* theta, int64_
     a.theta = (const T*)theta; a.x = (const T*)x; a.M = M; a.N = N;
     a.out = (T*)out; a.mean = (T*)mean; a.var = (T*)var; a.fused = fused ? 1 : 0;
     QbTcPlan tp;
-    if (!fused && out && make_tc_plan(net, dtype, &tp)) {
-        // tensor-core forward (qb_tc.cuh): 128-point tiles, weights staged once per block, >= 8 waves of blocks
+    if (!fused && out && make_tc_plan(net, dtype, &tp, 3)) {
+        // tensor-core forward (qb_tc.cuh / qb_tc3.cuh): 128-point tiles, weights staged once per block, >= 8 waves of blocks
         const long long t128 = cdiv(N, 128);
         long long ch = std::max<long long>(1, std::min<long long>(t128, cdiv((long long)QB_NUM_SMS * 2 * 8, M)));
         a.tiles_per_block = cdiv(t128, ch);

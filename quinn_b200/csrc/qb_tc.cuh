@@ -40,7 +40,7 @@ struct QbTcPlan {
     int nthreads;                       // 256 (pipelined) or 128
     int a_lo_col, d_col, tmem_cols;
     int smem_bytes;
-    int v3;                             // warp-specialised hot-shape path (qb_tc3.cuh): 288 threads, layouts below
+    int v3;                             // warp-specialised path (qb_tc3.cuh): 1 = hidden width 64 (288 threads), 2 = 128 (544); layouts below
     int v3_w0, v3_w1, v3_x;             // byte offsets: W0 tf32 hi|lo, W1 fp16 hi|lo, x tiles [2][hi|lo]
     int v3_c1;                          // float index of the accumulator scale of the hidden GEMM
     int v3_xbar;                        // byte offset of the three x_full mbarriers
@@ -712,10 +712,13 @@ __host__ __device__ __forceinline__ bool qb_tc_is_hot(const QbTcPlan& tp) {
     return tp.pipe == 2 && tp.ni == 4 && tp.act0 == QB_ACT_TANH && tp.out_dim == 1 && tp.h0 == 64 && tp.kl == 64 &&
            tp.L[1].n_out == 64;
 }
-// the shape the warp-specialised path (qb_tc3.cuh) covers
-__host__ __device__ __forceinline__ bool qb_tc_v3_shape(const QbTcPlan& tp) {
-    return tp.pipe == 2 && tp.in_dim <= 7 && tp.act0 == QB_ACT_TANH && tp.out_dim == 1 && tp.h0 == 64 && tp.kl == 64 &&
-           tp.L[1].n_out == 64;
+// the shapes the warp-specialised path (qb_tc3.cuh) covers: in -> H -> H -> 1 with tanh, H = 64 (in <= 7) or 128 (in <= 15);
+// returns H or 0
+__host__ __device__ __forceinline__ int qb_tc_v3_shape(const QbTcPlan& tp) {
+    if (!tp.pipe || tp.act0 != QB_ACT_TANH || tp.out_dim != 1 || tp.h0 != tp.kl || tp.L[1].n_out != tp.h0) return 0;
+    if (tp.h0 == 64 && tp.in_dim <= 7) return 64;
+    if (tp.h0 == 128 && tp.in_dim <= 15) return 128;
+    return 0;
 }
 template <bool HOT>
 __device__ __forceinline__ double qb_tc_eval(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem,

@@ -34,17 +34,22 @@
 #ifdef __CUDACC__
 // Development aid (-DQB3_TRACE, scripts/tc3_trace.py): SM-clock stamps of the phases of every compute warp.
 #ifdef QB3_TRACE
-enum { QB3_TR_BLOCKS = 296, QB3_TR_TILES = 82, QB3_TR_EV = 8 };
-__device__ unsigned int qb3_trace_buf[QB3_TR_BLOCKS * 9 * QB3_TR_TILES * QB3_TR_EV];
+enum { QB3_TR_BLOCKS = 296, QB3_TR_WARPS = 17, QB3_TR_TILES = 82, QB3_TR_EV = 8 };
+__device__ unsigned int qb3_trace_buf[QB3_TR_BLOCKS * QB3_TR_WARPS * QB3_TR_TILES * QB3_TR_EV];
 __device__ unsigned int qb3_trace_sm[QB3_TR_BLOCKS];
 #define QB3_STAMP(tile, ev) do { if ((threadIdx.x & 31) == 0 && blockIdx.x < QB3_TR_BLOCKS && blockIdx.y == 0 && (tile) < QB3_TR_TILES) \
-    qb3_trace_buf[((blockIdx.x * 9 + (threadIdx.x >> 5)) * QB3_TR_TILES + (tile)) * QB3_TR_EV + (ev)] = (unsigned int)clock64(); } while (0)
+    qb3_trace_buf[((blockIdx.x * QB3_TR_WARPS + (threadIdx.x >> 5)) * QB3_TR_TILES + (tile)) * QB3_TR_EV + (ev)] = (unsigned int)clock64(); } while (0)
 #else
 #define QB3_STAMP(tile, ev) do { } while (0)
 #endif
-enum { QB3_D0F = 320, QB3_ARDY = 336, QB3_D1F = 344, QB3_D1FREE = 352, QB3_D0F1 = 360,   // mbarriers in the shared-memory header
+enum { QB3_D0F = 320, QB3_ARDY = 336, QB3_D1F = 344, QB3_D1FREE = 352, QB3_D0F1 = 360 };   // mbarriers in the shared-memory header
        // (d0_full exists once per D0 buffer: layer 0 runs two tiles ahead and a parity wait must never fall two phases behind)
-       QB3_COL_AHI = 128, QB3_COL_ALO = 160, QB3_COL_D1 = 192, QB3_NCOMPUTE = 256 };
+// Hidden width H (64: config 5, two blocks per SM; 128: config 3, one block per SM): G = H/32 column groups of 128 compute
+// threads each, the issue warp comes after them; tensor-memory columns D0 x 2 | A_hi | -A_lo | D1
+template <int H> struct Qb3Dim {
+    static constexpr int G = H / 32, NCOMP = 128 * G, ISSUER = 4 * G;
+    static constexpr int COL_AHI = 2 * H, COL_ALO = 2 * H + H / 2, COL_D1 = 3 * H;
+};
 
 // mbarrier wait of the tile loops: try_wait suspends the thread until the phase completes or the 20 us hint expires, so a
 // plain counted loop is a bounded wait (2^20 x 20 us, then trap) with no state beyond its counter -- the timer-based
@@ -61,7 +66,9 @@ __device__ __forceinline__ void qb3_wait(uint32_t bar, uint32_t parity) {
 }
 
 // all threads; tensor-memory allocation (the mbarriers are (re)initialised by every evaluation)
+template <int H>
 __device__ __forceinline__ void qb_tc3_init(const QbTcPlan& tp, unsigned char* smem, QbTcCtx& cx) {
+    constexpr uint32_t QB3_NCOMPUTE = Qb3Dim<H>::NCOMP;
     if ((threadIdx.x >> 5) == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      :: "r"(qb_smem_u32(smem + QB_TC_SLOT_OFF)), "r"((uint32_t)tp.tmem_cols) : "memory");
@@ -85,7 +92,9 @@ __device__ __forceinline__ void qb_tc3_init(const QbTcPlan& tp, unsigned char* s
     cx.bar = cx.abar = cx.hbar = 0; cx.phase = cx.aphase = cx.hphase = 0;
 }
 // thread 0, between two block barriers: every phase of the previous evaluation has completed, start again at parity 0
+template <int H>
 __device__ __forceinline__ void qb_tc3_reset_barriers(unsigned char* smem) {
+    constexpr uint32_t QB3_NCOMPUTE = Qb3Dim<H>::NCOMP;
     const uint32_t b = qb_smem_u32(smem);
     const uint32_t off[5] = {QB3_D0F, QB3_ARDY, QB3_D1F, QB3_D1FREE, QB3_D0F1};
 #pragma unroll
@@ -119,7 +128,9 @@ __device__ __forceinline__ void qb3_split_f16(float x0, float x1, uint32_t& hi, 
 //   F[wl + k] = -2 * 2^-14 * sl * wl_k (the epilogue produces 2^14 s);  F[bl] = sl * (bl + sum_k wl_k)
 // wmax: this thread's share of max |W1| when the caller has already looked at every W1 entry (all threads pass >= 0,
 // block-uniformly), else < 0 and the entries are scanned here
+template <int H, int K0>
 __device__ __forceinline__ void qb_tc3_stage(const QbTcPlan& tp, unsigned char* smem, const float* __restrict__ theta, float wmax) {
+    constexpr int NCW = Qb3Dim<H>::ISSUER;          // compute warps
     float* F = reinterpret_cast<float*>(smem + tp.fl_base);
     double* red = reinterpret_cast<double*>(smem);
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
@@ -128,7 +139,7 @@ __device__ __forceinline__ void qb_tc3_stage(const QbTcPlan& tp, unsigned char* 
     // ---- scale of W1: largest magnitude -> [2^13, 2^14)
     float mx = fmaxf(wmax, 0.0f);
     if (wmax < 0.0f)
-        for (int e = tid; e < 64 * 64; e += nt) mx = fmaxf(mx, fabsf(theta[L.w_off + e]));
+        for (int e = tid; e < H * H; e += nt) mx = fmaxf(mx, fabsf(theta[L.w_off + e]));
     uint32_t mb = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
     __syncthreads();                       // the previous evaluation's readers of F / red are done
     if (lane == 0) reinterpret_cast<uint32_t*>(red)[wid] = mb;
@@ -142,43 +153,51 @@ __device__ __forceinline__ void qb_tc3_stage(const QbTcPlan& tp, unsigned char* 
         sW = max(-60, min(60, sW));
     }
     const float wscale = -2.0f * fold * __uint_as_float((uint32_t)(127 + sW) << 23);
-    // ---- W0 (tf32 hi / lo): element (n, k) at float index ((n/8)*2 + k/4)*32 + (n%8)*4 + k%4
+    // ---- W0 (tf32 hi / lo): element (n, k) at float index ((n/8)*(K0/4) + k/4)*32 + (n%8)*4 + k%4
     {
         float* hi = reinterpret_cast<float*>(smem + tp.v3_w0);
-        float* lo = hi + 64 * 8;
-        for (int e = tid; e < 64 * 8; e += nt) {
-            const int n = e >> 3, k = e & 7;
+        float* lo = hi + H * K0;
+        for (int e = tid; e < H * K0; e += nt) {
+            const int n = e / K0, k = e % K0;
             float v = 0.0f;
             if (k < tp.in_dim) v = theta[tp.w0_off + n * tp.in_dim + k] * fold;
             else if (k == tp.in_dim && tp.b0_off >= 0) v = theta[tp.b0_off + n] * fold;
             const float h = qb_tf32_hi(v);
-            const int idx = ((n >> 3) * 2 + (k >> 2)) * 32 + (n & 7) * 4 + (k & 3);
+            const int idx = ((n >> 3) * (K0 / 4) + (k >> 2)) * 32 + (n & 7) * 4 + (k & 3);
             hi[idx] = h; lo[idx] = v - h;
         }
     }
     // ---- W1 (fp16 hi / lo) and its row sums: warp w of the first eight takes rows w, w+8, ..; lane = a pair of columns
-    if (wid < 8) {
+    if (wid < NCW) {
         uint32_t* hi = reinterpret_cast<uint32_t*>(smem + tp.v3_w1);
-        uint32_t* lo = hi + 64 * 64 / 2;
-        uint32_t* nhi = lo + 64 * 64 / 2;
-        for (int n = wid; n < 64; n += 8) {
-            const int k = lane * 2;
-            const float w0 = theta[L.w_off + n * 64 + k], w1 = theta[L.w_off + n * 64 + k + 1];
-            uint32_t h2, l2;
-            qb3_split_f16(w0 * wscale, w1 * wscale, h2, l2);
-            const int idx = (((n >> 3) * 8 + (k >> 3)) * 64 + (n & 7) * 8 + (k & 7)) >> 1;      // 32-bit word index
-            hi[idx] = h2; lo[idx] = l2 ^ 0x80008000u; nhi[idx] = h2 ^ 0x80008000u;
-            float s = w0 + w1;                     // pairwise tree: the error stays below that of the GEMM's own fp32 sums
+        uint32_t* lo = hi + H * H / 2;
+        uint32_t* nhi = lo + H * H / 2;
+        for (int n = wid; n < H; n += NCW) {
+            float s = 0.0f;                        // pairwise tree: the error stays below that of the GEMM's own fp32 sums
+#pragma unroll
+            for (int jj = 0; jj < H / 64; ++jj) {
+                const int k = (lane + 32 * jj) * 2;
+                const float w0 = theta[L.w_off + n * H + k], w1 = theta[L.w_off + n * H + k + 1];
+                uint32_t h2, l2;
+                qb3_split_f16(w0 * wscale, w1 * wscale, h2, l2);
+                const int idx = (((n >> 3) * (H / 8) + (k >> 3)) * 64 + (n & 7) * 8 + (k & 7)) >> 1;      // 32-bit word index
+                hi[idx] = h2; lo[idx] = l2 ^ 0x80008000u; nhi[idx] = h2 ^ 0x80008000u;
+                s += w0 + w1;
+            }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
             if (lane == 0) F[L.bias + n] = fold * ((L.b_off >= 0 ? theta[L.b_off + n] : 0.0f) + s);
         }
-    } else if (wid == 8) {
+    } else if (wid == NCW) {
         // ---- output row: -2 sl wl, bias sl (bl + sum wl)
         const float sl = tp.act_last == QB_ACT_TANH ? fold : 1.0f;
-        const float a = theta[tp.wl_off + lane], b = theta[tp.wl_off + 32 + lane];
-        F[tp.wl + lane] = -1.220703125e-04f * sl * a; F[tp.wl + 32 + lane] = -1.220703125e-04f * sl * b;     // -2 * 2^-14
-        double s = (double)a + (double)b;
+        double s = 0.0;
+#pragma unroll
+        for (int jj = 0; jj < H / 32; ++jj) {
+            const float a = theta[tp.wl_off + lane + 32 * jj];
+            F[tp.wl + lane + 32 * jj] = -1.220703125e-04f * sl * a;     // -2 * 2^-14
+            s += (double)a;
+        }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
         if (lane == 0) {
@@ -242,7 +261,7 @@ __device__ __forceinline__ bool qb3_elect() {
 }
 
 // The issue warp's view of an x tile: lane l owns points 4l .. 4l+3
-template <int IN>          // IN: upper bound of the input width (3 or 7)
+template <int IN, int K0>          // IN: upper bound of the input width (3, 7 or 15), K0: padded K of layer 0 (8 or 16)
 struct Qb3X {
     float v[4][IN];
     int in_dim;
@@ -254,81 +273,103 @@ struct Qb3X {
             for (int q = 0; q < IN; ++q) v[i][q] = (p < n1 && q < in_dim) ? __ldg(x + p * in_dim + q) : 0.0f;
         }
     }
-    // canonical K-major tile [128 x 8]: element (m, k) at float index ((m/8)*2 + k/4)*32 + (m%8)*4 + k%4
+    // canonical K-major tile [128 x K0]: element (m, k) at float index ((m/8)*(K0/4) + k/4)*32 + (m%8)*4 + k%4
     __device__ __forceinline__ void store(float* hi, float* lo, int lane) const {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int m = lane * 4 + i;
-            float w[8], h[8], l[8];
+            float w[K0], h[K0], l[K0];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < K0; ++q) {
                 const float xv = q < IN ? v[i][q < IN ? q : 0] : 0.0f;
                 w[q] = (q == in_dim) ? 1.0f : xv;                // the bias slot (a select: no indexed store)
                 h[q] = qb_tf32_hi(w[q]); l[q] = w[q] - h[q];
             }
-            const int idx = ((m >> 3) * 2) * 32 + (m & 7) * 4;
-            *reinterpret_cast<float4*>(hi + idx) = make_float4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<float4*>(hi + idx + 32) = make_float4(h[4], h[5], h[6], h[7]);
-            *reinterpret_cast<float4*>(lo + idx) = make_float4(l[0], l[1], l[2], l[3]);
-            *reinterpret_cast<float4*>(lo + idx + 32) = make_float4(l[4], l[5], l[6], l[7]);
+            const int idx = ((m >> 3) * (K0 / 4)) * 32 + (m & 7) * 4;
+#pragma unroll
+            for (int c4 = 0; c4 < K0 / 4; ++c4) {
+                *reinterpret_cast<float4*>(hi + idx + 32 * c4) = make_float4(h[4 * c4], h[4 * c4 + 1], h[4 * c4 + 2], h[4 * c4 + 3]);
+                *reinterpret_cast<float4*>(lo + idx + 32 * c4) = make_float4(l[4 * c4], l[4 * c4 + 1], l[4 * c4 + 2], l[4 * c4 + 3]);
+            }
         }
     }
 };
 
-// sum of squared residuals over points [n0, n1) for the staged parameter vector (block-wide result); every thread of
-// the 288-thread block calls it.  PRESTAGE (chain kernel: same x, n0, n1 in every call): the issue warp leaves the first
-// three x tiles of the NEXT evaluation in the ring when it is done, so an evaluation does not start with global loads.
-template <int IN, bool PRESTAGE>
-__device__ __forceinline__ double qb_tc3_eval(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem,
-                                              const float* __restrict__ x, const float* __restrict__ y,
-                                              int64_t n0, int64_t n1, const float* __restrict__ xs) {
+// What happens to the network output of a point: squared residual against y (kernels 1, 3) or store (kernel 4)
+struct Qb3SinkSsq {
+    const float* __restrict__ y; float ssq;
+    __device__ __forceinline__ float prefetch(int64_t p, bool live) const { return live ? __ldg(y + p) : 0.0f; }
+    __device__ __forceinline__ void consume(int64_t, bool live, float yt, float yo) { if (live) { const float r = yt - yo; ssq = fmaf(r, r, ssq); } }
+};
+struct Qb3SinkStore {
+    float* __restrict__ out;
+    __device__ __forceinline__ float prefetch(int64_t, bool) const { return 0.0f; }
+    __device__ __forceinline__ void consume(int64_t p, bool live, float, float yo) { if (live) out[p] = yo; }
+};
+
+// The tile loop over points [n0, n1) for the staged parameter vector; every thread of the block (128 G compute threads + the
+// issue warp) calls it; returns the sink (its state is meaningful in group-0 threads).  PRESTAGE (chain kernel: same x, n0, n1
+// in every call): the issue warp leaves the first three x tiles of the NEXT evaluation in the ring when it is done, so an
+// evaluation does not start with global loads.
+template <int H, int K0, int IN, bool PRESTAGE, typename Sink>
+__device__ __forceinline__ Sink qb_tc3_run(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem, const float* __restrict__ x,
+                                           int64_t n0, int64_t n1, const float* __restrict__ xs, Sink sink) {
+    using D = Qb3Dim<H>;
+    constexpr int G = D::G;
+    constexpr uint32_t XT = 128u * K0 * 4u;                  // bytes of one half (hi or lo) of an x tile
     const float* F = reinterpret_cast<const float*>(smem + tp.fl_base);
     const uint32_t sb = qb_smem_u32(smem);
     const uint32_t bar_d0f = sb + QB3_D0F, bar_ardy = sb + QB3_ARDY, bar_d1f = sb + QB3_D1F, bar_d1free = sb + QB3_D1FREE;
     const int T = (int)((n1 - n0 + 127) / 128);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __syncthreads();                               // staging complete; nobody is still inside the previous evaluation
-    if (threadIdx.x == 0) qb_tc3_reset_barriers(smem);
+    if (threadIdx.x == 0) qb_tc3_reset_barriers<H>(smem);
     __syncthreads();
-    float ssq = 0.0f;
-    if (T > 0 && wid == 8) {
+    if (T > 0 && wid == D::ISSUER) {
         // ================================ issue warp ================================
-        float* xb = reinterpret_cast<float*>(smem + tp.v3_x);         // [3][hi 1024 | lo 1024] floats
-        const uint32_t dhi8 = ((128u * 2u) >> 4) | (1u << 14);        // K = 8 tf32: SBO 256 B
-        const uint32_t dhi64 = (1024u >> 4) | (1u << 14);             // K = 64 fp16: SBO 1024 B
+        float* xb = reinterpret_cast<float*>(smem + tp.v3_x);         // [3][hi | lo], 128 x K0 floats each
+        const uint32_t dhi0 = ((128u * (K0 / 4)) >> 4) | (1u << 14);  // tf32 operands with K = K0: SBO 128 K0/4 bytes
+        const uint32_t dhi1 = ((16u * H) >> 4) | (1u << 14);          // fp16 W1, K = H: SBO 16 H bytes
         const uint32_t lbo = (128u >> 4) << 16;
-        const uint32_t w0hi = ((qb_smem_u32(smem + tp.v3_w0) >> 4) & 0x3FFFu) | lbo, w0lo = w0hi + (64u * 8u * 4u >> 4);
-        const uint32_t w1hi = ((qb_smem_u32(smem + tp.v3_w1) >> 4) & 0x3FFFu) | lbo, w1lo = w1hi + (64u * 64u * 2u >> 4),
-                       w1nhi = w1lo + (64u * 64u * 2u >> 4);
-        const uint32_t xd = ((qb_smem_u32(xb) >> 4) & 0x3FFFu) | lbo;  // + 512 (16-byte units) per buffer, + 256 for lo
-        const uint32_t id_tf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-        const uint32_t id_f16 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-        const uint32_t d0 = cx.tmem, a_hi = cx.tmem + QB3_COL_AHI, a_lo = cx.tmem + QB3_COL_ALO;
-        // x tiles come either as ready-made operand images from global memory (xs: tile u = 8 KB, tf32 hi | lo in the
-        // canonical layout, written once per launch by k_tc3_xsplit; one bulk copy per tile, completion on x_full[u % 3]) or,
+        const uint32_t w0hi = ((qb_smem_u32(smem + tp.v3_w0) >> 4) & 0x3FFFu) | lbo, w0lo = w0hi + ((uint32_t)(H * K0 * 4) >> 4);
+        const uint32_t w1hi = ((qb_smem_u32(smem + tp.v3_w1) >> 4) & 0x3FFFu) | lbo, w1lo = w1hi + ((uint32_t)(H * H * 2) >> 4),
+                       w1nhi = w1lo + ((uint32_t)(H * H * 2) >> 4);
+        const uint32_t xd = ((qb_smem_u32(xb) >> 4) & 0x3FFFu) | lbo;  // + 2 XT / 16 per ring slot, + XT / 16 for lo
+        const uint32_t id_tf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t id_f16 = (1u << 4) | ((uint32_t)(H >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t d0 = cx.tmem, a_hi = cx.tmem + D::COL_AHI, a_lo = cx.tmem + D::COL_ALO;
+        // x tiles come either as ready-made operand images from global memory (xs: tile u = tf32 hi | lo in the canonical
+        // layout, written once per launch by k_tc3_xsplit; one bulk copy per tile, completion on x_full[u % 3]) or,
         // without such a buffer, are loaded, split and laid out by this warp (Qb3X)
         const bool bulk = xs != nullptr;
         const uint32_t bar_x = sb + (uint32_t)tp.v3_xbar;
         uint32_t xpar = cx.hphase;                 // parities of x_full[0..2] (they are never re-initialised)
         auto xcopy = [&](int u) {                  // one lane: start the bulk copy of tile u into ring slot u % 3
-            const uint32_t bar = bar_x + (uint32_t)(u % 3) * 8u, dst = qb_smem_u32(xb) + (uint32_t)(u % 3) * 8192u;
-            const float* src = xs + (int64_t)u * 2048;
-            asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" :: "r"(bar), "r"(8192u) : "memory");
+            const uint32_t bar = bar_x + (uint32_t)(u % 3) * 8u, dst = qb_smem_u32(xb) + (uint32_t)(u % 3) * 2u * XT;
+            const float* src = xs + (int64_t)u * (2 * 128 * K0);
+            asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" :: "r"(bar), "r"(2u * XT) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         :: "r"(dst), "l"(src), "r"(8192u), "r"(bar) : "memory");
+                         :: "r"(dst), "l"(src), "r"(2u * XT), "r"(bar) : "memory");
         };
         auto xwait = [&](int u) {                  // all lanes: tile u has landed
             const int sl = u % 3;
             qb3_wait(bar_x + (uint32_t)sl * 8u, (xpar >> sl) & 1u);
             xpar ^= 1u << sl;
         };
-        Qb3X<IN> X;
+        Qb3X<IN, K0> X;
         X.in_dim = tp.in_dim;
-        auto mma0 = [&](int u) {           // layer 0 of tile u: x buffer u % 3 -> D0[u & 1]
-            const uint32_t xa = xd + (uint32_t)(u % 3) * 512u, d = d0 + (uint32_t)(u & 1) * 64u;
-            qb3_mma_tf32_ss<false>(d, xa + 256u, w0hi, dhi8, id_tf32);
-            qb3_mma_tf32_ss<true>(d, xa, w0lo, dhi8, id_tf32);
-            qb3_mma_tf32_ss<true>(d, xa, w0hi, dhi8, id_tf32);
+        auto xstore = [&](int u) { float* b = xb + (u % 3) * (2 * 128 * K0); X.store(b, b + 128 * K0, lane); };
+        auto mma0 = [&](int u) {           // layer 0 of tile u: x ring slot u % 3 -> D0[u & 1]
+            const uint32_t xa = xd + (uint32_t)(u % 3) * (2u * XT >> 4), d = d0 + (uint32_t)(u & 1) * (uint32_t)H;
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+                for (int ks = 0; ks < K0 / 8; ++ks) {
+                    const uint32_t a = xa + (pass == 0 ? (XT >> 4) : 0u) + 16u * ks, b = (pass == 1 ? w0lo : w0hi) + 16u * ks;
+                    if (pass == 0 && ks == 0) qb3_mma_tf32_ss<false>(d, a, b, dhi0, id_tf32);
+                    else qb3_mma_tf32_ss<true>(d, a, b, dhi0, id_tf32);
+                }
+            }
             qb3_commit((u & 1) ? sb + QB3_D0F1 : bar_d0f);
         };
         // x tiles 0 .. 2 staged up front (unless the previous evaluation left them), layer 0 of tiles 0 and 1 started
@@ -339,7 +380,7 @@ __device__ __forceinline__ double qb_tc3_eval(const QbTcPlan& tp, QbTcCtx& cx, u
 #pragma unroll 1
                 for (int u = 0; u < 3 && u < T; ++u) {
                     X.load(x, n0 + (int64_t)u * 128, n1, lane);
-                    X.store(xb + u * 2048, xb + u * 2048 + 1024, lane);
+                    xstore(u);
                 }
             }
         }
@@ -355,7 +396,7 @@ __device__ __forceinline__ double qb_tc3_eval(const QbTcPlan& tp, QbTcCtx& cx, u
 #pragma unroll 1
         for (int t = 0; t < T; ++t) {
             if (bulk && t + 2 < T) xwait(t + 2);                                      // long since landed
-            qb3_wait(bar_ardy, (uint32_t)t & 1u);                                 // A(t) written, D0[t&1] read
+            qb3_wait(bar_ardy, (uint32_t)t & 1u);                                     // A(t) written, D0[t&1] read
             QB3_STAMP(t, 0);
             qb_tc_fence_after();
             __syncwarp();
@@ -366,27 +407,27 @@ __device__ __forceinline__ double qb_tc3_eval(const QbTcPlan& tp, QbTcCtx& cx, u
             __syncwarp();
             QB3_STAMP(t, 2);
             if (qb3_elect()) {
-                const uint32_t d1 = cx.tmem + QB3_COL_D1;
+                const uint32_t d1 = cx.tmem + D::COL_D1;
 #pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    if (s == 0) qb3_mma_f16_ts<false>(d1, a_lo, w1nhi, dhi64, id_f16);
-                    else qb3_mma_f16_ts<true>(d1, a_lo + 8u * s, w1nhi + 16u * s, dhi64, id_f16);
+                for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+                    for (int ks = 0; ks < H / 16; ++ks) {
+                        const uint32_t a = (pass == 0 ? a_lo : a_hi) + 8u * ks;
+                        const uint32_t b = (pass == 0 ? w1nhi : pass == 1 ? w1lo : w1hi) + 16u * ks;
+                        if (pass == 0 && ks == 0) qb3_mma_f16_ts<false>(d1, a, b, dhi1, id_f16);
+                        else qb3_mma_f16_ts<true>(d1, a, b, dhi1, id_f16);
+                    }
                 }
-#pragma unroll
-                for (int s = 0; s < 4; ++s) qb3_mma_f16_ts<true>(d1, a_hi + 8u * s, w1lo + 16u * s, dhi64, id_f16);
-#pragma unroll
-                for (int s = 0; s < 4; ++s) qb3_mma_f16_ts<true>(d1, a_hi + 8u * s, w1hi + 16u * s, dhi64, id_f16);
                 qb3_commit(bar_d1f);
             }
             __syncwarp();
             QB3_STAMP(t, 3);
             if (t + 3 < T) {
-                // x buffer t % 3 was read by MMA0(t), which completed before the compute warps arrived on a_ready(t)
+                // ring slot t % 3 was read by MMA0(t), which completed before the compute warps arrived on a_ready(t)
                 if (bulk) {
                     if (lane == 0) xcopy(t + 3);
                 } else {
-                    float* b = xb + (t % 3) * 2048;
-                    X.store(b, b + 1024, lane);
+                    xstore(t + 3);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     if (t + 4 < T) X.load(x, n0 + (int64_t)(t + 4) * 128, n1, lane);
                 }
@@ -400,7 +441,7 @@ __device__ __forceinline__ double qb_tc3_eval(const QbTcPlan& tp, QbTcCtx& cx, u
 #pragma unroll 1
                 for (int u = 0; u < 3 && u < T; ++u) {
                     X.load(x, n0 + (int64_t)u * 128, n1, lane);
-                    X.store(xb + u * 2048, xb + u * 2048 + 1024, lane);
+                    xstore(u);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             }
@@ -411,14 +452,14 @@ __device__ __forceinline__ double qb_tc3_eval(const QbTcPlan& tp, QbTcCtx& cx, u
         // ================================ compute warps ================================
         const int g = threadIdx.x >> 7, pt = threadIdx.x & 127;
         const uint32_t tl = cx.tmem + ((uint32_t)((wid & 3) * 32) << 16);
-        float* ybuf = reinterpret_cast<float*>(smem + tp.ybuf);           // [4][128] partial outputs of group 1
+        float* ybuf = reinterpret_cast<float*>(smem + tp.ybuf);           // [4][G-1][128] partial outputs of groups 1 .. G-1
         const float c1 = F[tp.v3_c1];
         const float4* B4 = reinterpret_cast<const float4*>(F + tp.L[1].bias + 32 * g);
         const float4* W4 = reinterpret_cast<const float4*>(F + tp.wl + 32 * g);
         const int64_t pbase = n0 + pt;
         float own0 = 0.0f, own1 = 0.0f, yt0 = 0.0f, yt1 = 0.0f;          // group 0: own partial sum / target of tiles t-1, t-2
 
-        // EPI0(u): D0 -> 2^14 * s -> fp16 hi / lo -> A.  `afree`: wait for d1_full(u - 1) before the stores.
+        // EPI0(u): D0 -> 2^14 * s -> fp16 hi / lo -> A; the stores wait for d1_full(u - 1) = "A is free"
         auto epi0 = [&](int u) {
             QB3_STAMP(u, 0);
             // layer 0 of tiles u >= 2 was issued BEFORE MMA1(u-2), whose commit (d1_full(u-2), waited for in EPI0(u-1))
@@ -428,8 +469,8 @@ __device__ __forceinline__ double qb_tc3_eval(const QbTcPlan& tp, QbTcCtx& cx, u
                 qb_tc_fence_after();
             }
             uint32_t v[2][16];
-            qb_tmem_ld16(tl + 64 * (u & 1) + 32 * g, v[0]);
-            qb_tmem_ld16(tl + 64 * (u & 1) + 32 * g + 16, v[1]);
+            qb_tmem_ld16(tl + H * (u & 1) + 32 * g, v[0]);
+            qb_tmem_ld16(tl + H * (u & 1) + 32 * g + 16, v[1]);
             qb_tmem_ld_wait16(v[0]);
             qb_tmem_ld_wait16(v[1]);
             QB3_STAMP(u, 1);
@@ -454,19 +495,19 @@ __device__ __forceinline__ double qb_tc3_eval(const QbTcPlan& tp, QbTcCtx& cx, u
             QB3_STAMP(u, 3);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                qb_tmem_st8(tl + QB3_COL_AHI + 16 * g + 8 * j, hi[j]);
-                qb_tmem_st8(tl + QB3_COL_ALO + 16 * g + 8 * j, lo[j]);
+                qb_tmem_st8(tl + D::COL_AHI + 16 * g + 8 * j, hi[j]);
+                qb_tmem_st8(tl + D::COL_ALO + 16 * g + 8 * j, lo[j]);
             }
             qb_tmem_st_wait();
             qb_tc_fence_before();
             qb_mbar_arrive(bar_ardy);
             QB3_STAMP(u, 4);
         };
-        // EPI1(u): D1[u&1] -> s -> partial dot product with the output row
+        // EPI1(u): D1 -> s -> partial dot product with the output row
         auto epi1 = [&](int u) -> float {
             QB3_STAMP(u, 5);
             uint32_t v[2][16];
-            const uint32_t dcol = QB3_COL_D1 + 32u * g;
+            const uint32_t dcol = D::COL_D1 + 32u * g;
             qb_tmem_ld16(tl + dcol, v[0]);
             qb_tmem_ld16(tl + dcol + 16, v[1]);
             qb_tmem_ld_wait16(v[0]);
@@ -499,28 +540,30 @@ __device__ __forceinline__ double qb_tc3_eval(const QbTcPlan& tp, QbTcCtx& cx, u
             QB3_STAMP(u, 7);
             return acc.x + acc.y;
         };
-        // group 0: residual of tile u (own partial sum + the partner's from ybuf)
+        // group 0: output of tile u (own partial sum + the partners' from ybuf) to the sink
         auto finish = [&](int u, float own, float yt) {
             const int64_t p = pbase + (int64_t)u * 128;
-            const float yo = qb_tc_out(tp, F, 0, own + ybuf[(u & 3) * 128 + pt]);
-            if (p < n1) { const float r = yt - yo; ssq = fmaf(r, r, ssq); }
+            float acc = own;
+#pragma unroll
+            for (int gg = 0; gg < G - 1; ++gg) acc += ybuf[((u & 3) * (G - 1) + gg) * 128 + pt];
+            sink.consume(p, p < n1, yt, qb_tc_out(tp, F, 0, acc));
         };
 
         epi0(0);
 #pragma unroll 1
         for (int t = 0; t < T; ++t) {
             if (t >= 1) {
-                // tile t-1 (d1_full(t-1) was waited for in EPI0(t)); the partner's partial sum of tile t-3 became visible
-                // with d1_full(t-1) at the latest (it arrived on a_ready(t-1) after writing it)
+                // tile t-1 (d1_full(t-1) was waited for in EPI0(t)); the partners' partial sums of tile t-3 became visible
+                // with d1_full(t-1) at the latest (they arrived on a_ready(t-1) after writing them)
                 const int u = t - 1;
                 float ytn = 0.0f;
-                if (g == 0) { const int64_t p = pbase + (int64_t)u * 128; if (p < n1) ytn = __ldg(y + p); }
+                if (g == 0) { const int64_t p = pbase + (int64_t)u * 128; ytn = sink.prefetch(p, p < n1); }
                 const float part = epi1(u);
                 if (g == 0) {
                     if (u >= 2) finish(u - 2, own1, yt1);
                     own1 = own0; yt1 = yt0; own0 = part; yt0 = ytn;
                 } else {
-                    ybuf[(u & 3) * 128 + pt] = part;
+                    ybuf[((u & 3) * (G - 1) + g - 1) * 128 + pt] = part;
                 }
             }
             if (t + 1 < T) epi0(t + 1);
@@ -529,10 +572,10 @@ __device__ __forceinline__ double qb_tc3_eval(const QbTcPlan& tp, QbTcCtx& cx, u
         {
             const int u = T - 1;
             float ytn = 0.0f;
-            if (g == 0) { const int64_t p = pbase + (int64_t)u * 128; if (p < n1) ytn = __ldg(y + p); }
+            if (g == 0) { const int64_t p = pbase + (int64_t)u * 128; ytn = sink.prefetch(p, p < n1); }
             const float part = epi1(u);
-            if (g != 0) ybuf[(u & 3) * 128 + pt] = part;
-            asm volatile("bar.sync 1, 256;" ::: "memory");               // the compute warps only
+            if (g != 0) ybuf[((u & 3) * (G - 1) + g - 1) * 128 + pt] = part;
+            asm volatile("bar.sync 1, %0;" :: "n"(D::NCOMP) : "memory");               // the compute warps only
             if (g == 0) {
                 if (u >= 2) finish(u - 2, own1, yt1);
                 if (u >= 1) finish(u - 1, own0, yt0);
@@ -540,13 +583,30 @@ __device__ __forceinline__ double qb_tc3_eval(const QbTcPlan& tp, QbTcCtx& cx, u
             }
         }
     }
-    return qb_block_sum((double)ssq, reinterpret_cast<double*>(smem));
+    return sink;
 }
-template <bool PRESTAGE>
+
+// shape dispatch: hidden width 64 -> K0 = 8 (in <= 7), 128 -> K0 = 16 (in <= 15)
+template <int H, bool PRESTAGE, typename Sink>
+__device__ __forceinline__ Sink qb_tc3_dispatch(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem, const float* __restrict__ x,
+                                                int64_t n0, int64_t n1, const float* __restrict__ xs, Sink sink) {
+    if constexpr (H == 64) {
+        if (tp.in_dim <= 3) return qb_tc3_run<64, 8, 3, PRESTAGE>(tp, cx, smem, x, n0, n1, xs, sink);
+        return qb_tc3_run<64, 8, 7, PRESTAGE>(tp, cx, smem, x, n0, n1, xs, sink);
+    } else {
+        return qb_tc3_run<128, 16, 15, PRESTAGE>(tp, cx, smem, x, n0, n1, xs, sink);
+    }
+}
+template <int H> struct Qb3K0 { static constexpr int value = H == 64 ? 8 : 16; };
+
+// sum of squared residuals over points [n0, n1) (block-wide result): kernels 1 and 3
+template <int H, bool PRESTAGE>
 __device__ __forceinline__ double qb_tc3_eval_any(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem,
                                                   const float* __restrict__ x, const float* __restrict__ y,
                                                   int64_t n0, int64_t n1, const float* __restrict__ xs) {
-    if (tp.in_dim <= 3) return qb_tc3_eval<3, PRESTAGE>(tp, cx, smem, x, y, n0, n1, xs);
-    return qb_tc3_eval<7, PRESTAGE>(tp, cx, smem, x, y, n0, n1, xs);
+    Qb3SinkSsq sink;
+    sink.y = y; sink.ssq = 0.0f;
+    sink = qb_tc3_dispatch<H, PRESTAGE>(tp, cx, smem, x, n0, n1, xs, sink);
+    return qb_block_sum((double)sink.ssq, reinterpret_cast<double*>(smem));
 }
 #endif  // __CUDACC__

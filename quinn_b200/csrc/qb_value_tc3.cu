@@ -24,20 +24,21 @@
 #include "qb_tc3.cuh"
 #include "qb_value_tc3.h"
 
-// x[N, in] -> operand tiles: tile u = points 128u .. 128u+127 as [hi 1024 floats | lo 1024 floats], element (m, k) at
-// ((m/8)*2 + k/4)*32 + (m%8)*4 + k%4; k < in: x, k == in: 1 (the bias slot), else 0; rows past N: zeros (never used)
+// x[N, in] -> operand tiles: tile u = points 128u .. 128u+127 as [hi 128 K0 floats | lo 128 K0 floats], element (m, k) at
+// ((m/8)*(K0/4) + k/4)*32 + (m%8)*4 + k%4; k < in: x, k == in: 1 (the bias slot), else 0; rows past N: zeros (never used)
+template <int K0>
 __global__ void __launch_bounds__(128) k_tc3_xsplit(const float* __restrict__ x, long long N, int in_dim, float* __restrict__ out) {
     const long long u = blockIdx.x, p = u * 128 + threadIdx.x;
     const int m = threadIdx.x;
-    float* hi = out + u * 2048;
-    float* lo = hi + 1024;
+    float* hi = out + u * (2 * 128 * K0);
+    float* lo = hi + 128 * K0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < K0; ++k) {
         float w = 0.0f;
         if (k < in_dim && p < N) w = x[p * in_dim + k];
         if (k == in_dim) w = 1.0f;
         const float h = qb_tf32_hi(w);
-        const int idx = ((m >> 3) * 2 + (k >> 2)) * 32 + (m & 7) * 4 + (k & 3);
+        const int idx = ((m >> 3) * (K0 / 4) + (k >> 2)) * 32 + (m & 7) * 4 + (k & 3);
         hi[idx] = h; lo[idx] = w - h;
     }
 }
@@ -55,23 +56,24 @@ __device__ __forceinline__ void qb_tc3_drain(const QbTcPlan& tp, const QbTcCtx& 
 static __device__ __noinline__ double qb_tc3_eval_chain(const QbTcPlan& tp, QbTcCtx& cx, unsigned char* smem, const float* __restrict__ x,
                                                         const float* __restrict__ y, long long N, const float* __restrict__ xs) {
     QbTcCtx c2 = cx;
-    const double r = qb_tc3_eval_any<true>(tp, c2, smem, x, y, 0, N, xs);
+    const double r = qb_tc3_eval_any<64, true>(tp, c2, smem, x, y, 0, N, xs);
     cx.phase = c2.phase; cx.hphase = c2.hphase;
     return r;
 }
 
-__global__ void __launch_bounds__(288, 2) k_logpost_tc3(const __grid_constant__ QbTcPlan tp, const EvalArgs<float> a) {
+template <int H>
+__global__ void __launch_bounds__(Qb3Dim<H>::NCOMP + 32, H == 64 ? 2 : 1) k_logpost_tc3(const __grid_constant__ QbTcPlan tp, const EvalArgs<float> a) {
     extern __shared__ __align__(128) unsigned char smem_tc[];
     QbTcCtx cx;
     const long long k = blockIdx.x, s = blockIdx.y;
     const long long n0 = s * a.pps, n1 = min(a.N, n0 + a.pps);
-    qb_tc3_init(tp, smem_tc, cx);
+    qb_tc3_init<H>(tp, smem_tc, cx);
 #ifdef QB3_TRACE
     if (threadIdx.x == 0 && blockIdx.x < QB3_TR_BLOCKS && blockIdx.y == 0) { unsigned int id; asm("mov.u32 %0, %%smid;" : "=r"(id)); qb3_trace_sm[blockIdx.x] = id; }
 #endif
-    qb_tc3_stage(tp, smem_tc, a.theta + k * tp.n_params, -1.0f);
-    const float* xs = a.xsplit ? a.xsplit + (n0 >> 7) * 2048 : nullptr;
-    const double ssq = qb_tc3_eval_any<false>(tp, cx, smem_tc, a.x + k * a.xs, a.y + k * a.ys, n0, n1, xs);
+    qb_tc3_stage<H, Qb3K0<H>::value>(tp, smem_tc, a.theta + k * tp.n_params, -1.0f);
+    const float* xs = a.xsplit ? a.xsplit + (n0 >> 7) * (2 * 128 * Qb3K0<H>::value) : nullptr;
+    const double ssq = qb_tc3_eval_any<H, false>(tp, cx, smem_tc, a.x + k * a.xs, a.y + k * a.ys, n0, n1, xs);
     if (threadIdx.x == 0) a.part[k * a.S + s] = ssq;
     qb_tc_fini(tp, cx);
 }
@@ -82,7 +84,7 @@ k_amcmc_tc3(const __grid_constant__ QbTcPlan tp, const __grid_constant__ ChainAr
     extern __shared__ __align__(128) unsigned char smem[];
     QbTcCtx cx;
     QB3_STAMP(80, 0);
-    qb_tc3_init(tp, smem, cx);
+    qb_tc3_init<64>(tp, smem, cx);
     QB3_STAMP(80, 1);
 #ifdef QB3_TRACE
     if (threadIdx.x == 0 && blockIdx.x < QB3_TR_BLOCKS) { unsigned int id; asm("mov.u32 %0, %%smid;" : "=r"(id)); qb3_trace_sm[blockIdx.x] = id; }
@@ -187,7 +189,7 @@ k_amcmc_tc3(const __grid_constant__ QbTcPlan tp, const __grid_constant__ ChainAr
         // ---- evaluate
         QB3_STAMP(81, 1);
         __syncthreads();                           // the proposal is complete in shared memory
-        qb_tc3_stage(tp, smem, evalp, wmax);
+        qb_tc3_stage<64, 8>(tp, smem, evalp, wmax);
         QB3_STAMP(81, 2);
         const double ssq = qb_tc3_eval_chain(tp, cx, smem, c.x, c.y, c.N, xs);
         QB3_STAMP(81, 3);
@@ -245,17 +247,61 @@ k_amcmc_tc3(const __grid_constant__ QbTcPlan tp, const __grid_constant__ ChainAr
 #ifdef QB3_TRACE
 // development aid: copy the phase stamps of the last launches to the host
 extern "C" int qb_tc3_trace_dump(unsigned int* buf, unsigned int* sm) {
-    if (cudaMemcpyFromSymbol(buf, qb3_trace_buf, sizeof(unsigned int) * QB3_TR_BLOCKS * 9 * QB3_TR_TILES * QB3_TR_EV) != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(buf, qb3_trace_buf, sizeof(unsigned int) * QB3_TR_BLOCKS * QB3_TR_WARPS * QB3_TR_TILES * QB3_TR_EV) != cudaSuccess) return -1;
     if (cudaMemcpyFromSymbol(sm, qb3_trace_sm, sizeof(unsigned int) * QB3_TR_BLOCKS) != cudaSuccess) return -1;
     return 0;
 }
 #endif
 
+// kernel 4: network outputs of member blockIdx.x over its chunk of tiles -> out[m, p] (one output per point)
+template <int H>
+__global__ void __launch_bounds__(Qb3Dim<H>::NCOMP + 32, H == 64 ? 2 : 1)
+k_predict_tc3(const __grid_constant__ QbTcPlan tp, const float* __restrict__ theta, const float* __restrict__ x, long long N,
+              float* __restrict__ out, long long tiles_per_block) {
+    extern __shared__ __align__(128) unsigned char smem_tc[];
+    QbTcCtx cx;
+    const long long m = blockIdx.x;
+    const long long n0 = (long long)blockIdx.y * tiles_per_block * 128, n1 = min(N, n0 + tiles_per_block * 128);
+    qb_tc3_init<H>(tp, smem_tc, cx);
+#ifdef QB3_TRACE
+    if (threadIdx.x == 0 && blockIdx.x < QB3_TR_BLOCKS && blockIdx.y == 0) { unsigned int id; asm("mov.u32 %0, %%smid;" : "=r"(id)); qb3_trace_sm[blockIdx.x] = id; }
+#endif
+    qb_tc3_stage<H, Qb3K0<H>::value>(tp, smem_tc, theta + m * tp.n_params, -1.0f);
+    Qb3SinkStore sink;
+    sink.out = out + m * N;
+    qb_tc3_dispatch<H, false>(tp, cx, smem_tc, x, n0, n1, nullptr, sink);
+    qb_tc_fini(tp, cx);
+}
+
 cudaError_t qb_tc3_launch_logpost(const QbTcPlan& tp, const EvalArgs<float>& a, dim3 grid, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(k_logpost_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, tp.smem_bytes);
-    if (e != cudaSuccess) return e;
-    if (a.xsplit) k_tc3_xsplit<<<(unsigned)((a.N + 127) / 128), 128, 0, st>>>(a.x, a.N, tp.in_dim, const_cast<float*>(a.xsplit));
-    k_logpost_tc3<<<grid, tp.nthreads, tp.smem_bytes, st>>>(tp, a);
+    const unsigned nt = (unsigned)((a.N + 127) / 128);
+    cudaError_t e;
+    if (tp.v3 == 1) {
+        e = cudaFuncSetAttribute(k_logpost_tc3<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tp.smem_bytes);
+        if (e != cudaSuccess) return e;
+        if (a.xsplit) k_tc3_xsplit<8><<<nt, 128, 0, st>>>(a.x, a.N, tp.in_dim, const_cast<float*>(a.xsplit));
+        k_logpost_tc3<64><<<grid, tp.nthreads, tp.smem_bytes, st>>>(tp, a);
+    } else {
+        e = cudaFuncSetAttribute(k_logpost_tc3<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tp.smem_bytes);
+        if (e != cudaSuccess) return e;
+        if (a.xsplit) k_tc3_xsplit<16><<<nt, 128, 0, st>>>(a.x, a.N, tp.in_dim, const_cast<float*>(a.xsplit));
+        k_logpost_tc3<128><<<grid, tp.nthreads, tp.smem_bytes, st>>>(tp, a);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t qb_tc3_launch_predict(const QbTcPlan& tp, const float* theta, const float* x, long long N, float* out,
+                                  long long tiles_per_block, dim3 grid, cudaStream_t st) {
+    cudaError_t e;
+    if (tp.v3 == 1) {
+        e = cudaFuncSetAttribute(k_predict_tc3<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tp.smem_bytes);
+        if (e != cudaSuccess) return e;
+        k_predict_tc3<64><<<grid, tp.nthreads, tp.smem_bytes, st>>>(tp, theta, x, N, out, tiles_per_block);
+    } else {
+        e = cudaFuncSetAttribute(k_predict_tc3<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tp.smem_bytes);
+        if (e != cudaSuccess) return e;
+        k_predict_tc3<128><<<grid, tp.nthreads, tp.smem_bytes, st>>>(tp, theta, x, N, out, tiles_per_block);
+    }
     return cudaGetLastError();
 }
 
@@ -264,9 +310,9 @@ cudaError_t qb_tc3_launch_amcmc(const QbTcPlan& tp, const ChainArgs<float>& c, c
     if (e != cudaSuccess) return e;
     // the generic kernel's proposal scratch ([K,P] floats) is free here: it holds the x tiles when it is large enough
     float* xs = nullptr;
-    if ((size_t)K * (size_t)tp.n_params * sizeof(float) >= qb_tc3_xsplit_bytes(c.N)) {
+    if ((size_t)K * (size_t)tp.n_params * sizeof(float) >= qb_tc3_xsplit_bytes(c.N, 8)) {
         xs = a.prop;
-        k_tc3_xsplit<<<(unsigned)((c.N + 127) / 128), 128, 0, st>>>(c.x, c.N, tp.in_dim, xs);
+        k_tc3_xsplit<8><<<(unsigned)((c.N + 127) / 128), 128, 0, st>>>(c.x, c.N, tp.in_dim, xs);
     }
     k_amcmc_tc3<<<(unsigned)K, tp.nthreads, tp.smem_bytes, st>>>(tp, c, a, xs);
     return cudaGetLastError();

@@ -15,9 +15,9 @@ from gpu_probe import mlp_desc, timeit          # noqa: E402
 from quinn_b200 import ops                      # noqa: E402
 
 
-def run(d, N, K, sigma=0.1, seed=0, wscale=0.5, prior=False):
+def run(d, N, K, sigma=0.1, seed=0, wscale=0.5, prior=False, H=64):
     rs = np.random.RandomState(seed)
-    desc = mlp_desc(d, 1, (64, 64))
+    desc = mlp_desc(d, 1, (H, H))
     x = rs.rand(N, d) * 2 - 1
     y = np.sin(x.sum(1, keepdims=True)) + 0.1 * rs.randn(N, 1)
     th0 = wscale * rs.randn(K, desc.n_params)
@@ -31,7 +31,7 @@ def run(d, N, K, sigma=0.1, seed=0, wscale=0.5, prior=False):
         torch.cuda.synchronize()
         res[name] = (lp.cpu().numpy(), info)
     ref = res['f64'][0]
-    line = f'net {d}-64-64-1 N={N} K={K} w~{wscale} prior={prior} plan(v3)={res["v3"][1]["tensor_core"]} threads={res["v3"][1]["threads"]} splits={res["v3"][1]["splits"]}:'
+    line = f'net {d}-{H}-{H}-1 N={N} K={K} w~{wscale} prior={prior} plan(v3)={res["v3"][1]["tensor_core"]} threads={res["v3"][1]["threads"]} splits={res["v3"][1]["splits"]}:'
     for name in ('old', 'v3'):
         e = np.abs(res[name][0] - ref) / np.abs(ref)
         line += f'  {name} max {e.max():.2e} mean {e.mean():.2e}'
@@ -52,6 +52,22 @@ if __name__ == '__main__':
     run(2, 300, 4)
     run(5, 300, 4)
     run(7, 1000, 4)
+    for d, N, K in ((10, 100, 2), (10, 129, 3), (10, 1000, 5), (10, 10000, 16), (1, 300, 4), (15, 777, 4), (8, 500, 3)):
+        run(d, N, K, H=128, wscale=0.3)
+    run(10, 5000, 8, H=128, wscale=2.0)
+    # kernel 4 (predict): 64- and 128-wide, against the fp64 CUDA-core kernel
+    for d, H, M, N in ((3, 64, 5, 1000), (10, 128, 7, 3333), (10, 128, 3, 129)):
+        rs = np.random.RandomState(3)
+        desc = mlp_desc(d, 1, (H, H))
+        xx = rs.rand(N, d) * 2 - 1
+        th = 0.4 * rs.randn(M, desc.n_params)
+        ref = ops.predict(desc, th, xx, dtype=torch.float64, want_out=True, want_moments=False)[0].cpu().numpy()
+        outs = {}
+        for name, env in (('old', '1'), ('v3', '0')):
+            os.environ['QB_NO_V3'] = env
+            outs[name] = ops.predict(desc, th, xx, dtype=torch.float32, want_out=True, want_moments=False)[0].double().cpu().numpy()
+        sc = np.abs(ref).max()
+        print(f'predict {d}-{H}-{H}-1 M={M} N={N}: old max err {np.abs(outs["old"] - ref).max() / sc:.2e}  v3 max err {np.abs(outs["v3"] - ref).max() / sc:.2e}', flush=True)
     if not quick:
         d, N, K = 3, 10000, 2368
         rs = np.random.RandomState(0)
@@ -66,3 +82,13 @@ if __name__ == '__main__':
             lp = torch.empty(K, dtype=torch.float64, device='cuda')
             med, best = timeit(lambda: ops.logpost(prob, th, lp), reps=7, warm=2)
             print(f'net 3-64-64-1 N={N} K={K} QB_NO_V3={nov3}: logpost ms {med:.3f} evals/s {K / med * 1e3:.4g} TFLOP/s {K * F_v / med / 1e9:.2f}', flush=True)
+        # config-3 predictive: 256 members x 1e6 points, 10-128-128-1
+        d, H, M, N = 10, 128, 256, 1000000
+        desc = mlp_desc(d, 1, (H, H))
+        xx = torch.as_tensor(rs.rand(N, d), dtype=torch.float32, device='cuda')
+        th = torch.as_tensor((2 * rs.rand(M, desc.n_params) - 1) / np.sqrt(H), dtype=torch.float32, device='cuda')
+        cnet = desc.to_c()
+        for nov3 in ('1', '0'):
+            os.environ['QB_NO_V3'] = nov3
+            med, best = timeit(lambda: ops.predict(desc, th, xx, dtype=torch.float32, want_out=False, want_moments=True, cnet=cnet), reps=5, warm=2)
+            print(f'predict 10-128-128-1 M={M} N={N} QB_NO_V3={nov3}: ms {med:.2f} member-points/s {M * N / med * 1e3:.4g}', flush=True)

@@ -30,11 +30,11 @@ for _ in range(3):
 torch.cuda.synchronize()
 lib = _lib.load()
 NB, NT, NE = 296, 82, 8
-buf = np.zeros(NB * 9 * NT * NE, dtype=np.uint32)
+buf = np.zeros(NB * 17 * NT * NE, dtype=np.uint32)
 sm = np.zeros(NB, dtype=np.uint32)
 rc = lib.qb_tc3_trace_dump(buf.ctypes.data_as(C.c_void_p), sm.ctypes.data_as(C.c_void_p))
 assert rc == 0
-buf = buf.reshape(NB, 9, NT, NE).astype(np.int64)
+buf = buf.reshape(NB, 17, NT, NE).astype(np.int64)
 sm = sm[:min(K, NB)]
 sm0 = sm[0]
 blocks = [b for b in range(min(K, NB)) if sm[b] == sm0]

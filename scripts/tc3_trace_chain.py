@@ -34,10 +34,10 @@ torch.cuda.synchronize()
 print(f'K={K} steps={steps}: launch {e0.elapsed_time(e1) * 1e3:.1f} us -> {e0.elapsed_time(e1) * 1e3 / steps:.1f} us per step')
 lib = _lib.load()
 NB, NT, NE = 296, 82, 8
-buf = np.zeros(NB * 9 * NT * NE, dtype=np.uint32)
+buf = np.zeros(NB * 17 * NT * NE, dtype=np.uint32)
 sm = np.zeros(NB, dtype=np.uint32)
 assert lib.qb_tc3_trace_dump(buf.ctypes.data_as(C.c_void_p), sm.ctypes.data_as(C.c_void_p)) == 0
-buf = buf.reshape(NB, 9, NT, NE).astype(np.int64)
+buf = buf.reshape(NB, 17, NT, NE).astype(np.int64)
 nb = min(K, NB)
 M = 0xFFFFFFFF
 ph = buf[:nb, 0, 81]                  # warp 0 of every block: stamps of the LAST step
