@@ -549,11 +549,12 @@ def run_native(spec, args, steps, warmup, rank, world, local, headline):
         # half of it and the 3 passes divide it by three again, so 1/6 of it is the ceiling of this algorithm on the tensor pipe.
         peak_bf16, src = measured_bf16_peak()
         sm_mhz = (clk or {}).get('sm_mhz') or 1965.0
-        v3 = spec['sampler'] == 'amcmc' and int(plan.get('threads', 0)) == 288      # warp-specialised hot-shape kernel
+        v3 = spec['sampler'] in ('amcmc', 'predict') and int(plan.get('threads', 0)) in (288, 544)      # warp-specialised kernels (qb_tc3.cuh)
         kname = {'amcmc': 'k_amcmc_tc3 (tcgen05.mma: layer 0 kind::tf32 x3 passes, hidden GEMM kind::f16 x3 passes with exact power-of-two '
                           'scaling, issued by a dedicated warp; sigmoid epilogues on MUFU; chain state in shared memory)' if v3 else
                           'k_amcmc<float,2> (tcgen05.mma kind::tf32 x3 passes + MUFU tanh epilogue)',
-                 'predict': 'k_predict_tc (tcgen05.mma kind::tf32 x3 passes + MUFU tanh epilogue)',
+                 'predict': 'k_predict_tc3 (tcgen05.mma: layer 0 kind::tf32 x3 passes, hidden GEMM kind::f16 x3 passes, dedicated issue warp; '
+                            'sigmoid epilogues on MUFU)' if v3 else 'k_predict_tc (tcgen05.mma kind::tf32 x3 passes + MUFU tanh epilogue)',
                  'hmc': 'k_hmc_tc (forward, back-propagation and weight-gradient GEMMs on tcgen05.mma kind::tf32 x3 passes)'
                  }.get(spec['sampler'], 'k_logpost_grad_tc (tcgen05.mma kind::tf32 x3 passes)')
         roofline = dict(bound='tensor', kernel=kname, achieved=achieved / 1e12, peak=peak_bf16, unit='TFLOP/s',
@@ -568,9 +569,11 @@ def run_native(spec, args, steps, warmup, rank, world, local, headline):
         if v3:
             # tensor-pipe ceiling of THIS algorithm: per point 3 x (8 x 64) tf32 MAC slots (layer 0, K padded to 8; tf32 = half the
             # bf16 rate) + 3 x (64 x 64) f16 slots against S algorithmic MACs
-            slots = 2.0 * 3 * 8 * 64 + 3.0 * 64 * 64
+            Hh = int(spec['hls'][0])
+            K0 = 8 if Hh == 64 else 16
+            slots = 2.0 * 3 * K0 * Hh + 3.0 * Hh * Hh
             roofline.update(algo_ceiling=peak_bf16 * S / slots, frac_of_algo_ceiling=achieved / 1e12 / (peak_bf16 * S / slots),
-                            algo_ceiling_note='peak x S / (bf16-equivalent MMA slots per point): layer 0 3 tf32 passes over K=8, '
+                            algo_ceiling_note='peak x S / (bf16-equivalent MMA slots per point): layer 0 3 tf32 passes over K=8 (16 for 128-wide nets), '
                                               'hidden layer 3 fp16 passes (hi*hi + lo*hi + hi*lo)')
         if spec['sampler'] in ('amcmc', 'predict'):
             # what bounds the value kernels is the sigmoid/tanh epilogue on the MUFU pipe (16 results/clk/SM): one ex2 per

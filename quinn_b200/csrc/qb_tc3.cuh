@@ -324,6 +324,37 @@ __device__ __forceinline__ Sink qb_tc3_run(const QbTcPlan& tp, QbTcCtx& cx, unsi
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __syncthreads();                               // staging complete; nobody is still inside the previous evaluation
     if (threadIdx.x == 0) qb_tc3_reset_barriers<H>(smem);
+    // Without ready-made x tiles (xs == nullptr) the COMPUTE threads lay the x tiles out: thread (point, group g) owns the four K
+    // slots 4g .. 4g+3 of its point = one 16-byte row of a core matrix of the hi and of the lo tile.  Tile u+2 is written
+    // inside EPI0(u), ahead of the arrival on a_ready(u) that lets the issue warp start layer 0 of tile u+2; tiles 0 and 1
+    // here, ahead of the block barrier.  (An issue warp that stages x itself needs ~4000 cycles per 128 x 16 tile and
+    // becomes the critical path of the 128-wide kernel: profiles/r2_tc3_trace_predict_*.log.)
+    const bool bulk = xs != nullptr;
+    auto xstage = [&](int u, const float (&xv)[4]) {
+        const int g = threadIdx.x >> 7, pt = threadIdx.x & 127;
+        float* hi = reinterpret_cast<float*>(smem + tp.v3_x) + (u % 3) * (2 * 128 * K0) + ((pt >> 3) * (K0 / 4) + g) * 32 + (pt & 7) * 4;
+        float h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = qb_tf32_hi(xv[j]);
+        *reinterpret_cast<float4*>(hi) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(hi + 128 * K0) = make_float4(xv[0] - h[0], xv[1] - h[1], xv[2] - h[2], xv[3] - h[3]);
+    };
+    auto xfetch = [&](int u, float (&xv)[4]) {
+        const int g = threadIdx.x >> 7, pt = threadIdx.x & 127;
+        const int64_t p = n0 + (int64_t)u * 128 + pt;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = 4 * g + j;
+            float v = 0.0f;
+            if (k < tp.in_dim && p < n1) v = __ldg(x + p * tp.in_dim + k);
+            xv[j] = (k == tp.in_dim) ? 1.0f : v;
+        }
+    };
+    if (!bulk && wid < D::ISSUER && 4 * (int)(threadIdx.x >> 7) < K0) {
+        float xv[4];
+        for (int u = 0; u < 2 && u < T; ++u) { xfetch(u, xv); xstage(u, xv); }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     __syncthreads();
     if (T > 0 && wid == D::ISSUER) {
         // ================================ issue warp ================================
@@ -340,8 +371,7 @@ __device__ __forceinline__ Sink qb_tc3_run(const QbTcPlan& tp, QbTcCtx& cx, unsi
         const uint32_t d0 = cx.tmem, a_hi = cx.tmem + D::COL_AHI, a_lo = cx.tmem + D::COL_ALO;
         // x tiles come either as ready-made operand images from global memory (xs: tile u = tf32 hi | lo in the canonical
         // layout, written once per launch by k_tc3_xsplit; one bulk copy per tile, completion on x_full[u % 3]) or,
-        // without such a buffer, are loaded, split and laid out by this warp (Qb3X)
-        const bool bulk = xs != nullptr;
+        // without such a buffer, from the compute threads (see above)
         const uint32_t bar_x = sb + (uint32_t)tp.v3_xbar;
         uint32_t xpar = cx.hphase;                 // parities of x_full[0..2] (they are never re-initialised)
         auto xcopy = [&](int u) {                  // one lane: start the bulk copy of tile u into ring slot u % 3
@@ -356,9 +386,6 @@ __device__ __forceinline__ Sink qb_tc3_run(const QbTcPlan& tp, QbTcCtx& cx, unsi
             qb3_wait(bar_x + (uint32_t)sl * 8u, (xpar >> sl) & 1u);
             xpar ^= 1u << sl;
         };
-        Qb3X<IN, K0> X;
-        X.in_dim = tp.in_dim;
-        auto xstore = [&](int u) { float* b = xb + (u % 3) * (2 * 128 * K0); X.store(b, b + 128 * K0, lane); };
         auto mma0 = [&](int u) {           // layer 0 of tile u: x ring slot u % 3 -> D0[u & 1]
             const uint32_t xa = xd + (uint32_t)(u % 3) * (2u * XT >> 4), d = d0 + (uint32_t)(u & 1) * (uint32_t)H;
 #pragma unroll
@@ -373,20 +400,9 @@ __device__ __forceinline__ Sink qb_tc3_run(const QbTcPlan& tp, QbTcCtx& cx, unsi
             qb3_commit((u & 1) ? sb + QB3_D0F1 : bar_d0f);
         };
         // x tiles 0 .. 2 staged up front (unless the previous evaluation left them), layer 0 of tiles 0 and 1 started
-        if (!(PRESTAGE && cx.phase)) {
-            if (bulk) {
-                if (lane == 0) for (int u = 0; u < 3 && u < T; ++u) xcopy(u);
-            } else {
-#pragma unroll 1
-                for (int u = 0; u < 3 && u < T; ++u) {
-                    X.load(x, n0 + (int64_t)u * 128, n1, lane);
-                    xstore(u);
-                }
-            }
-        }
+        if (bulk && !(PRESTAGE && cx.phase) && lane == 0)
+            for (int u = 0; u < 3 && u < T; ++u) xcopy(u);
         if (bulk) { xwait(0); if (T > 1) xwait(1); }
-        else if (T > 3) X.load(x, n0 + 3 * 128, n1, lane);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (qb3_elect()) {
             mma0(0);
@@ -424,27 +440,12 @@ __device__ __forceinline__ Sink qb_tc3_run(const QbTcPlan& tp, QbTcCtx& cx, unsi
             QB3_STAMP(t, 3);
             if (t + 3 < T) {
                 // ring slot t % 3 was read by MMA0(t), which completed before the compute warps arrived on a_ready(t)
-                if (bulk) {
-                    if (lane == 0) xcopy(t + 3);
-                } else {
-                    xstore(t + 3);
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    if (t + 4 < T) X.load(x, n0 + (int64_t)(t + 4) * 128, n1, lane);
-                }
+                if (bulk && lane == 0) xcopy(t + 3);
             }
         }
-        if (PRESTAGE) {
+        if (PRESTAGE && bulk) {
             // every MMA0 has completed (a_ready(T-1) was waited for): the ring is free
-            if (bulk) {
-                if (lane == 0) for (int u = 0; u < 3 && u < T; ++u) xcopy(u);
-            } else {
-#pragma unroll 1
-                for (int u = 0; u < 3 && u < T; ++u) {
-                    X.load(x, n0 + (int64_t)u * 128, n1, lane);
-                    xstore(u);
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            }
+            if (lane == 0) for (int u = 0; u < 3 && u < T; ++u) xcopy(u);
             cx.phase = 1u;
         }
         cx.hphase = xpar;
@@ -460,8 +461,11 @@ __device__ __forceinline__ Sink qb_tc3_run(const QbTcPlan& tp, QbTcCtx& cx, unsi
         float own0 = 0.0f, own1 = 0.0f, yt0 = 0.0f, yt1 = 0.0f;          // group 0: own partial sum / target of tiles t-1, t-2
 
         // EPI0(u): D0 -> 2^14 * s -> fp16 hi / lo -> A; the stores wait for d1_full(u - 1) = "A is free"
+        const bool xmine = !bulk && 4 * g < K0;                       // this thread lays out a row of the x tiles
         auto epi0 = [&](int u) {
             QB3_STAMP(u, 0);
+            float xv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            if (xmine && u + 2 < T) xfetch(u + 2, xv);                // consumed at the end of this epilogue
             // layer 0 of tiles u >= 2 was issued BEFORE MMA1(u-2), whose commit (d1_full(u-2), waited for in EPI0(u-1))
             // covers every earlier tcgen05 operation of the issuing thread: only the first two tiles wait on d0_full
             if (u < 2) {
@@ -497,6 +501,10 @@ __device__ __forceinline__ Sink qb_tc3_run(const QbTcPlan& tp, QbTcCtx& cx, unsi
             for (int j = 0; j < 2; ++j) {
                 qb_tmem_st8(tl + D::COL_AHI + 16 * g + 8 * j, hi[j]);
                 qb_tmem_st8(tl + D::COL_ALO + 16 * g + 8 * j, lo[j]);
+            }
+            if (xmine && u + 2 < T) {
+                xstage(u + 2, xv);        // slot (u+2) % 3 was last read by MMA0(u-1), whose D0 this thread consumed a tile ago
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             }
             qb_tmem_st_wait();
             qb_tc_fence_before();

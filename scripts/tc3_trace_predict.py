@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.join(ROOT, 'scripts'))
 from gpu_probe import mlp_desc                  # noqa: E402
 from quinn_b200 import ops, _lib                # noqa: E402
 
-d, H, M, N = 10, 128, 148, 128 * 79
+d, H, M, N = 10, 128, 148, 128 * 79 * 16
 rs = np.random.RandomState(0)
 desc = mlp_desc(d, 1, (H, H))
 xx = torch.as_tensor(rs.rand(N, d), dtype=torch.float32, device='cuda')
