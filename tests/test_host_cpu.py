@@ -115,7 +115,7 @@ def test_nn_vi_num_batches_formula():
 
 def test_tensor_core_plan_selection_is_host_logic():
     """qb_plan_info reports which value-path kernel a call will take (include/quinn_b200.h): tcgen05 for eligible fp32
-    MLPs (config 5: 256 threads / 256 tensor-memory columns; config 3: 512 / 512), CUDA cores for fp64 and for
+    MLPs (config 5: 256 compute threads + the issue warp / 256 tensor-memory columns; config 3: 512 + 32 / 512), CUDA cores for fp64 and for
     ineligible shapes, and for everything when QB_NO_TC=1."""
     import os
     from quinn_b200 import _lib
@@ -129,9 +129,9 @@ def test_tensor_core_plan_selection_is_host_logic():
         return list(out)
 
     c5 = info('mlp_c5', _lib.QB_F32)
-    assert c5[0] == 128 and c5[1] == 256 and c5[6] == 2 and c5[7] == 256 and 76 * 1024 < c5[2] <= 227 * 1024
+    assert c5[0] == 128 and c5[1] == 288 and c5[6] == 2 and c5[7] == 256 and 76 * 1024 < c5[2] <= 227 * 1024
     c3 = info('mlp_c3', _lib.QB_F32)
-    assert c3[1] == 512 and c3[6] == 2 and c3[7] == 512
+    assert c3[1] == 544 and c3[6] == 2 and c3[7] == 512
     c2 = info('mlp_c2', _lib.QB_F32)
     assert c2[6] == 2 and c2[7] == 128
     assert info('mlp_c5', _lib.QB_F64)[6] == 0                  # fp64 stays on the CUDA cores
