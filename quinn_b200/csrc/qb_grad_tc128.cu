@@ -1,0 +1,107 @@
+// quinn_b200: kernel 2 (log-posterior + gradient) on the tensor cores for the 128-wide MLPs (configs 3 / 4: ensemble
+// training, VI).  Device code: qb_tg8.cuh.  Separate translation unit so that it compiles in parallel with the others.
+#include <cuda_runtime.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+
+#include "quinn_b200.h"
+#include "qb_plan.h"
+#include "qb_device.cuh"
+#include "qb_chain.cuh"
+#include "qb_tc.cuh"
+#include "qb_tg8.cuh"
+#include "qb_grad_tc128.h"
+
+static int tg8_env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+bool qb_tg8_make_plan(const qb_net_t* net, int dtype, QbTg8Plan* tp) {
+    memset(tp, 0, sizeof(*tp));
+    if (dtype != QB_F32 || tg8_env_int("QB_NO_TC", 0) || tg8_env_int("QB_NO_TCG", 0) || tg8_env_int("QB_NO_TG8", 0)) return false;
+    if (net->n_layers != 3 || net->in_dim > 11 || net->out_dim != 1 || net->final_exp) return false;
+    const qb_layer_t& L0 = net->layers[0];
+    const qb_layer_t& L1 = net->layers[1];
+    const qb_layer_t& L2 = net->layers[2];
+    if (L0.res_step != 0.0 || L1.res_step != 0.0 || L2.res_step != 0.0) return false;
+    if (L0.n_terms > 1 || L1.n_terms > 1 || L2.n_terms > 1) return false;
+    if (L0.n_out != 128 || L1.n_out != 128) return false;
+    if (L0.act != QB_ACT_TANH || L1.act != QB_ACT_TANH || L2.act != QB_ACT_IDENTITY) return false;
+    tp->in_dim = net->in_dim; tp->ni = (net->in_dim + 1 + 3) / 4 * 4; tp->n_params = net->n_params;
+    tp->w0_off = L0.w_off; tp->b0_off = L0.b_off; tp->w1_off = L1.w_off; tp->b1_off = L1.b_off;
+    tp->wl_off = L2.w_off; tp->bl_off = L2.b_off;
+    int off = QB_TG8_HDR;
+    tp->w_img = off; off += 2 * QB_TG8_IMG;
+    tp->a_img = off; off += 2 * QB_TG8_AIMG;
+    tp->z_img = off; off += 2 * QB_TG8_IMG;
+    tp->x_img = off; off += 4 * QB_TG8_XIMG;            // directly behind the z image (the final reduction runs into it)
+    tp->fl_base = off;
+    int f = 0;
+    tp->w0 = f; f += 128 * tp->ni;
+    tp->b1 = f; f += 128;
+    tp->wl = f; f += 128;
+    tp->bl = f; f += 4;
+    tp->sc = f; f += 8;
+    off += f * 4;
+    off = (off + 15) / 16 * 16;
+    tp->ybuf = off; off += 4 * 128 * 4;
+    tp->tmem_cols = 512;
+    tp->nthreads = QB_TG8_NCOMP + 32;
+    if (off > 227 * 1024) return false;
+    tp->smem_bytes = off;
+    return true;
+}
+
+// max |x|, max |y| as float bit patterns (non-negative floats order like unsigned integers)
+__global__ void __launch_bounds__(256) k_tg8_absmax(const float* __restrict__ x, long long nx, const float* __restrict__ y, long long ny,
+                                                    unsigned int* out) {
+    float mx = 0.0f, my = 0.0f;
+    const long long stride = (long long)gridDim.x * blockDim.x, i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long i = i0; i < nx; i += stride) mx = fmaxf(mx, fabsf(__ldg(x + i)));
+    for (long long i = i0; i < ny; i += stride) my = fmaxf(my, fabsf(__ldg(y + i)));
+    unsigned int ux = __reduce_max_sync(0xffffffffu, __float_as_uint(mx)), uy = __reduce_max_sync(0xffffffffu, __float_as_uint(my));
+    if ((threadIdx.x & 31) == 0) {
+        if (ux) atomicMax(out, ux);
+        if (uy) atomicMax(out + 1, uy);
+    }
+}
+
+template <int NI>
+__global__ void __launch_bounds__(QB_TG8_NCOMP + 32, 1) k_logpost_grad_tc128(const __grid_constant__ QbTg8Plan tp, const EvalArgs<float> a,
+                                                                             const float* __restrict__ absmax) {
+    extern __shared__ __align__(1024) unsigned char smem_g[];
+    const uint32_t tmem = qb_tg8_init(tp, smem_g);
+    const long long k = blockIdx.x, s = blockIdx.y;
+    const long long n0 = s * a.pps, n1 = min(a.N, n0 + a.pps);
+    float* g = (a.S == 1) ? a.grad + k * tp.n_params : a.gpart + (k * a.S + s) * tp.n_params;
+    const float is2 = (float)a.lk.inv_sigma2;
+    qb_tg8_stage(tp, smem_g, a.theta + k * tp.n_params, absmax, is2);
+    const double ssq = qb_tg8_eval<NI>(tp, tmem, smem_g, a.x + k * a.xs, a.y + k * a.ys, n0, n1, is2, g);
+    if (threadIdx.x == 0) a.part[k * a.S + s] = ssq;
+    qb_tg8_fini(tp, tmem);
+}
+
+template <int NI>
+static cudaError_t launch_eval_t(const QbTg8Plan& tp, const EvalArgs<float>& a, const float* absmax, dim3 grid, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(k_logpost_grad_tc128<NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, tp.smem_bytes);
+    if (e != cudaSuccess) return e;
+    k_logpost_grad_tc128<NI><<<grid, tp.nthreads, tp.smem_bytes, st>>>(tp, a, absmax);
+    return cudaGetLastError();
+}
+
+cudaError_t qb_tg8_launch_eval(const QbTg8Plan& tp, const EvalArgs<float>& a, void* scratch, dim3 grid, cudaStream_t st) {
+    // scales of the fp16 operand images need max |x| and max |y| of everything this launch reads
+    cudaError_t e = cudaMemsetAsync(scratch, 0, 8, st);
+    if (e != cudaSuccess) return e;
+    const long long nx = (a.xs > 0 ? (a.K - 1) * a.xs : 0) + a.N * tp.in_dim, ny = (a.ys > 0 ? (a.K - 1) * a.ys : 0) + a.N;
+    const int blocks = (int)std::min<long long>(1184, (nx + 255) / 256);
+    k_tg8_absmax<<<blocks, 256, 0, st>>>(a.x, nx, a.y, ny, (unsigned int*)scratch);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const float* am = (const float*)scratch;
+    if (tp.ni == 4) return launch_eval_t<4>(tp, a, am, grid, st);
+    if (tp.ni == 8) return launch_eval_t<8>(tp, a, am, grid, st);
+    return launch_eval_t<12>(tp, a, am, grid, st);
+}

@@ -14,6 +14,7 @@
 #include "qb_tc.cuh"
 #include "qb_value_tc3.h"
 #include "qb_grad_tc.h"
+#include "qb_grad_tc128.h"
 
 #ifndef QB_LB_T
 #define QB_LB_T 256
@@ -454,6 +455,12 @@ template <> int launch_grad_tc<float>(const QbTcgPlan& tg, const EvalArgs<float>
     QB_CUDA(qb_tcg_launch_eval(tg, a, grid, st));
     return 0;
 }
+// kernel 2 on the tensor cores, 128-wide nets (qb_grad_tc128.cu)
+template <typename T> static int launch_grad_tc128(const QbTg8Plan&, const EvalArgs<T>&, void*, dim3, cudaStream_t) { return qb_fail("tensor-core path is fp32 only"); }
+template <> int launch_grad_tc128<float>(const QbTg8Plan& tg, const EvalArgs<float>& a, void* scratch, dim3 grid, cudaStream_t st) {
+    QB_CUDA(qb_tg8_launch_eval(tg, a, scratch, grid, st));
+    return 0;
+}
 template <typename T> static int launch_hmc_tc(const QbTcgPlan&, const ChainArgs<T>&, const HmcArgs<T>&, long long, cudaStream_t) { return qb_fail("tensor-core path is fp32 only"); }
 template <> int launch_hmc_tc<float>(const QbTcgPlan& tg, const ChainArgs<float>& c, const HmcArgs<float>& h, long long K, cudaStream_t st) {
     QB_CUDA(qb_tcg_launch_hmc(tg, c, h, K, st));
@@ -507,8 +514,13 @@ static int run_eval(const qb_net_t* net, int dtype, const void* theta, int64_t K
     dim3 grid((unsigned)K, (unsigned)L.S);
     if (want_grad) {
         QbTcgPlan tg;
+        QbTg8Plan t8;
         if (qb_tcg_make_plan(net, dtype, &tg)) {
             if (launch_grad_tc<T>(tg, a, grid, st)) return -2;
+        } else if (qb_tg8_make_plan(net, dtype, &t8)) {
+            // 128-wide nets: fp16-split operands, scaled with max |x|, max |y| (8 bytes at the end of the workspace)
+            if (launch_grad_tc128<T>(t8, a, (char*)ws + need - QB_TG8_SCRATCH_BYTES, grid, st)) return -2;
+            g_launches += 1;
         } else {
             if (set_smem(k_logpost_grad<T>, L.plan.smem_bytes)) return -2;
             k_logpost_grad<T><<<grid, L.plan.nthreads, L.plan.smem_bytes, st>>>(L.plan, a);
@@ -538,6 +550,9 @@ extern "C" size_t qb_eval_workspace_bytes(const qb_net_t* net, int dtype, int64_
     if (want_grad && L.S > 1) b += (size_t)K * L.S * net->n_params * (dtype == QB_F64 ? 8 : 4);
     QbTcPlan tp;
     if (!want_grad && make_tc_plan(net, dtype, &tp, 1) && tp.v3) b = (b + 255) / 256 * 256 + qb_tc3_xsplit_bytes(N, tp.v3 == 1 ? 8 : 16);
+    QbTcgPlan tg;
+    QbTg8Plan t8;
+    if (want_grad && !qb_tcg_make_plan(net, dtype, &tg) && qb_tg8_make_plan(net, dtype, &t8)) b = (b + 255) / 256 * 256 + QB_TG8_SCRATCH_BYTES;
     return b;
 }
 
@@ -550,6 +565,12 @@ extern "C" int qb_plan_info(const qb_net_t* net, int dtype, int64_t K, int64_t N
     if (want_grad && qb_tcg_make_plan(net, dtype, &tg)) {
         // gradient path on the tensor cores: out[6] = 3
         out[0] = 128; out[1] = tg.nthreads; out[2] = tg.smem_bytes; out[5] = 0; out[6] = 3; out[7] = tg.tmem_cols;
+    } else {
+        QbTg8Plan t8;
+        if (want_grad && qb_tg8_make_plan(net, dtype, &t8)) {
+            // 128-wide gradient path on the tensor cores (qb_tg8.cuh): out[6] = 4
+            out[0] = 128; out[1] = t8.nthreads; out[2] = t8.smem_bytes; out[5] = 0; out[6] = 4; out[7] = t8.tmem_cols;
+        }
     }
     QbTcPlan tp;
     if (!want_grad && make_tc_plan(net, dtype, &tp, 1)) {

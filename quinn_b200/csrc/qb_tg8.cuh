@@ -1,0 +1,587 @@
+// Tensor-core evaluation of the log-posterior AND its gradient (kernel 2 on tcgen05) for the 128-wide fp32 MLPs
+//   in (d <= 11) -> 128 -> 128 -> 1, tanh on both hidden layers, linear output     (BASELINE configs 3 and 4: 10-128-128-1)
+// Reverse mode of nnwrap.py:128-150 (autograd over NegLogPost, losses.py:186-206), restated in oracle/quinn_oracle.py.
+// qb_tcg.cuh (widths 32 / 64, kind::tf32) does not scale to this width: its four fp32 copies of W1 alone are 256 KB.
+//
+// Everything here is "3 x FP16": kind::f16 MMAs (K = 16 per instruction) on operands split into fp16 hi + lo
+// (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, fp32 accumulation in tensor memory), with exact power-of-two scaling so that the
+// 5-bit exponent never costs accuracy (qb_tc3.cuh uses the same arithmetic for the value path).  kind::f16 does not
+// accept an fp16 operand next to a bf16 one (scripts/tc_probe5.cu: illegal instruction), so the back-propagated
+// quantities are fp16 as well, scaled by a bound that is known BEFORE the tile loop (see qb_tg8_stage).
+//
+// One tile = 128 data points = the 128 lanes of tensor memory.  16 compute warps: thread = (point, 32 of the 128 units);
+// warp 16 only issues MMAs.  Per tile (p = point, i = layer-0 unit, j = layer-1 unit):
+//   L0    CUDA cores   a0 = tanh(W0 x + b0)                          -> a0 image, X image
+//   FWD   tcgen05      D1[p][j] = sum_i a0[p][i] W1[j][i]            A = a0 image (K-major view), B = W image (K-major view)
+//   EPI1  CUDA cores   a1 = tanh(D1 + b1); y = wl.a1 + bl; dy = (ydata - y)/sigma^2; z1 = dy wl (1 - a1^2); dwl += dy a1
+//                                                                    -> z image
+//   BWD   tcgen05      D0[p][i] = sum_j z1[p][j] W1[j][i]            A = z image (K-major view), B = W image (MN-major view)
+//   DW1   tcgen05      G1[j][i] += sum_p z1[p][j] a0[p][i]           A = z image, B = a0 image (+ a block of ones: db1), MN-major views
+//   EPI0  CUDA cores   z0 = D0 (1 - a0^2)                            -> z image (over z1, once DW1 has read it)
+//   DW0   tcgen05      G0[i][c] += sum_p z0[p][i] X[p][c]            A = z image, B = X image = [x | 1 | 0] (column d: db0)
+// G1 (128 x 144) and G0 (128 x 16) stay in tensor memory for the whole evaluation.
+//
+// Shared-memory operands: ONE image per matrix serves both of its uses (scripts/tc_probe5.cu, no swizzle):
+//   point image P (a0, z, X):  element (point p, unit u) at (u/8)*2048 + (p/8)*128 + (p%8)*16 + (u%8)*2
+//       K-major view  (rows = points, k = units):  LBO 2048 (8-unit chunks),  SBO 128 (8-point groups), k-step +4096
+//       MN-major view (rows = units,  k = points): LBO 128 (8-point groups),  SBO 2048 (8-unit chunks), k-step +256
+//   weight image W (W1[j][i]): element (j, i) at (j/8)*2048 + (i/8)*128 + (j%8)*16 + (i%8)*2
+//       K-major view  (rows = j, k = i):           LBO 128,  SBO 2048, k-step +256
+//       MN-major view (rows = i, k = j):           LBO 2048, SBO 128,  k-step +4096
+// A thread writes its point's 8-unit chunk with one 16-byte store; the 32 lanes of a warp cover 512 contiguous bytes.
+//
+// Pipeline (two block-wide hand-overs per tile, as in qb_tcg.cuh):
+//   phase B(t): wait FWD(t) -> EPI1(t) -> [wait DW0(t-1)] z1 -> z image                        => issue BWD(t), DW1(t)
+//   phase A(t): wait BWD(t) -> EPI0(t) (z0 parked in the D1 columns of tensor memory) and L0(t+1) (registers) while
+//               DW1(t) still reads both images -> wait DW1(t) -> z0 -> z image, a0(t+1) -> a0 image   => issue FWD(t+1), DW0(t)
+//   DW0(t) runs under EPI1(t+1).
+#pragma once
+#include <stdint.h>
+#include "qb_plan.h"
+#include "qb_tc.cuh"
+#include "qb_tc3.cuh"
+
+struct QbTg8Plan {
+    int in_dim, ni, n_params;
+    int w0_off, b0_off, w1_off, b1_off, wl_off, bl_off;   // offsets in theta (b*_off < 0: no bias)
+    int w_img, a_img, z_img, x_img;                       // byte offsets: hi image, then lo image (X: two tiles of hi | lo)
+    int fl_base, w0, b1, wl, bl, sc;                      // float area (byte offset) and float indices in it
+    int ybuf;                                             // byte offset: [4][128] partial outputs
+    int tmem_cols, nthreads, smem_bytes;
+};
+
+#ifdef __CUDACC__
+enum { QB_TG8_BAR_F = 320, QB_TG8_BAR_B = 328, QB_TG8_BAR_W = 336, QB_TG8_BAR_Z = 344, QB_TG8_BAR_RDY = 352, QB_TG8_SLOT = 360,
+       QB_TG8_HDR = 512, QB_TG8_IMG = 32768, QB_TG8_AIMG = 36864, QB_TG8_XIMG = 4096, QB_TG8_NCOMP = 512 };
+enum { QB_TG8_C_D1 = 0, QB_TG8_C_D0 = 128, QB_TG8_C_DW1 = 256, QB_TG8_C_DW0 = 400 };
+// float slots behind tp.sc
+enum { QB_TG8_S_C1 = 0, QB_TG8_S_SZ1 = 1, QB_TG8_S_K0 = 2, QB_TG8_S_UW1 = 3, QB_TG8_S_UW0 = 4, QB_TG8_S_SX = 5 };
+
+__device__ __forceinline__ float qb_tg8_pow2(int e) { return __uint_as_float((uint32_t)(127 + max(-126, min(127, e))) << 23); }
+
+// all threads: tensor-memory allocation and the mbarriers
+__device__ __forceinline__ uint32_t qb_tg8_init(const QbTg8Plan& tp, unsigned char* smem) {
+    if ((threadIdx.x >> 5) == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(qb_smem_u32(smem + QB_TG8_SLOT)), "r"((uint32_t)tp.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x == 0) {
+        const uint32_t b = qb_smem_u32(smem);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB_TG8_BAR_F), "r"(1u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB_TG8_BAR_B), "r"(1u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB_TG8_BAR_W), "r"(1u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB_TG8_BAR_Z), "r"(1u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB_TG8_BAR_RDY), "r"((uint32_t)QB_TG8_NCOMP) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    qb_tc_fence_before();
+    __syncthreads();
+    qb_tc_fence_after();
+    return *reinterpret_cast<volatile uint32_t*>(smem + QB_TG8_SLOT);
+}
+__device__ __forceinline__ void qb_tg8_fini(const QbTg8Plan& tp, uint32_t tmem) {
+    qb_tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)tp.tmem_cols) : "memory");
+}
+// thread 0, between two block barriers: every phase of the previous evaluation has completed, start again at parity 0
+__device__ __forceinline__ void qb_tg8_reset_barriers(unsigned char* smem) {
+    const uint32_t b = qb_smem_u32(smem);
+    const uint32_t off[5] = {QB_TG8_BAR_F, QB_TG8_BAR_B, QB_TG8_BAR_W, QB_TG8_BAR_Z, QB_TG8_BAR_RDY};
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"(b + off[i]) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + off[i]), "r"(i == 4 ? (uint32_t)QB_TG8_NCOMP : 1u) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void qb_tg8_st4(uint32_t taddr, const uint32_t (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
+// fp16 pair -> two floats
+__device__ __forceinline__ float2 qb_tg8_unpack(uint32_t w) {
+    float a, b;
+    asm("{ .reg .b16 l, h; mov.b32 {l, h}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, h; }" : "=f"(a), "=f"(b) : "r"(w));
+    return make_float2(a, b);
+}
+// (x0, x1) -> fp16 pair hi (round to nearest) and fp16 pair lo = x - hi
+__device__ __forceinline__ void qb_tg8_split(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    uint32_t nlo;
+    qb3_split_f16(x0, x1, hi, nlo);
+    lo = nlo ^ 0x80008000u;
+}
+// S * tanh of four pre-activations that were already multiplied by 2 log2 e (one reciprocal for the four, as
+// qb_tanh4_prescaled)
+__device__ __forceinline__ void qb_tg8_tanh4(float2& a, float2& b, float S) {
+    const float2 one = make_float2(1.0f, 1.0f), s2 = make_float2(S, S), m2 = make_float2(-2.0f * S, -2.0f * S);
+    float2 ea, eb;
+    ea.x = qb_ex2(qb_min_nan(a.x, 30.0f)); ea.y = qb_ex2(qb_min_nan(a.y, 30.0f));
+    eb.x = qb_ex2(qb_min_nan(b.x, 30.0f)); eb.y = qb_ex2(qb_min_nan(b.y, 30.0f));
+    const float2 da = __fadd2_rn(ea, one), db = __fadd2_rn(eb, one);
+    const float2 m = __fmul2_rn(da, db);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(m.x * m.y));
+    float2 rr;
+    rr.x = r * m.y; rr.y = r * m.x;
+    const float2 ia = __fmul2_rn(rr, db), ib = __fmul2_rn(rr, da);
+    a = __ffma2_rn(ia, m2, s2);
+    b = __ffma2_rn(ib, m2, s2);
+}
+
+// flat theta (global) -> shared.  All threads of the block; ends with the async-proxy fence.
+//   F[w0 ..]  : layer-0 rows (paired units, bias in slot in_dim), times 2 log2 e
+//   W image   : fp16 hi / lo of 2^sW * W1, max |2^sW W1| in [2^13, 2^14)
+//   F[b1 + j] = 2 log2 e * b1_j;  F[wl + j] = wl_j;  F[bl]
+//   ones block of the a0 image (units 128 .. 143 of every point: 2^14, 0, 0, ..): column 128 of G1 becomes db1
+//   scales (all powers of two, exact):
+//     a0 image = 2^14 a0;  X image = 2^sX x (max |x| from absmax[0], ones column 2^sX);
+//     z1 image = sz1 z1 with sz1 * B1 <= 2^14 where |z1| <= B1 = (max|y| + |bl| + sum|wl|) / sigma^2 * max|wl|   (|a1| <= 1)
+//     z0 image = sz0 z0 with sz0 * B0 <= 2^14 where |z0| <= B0 = B1 * max_i sum_j |W1[j][i]|
+//   A value far below its bound loses nothing until it is 2^17 below it (fp16 keeps 2^15 .. 2^-24; hi and lo need 22 bits).
+__device__ __forceinline__ void qb_tg8_stage(const QbTg8Plan& tp, unsigned char* smem, const float* __restrict__ theta,
+                                             const float* __restrict__ absmax, float is2) {
+    constexpr int H = 128;
+    float* F = reinterpret_cast<float*>(smem + tp.fl_base);
+    float* sred = reinterpret_cast<float*>(smem);                      // [17][4]
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const float fold = 2.8853900817779268f;
+    float mx = 0.0f, cs = 0.0f, wa = 0.0f;
+    for (int e = tid; e < H * H; e += nt) mx = fmaxf(mx, fabsf(theta[tp.w1_off + e]));
+    if (tid < H) {
+        for (int j = 0; j < H; ++j) cs += fabsf(theta[tp.w1_off + j * H + tid]);
+        wa = fabsf(theta[tp.wl_off + tid]);
+    }
+    float ws = wa;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        cs = fmaxf(cs, __shfl_xor_sync(0xffffffffu, cs, off));
+        wa = fmaxf(wa, __shfl_xor_sync(0xffffffffu, wa, off));
+        ws += __shfl_xor_sync(0xffffffffu, ws, off);
+    }
+    __syncthreads();                       // the previous evaluation's readers of the header / float area are done
+    if (lane == 0) { sred[4 * wid + 0] = mx; sred[4 * wid + 1] = cs; sred[4 * wid + 2] = wa; sred[4 * wid + 3] = ws; }
+    __syncthreads();
+    mx = cs = wa = ws = 0.0f;
+    for (int w = 0; w < (nt + 31) >> 5; ++w) {
+        mx = fmaxf(mx, sred[4 * w + 0]); cs = fmaxf(cs, sred[4 * w + 1]); wa = fmaxf(wa, sred[4 * w + 2]); ws += sred[4 * w + 3];
+    }
+    auto ilog = [](float v, int dflt) { return (v > 0.0f && v < 3.0e38f) ? ilogbf(v) : dflt; };
+    const int sW = max(-40, min(40, 13 - ilog(mx, 13)));
+    const int sX = max(-24, min(14, 13 - ilog(absmax[0], 13)));
+    const float blv = tp.bl_off >= 0 ? theta[tp.bl_off] : 0.0f;
+    const float B1 = (absmax[1] + fabsf(blv) + ws) * is2 * wa;
+    const int e1 = max(-50, min(50, ilog(B1, -1) + 1));
+    const int e0 = max(-50, min(50, ilog(B1 * cs, -1) + 1));
+    const float wscale = qb_tg8_pow2(sW);
+    // ---- layer 0 (CUDA cores): pairs of units
+    for (int e = tid; e < H * tp.ni; e += nt) {
+        const int u = e & 1, q = (e >> 1) % tp.ni, j = ((e >> 1) / tp.ni) * 2 + u;
+        float v = 0.0f;
+        if (q < tp.in_dim) v = theta[tp.w0_off + j * tp.in_dim + q] * fold;
+        else if (q == tp.in_dim && tp.b0_off >= 0) v = theta[tp.b0_off + j] * fold;
+        F[tp.w0 + e] = v;
+    }
+    // ---- W image: word index of the pair (j, i), (j, i + 1)
+    {
+        uint32_t* hi = reinterpret_cast<uint32_t*>(smem + tp.w_img);
+        uint32_t* lo = hi + QB_TG8_IMG / 4;
+        for (int e = tid; e < H * H / 2; e += nt) {
+            const int j = e >> 6, i = (e & 63) * 2;
+            const float w0 = theta[tp.w1_off + j * H + i], w1 = theta[tp.w1_off + j * H + i + 1];
+            uint32_t h2, l2;
+            qb_tg8_split(w0 * wscale, w1 * wscale, h2, l2);
+            const int idx = (((j >> 3) * (H / 8) + (i >> 3)) * 64 + (j & 7) * 8 + (i & 7)) >> 1;
+            hi[idx] = h2; lo[idx] = l2;
+        }
+    }
+    // ---- ones block of the a0 image
+    {
+        uint32_t* hi = reinterpret_cast<uint32_t*>(smem + tp.a_img + QB_TG8_IMG);            // units 128 .. 143
+        uint32_t* lo = reinterpret_cast<uint32_t*>(smem + tp.a_img + QB_TG8_AIMG + QB_TG8_IMG);
+        for (int e = tid; e < 2 * 2048 / 4; e += nt) {
+            // chunk 16 (units 128 .. 135): word 0 of every point's 16-byte row holds (2^14, 0)
+            hi[e] = (e < 512 && (e & 3) == 0) ? 0x00007400u : 0u;
+            lo[e] = 0u;
+        }
+    }
+    for (int j = tid; j < H; j += nt) {
+        F[tp.b1 + j] = tp.b1_off >= 0 ? theta[tp.b1_off + j] * fold : 0.0f;
+        F[tp.wl + j] = theta[tp.wl_off + j];
+    }
+    if (tid == 0) {
+        F[tp.bl] = blv;
+        F[tp.sc + QB_TG8_S_C1] = fold * qb_tg8_pow2(-14 - sW);
+        F[tp.sc + QB_TG8_S_SZ1] = qb_tg8_pow2(14 - e1);
+        F[tp.sc + QB_TG8_S_K0] = qb_tg8_pow2(-sW + e1 - e0);            // D0 / (sz1 2^sW) * sz0
+        F[tp.sc + QB_TG8_S_UW1] = qb_tg8_pow2(-14 - (14 - e1));
+        F[tp.sc + QB_TG8_S_UW0] = qb_tg8_pow2(-sX - (14 - e0));
+        F[tp.sc + QB_TG8_S_SX] = qb_tg8_pow2(sX);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---- MMA issue (one elected lane of the issue warp).  Descriptors are {lo, hi} 32-bit halves; k-steps add a constant to lo.
+__device__ __forceinline__ void qb_tg8_mma(uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t acc) {
+    asm volatile("{ .reg .pred p; .reg .b64 da, db; setp.ne.b32 p, %6, 0; mov.b64 da, {%1, %2}; mov.b64 db, {%3, %4}; "
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p; }"
+                 :: "r"(d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ uint32_t qb_tg8_dlo(uint32_t saddr, uint32_t lbo) { return ((saddr >> 4) & 0x3FFFu) | ((lbo >> 4) << 16); }
+__device__ __forceinline__ uint32_t qb_tg8_dhi(uint32_t sbo) { return (sbo >> 4) | (1u << 14); }
+// three passes (a_lo*b_hi, a_hi*b_lo, a_hi*b_hi) x 8 k-steps of 16; *_lo32 are descriptor low words of the hi / lo images
+__device__ __forceinline__ void qb_tg8_issue3(uint32_t d, uint32_t a_hi_img, uint32_t a_lo_img, uint32_t a_dhi, uint32_t a_step,
+                                              uint32_t b_hi_img, uint32_t b_lo_img, uint32_t b_dhi, uint32_t b_step, uint32_t idesc,
+                                              uint32_t acc0) {
+    // the bases are laundered so that ptxas forms the 24 descriptor pairs here, next to their MMAs: hoisted out of the tile
+    // loop, the ~120 pairs of the four GEMMs overflow the uniform register file and come back from local memory
+    asm volatile("" : "+r"(a_hi_img), "+r"(a_lo_img), "+r"(b_hi_img), "+r"(b_lo_img));
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const uint32_t a = (pass == 0 ? a_lo_img : a_hi_img) + a_step * s;
+            const uint32_t b = (pass == 1 ? b_lo_img : b_hi_img) + b_step * s;
+            qb_tg8_mma(d, a, a_dhi, b, b_dhi, idesc, (pass == 0 && s == 0) ? acc0 : 1u);
+        }
+    }
+}
+
+// Value + gradient of the data term over points [n0, n1) for the staged parameter vector.  Every thread of the block
+// (512 compute threads + the issue warp) calls it.  Returns the block-wide sum of squared residuals; g[0..P) (global, this
+// block's row) receives d/dtheta of -0.5*ssq/sigma^2.
+template <int NI>
+__device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem, unsigned char* smem, const float* __restrict__ x,
+                                              const float* __restrict__ y, int64_t n0, int64_t n1, float is2, float* __restrict__ g) {
+    constexpr int H = 128;
+    const float* F = reinterpret_cast<const float*>(smem + tp.fl_base);
+    const uint32_t sb = qb_smem_u32(smem);
+    const uint32_t bar_f = sb + QB_TG8_BAR_F, bar_b = sb + QB_TG8_BAR_B, bar_w = sb + QB_TG8_BAR_W, bar_z = sb + QB_TG8_BAR_Z,
+                   bar_rdy = sb + QB_TG8_BAR_RDY;
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T = (int)((n1 - n0 + 127) / 128);
+    __syncthreads();                               // staging complete; nobody is still inside the previous evaluation
+    if (threadIdx.x == 0) qb_tg8_reset_barriers(smem);
+    __syncthreads();
+    float ssq = 0.0f, dbl = 0.0f;
+    float dwl[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) dwl[i] = 0.0f;
+
+    if (wid == QB_TG8_NCOMP / 32) {
+        // ================================ issue warp ================================
+        const uint32_t id_base = (1u << 4) | ((128u >> 4) << 24);
+        const uint32_t id_fwd = id_base | ((128u >> 3) << 17);
+        const uint32_t id_bwd = id_fwd | (1u << 16);
+        const uint32_t id_dw1 = id_base | (1u << 15) | (1u << 16) | ((144u >> 3) << 17);
+        const uint32_t id_dw0 = id_base | (1u << 15) | (1u << 16) | ((16u >> 3) << 17);
+        const uint32_t dh_a = qb_tg8_dhi(128u), dh_b = qb_tg8_dhi(2048u);          // (LBO 2048, SBO 128) / (LBO 128, SBO 2048)
+        const uint32_t a_img = sb + (uint32_t)tp.a_img, z_img = sb + (uint32_t)tp.z_img, w_img = sb + (uint32_t)tp.w_img;
+        // K-major views of the point images and the MN-major view of W: LBO 2048; the other views: LBO 128
+        const uint32_t aK_hi = qb_tg8_dlo(a_img, 2048u), aK_lo = qb_tg8_dlo(a_img + QB_TG8_AIMG, 2048u);
+        const uint32_t aM_hi = qb_tg8_dlo(a_img, 128u), aM_lo = qb_tg8_dlo(a_img + QB_TG8_AIMG, 128u);
+        const uint32_t zK_hi = qb_tg8_dlo(z_img, 2048u), zK_lo = qb_tg8_dlo(z_img + QB_TG8_IMG, 2048u);
+        const uint32_t zM_hi = qb_tg8_dlo(z_img, 128u), zM_lo = qb_tg8_dlo(z_img + QB_TG8_IMG, 128u);
+        const uint32_t wK_hi = qb_tg8_dlo(w_img, 128u), wK_lo = qb_tg8_dlo(w_img + QB_TG8_IMG, 128u);
+        const uint32_t wM_hi = qb_tg8_dlo(w_img, 2048u), wM_lo = qb_tg8_dlo(w_img + QB_TG8_IMG, 2048u);
+        uint32_t n = 0;
+        auto wait_rdy = [&]() {
+            qb3_wait(bar_rdy, n & 1u);
+            ++n;
+            qb_tc_fence_after();
+            __syncwarp();
+        };
+        if (T > 0) {
+            wait_rdy();
+            if (qb3_elect()) {
+                qb_tg8_issue3(tmem + QB_TG8_C_D1, aK_hi, aK_lo, dh_a, 256u, wK_hi, wK_lo, dh_b, 16u, id_fwd, 0u);
+                qb3_commit(bar_f);
+            }
+            __syncwarp();
+        }
+#pragma unroll 1
+        for (int t = 0; t < T; ++t) {
+            const uint32_t acc0 = t > 0 ? 1u : 0u;
+            wait_rdy();                                                   // z1(t) is in the z image
+            if (qb3_elect()) {
+                qb_tg8_issue3(tmem + QB_TG8_C_D0, zK_hi, zK_lo, dh_a, 256u, wM_hi, wM_lo, dh_a, 256u, id_bwd, 0u);
+                qb3_commit(bar_b);
+                qb_tg8_issue3(tmem + QB_TG8_C_DW1, zM_hi, zM_lo, dh_b, 16u, aM_hi, aM_lo, dh_b, 16u, id_dw1, acc0);
+                qb3_commit(bar_w);
+            }
+            __syncwarp();
+            wait_rdy();                                                   // z0(t) is in the z image, a0(t+1) in the a0 image
+            if (qb3_elect()) {
+                if (t + 1 < T) {
+                    qb_tg8_issue3(tmem + QB_TG8_C_D1, aK_hi, aK_lo, dh_a, 256u, wK_hi, wK_lo, dh_b, 16u, id_fwd, 0u);
+                    qb3_commit(bar_f);
+                }
+                const uint32_t x_img = sb + (uint32_t)tp.x_img + (uint32_t)(t & 1) * 2u * QB_TG8_XIMG;
+                qb_tg8_issue3(tmem + QB_TG8_C_DW0, zM_hi, zM_lo, dh_b, 16u, qb_tg8_dlo(x_img, 128u), qb_tg8_dlo(x_img + QB_TG8_XIMG, 128u),
+                              dh_b, 16u, id_dw0, acc0);
+                qb3_commit(bar_z);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ================================ compute warps ================================
+        const int quarter = wid & 3, grp = wid >> 2;
+        const uint32_t pt = (uint32_t)(quarter * 32 + lane);               // this thread's point of the tile = tensor-memory lane
+        const int c = grp * 32;                                            // this thread's units
+        const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t poff = (pt >> 3) * 128u + (pt & 7u) * 16u + (uint32_t)(c >> 3) * 2048u;     // chunk j of this thread: + 2048 j
+        unsigned char* a_hi = smem + tp.a_img + poff; unsigned char* a_lo = a_hi + QB_TG8_AIMG;
+        unsigned char* z_hi = smem + tp.z_img + poff; unsigned char* z_lo = z_hi + QB_TG8_IMG;
+        float* ybuf = reinterpret_cast<float*>(smem + tp.ybuf);
+        const float c1 = F[tp.sc + QB_TG8_S_C1], sz1 = F[tp.sc + QB_TG8_S_SZ1], k0 = F[tp.sc + QB_TG8_S_K0], sx = F[tp.sc + QB_TG8_S_SX];
+        const float4* B4 = reinterpret_cast<const float4*>(F + tp.b1 + c);
+        const float4* W4 = reinterpret_cast<const float4*>(F + tp.wl + c);
+
+        auto publish = [&]() {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            qb_tc_fence_before();
+            qb_mbar_arrive(bar_rdy);
+        };
+        // 32 packed columns (16 hi words | 16 lo words of this thread's 32 units) parked at tensor-memory column `col` -> images
+        auto unpark = [&](uint32_t col, unsigned char* hi, unsigned char* lo) {
+            uint32_t v[16];
+            qb_tmem_ld16(tl + col + c, v);
+            qb_tmem_ld_wait16(v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(hi + 2048 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            qb_tmem_ld16(tl + col + c + 16, v);
+            qb_tmem_ld_wait16(v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(lo + 2048 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        };
+        // layer 0 of tile tt: X image (groups 0 and 1: one 8-column chunk each) and 2^14 a0, packed, parked in the D0 columns
+        // (free between EPI0(t) and BWD(t+1)).  Returns the target of this thread's point.
+        auto layer0 = [&](int tt) -> float {
+            const int64_t pp = n0 + (int64_t)tt * 128 + pt;
+            float xr[NI];
+#pragma unroll
+            for (int q = 0; q < NI; ++q) xr[q] = (q < tp.in_dim && pp < n1) ? __ldg(x + pp * tp.in_dim + q) : 0.0f;
+            const float yt = pp < n1 ? __ldg(y + pp) : 0.0f;
+#pragma unroll
+            for (int q = 0; q < NI; ++q) xr[q] = (q == tp.in_dim) ? 1.0f : xr[q];
+            if (grp < 2) {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    float v0 = 0.0f, v1 = 0.0f;
+#pragma unroll
+                    for (int q = 0; q < NI; ++q) {              // selects: no indexed register access
+                        if (q == 8 * grp + 2 * w) v0 = xr[q] * sx;
+                        if (q == 8 * grp + 2 * w + 1) v1 = xr[q] * sx;
+                    }
+                    qb_tg8_split(v0, v1, h[w], l[w]);
+                }
+                unsigned char* xi = smem + tp.x_img + (tt & 1) * 2 * QB_TG8_XIMG + grp * 2048 + (pt >> 3) * 128u + (pt & 7u) * 16u;
+                *reinterpret_cast<uint4*>(xi) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(xi + QB_TG8_XIMG) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+            const float4* W = reinterpret_cast<const float4*>(F + tp.w0 + c * NI);
+#pragma unroll
+            for (int jc = 0; jc < 4; ++jc) {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int g2 = 0; g2 < 2; ++g2) {
+                    const int gq = 2 * jc + g2;
+                    float2 z0 = make_float2(0.0f, 0.0f), z1 = make_float2(0.0f, 0.0f);
+#pragma unroll
+                    for (int q = 0; q < NI; q += 2) {
+                        const float4 wa = W[(2 * gq) * (NI / 2) + q / 2], wb = W[(2 * gq + 1) * (NI / 2) + q / 2];
+                        z0 = __ffma2_rn(make_float2(wa.x, wa.y), make_float2(xr[q], xr[q]), z0);
+                        z0 = __ffma2_rn(make_float2(wa.z, wa.w), make_float2(xr[q + 1], xr[q + 1]), z0);
+                        z1 = __ffma2_rn(make_float2(wb.x, wb.y), make_float2(xr[q], xr[q]), z1);
+                        z1 = __ffma2_rn(make_float2(wb.z, wb.w), make_float2(xr[q + 1], xr[q + 1]), z1);
+                    }
+                    qb_tg8_tanh4(z0, z1, 16384.0f);
+                    qb_tg8_split(z0.x, z0.y, h[2 * g2], l[2 * g2]);
+                    qb_tg8_split(z1.x, z1.y, h[2 * g2 + 1], l[2 * g2 + 1]);
+                }
+                qb_tg8_st4(tl + QB_TG8_C_D0 + c + 4 * jc, h);
+                qb_tg8_st4(tl + QB_TG8_C_D0 + c + 16 + 4 * jc, l);
+            }
+            return yt;
+        };
+
+        float yv = 0.0f;                                             // target of this thread's point of the current tile
+        if (T > 0) {
+            yv = layer0(0);
+            qb_tmem_st_wait();
+            unpark(QB_TG8_C_D0, a_hi, a_lo);
+            publish();
+        }
+#pragma unroll 1
+        for (int t = 0; t < T; ++t) {
+            const int64_t p = n0 + (int64_t)t * 128 + pt;
+            const bool live = p < n1;
+            const bool more = t + 1 < T;
+            // ---------------- phase B: EPI1(t)
+            qb3_wait(bar_f, (uint32_t)t & 1u);
+            qb_tc_fence_after();
+            {
+                float2 acc = make_float2(0.0f, 0.0f);
+                const float2 c2 = make_float2(c1, c1);
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t v[16];
+                    qb_tmem_ld16(tl + QB_TG8_C_D1 + c + 16 * hf, v);
+                    qb_tmem_ld_wait16(v);
+#pragma unroll
+                    for (int gq = 0; gq < 4; ++gq) {
+                        const float4 b = B4[4 * hf + gq], w = W4[4 * hf + gq];
+                        float2 z0 = __ffma2_rn(make_float2(__uint_as_float(v[4 * gq]), __uint_as_float(v[4 * gq + 1])), c2, make_float2(b.x, b.y));
+                        float2 z1 = __ffma2_rn(make_float2(__uint_as_float(v[4 * gq + 2]), __uint_as_float(v[4 * gq + 3])), c2, make_float2(b.z, b.w));
+                        qb_tg8_tanh4(z0, z1, 1.0f);
+                        acc = __ffma2_rn(make_float2(w.x, w.y), z0, acc);
+                        acc = __ffma2_rn(make_float2(w.z, w.w), z1, acc);
+                        v[4 * gq] = __float_as_uint(z0.x); v[4 * gq + 1] = __float_as_uint(z0.y);
+                        v[4 * gq + 2] = __float_as_uint(z1.x); v[4 * gq + 3] = __float_as_uint(z1.y);
+                    }
+                    qb_tmem_st16(tl + QB_TG8_C_D1 + c + 16 * hf, v);           // a1 waits in the accumulator's columns
+                }
+                ybuf[grp * 128 + pt] = acc.x + acc.y;
+                qb_tmem_st_wait();
+                asm volatile("bar.sync %0, %1;" :: "r"(1 + quarter), "n"(128) : "memory");
+                float yo = F[tp.bl];
+#pragma unroll
+                for (int gg = 0; gg < 4; ++gg) yo += ybuf[gg * 128 + pt];
+                const float r = live ? yv - yo : 0.0f;
+                const float dy = r * is2, dyz = dy * sz1;
+                if (grp == 0) { ssq = fmaf(r, r, ssq); dbl += dy; }
+                if (t > 0) { qb3_wait(bar_z, (uint32_t)(t - 1) & 1u); qb_tc_fence_after(); }     // DW0(t-1) has read the z image
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t v[16];
+                    qb_tmem_ld16(tl + QB_TG8_C_D1 + c + 16 * hf, v);
+                    qb_tmem_ld_wait16(v);
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) {
+                        uint32_t h[4], l[4];
+#pragma unroll
+                        for (int g2 = 0; g2 < 2; ++g2) {
+                            const int gq = 2 * jj + g2;
+                            const float4 w = W4[4 * hf + gq];
+                            const float wv[4] = {w.x, w.y, w.z, w.w};
+                            float z[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float a = __uint_as_float(v[4 * gq + e]);
+                                z[e] = dyz * wv[e] * fmaf(-a, a, 1.0f);
+                                dwl[16 * hf + 4 * gq + e] = fmaf(dy, a, dwl[16 * hf + 4 * gq + e]);
+                            }
+                            qb_tg8_split(z[0], z[1], h[2 * g2], l[2 * g2]);
+                            qb_tg8_split(z[2], z[3], h[2 * g2 + 1], l[2 * g2 + 1]);
+                        }
+                        *reinterpret_cast<uint4*>(z_hi + 2048 * (2 * hf + jj)) = make_uint4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<uint4*>(z_lo + 2048 * (2 * hf + jj)) = make_uint4(l[0], l[1], l[2], l[3]);
+                    }
+                }
+            }
+            publish();
+            // ---------------- phase A: EPI0(t) and L0(t+1) while DW1(t) runs; both results parked in tensor memory
+            qb3_wait(bar_b, (uint32_t)t & 1u);
+            qb_tc_fence_after();
+            {
+                const float2 k2 = make_float2(k0, k0), sa = make_float2(6.103515625e-05f, 6.103515625e-05f), one = make_float2(1.0f, 1.0f);
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t v[16];
+                    qb_tmem_ld16(tl + QB_TG8_C_D0 + c + 16 * hf, v);
+                    qb_tmem_ld_wait16(v);
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) {
+                        const uint4 h4 = *reinterpret_cast<const uint4*>(a_hi + 2048 * (2 * hf + jj));
+                        const uint4 l4 = *reinterpret_cast<const uint4*>(a_lo + 2048 * (2 * hf + jj));
+                        const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+                        uint32_t h[4], l[4];
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) {
+                            float2 a = __fadd2_rn(qb_tg8_unpack(hw[w]), qb_tg8_unpack(lw[w]));
+                            a = __fmul2_rn(a, sa);
+                            const float2 da = __ffma2_rn(make_float2(-a.x, -a.y), a, one);
+                            const float2 d = make_float2(__uint_as_float(v[8 * jj + 2 * w]), __uint_as_float(v[8 * jj + 2 * w + 1]));
+                            const float2 z = __fmul2_rn(__fmul2_rn(d, k2), da);
+                            qb_tg8_split(z.x, z.y, h[w], l[w]);
+                        }
+                        // parked in the D1 columns (free between EPI1(t) and FWD(t+1)): the z image is still an operand of DW1(t)
+                        qb_tg8_st4(tl + QB_TG8_C_D1 + c + 4 * (2 * hf + jj), h);
+                        qb_tg8_st4(tl + QB_TG8_C_D1 + c + 16 + 4 * (2 * hf + jj), l);
+                    }
+                }
+            }
+            if (more) yv = layer0(t + 1);
+            qb_tmem_st_wait();
+            qb3_wait(bar_w, (uint32_t)t & 1u);                      // DW1(t) has read the z and a0 images
+            qb_tc_fence_after();
+            unpark(QB_TG8_C_D1, z_hi, z_lo);
+            if (more) unpark(QB_TG8_C_D0, a_hi, a_lo);
+            publish();
+        }
+        if (T > 0) { qb3_wait(bar_z, (uint32_t)(T - 1) & 1u); qb_tc_fence_after(); }
+
+        // ---------------- gradient out: row j (G1) / i (G0) = this thread's tensor-memory lane
+        const int d = tp.in_dim;
+        if (T > 0) {
+            const float uw1 = F[tp.sc + QB_TG8_S_UW1], uw0 = F[tp.sc + QB_TG8_S_UW0];
+            const bool al16 = (reinterpret_cast<uintptr_t>(g + tp.w1_off) & 15) == 0;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t v[16];
+                qb_tmem_ld16(tl + QB_TG8_C_DW1 + c + 16 * hf, v);
+                qb_tmem_ld_wait16(v);
+                float* dst = g + tp.w1_off + pt * H + c + 16 * hf;
+                if (al16) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        reinterpret_cast<float4*>(dst)[q] = make_float4(__uint_as_float(v[4 * q]) * uw1, __uint_as_float(v[4 * q + 1]) * uw1,
+                                                                        __uint_as_float(v[4 * q + 2]) * uw1, __uint_as_float(v[4 * q + 3]) * uw1);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) dst[q] = __uint_as_float(v[q]) * uw1;
+                }
+            }
+            if (grp == 0) {
+                uint32_t v[16];
+                qb_tmem_ld16(tl + QB_TG8_C_DW1 + 128, v);              // column 128: db1
+                qb_tmem_ld_wait16(v);
+                if (tp.b1_off >= 0) g[tp.b1_off + pt] = __uint_as_float(v[0]) * uw1;
+                qb_tmem_ld16(tl + QB_TG8_C_DW0, v);                    // columns < d: dW0, column d: db0
+                qb_tmem_ld_wait16(v);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    if (q < d) g[tp.w0_off + pt * d + q] = __uint_as_float(v[q]) * uw0;
+                    else if (q == d && tp.b0_off >= 0) g[tp.b0_off + pt] = __uint_as_float(v[q]) * uw0;
+                }
+            }
+        }
+    }
+    if (T <= 0)
+        for (int i = threadIdx.x; i < tp.n_params; i += blockDim.x) g[i] = 0.0f;
+    // dWl[j] = sum over the 128 point slots of the per-thread partial sums (fixed order); the z / X images are free now
+    qb_tc_fence_before();
+    __syncthreads();
+    if (T > 0) {
+        float* scr = reinterpret_cast<float*>(smem + tp.z_img);            // [128][129] floats: runs into the X images
+        if (wid < QB_TG8_NCOMP / 32) {
+            const int pt = (wid & 3) * 32 + lane, c = (wid >> 2) * 32;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) scr[(c + e) * 129 + pt] = dwl[e];
+        }
+        __syncthreads();
+        if (threadIdx.x < H) {
+            float s = 0.0f;
+            for (int q = 0; q < 128; ++q) s += scr[threadIdx.x * 129 + q];
+            g[tp.wl_off + threadIdx.x] = s;
+        }
+    }
+    const double sbl = qb_block_sum((double)dbl, reinterpret_cast<double*>(smem));
+    if (threadIdx.x == 0 && tp.bl_off >= 0) g[tp.bl_off] = (float)sbl;
+    return qb_block_sum((double)ssq, reinterpret_cast<double*>(smem));
+}
+#endif  // __CUDACC__
