@@ -21,7 +21,7 @@ static int tg8_env_int(const char* name, int dflt) {
 bool qb_tg8_make_plan(const qb_net_t* net, int dtype, QbTg8Plan* tp) {
     memset(tp, 0, sizeof(*tp));
     if (dtype != QB_F32 || tg8_env_int("QB_NO_TC", 0) || tg8_env_int("QB_NO_TCG", 0) || tg8_env_int("QB_NO_TG8", 0)) return false;
-    if (net->n_layers != 3 || net->in_dim > 11 || net->out_dim != 1 || net->final_exp) return false;
+    if (net->n_layers != 3 || net->in_dim > 15 || net->out_dim != 1 || net->final_exp) return false;
     const qb_layer_t& L0 = net->layers[0];
     const qb_layer_t& L1 = net->layers[1];
     const qb_layer_t& L2 = net->layers[2];
@@ -29,17 +29,17 @@ bool qb_tg8_make_plan(const qb_net_t* net, int dtype, QbTg8Plan* tp) {
     if (L0.n_terms > 1 || L1.n_terms > 1 || L2.n_terms > 1) return false;
     if (L0.n_out != 128 || L1.n_out != 128) return false;
     if (L0.act != QB_ACT_TANH || L1.act != QB_ACT_TANH || L2.act != QB_ACT_IDENTITY) return false;
-    tp->in_dim = net->in_dim; tp->ni = (net->in_dim + 1 + 3) / 4 * 4; tp->n_params = net->n_params;
+    tp->in_dim = net->in_dim; tp->n_params = net->n_params;
     tp->w0_off = L0.w_off; tp->b0_off = L0.b_off; tp->w1_off = L1.w_off; tp->b1_off = L1.b_off;
     tp->wl_off = L2.w_off; tp->bl_off = L2.b_off;
     int off = QB_TG8_HDR;
     tp->w_img = off; off += 2 * QB_TG8_IMG;
-    tp->a_img = off; off += 2 * QB_TG8_AIMG;
+    tp->w0_img = off; off += 2 * QB_TG8_W0IMG;
+    tp->a_img = off; off += QB_TG8_AIMG + QB_TG8_IMG;       // hi image + ones block | lo image
     tp->z_img = off; off += 2 * QB_TG8_IMG;
     tp->x_img = off; off += 4 * QB_TG8_XIMG;            // directly behind the z image (the final reduction runs into it)
     tp->fl_base = off;
     int f = 0;
-    tp->w0 = f; f += 128 * tp->ni;
     tp->b1 = f; f += 128;
     tp->wl = f; f += 128;
     tp->bl = f; f += 4;
@@ -68,7 +68,6 @@ __global__ void __launch_bounds__(256) k_tg8_absmax(const float* __restrict__ x,
     }
 }
 
-template <int NI>
 __global__ void __launch_bounds__(QB_TG8_NCOMP + 32, 1) k_logpost_grad_tc128(const __grid_constant__ QbTg8Plan tp, const EvalArgs<float> a,
                                                                              const float* __restrict__ absmax) {
     extern __shared__ __align__(1024) unsigned char smem_g[];
@@ -78,17 +77,9 @@ __global__ void __launch_bounds__(QB_TG8_NCOMP + 32, 1) k_logpost_grad_tc128(con
     float* g = (a.S == 1) ? a.grad + k * tp.n_params : a.gpart + (k * a.S + s) * tp.n_params;
     const float is2 = (float)a.lk.inv_sigma2;
     qb_tg8_stage(tp, smem_g, a.theta + k * tp.n_params, absmax, is2);
-    const double ssq = qb_tg8_eval<NI>(tp, tmem, smem_g, a.x + k * a.xs, a.y + k * a.ys, n0, n1, is2, g);
+    const double ssq = qb_tg8_eval(tp, tmem, smem_g, a.x + k * a.xs, a.y + k * a.ys, n0, n1, is2, g);
     if (threadIdx.x == 0) a.part[k * a.S + s] = ssq;
     qb_tg8_fini(tp, tmem);
-}
-
-template <int NI>
-static cudaError_t launch_eval_t(const QbTg8Plan& tp, const EvalArgs<float>& a, const float* absmax, dim3 grid, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(k_logpost_grad_tc128<NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, tp.smem_bytes);
-    if (e != cudaSuccess) return e;
-    k_logpost_grad_tc128<NI><<<grid, tp.nthreads, tp.smem_bytes, st>>>(tp, a, absmax);
-    return cudaGetLastError();
 }
 
 cudaError_t qb_tg8_launch_eval(const QbTg8Plan& tp, const EvalArgs<float>& a, void* scratch, dim3 grid, cudaStream_t st) {
@@ -100,8 +91,15 @@ cudaError_t qb_tg8_launch_eval(const QbTg8Plan& tp, const EvalArgs<float>& a, vo
     k_tg8_absmax<<<blocks, 256, 0, st>>>(a.x, nx, a.y, ny, (unsigned int*)scratch);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    const float* am = (const float*)scratch;
-    if (tp.ni == 4) return launch_eval_t<4>(tp, a, am, grid, st);
-    if (tp.ni == 8) return launch_eval_t<8>(tp, a, am, grid, st);
-    return launch_eval_t<12>(tp, a, am, grid, st);
+    e = cudaFuncSetAttribute(k_logpost_grad_tc128, cudaFuncAttributeMaxDynamicSharedMemorySize, tp.smem_bytes);
+    if (e != cudaSuccess) return e;
+    k_logpost_grad_tc128<<<grid, tp.nthreads, tp.smem_bytes, st>>>(tp, a, (const float*)scratch);
+    return cudaGetLastError();
 }
+
+#ifdef QB_TG8_TRACE
+// development aid: copy the phase stamps of the last launch to the host
+extern "C" int qb_tg8_trace_dump(unsigned int* buf) {
+    return cudaMemcpyFromSymbol(buf, qb_tg8_trace_buf, sizeof(unsigned int) * QB_TG8_TR_BLOCKS * QB_TG8_TR_WARPS * QB_TG8_TR_TILES * QB_TG8_TR_EV) == cudaSuccess ? 0 : -1;
+}
+#endif

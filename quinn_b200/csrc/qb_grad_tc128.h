@@ -2,11 +2,11 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "quinn_b200.h"
-#include "qb_tg8.cuh"
+#include "qb_tg8_plan.h"
 
 template <typename T> struct EvalArgs;
 
-// eligibility + plan of the 128-wide tcgen05 gradient path (fp32, in <= 11 -> 128 -> 128 -> 1, tanh); false: not eligible
+// eligibility + plan of the 128-wide tcgen05 gradient path (fp32, in <= 15 -> 128 -> 128 -> 1, tanh); false: not eligible
 bool qb_tg8_make_plan(const qb_net_t* net, int dtype, QbTg8Plan* tp);
 // scratch: 8 bytes of device memory (max |x|, max |y| of the launch), written by a small kernel ahead of the evaluation
 cudaError_t qb_tg8_launch_eval(const QbTg8Plan& tp, const EvalArgs<float>& a, void* scratch, dim3 grid, cudaStream_t st);

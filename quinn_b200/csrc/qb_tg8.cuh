@@ -1,5 +1,5 @@
 // Tensor-core evaluation of the log-posterior AND its gradient (kernel 2 on tcgen05) for the 128-wide fp32 MLPs
-//   in (d <= 11) -> 128 -> 128 -> 1, tanh on both hidden layers, linear output     (BASELINE configs 3 and 4: 10-128-128-1)
+//   in (d <= 15) -> 128 -> 128 -> 1, tanh on both hidden layers, linear output     (BASELINE configs 3 and 4: 10-128-128-1)
 // Reverse mode of nnwrap.py:128-150 (autograd over NegLogPost, losses.py:186-206), restated in oracle/quinn_oracle.py.
 // qb_tcg.cuh (widths 32 / 64, kind::tf32) does not scale to this width: its four fp32 copies of W1 alone are 256 KB.
 //
@@ -11,7 +11,8 @@
 //
 // One tile = 128 data points = the 128 lanes of tensor memory.  16 compute warps: thread = (point, 32 of the 128 units);
 // warp 16 only issues MMAs.  Per tile (p = point, i = layer-0 unit, j = layer-1 unit):
-//   L0    CUDA cores   a0 = tanh(W0 x + b0)                          -> a0 image, X image
+//   L0    tcgen05      DL[p][i] = sum_c X[p][c] W0'[i][c]            A = X image = [x | 1 | 0] (K-major view), B = W0 image = [W0 | b0 | 0]
+//   EPIL  CUDA cores   a0 = tanh(DL)                                 -> a0 image
 //   FWD   tcgen05      D1[p][j] = sum_i a0[p][i] W1[j][i]            A = a0 image (K-major view), B = W image (K-major view)
 //   EPI1  CUDA cores   a1 = tanh(D1 + b1); y = wl.a1 + bl; dy = (ydata - y)/sigma^2; z1 = dy wl (1 - a1^2); dwl += dy a1
 //                                                                    -> z image
@@ -30,32 +31,37 @@
 //       MN-major view (rows = i, k = j):           LBO 2048, SBO 128,  k-step +4096
 // A thread writes its point's 8-unit chunk with one 16-byte store; the 32 lanes of a warp cover 512 contiguous bytes.
 //
-// Pipeline (two block-wide hand-overs per tile, as in qb_tcg.cuh):
-//   phase B(t): wait FWD(t) -> EPI1(t) -> [wait DW0(t-1)] z1 -> z image                        => issue BWD(t), DW1(t)
-//   phase A(t): wait BWD(t) -> EPI0(t) (z0 parked in the D1 columns of tensor memory) and L0(t+1) (registers) while
-//               DW1(t) still reads both images -> wait DW1(t) -> z0 -> z image, a0(t+1) -> a0 image   => issue FWD(t+1), DW0(t)
+// Pipeline (two block-wide hand-overs per tile, as in qb_tcg.cuh); tensor memory: R1 = columns [0,128), R0 = [128,256),
+// G1 = [256,400), G0 = [400,416):
+//   phase B(t): wait FWD(t) -> EPI1(t) from R1 (a1 waits in R1 across the reduction of y over the four thread groups)
+//               -> [wait DW0(t-1)] X(t+1) -> X image, z1 -> z image                     => issue L0(t+1) -> R1, BWD(t) -> R0, DW1(t)
+//   phase A(t): wait BWD(t) -> EPI0(t): R0 -> z0, packed, back into R0; EPIL(t+1): R1 -> a0(t+1), packed, back into R1 (DW1(t)
+//               still reads both images) -> wait DW1(t) -> R0 -> z image, R1 -> a0 image   => issue FWD(t+1) -> R1, DW0(t)
 //   DW0(t) runs under EPI1(t+1).
 #pragma once
 #include <stdint.h>
 #include "qb_plan.h"
 #include "qb_tc.cuh"
 #include "qb_tc3.cuh"
+#include "qb_tg8_plan.h"
 
-struct QbTg8Plan {
-    int in_dim, ni, n_params;
-    int w0_off, b0_off, w1_off, b1_off, wl_off, bl_off;   // offsets in theta (b*_off < 0: no bias)
-    int w_img, a_img, z_img, x_img;                       // byte offsets: hi image, then lo image (X: two tiles of hi | lo)
-    int fl_base, w0, b1, wl, bl, sc;                      // float area (byte offset) and float indices in it
-    int ybuf;                                             // byte offset: [4][128] partial outputs
-    int tmem_cols, nthreads, smem_bytes;
-};
 
 #ifdef __CUDACC__
-enum { QB_TG8_BAR_F = 320, QB_TG8_BAR_B = 328, QB_TG8_BAR_W = 336, QB_TG8_BAR_Z = 344, QB_TG8_BAR_RDY = 352, QB_TG8_SLOT = 360,
-       QB_TG8_HDR = 512, QB_TG8_IMG = 32768, QB_TG8_AIMG = 36864, QB_TG8_XIMG = 4096, QB_TG8_NCOMP = 512 };
+enum { QB_TG8_BAR_F = 400, QB_TG8_BAR_B = 408, QB_TG8_BAR_W = 416, QB_TG8_BAR_Z = 424, QB_TG8_BAR_RDY = 432, QB_TG8_SLOT = 440, QB_TG8_BAR_L = 448,
+       QB_TG8_HDR = 512, QB_TG8_IMG = 32768, QB_TG8_AIMG = 36864, QB_TG8_XIMG = 4096, QB_TG8_W0IMG = 4096, QB_TG8_NCOMP = 512 };
 enum { QB_TG8_C_D1 = 0, QB_TG8_C_D0 = 128, QB_TG8_C_DW1 = 256, QB_TG8_C_DW0 = 400 };
 // float slots behind tp.sc
-enum { QB_TG8_S_C1 = 0, QB_TG8_S_SZ1 = 1, QB_TG8_S_K0 = 2, QB_TG8_S_UW1 = 3, QB_TG8_S_UW0 = 4, QB_TG8_S_SX = 5 };
+enum { QB_TG8_S_C1 = 0, QB_TG8_S_SZ1 = 1, QB_TG8_S_K0 = 2, QB_TG8_S_UW1 = 3, QB_TG8_S_UW0 = 4, QB_TG8_S_SX = 5, QB_TG8_S_C0 = 6 };
+
+// Development aid (-DQB_TG8_TRACE, scripts/tg8_trace.py): SM-clock stamps of the phases of every warp of the first blocks.
+#ifdef QB_TG8_TRACE
+enum { QB_TG8_TR_BLOCKS = 8, QB_TG8_TR_WARPS = 17, QB_TG8_TR_TILES = 48, QB_TG8_TR_EV = 10 };
+__device__ unsigned int qb_tg8_trace_buf[QB_TG8_TR_BLOCKS * QB_TG8_TR_WARPS * QB_TG8_TR_TILES * QB_TG8_TR_EV];
+#define QB_TG8_STAMP(tile, ev) do { if ((threadIdx.x & 31) == 0 && blockIdx.x < QB_TG8_TR_BLOCKS && blockIdx.y == 0 && (tile) < QB_TG8_TR_TILES) \
+    qb_tg8_trace_buf[((blockIdx.x * QB_TG8_TR_WARPS + (threadIdx.x >> 5)) * QB_TG8_TR_TILES + (tile)) * QB_TG8_TR_EV + (ev)] = (unsigned int)clock64(); } while (0)
+#else
+#define QB_TG8_STAMP(tile, ev) do { } while (0)
+#endif
 
 __device__ __forceinline__ float qb_tg8_pow2(int e) { return __uint_as_float((uint32_t)(127 + max(-126, min(127, e))) << 23); }
 
@@ -73,6 +79,7 @@ __device__ __forceinline__ uint32_t qb_tg8_init(const QbTg8Plan& tp, unsigned ch
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB_TG8_BAR_W), "r"(1u) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB_TG8_BAR_Z), "r"(1u) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB_TG8_BAR_RDY), "r"((uint32_t)QB_TG8_NCOMP) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB_TG8_BAR_L), "r"(1u) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     qb_tc_fence_before();
@@ -89,9 +96,9 @@ __device__ __forceinline__ void qb_tg8_fini(const QbTg8Plan& tp, uint32_t tmem) 
 // thread 0, between two block barriers: every phase of the previous evaluation has completed, start again at parity 0
 __device__ __forceinline__ void qb_tg8_reset_barriers(unsigned char* smem) {
     const uint32_t b = qb_smem_u32(smem);
-    const uint32_t off[5] = {QB_TG8_BAR_F, QB_TG8_BAR_B, QB_TG8_BAR_W, QB_TG8_BAR_Z, QB_TG8_BAR_RDY};
+    const uint32_t off[6] = {QB_TG8_BAR_F, QB_TG8_BAR_B, QB_TG8_BAR_W, QB_TG8_BAR_Z, QB_TG8_BAR_RDY, QB_TG8_BAR_L};
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 0; i < 6; ++i) {
         asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"(b + off[i]) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + off[i]), "r"(i == 4 ? (uint32_t)QB_TG8_NCOMP : 1u) : "memory");
     }
@@ -132,24 +139,28 @@ __device__ __forceinline__ void qb_tg8_tanh4(float2& a, float2& b, float S) {
 }
 
 // flat theta (global) -> shared.  All threads of the block; ends with the async-proxy fence.
-//   F[w0 ..]  : layer-0 rows (paired units, bias in slot in_dim), times 2 log2 e
+//   W0 image  : fp16 hi / lo of 2^s0 * 2 log2 e * [W0 | b0 | 0] (128 x 16, K-major: LBO 128, SBO 256), max in [2^13, 2^14)
 //   W image   : fp16 hi / lo of 2^sW * W1, max |2^sW W1| in [2^13, 2^14)
 //   F[b1 + j] = 2 log2 e * b1_j;  F[wl + j] = wl_j;  F[bl]
 //   ones block of the a0 image (units 128 .. 143 of every point: 2^14, 0, 0, ..): column 128 of G1 becomes db1
 //   scales (all powers of two, exact):
 //     a0 image = 2^14 a0;  X image = 2^sX x (max |x| from absmax[0], ones column 2^sX);
-//     z1 image = sz1 z1 with sz1 * B1 <= 2^14 where |z1| <= B1 = (max|y| + |bl| + sum|wl|) / sigma^2 * max|wl|   (|a1| <= 1)
-//     z0 image = sz0 z0 with sz0 * B0 <= 2^14 where |z0| <= B0 = B1 * max_i sum_j |W1[j][i]|
-//   A value far below its bound loses nothing until it is 2^17 below it (fp16 keeps 2^15 .. 2^-24; hi and lo need 22 bits).
+//     z1 image = sz1 z1 with sz1 * B1 <= 60000 where |z1| <= B1 = (max|y| + |bl| + sum|wl|) / sigma^2 * max|wl|   (|a1| <= 1)
+//     z0 image = sz0 z0 with sz0 * B0 <= 60000 where |z0| <= B0 = B1 * max_i sum_j |W1[j][i]|
+//   A value far below its bound loses nothing until it is ~2^17 below it (fp16 keeps 2^16 .. 2^-24; hi and lo need 22 bits);
+//   further down the lo part runs out of bits one by one (absolute error 2^-25 in image units) - only gradients that are
+//   tiny against these bounds in EVERY entry (saturated units AND residuals far below sigma) see it, at the 1e-5 level.
 __device__ __forceinline__ void qb_tg8_stage(const QbTg8Plan& tp, unsigned char* smem, const float* __restrict__ theta,
                                              const float* __restrict__ absmax, float is2) {
     constexpr int H = 128;
     float* F = reinterpret_cast<float*>(smem + tp.fl_base);
-    float* sred = reinterpret_cast<float*>(smem);                      // [17][4]
+    float* sred = reinterpret_cast<float*>(smem);                      // [17][4] + [17]
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
     const float fold = 2.8853900817779268f;
-    float mx = 0.0f, cs = 0.0f, wa = 0.0f;
+    float mx = 0.0f, cs = 0.0f, wa = 0.0f, m0 = 0.0f;
     for (int e = tid; e < H * H; e += nt) mx = fmaxf(mx, fabsf(theta[tp.w1_off + e]));
+    for (int e = tid; e < H * tp.in_dim; e += nt) m0 = fmaxf(m0, fabsf(theta[tp.w0_off + e]));
+    if (tid < H && tp.b0_off >= 0) m0 = fmaxf(m0, fabsf(theta[tp.b0_off + tid]));
     if (tid < H) {
         for (int j = 0; j < H; ++j) cs += fabsf(theta[tp.w1_off + j * H + tid]);
         wa = fabsf(theta[tp.wl_off + tid]);
@@ -160,30 +171,46 @@ __device__ __forceinline__ void qb_tg8_stage(const QbTg8Plan& tp, unsigned char*
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
         cs = fmaxf(cs, __shfl_xor_sync(0xffffffffu, cs, off));
         wa = fmaxf(wa, __shfl_xor_sync(0xffffffffu, wa, off));
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, off));
         ws += __shfl_xor_sync(0xffffffffu, ws, off);
     }
     __syncthreads();                       // the previous evaluation's readers of the header / float area are done
-    if (lane == 0) { sred[4 * wid + 0] = mx; sred[4 * wid + 1] = cs; sred[4 * wid + 2] = wa; sred[4 * wid + 3] = ws; }
+    if (lane == 0) { sred[4 * wid + 0] = mx; sred[4 * wid + 1] = cs; sred[4 * wid + 2] = wa; sred[4 * wid + 3] = ws; sred[68 + wid] = m0; }
     __syncthreads();
-    mx = cs = wa = ws = 0.0f;
+    mx = cs = wa = ws = m0 = 0.0f;
     for (int w = 0; w < (nt + 31) >> 5; ++w) {
         mx = fmaxf(mx, sred[4 * w + 0]); cs = fmaxf(cs, sred[4 * w + 1]); wa = fmaxf(wa, sred[4 * w + 2]); ws += sred[4 * w + 3];
+        m0 = fmaxf(m0, sred[68 + w]);
     }
     auto ilog = [](float v, int dflt) { return (v > 0.0f && v < 3.0e38f) ? ilogbf(v) : dflt; };
     const int sW = max(-40, min(40, 13 - ilog(mx, 13)));
     const int sX = max(-24, min(14, 13 - ilog(absmax[0], 13)));
+    const int s0 = max(-40, min(40, 13 - ilog(m0 * fold, 13)));
     const float blv = tp.bl_off >= 0 ? theta[tp.bl_off] : 0.0f;
     const float B1 = (absmax[1] + fabsf(blv) + ws) * is2 * wa;
-    const int e1 = max(-50, min(50, ilog(B1, -1) + 1));
-    const int e0 = max(-50, min(50, ilog(B1 * cs, -1) + 1));
+    // 2^(14 - e) * B <= 60000 (fp16 holds 65504): e = 14 - floor(log2(60000 / B))
+    const int e1 = max(-50, min(50, 14 - ilog(60000.0f / B1, 14)));
+    const int e0 = max(-50, min(50, 14 - ilog(60000.0f / (B1 * cs), 14)));
     const float wscale = qb_tg8_pow2(sW);
-    // ---- layer 0 (CUDA cores): pairs of units
-    for (int e = tid; e < H * tp.ni; e += nt) {
-        const int u = e & 1, q = (e >> 1) % tp.ni, j = ((e >> 1) / tp.ni) * 2 + u;
-        float v = 0.0f;
-        if (q < tp.in_dim) v = theta[tp.w0_off + j * tp.in_dim + q] * fold;
-        else if (q == tp.in_dim && tp.b0_off >= 0) v = theta[tp.b0_off + j] * fold;
-        F[tp.w0 + e] = v;
+    // ---- W0 image: element (unit i, column q) at halfword (i/8)*128 + (q/8)*64 + (i%8)*8 + q%8
+    {
+        uint32_t* hi = reinterpret_cast<uint32_t*>(smem + tp.w0_img);
+        uint32_t* lo = hi + QB_TG8_W0IMG / 4;
+        const float sc0 = fold * qb_tg8_pow2(s0);
+        for (int e = tid; e < H * 8; e += nt) {
+            const int i = e >> 3, q = (e & 7) * 2;
+            float v[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                v[u] = 0.0f;
+                if (q + u < tp.in_dim) v[u] = theta[tp.w0_off + i * tp.in_dim + q + u] * sc0;
+                else if (q + u == tp.in_dim && tp.b0_off >= 0) v[u] = theta[tp.b0_off + i] * sc0;
+            }
+            uint32_t h2, l2;
+            qb_tg8_split(v[0], v[1], h2, l2);
+            const int idx = ((i >> 3) * 128 + (q >> 3) * 64 + (i & 7) * 8 + (q & 7)) >> 1;
+            hi[idx] = h2; lo[idx] = l2;
+        }
     }
     // ---- W image: word index of the pair (j, i), (j, i + 1)
     {
@@ -198,15 +225,11 @@ __device__ __forceinline__ void qb_tg8_stage(const QbTg8Plan& tp, unsigned char*
             hi[idx] = h2; lo[idx] = l2;
         }
     }
-    // ---- ones block of the a0 image
+    // ---- ones block of the a0 hi image (the lo image has none: its pass of DW1 runs with N = 128)
     {
         uint32_t* hi = reinterpret_cast<uint32_t*>(smem + tp.a_img + QB_TG8_IMG);            // units 128 .. 143
-        uint32_t* lo = reinterpret_cast<uint32_t*>(smem + tp.a_img + QB_TG8_AIMG + QB_TG8_IMG);
-        for (int e = tid; e < 2 * 2048 / 4; e += nt) {
-            // chunk 16 (units 128 .. 135): word 0 of every point's 16-byte row holds (2^14, 0)
-            hi[e] = (e < 512 && (e & 3) == 0) ? 0x00007400u : 0u;
-            lo[e] = 0u;
-        }
+        for (int e = tid; e < 2 * 2048 / 4; e += nt)
+            hi[e] = (e < 512 && (e & 3) == 0) ? 0x00007400u : 0u;      // chunk 16: word 0 of every point's 16-byte row = (2^14, 0)
     }
     for (int j = tid; j < H; j += nt) {
         F[tp.b1 + j] = tp.b1_off >= 0 ? theta[tp.b1_off + j] * fold : 0.0f;
@@ -220,6 +243,7 @@ __device__ __forceinline__ void qb_tg8_stage(const QbTg8Plan& tp, unsigned char*
         F[tp.sc + QB_TG8_S_UW1] = qb_tg8_pow2(-14 - (14 - e1));
         F[tp.sc + QB_TG8_S_UW0] = qb_tg8_pow2(-sX - (14 - e0));
         F[tp.sc + QB_TG8_S_SX] = qb_tg8_pow2(sX);
+        F[tp.sc + QB_TG8_S_C0] = qb_tg8_pow2(-sX - s0);                // DL -> 2 log2 e * (W0 x + b0)
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -232,20 +256,22 @@ __device__ __forceinline__ void qb_tg8_mma(uint32_t d, uint32_t alo, uint32_t ah
 }
 __device__ __forceinline__ uint32_t qb_tg8_dlo(uint32_t saddr, uint32_t lbo) { return ((saddr >> 4) & 0x3FFFu) | ((lbo >> 4) << 16); }
 __device__ __forceinline__ uint32_t qb_tg8_dhi(uint32_t sbo) { return (sbo >> 4) | (1u << 14); }
-// three passes (a_lo*b_hi, a_hi*b_lo, a_hi*b_hi) x 8 k-steps of 16; *_lo32 are descriptor low words of the hi / lo images
+// three passes (a_lo*b_hi, a_hi*b_lo, a_hi*b_hi) x KS k-steps of 16; *_img are descriptor low words of the hi / lo images;
+// idesc1: instruction descriptor of the pass that reads b_lo (DW1: the lo image of a0 has no ones block, N = 128 there)
+template <int KS>
 __device__ __forceinline__ void qb_tg8_issue3(uint32_t d, uint32_t a_hi_img, uint32_t a_lo_img, uint32_t a_dhi, uint32_t a_step,
                                               uint32_t b_hi_img, uint32_t b_lo_img, uint32_t b_dhi, uint32_t b_step, uint32_t idesc,
-                                              uint32_t acc0) {
-    // the bases are laundered so that ptxas forms the 24 descriptor pairs here, next to their MMAs: hoisted out of the tile
-    // loop, the ~120 pairs of the four GEMMs overflow the uniform register file and come back from local memory
+                                              uint32_t idesc1, uint32_t acc0) {
+    // the bases are laundered so that ptxas forms the descriptor pairs here, next to their MMAs: hoisted out of the tile
+    // loop, the ~120 pairs of the GEMMs overflow the uniform register file and come back from local memory
     asm volatile("" : "+r"(a_hi_img), "+r"(a_lo_img), "+r"(b_hi_img), "+r"(b_lo_img));
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
+        for (int s = 0; s < KS; ++s) {
             const uint32_t a = (pass == 0 ? a_lo_img : a_hi_img) + a_step * s;
             const uint32_t b = (pass == 1 ? b_lo_img : b_hi_img) + b_step * s;
-            qb_tg8_mma(d, a, a_dhi, b, b_dhi, idesc, (pass == 0 && s == 0) ? acc0 : 1u);
+            qb_tg8_mma(d, a, a_dhi, b, b_dhi, pass == 1 ? idesc1 : idesc, (pass == 0 && s == 0) ? acc0 : 1u);
         }
     }
 }
@@ -253,14 +279,13 @@ __device__ __forceinline__ void qb_tg8_issue3(uint32_t d, uint32_t a_hi_img, uin
 // Value + gradient of the data term over points [n0, n1) for the staged parameter vector.  Every thread of the block
 // (512 compute threads + the issue warp) calls it.  Returns the block-wide sum of squared residuals; g[0..P) (global, this
 // block's row) receives d/dtheta of -0.5*ssq/sigma^2.
-template <int NI>
 __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem, unsigned char* smem, const float* __restrict__ x,
                                               const float* __restrict__ y, int64_t n0, int64_t n1, float is2, float* __restrict__ g) {
     constexpr int H = 128;
     const float* F = reinterpret_cast<const float*>(smem + tp.fl_base);
     const uint32_t sb = qb_smem_u32(smem);
     const uint32_t bar_f = sb + QB_TG8_BAR_F, bar_b = sb + QB_TG8_BAR_B, bar_w = sb + QB_TG8_BAR_W, bar_z = sb + QB_TG8_BAR_Z,
-                   bar_rdy = sb + QB_TG8_BAR_RDY;
+                   bar_rdy = sb + QB_TG8_BAR_RDY, bar_l = sb + QB_TG8_BAR_L;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = (int)((n1 - n0 + 127) / 128);
     __syncthreads();                               // staging complete; nobody is still inside the previous evaluation
@@ -277,9 +302,11 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
         const uint32_t id_fwd = id_base | ((128u >> 3) << 17);
         const uint32_t id_bwd = id_fwd | (1u << 16);
         const uint32_t id_dw1 = id_base | (1u << 15) | (1u << 16) | ((144u >> 3) << 17);
+        const uint32_t id_dw1n = id_base | (1u << 15) | (1u << 16) | ((128u >> 3) << 17);
         const uint32_t id_dw0 = id_base | (1u << 15) | (1u << 16) | ((16u >> 3) << 17);
         const uint32_t dh_a = qb_tg8_dhi(128u), dh_b = qb_tg8_dhi(2048u);          // (LBO 2048, SBO 128) / (LBO 128, SBO 2048)
-        const uint32_t a_img = sb + (uint32_t)tp.a_img, z_img = sb + (uint32_t)tp.z_img, w_img = sb + (uint32_t)tp.w_img;
+        const uint32_t a_img = sb + (uint32_t)tp.a_img, z_img = sb + (uint32_t)tp.z_img, w_img = sb + (uint32_t)tp.w_img,
+                       w0_img = sb + (uint32_t)tp.w0_img;
         // K-major views of the point images and the MN-major view of W: LBO 2048; the other views: LBO 128
         const uint32_t aK_hi = qb_tg8_dlo(a_img, 2048u), aK_lo = qb_tg8_dlo(a_img + QB_TG8_AIMG, 2048u);
         const uint32_t aM_hi = qb_tg8_dlo(a_img, 128u), aM_lo = qb_tg8_dlo(a_img + QB_TG8_AIMG, 128u);
@@ -287,6 +314,7 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
         const uint32_t zM_hi = qb_tg8_dlo(z_img, 128u), zM_lo = qb_tg8_dlo(z_img + QB_TG8_IMG, 128u);
         const uint32_t wK_hi = qb_tg8_dlo(w_img, 128u), wK_lo = qb_tg8_dlo(w_img + QB_TG8_IMG, 128u);
         const uint32_t wM_hi = qb_tg8_dlo(w_img, 2048u), wM_lo = qb_tg8_dlo(w_img + QB_TG8_IMG, 2048u);
+        const uint32_t w0_hi = qb_tg8_dlo(w0_img, 128u), w0_lo = qb_tg8_dlo(w0_img + QB_TG8_W0IMG, 128u), dh_w0 = qb_tg8_dhi(256u);
         uint32_t n = 0;
         auto wait_rdy = [&]() {
             qb3_wait(bar_rdy, n & 1u);
@@ -294,10 +322,19 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
             qb_tc_fence_after();
             __syncwarp();
         };
+        // layer 0 of tile u: X image (K-major view, K = 16: one k-step) x W0 image -> R1
+        auto issue_l0 = [&](int u) {
+            const uint32_t x_img = sb + (uint32_t)tp.x_img + (uint32_t)(u & 1) * 2u * QB_TG8_XIMG;
+            qb_tg8_issue3<1>(tmem + QB_TG8_C_D1, qb_tg8_dlo(x_img, 2048u), qb_tg8_dlo(x_img + QB_TG8_XIMG, 2048u), dh_a, 0u,
+                             w0_hi, w0_lo, dh_w0, 0u, id_fwd, id_fwd, 0u);
+        };
         if (T > 0) {
-            wait_rdy();
+            wait_rdy();                                                   // X(0) is in the X image
+            if (qb3_elect()) { issue_l0(0); qb3_commit(bar_l); }
+            __syncwarp();
+            wait_rdy();                                                   // a0(0) is in the a0 image
             if (qb3_elect()) {
-                qb_tg8_issue3(tmem + QB_TG8_C_D1, aK_hi, aK_lo, dh_a, 256u, wK_hi, wK_lo, dh_b, 16u, id_fwd, 0u);
+                qb_tg8_issue3<8>(tmem + QB_TG8_C_D1, aK_hi, aK_lo, dh_a, 256u, wK_hi, wK_lo, dh_b, 16u, id_fwd, id_fwd, 0u);
                 qb3_commit(bar_f);
             }
             __syncwarp();
@@ -305,26 +342,31 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
 #pragma unroll 1
         for (int t = 0; t < T; ++t) {
             const uint32_t acc0 = t > 0 ? 1u : 0u;
-            wait_rdy();                                                   // z1(t) is in the z image
+            wait_rdy();                                                   // z1(t) is in the z image, X(t+1) in the X image; R1 is free
+            QB_TG8_STAMP(t, 0);
             if (qb3_elect()) {
-                qb_tg8_issue3(tmem + QB_TG8_C_D0, zK_hi, zK_lo, dh_a, 256u, wM_hi, wM_lo, dh_a, 256u, id_bwd, 0u);
+                if (t + 1 < T) issue_l0(t + 1);
+                qb_tg8_issue3<8>(tmem + QB_TG8_C_D0, zK_hi, zK_lo, dh_a, 256u, wM_hi, wM_lo, dh_a, 256u, id_bwd, id_bwd, 0u);
                 qb3_commit(bar_b);
-                qb_tg8_issue3(tmem + QB_TG8_C_DW1, zM_hi, zM_lo, dh_b, 16u, aM_hi, aM_lo, dh_b, 16u, id_dw1, acc0);
+                qb_tg8_issue3<8>(tmem + QB_TG8_C_DW1, zM_hi, zM_lo, dh_b, 16u, aM_hi, aM_lo, dh_b, 16u, id_dw1, id_dw1n, acc0);
                 qb3_commit(bar_w);
             }
             __syncwarp();
+            QB_TG8_STAMP(t, 1);
             wait_rdy();                                                   // z0(t) is in the z image, a0(t+1) in the a0 image
+            QB_TG8_STAMP(t, 2);
             if (qb3_elect()) {
                 if (t + 1 < T) {
-                    qb_tg8_issue3(tmem + QB_TG8_C_D1, aK_hi, aK_lo, dh_a, 256u, wK_hi, wK_lo, dh_b, 16u, id_fwd, 0u);
+                    qb_tg8_issue3<8>(tmem + QB_TG8_C_D1, aK_hi, aK_lo, dh_a, 256u, wK_hi, wK_lo, dh_b, 16u, id_fwd, id_fwd, 0u);
                     qb3_commit(bar_f);
                 }
                 const uint32_t x_img = sb + (uint32_t)tp.x_img + (uint32_t)(t & 1) * 2u * QB_TG8_XIMG;
-                qb_tg8_issue3(tmem + QB_TG8_C_DW0, zM_hi, zM_lo, dh_b, 16u, qb_tg8_dlo(x_img, 128u), qb_tg8_dlo(x_img + QB_TG8_XIMG, 128u),
-                              dh_b, 16u, id_dw0, acc0);
+                qb_tg8_issue3<8>(tmem + QB_TG8_C_DW0, zM_hi, zM_lo, dh_b, 16u, qb_tg8_dlo(x_img, 128u), qb_tg8_dlo(x_img + QB_TG8_XIMG, 128u),
+                                 dh_b, 16u, id_dw0, id_dw0, acc0);
                 qb3_commit(bar_z);
             }
             __syncwarp();
+            QB_TG8_STAMP(t, 3);
         }
     } else {
         // ================================ compute warps ================================
@@ -332,11 +374,15 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
         const uint32_t pt = (uint32_t)(quarter * 32 + lane);               // this thread's point of the tile = tensor-memory lane
         const int c = grp * 32;                                            // this thread's units
         const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16);
-        const uint32_t poff = (pt >> 3) * 128u + (pt & 7u) * 16u + (uint32_t)(c >> 3) * 2048u;     // chunk j of this thread: + 2048 j
+        const uint32_t prow = (pt >> 3) * 128u + (pt & 7u) * 16u;           // this point's 16-byte row inside an 8-unit chunk
+        const uint32_t poff = prow + (uint32_t)(c >> 3) * 2048u;            // chunk j of this thread: + 2048 j
         unsigned char* a_hi = smem + tp.a_img + poff; unsigned char* a_lo = a_hi + QB_TG8_AIMG;
         unsigned char* z_hi = smem + tp.z_img + poff; unsigned char* z_lo = z_hi + QB_TG8_IMG;
+        // X image: thread group g lays out columns 4g .. 4g+3 of its point (half of a 16-byte row)
+        unsigned char* x_row = smem + tp.x_img + (grp >> 1) * 2048 + prow + (grp & 1) * 8;
         float* ybuf = reinterpret_cast<float*>(smem + tp.ybuf);
-        const float c1 = F[tp.sc + QB_TG8_S_C1], sz1 = F[tp.sc + QB_TG8_S_SZ1], k0 = F[tp.sc + QB_TG8_S_K0], sx = F[tp.sc + QB_TG8_S_SX];
+        const float c1 = F[tp.sc + QB_TG8_S_C1], sz1 = F[tp.sc + QB_TG8_S_SZ1], k0 = F[tp.sc + QB_TG8_S_K0], sx = F[tp.sc + QB_TG8_S_SX],
+                    c0 = F[tp.sc + QB_TG8_S_C0];
         const float4* B4 = reinterpret_cast<const float4*>(F + tp.b1 + c);
         const float4* W4 = reinterpret_cast<const float4*>(F + tp.wl + c);
 
@@ -345,75 +391,73 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
             qb_tc_fence_before();
             qb_mbar_arrive(bar_rdy);
         };
-        // 32 packed columns (16 hi words | 16 lo words of this thread's 32 units) parked at tensor-memory column `col` -> images
+        // this thread's 32 columns of region `col` hold packed results: per half of 16 columns, 8 hi words then 8 lo words
+        // (units 16 hf .. 16 hf + 15).  Copy them into the images.
         auto unpark = [&](uint32_t col, unsigned char* hi, unsigned char* lo) {
-            uint32_t v[16];
-            qb_tmem_ld16(tl + col + c, v);
-            qb_tmem_ld_wait16(v);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(hi + 2048 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            qb_tmem_ld16(tl + col + c + 16, v);
-            qb_tmem_ld_wait16(v);
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t v[16];
+                qb_tmem_ld16(tl + col + c + 16 * hf, v);
+                qb_tmem_ld_wait16(v);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(lo + 2048 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                for (int jj = 0; jj < 2; ++jj) {
+                    *reinterpret_cast<uint4*>(hi + 2048 * (2 * hf + jj)) = make_uint4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+                    *reinterpret_cast<uint4*>(lo + 2048 * (2 * hf + jj)) = make_uint4(v[8 + 4 * jj], v[9 + 4 * jj], v[10 + 4 * jj], v[11 + 4 * jj]);
+                }
+            }
         };
-        // layer 0 of tile tt: X image (groups 0 and 1: one 8-column chunk each) and 2^14 a0, packed, parked in the D0 columns
-        // (free between EPI0(t) and BWD(t+1)).  Returns the target of this thread's point.
-        auto layer0 = [&](int tt) -> float {
+        // inputs of tile tt: this thread's four columns of its point (x, then the constant 1, then zeros) and the target
+        float xq[4], yn = 0.0f;
+        auto fetch = [&](int tt) {
             const int64_t pp = n0 + (int64_t)tt * 128 + pt;
-            float xr[NI];
 #pragma unroll
-            for (int q = 0; q < NI; ++q) xr[q] = (q < tp.in_dim && pp < n1) ? __ldg(x + pp * tp.in_dim + q) : 0.0f;
-            const float yt = pp < n1 ? __ldg(y + pp) : 0.0f;
-#pragma unroll
-            for (int q = 0; q < NI; ++q) xr[q] = (q == tp.in_dim) ? 1.0f : xr[q];
-            if (grp < 2) {
-                uint32_t h[4], l[4];
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    float v0 = 0.0f, v1 = 0.0f;
-#pragma unroll
-                    for (int q = 0; q < NI; ++q) {              // selects: no indexed register access
-                        if (q == 8 * grp + 2 * w) v0 = xr[q] * sx;
-                        if (q == 8 * grp + 2 * w + 1) v1 = xr[q] * sx;
-                    }
-                    qb_tg8_split(v0, v1, h[w], l[w]);
-                }
-                unsigned char* xi = smem + tp.x_img + (tt & 1) * 2 * QB_TG8_XIMG + grp * 2048 + (pt >> 3) * 128u + (pt & 7u) * 16u;
-                *reinterpret_cast<uint4*>(xi) = make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4*>(xi + QB_TG8_XIMG) = make_uint4(l[0], l[1], l[2], l[3]);
+            for (int j = 0; j < 4; ++j) {
+                const int q = 4 * grp + j;
+                float v = 0.0f;
+                if (q < tp.in_dim && pp < n1) v = __ldg(x + pp * tp.in_dim + q);
+                xq[j] = (q == tp.in_dim) ? 1.0f : v;
             }
-            const float4* W = reinterpret_cast<const float4*>(F + tp.w0 + c * NI);
+            yn = pp < n1 ? __ldg(y + pp) : 0.0f;
+        };
+        auto xstore = [&](int tt) {
+            uint32_t h0, l0, h1, l1;
+            qb_tg8_split(xq[0] * sx, xq[1] * sx, h0, l0);
+            qb_tg8_split(xq[2] * sx, xq[3] * sx, h1, l1);
+            unsigned char* xi = x_row + (tt & 1) * 2 * QB_TG8_XIMG;
+            *reinterpret_cast<uint2*>(xi) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(xi + QB_TG8_XIMG) = make_uint2(l0, l1);
+        };
+        // EPIL: R1 holds layer 0 of a tile (this thread's 32 columns) -> 2^14 tanh, packed, back into the same columns
+        auto epil = [&]() {
+            const float2 c2 = make_float2(c0, c0);
 #pragma unroll
-            for (int jc = 0; jc < 4; ++jc) {
-                uint32_t h[4], l[4];
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t v[16], o[16];
+                qb_tmem_ld16(tl + QB_TG8_C_D1 + c + 16 * hf, v);
+                qb_tmem_ld_wait16(v);
 #pragma unroll
-                for (int g2 = 0; g2 < 2; ++g2) {
-                    const int gq = 2 * jc + g2;
-                    float2 z0 = make_float2(0.0f, 0.0f), z1 = make_float2(0.0f, 0.0f);
-#pragma unroll
-                    for (int q = 0; q < NI; q += 2) {
-                        const float4 wa = W[(2 * gq) * (NI / 2) + q / 2], wb = W[(2 * gq + 1) * (NI / 2) + q / 2];
-                        z0 = __ffma2_rn(make_float2(wa.x, wa.y), make_float2(xr[q], xr[q]), z0);
-                        z0 = __ffma2_rn(make_float2(wa.z, wa.w), make_float2(xr[q + 1], xr[q + 1]), z0);
-                        z1 = __ffma2_rn(make_float2(wb.x, wb.y), make_float2(xr[q], xr[q]), z1);
-                        z1 = __ffma2_rn(make_float2(wb.z, wb.w), make_float2(xr[q + 1], xr[q + 1]), z1);
-                    }
+                for (int gq = 0; gq < 4; ++gq) {
+                    float2 z0 = __fmul2_rn(make_float2(__uint_as_float(v[4 * gq]), __uint_as_float(v[4 * gq + 1])), c2);
+                    float2 z1 = __fmul2_rn(make_float2(__uint_as_float(v[4 * gq + 2]), __uint_as_float(v[4 * gq + 3])), c2);
                     qb_tg8_tanh4(z0, z1, 16384.0f);
-                    qb_tg8_split(z0.x, z0.y, h[2 * g2], l[2 * g2]);
-                    qb_tg8_split(z1.x, z1.y, h[2 * g2 + 1], l[2 * g2 + 1]);
+                    qb_tg8_split(z0.x, z0.y, o[2 * gq], o[8 + 2 * gq]);
+                    qb_tg8_split(z1.x, z1.y, o[2 * gq + 1], o[8 + 2 * gq + 1]);
                 }
-                qb_tg8_st4(tl + QB_TG8_C_D0 + c + 4 * jc, h);
-                qb_tg8_st4(tl + QB_TG8_C_D0 + c + 16 + 4 * jc, l);
+                qb_tmem_st16(tl + QB_TG8_C_D1 + c + 16 * hf, o);
             }
-            return yt;
         };
 
         float yv = 0.0f;                                             // target of this thread's point of the current tile
         if (T > 0) {
-            yv = layer0(0);
+            fetch(0);
+            yv = yn;
+            xstore(0);
+            publish();
+            qb3_wait(bar_l, 0u);
+            qb_tc_fence_after();
+            epil();
             qb_tmem_st_wait();
-            unpark(QB_TG8_C_D0, a_hi, a_lo);
+            unpark(QB_TG8_C_D1, a_hi, a_lo);
             publish();
         }
 #pragma unroll 1
@@ -422,8 +466,11 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
             const bool live = p < n1;
             const bool more = t + 1 < T;
             // ---------------- phase B: EPI1(t)
+            QB_TG8_STAMP(t, 0);
+            if (more) fetch(t + 1);
             qb3_wait(bar_f, (uint32_t)t & 1u);
             qb_tc_fence_after();
+            QB_TG8_STAMP(t, 1);
             {
                 float2 acc = make_float2(0.0f, 0.0f);
                 const float2 c2 = make_float2(c1, c1);
@@ -447,6 +494,7 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
                 }
                 ybuf[grp * 128 + pt] = acc.x + acc.y;
                 qb_tmem_st_wait();
+                QB_TG8_STAMP(t, 2);
                 asm volatile("bar.sync %0, %1;" :: "r"(1 + quarter), "n"(128) : "memory");
                 float yo = F[tp.bl];
 #pragma unroll
@@ -454,7 +502,9 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
                 const float r = live ? yv - yo : 0.0f;
                 const float dy = r * is2, dyz = dy * sz1;
                 if (grp == 0) { ssq = fmaf(r, r, ssq); dbl += dy; }
-                if (t > 0) { qb3_wait(bar_z, (uint32_t)(t - 1) & 1u); qb_tc_fence_after(); }     // DW0(t-1) has read the z image
+                if (t > 0) { qb3_wait(bar_z, (uint32_t)(t - 1) & 1u); qb_tc_fence_after(); }     // DW0(t-1) has read the z and X images
+                QB_TG8_STAMP(t, 3);
+                if (more) xstore(t + 1);
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                     uint32_t v[16];
@@ -483,15 +533,17 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
                     }
                 }
             }
+            QB_TG8_STAMP(t, 4);
             publish();
-            // ---------------- phase A: EPI0(t) and L0(t+1) while DW1(t) runs; both results parked in tensor memory
+            // ---------------- phase A: EPI0(t) and EPIL(t+1) while DW1(t) runs; results stay in tensor memory until DW1(t) is done
             qb3_wait(bar_b, (uint32_t)t & 1u);
             qb_tc_fence_after();
+            QB_TG8_STAMP(t, 5);
             {
                 const float2 k2 = make_float2(k0, k0), sa = make_float2(6.103515625e-05f, 6.103515625e-05f), one = make_float2(1.0f, 1.0f);
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
-                    uint32_t v[16];
+                    uint32_t v[16], o[16];
                     qb_tmem_ld16(tl + QB_TG8_C_D0 + c + 16 * hf, v);
                     qb_tmem_ld_wait16(v);
 #pragma unroll
@@ -499,7 +551,6 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
                         const uint4 h4 = *reinterpret_cast<const uint4*>(a_hi + 2048 * (2 * hf + jj));
                         const uint4 l4 = *reinterpret_cast<const uint4*>(a_lo + 2048 * (2 * hf + jj));
                         const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
-                        uint32_t h[4], l[4];
 #pragma unroll
                         for (int w = 0; w < 4; ++w) {
                             float2 a = __fadd2_rn(qb_tg8_unpack(hw[w]), qb_tg8_unpack(lw[w]));
@@ -507,21 +558,23 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
                             const float2 da = __ffma2_rn(make_float2(-a.x, -a.y), a, one);
                             const float2 d = make_float2(__uint_as_float(v[8 * jj + 2 * w]), __uint_as_float(v[8 * jj + 2 * w + 1]));
                             const float2 z = __fmul2_rn(__fmul2_rn(d, k2), da);
-                            qb_tg8_split(z.x, z.y, h[w], l[w]);
+                            qb_tg8_split(z.x, z.y, o[4 * jj + w], o[8 + 4 * jj + w]);
                         }
-                        // parked in the D1 columns (free between EPI1(t) and FWD(t+1)): the z image is still an operand of DW1(t)
-                        qb_tg8_st4(tl + QB_TG8_C_D1 + c + 4 * (2 * hf + jj), h);
-                        qb_tg8_st4(tl + QB_TG8_C_D1 + c + 16 + 4 * (2 * hf + jj), l);
                     }
+                    qb_tmem_st16(tl + QB_TG8_C_D0 + c + 16 * hf, o);      // the z image is still an operand of DW1(t)
                 }
             }
-            if (more) yv = layer0(t + 1);
+            QB_TG8_STAMP(t, 6);
+            if (more) { epil(); yv = yn; }
             qb_tmem_st_wait();
+            QB_TG8_STAMP(t, 7);
             qb3_wait(bar_w, (uint32_t)t & 1u);                      // DW1(t) has read the z and a0 images
             qb_tc_fence_after();
-            unpark(QB_TG8_C_D1, z_hi, z_lo);
-            if (more) unpark(QB_TG8_C_D0, a_hi, a_lo);
+            QB_TG8_STAMP(t, 8);
+            unpark(QB_TG8_C_D0, z_hi, z_lo);
+            if (more) unpark(QB_TG8_C_D1, a_hi, a_lo);
             publish();
+            QB_TG8_STAMP(t, 9);
         }
         if (T > 0) { qb3_wait(bar_z, (uint32_t)(T - 1) & 1u); qb_tc_fence_after(); }
 

@@ -139,11 +139,13 @@ def test_tensor_core_plan_selection_is_host_logic():
     assert g5[6] == 3 and g5[1] == 512 and g5[7] == 512 and g5[2] <= 227 * 1024
     g2 = info('mlp_c2', _lib.QB_F32, grad=1)
     assert g2[6] == 3 and g2[1] == 256 and g2[7] == 256
-    assert info('mlp_c3', _lib.QB_F32, grad=1)[6] == 0          # 128-wide: operands exceed shared memory -> CUDA cores
+    g3 = info('mlp_c3', _lib.QB_F32, grad=1)                    # 128-wide: fp16-split kernel 2 (qb_tg8.cuh)
+    assert g3[6] == 4 and g3[1] == 544 and g3[7] == 512 and g3[2] <= 227 * 1024
     assert info('mlp_c5', _lib.QB_F64, grad=1)[6] == 0
     os.environ['QB_NO_TCG'] = '1'
     try:
         assert info('mlp_c5', _lib.QB_F32, grad=1)[6] == 0 and info('mlp_c5', _lib.QB_F32)[6] == 2
+        assert info('mlp_c3', _lib.QB_F32, grad=1)[6] == 0
     finally:
         del os.environ['QB_NO_TCG']
     assert info('rnet_c1', _lib.QB_F32)[6] == 0                 # residual nets are not eligible
