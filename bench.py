@@ -391,10 +391,11 @@ def main():
     args.warmup = max(args.warmup, 3)
     line = run_native(spec, args, args.steps, args.warmup, rank, world, local, headline=True)
     # the other halves of BASELINE.json's metric ("log-post+grad evals/s", "predictive pts/s"), outside the headline timed
-    # region: HMC at the north_star target shape (tensor-core gradient kernel) and the config-3 predictive sweep
+    # region: HMC at the north_star target shape (tensor-core gradient kernel), the config-3 predictive sweep, config 4 (VI ELBO
+    # value + gradient) and the config-3 ensemble fit, each on its own tensor-core kernel
     if args.workload == 'c5' and not args.no_extra and not args.chains:
         extra = {}
-        for name in ('c5h', 'c3'):
+        for name in ('c5h', 'c3', 'c4', 'c3fit', 'c2'):
             torch.cuda.empty_cache()
             sub = run_native(workload_spec(name), args, 3, 3, rank, world, local, headline=False)
             if rank == 0:
@@ -557,6 +558,11 @@ def run_native(spec, args, steps, warmup, rank, world, local, headline):
                             'sigmoid epilogues on MUFU)' if v3 else 'k_predict_tc (tcgen05.mma kind::tf32 x3 passes + MUFU tanh epilogue)',
                  'hmc': 'k_hmc_tc (forward, back-propagation and weight-gradient GEMMs on tcgen05.mma kind::tf32 x3 passes)'
                  }.get(spec['sampler'], 'k_logpost_grad_tc (tcgen05.mma kind::tf32 x3 passes)')
+        if tc == 4:            # fp16-split gradient kernels (qb_tg8.cuh)
+            kname = ('k_hmc_tc128' if spec['sampler'] == 'hmc' else 'k_logpost_grad_tc128') + \
+                    '<%d> (layer 0, forward, back-propagation and both weight-gradient GEMMs on tcgen05.mma kind::f16 x3 passes, fp16 hi/lo ' \
+                    'operands with exact power-of-two scaling, one shared-memory image per matrix for its K-major and MN-major use, ' \
+                    'dedicated issue warp)' % int(spec['hls'][0])
         roofline = dict(bound='tensor', kernel=kname, achieved=achieved / 1e12, peak=peak_bf16, unit='TFLOP/s',
                         frac=achieved / 1e12 / peak_bf16, traffic=traffic, peak_source=src,
                         tf32_peak=peak_bf16 / 2.0, frac_of_tf32_peak=achieved / 1e12 / (peak_bf16 / 2.0),
@@ -566,6 +572,13 @@ def run_native(spec, args, steps, warmup, rank, world, local, headline):
                              'dense bf16 TFLOP/s (%s); kind::tf32 runs at half of it (tf32_peak) and these kernels do 3 TF32 passes '
                              'per GEMM for fp32 accuracy (ceiling = peak/6, frac_of_tf32x3_peak); x_fp32_core_peak compares with the '
                              'live CUDA-core FMA peak that bounds the SIMT kernels' % src)
+        if tc == 4:
+            # every GEMM of the gradient kernel is 3 kind::f16 passes: ceiling of the algorithm on the tensor pipe = peak / 3
+            roofline.update(f16x3_peak=peak_bf16 / 3.0, frac_of_f16x3_peak=achieved / 1e12 / (peak_bf16 / 3.0))
+            roofline['note'] = ('achieved = algorithmic fp32 GEMM flops (2 flop/MAC, SURVEY 8d: value + gradient = 6 N S - 2 N n0 n1) / '
+                                'CUDA-event time; peak = measured dense bf16 TFLOP/s (%s); this kernel does 3 kind::f16 passes per GEMM for '
+                                'fp32-level accuracy (ceiling = peak/3, frac_of_f16x3_peak); its MMAs take both operands from shared memory '
+                                'and are bound by that operand traffic (8 KB per 128x128x16 MMA = 64 cycles), see DESIGN.md 4d' % src)
         if v3:
             # tensor-pipe ceiling of THIS algorithm: per point 3 x (8 x 64) tf32 MAC slots (layer 0, K padded to 8; tf32 = half the
             # bf16 rate) + 3 x (64 x 64) f16 slots against S algorithmic MACs

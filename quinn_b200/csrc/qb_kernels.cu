@@ -461,6 +461,11 @@ template <> int launch_grad_tc128<float>(const QbTg8Plan& tg, const EvalArgs<flo
     QB_CUDA(qb_tg8_launch_eval(tg, a, scratch, grid, st));
     return 0;
 }
+template <typename T> static int launch_hmc_tc128(const QbTg8Plan&, const ChainArgs<T>&, const HmcArgs<T>&, long long, cudaStream_t) { return qb_fail("tensor-core path is fp32 only"); }
+template <> int launch_hmc_tc128<float>(const QbTg8Plan& tg, const ChainArgs<float>& c, const HmcArgs<float>& h, long long K, cudaStream_t st) {
+    QB_CUDA(qb_tg8_launch_hmc(tg, c, h, K, st));
+    return 0;
+}
 template <typename T> static int launch_hmc_tc(const QbTcgPlan&, const ChainArgs<T>&, const HmcArgs<T>&, long long, cudaStream_t) { return qb_fail("tensor-core path is fp32 only"); }
 template <> int launch_hmc_tc<float>(const QbTcgPlan& tg, const ChainArgs<float>& c, const HmcArgs<float>& h, long long K, cudaStream_t st) {
     QB_CUDA(qb_tcg_launch_hmc(tg, c, h, K, st));
@@ -515,12 +520,12 @@ static int run_eval(const qb_net_t* net, int dtype, const void* theta, int64_t K
     if (want_grad) {
         QbTcgPlan tg;
         QbTg8Plan t8;
-        if (qb_tcg_make_plan(net, dtype, &tg)) {
-            if (launch_grad_tc<T>(tg, a, grid, st)) return -2;
-        } else if (qb_tg8_make_plan(net, dtype, &t8)) {
-            // 128-wide nets: fp16-split operands, scaled with max |x|, max |y| (8 bytes at the end of the workspace)
+        if (qb_tg8_make_plan(net, dtype, &t8)) {
+            // tanh nets of width 64 / 128: fp16-split operands, scaled with max |x|, max |y| (8 bytes at the end of the workspace)
             if (launch_grad_tc128<T>(t8, a, (char*)ws + need - QB_TG8_SCRATCH_BYTES, grid, st)) return -2;
             g_launches += 1;
+        } else if (qb_tcg_make_plan(net, dtype, &tg)) {
+            if (launch_grad_tc<T>(tg, a, grid, st)) return -2;
         } else {
             if (set_smem(k_logpost_grad<T>, L.plan.smem_bytes)) return -2;
             k_logpost_grad<T><<<grid, L.plan.nthreads, L.plan.smem_bytes, st>>>(L.plan, a);
@@ -552,7 +557,8 @@ extern "C" size_t qb_eval_workspace_bytes(const qb_net_t* net, int dtype, int64_
     if (!want_grad && make_tc_plan(net, dtype, &tp, 1) && tp.v3) b = (b + 255) / 256 * 256 + qb_tc3_xsplit_bytes(N, tp.v3 == 1 ? 8 : 16);
     QbTcgPlan tg;
     QbTg8Plan t8;
-    if (want_grad && !qb_tcg_make_plan(net, dtype, &tg) && qb_tg8_make_plan(net, dtype, &t8)) b = (b + 255) / 256 * 256 + QB_TG8_SCRATCH_BYTES;
+    (void)tg;
+    if (want_grad && qb_tg8_make_plan(net, dtype, &t8)) b = (b + 255) / 256 * 256 + QB_TG8_SCRATCH_BYTES;
     return b;
 }
 
@@ -562,15 +568,13 @@ extern "C" int qb_plan_info(const qb_net_t* net, int dtype, int64_t K, int64_t N
     out[0] = L.plan.TM; out[1] = L.plan.nthreads; out[2] = L.plan.smem_bytes; out[3] = L.S;
     out[4] = (int64_t)K * L.S; out[5] = L.plan.inplace; out[6] = 0; out[7] = 0;
     QbTcgPlan tg;
-    if (want_grad && qb_tcg_make_plan(net, dtype, &tg)) {
-        // gradient path on the tensor cores: out[6] = 3
+    QbTg8Plan t8;
+    if (want_grad && qb_tg8_make_plan(net, dtype, &t8)) {
+        // gradient path on the tensor cores, fp16-split operands (qb_tg8.cuh: tanh nets of width 64 / 128): out[6] = 4
+        out[0] = 128; out[1] = t8.nthreads; out[2] = t8.smem_bytes; out[5] = 0; out[6] = 4; out[7] = t8.tmem_cols;
+    } else if (want_grad && qb_tcg_make_plan(net, dtype, &tg)) {
+        // gradient path on the tensor cores, 3xTF32 (qb_tcg.cuh: widths 32 / 64, tanh / relu): out[6] = 3
         out[0] = 128; out[1] = tg.nthreads; out[2] = tg.smem_bytes; out[5] = 0; out[6] = 3; out[7] = tg.tmem_cols;
-    } else {
-        QbTg8Plan t8;
-        if (want_grad && qb_tg8_make_plan(net, dtype, &t8)) {
-            // 128-wide gradient path on the tensor cores (qb_tg8.cuh): out[6] = 4
-            out[0] = 128; out[1] = t8.nthreads; out[2] = t8.smem_bytes; out[5] = 0; out[6] = 4; out[7] = t8.tmem_cols;
-        }
     }
     QbTcPlan tp;
     if (!want_grad && make_tc_plan(net, dtype, &tp, 1)) {
@@ -967,7 +971,11 @@ static int run_hmc(const qb_net_t* net, int dtype, const qb_data_t* data, const 
     h.method = hm->method; h.L = hm->L; h.eps = hm->epsilon;
     h.gcur = (T*)hm->grad_cur; h.mom = (T*)hm->mom; h.prop = (T*)hm->prop; h.gprop = (T*)hm->grad_prop;
     QbTcgPlan tg;
-    if (qb_tcg_make_plan(net, dtype, &tg)) {
+    QbTg8Plan t8;
+    if (qb_tg8_make_plan(net, dtype, &t8)) {
+        if (launch_hmc_tc128<T>(t8, c, h, ch->K, st)) return -2;
+        g_launches += 1;
+    } else if (qb_tcg_make_plan(net, dtype, &tg)) {
         if (launch_hmc_tc<T>(tg, c, h, ch->K, st)) return -2;
     } else {
         if (set_smem(k_hmc<T>, L.plan.smem_bytes)) return -2;

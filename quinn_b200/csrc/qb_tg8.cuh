@@ -1,5 +1,6 @@
 // Tensor-core evaluation of the log-posterior AND its gradient (kernel 2 on tcgen05) for the 128-wide fp32 MLPs
-//   in (d <= 15) -> 128 -> 128 -> 1, tanh on both hidden layers, linear output     (BASELINE configs 3 and 4: 10-128-128-1)
+//   in (d <= 15) -> H -> H -> 1, H in {64, 128}, tanh on both hidden layers, linear output
+//   (BASELINE configs 3 and 4: 10-128-128-1; config 5 / north_star's HMC target: 3-64-64-1)
 // Reverse mode of nnwrap.py:128-150 (autograd over NegLogPost, losses.py:186-206), restated in oracle/quinn_oracle.py.
 // qb_tcg.cuh (widths 32 / 64, kind::tf32) does not scale to this width: its four fp32 copies of W1 alone are 256 KB.
 //
@@ -9,8 +10,8 @@
 // accept an fp16 operand next to a bf16 one (scripts/tc_probe5.cu: illegal instruction), so the back-propagated
 // quantities are fp16 as well, scaled by a bound that is known BEFORE the tile loop (see qb_tg8_stage).
 //
-// One tile = 128 data points = the 128 lanes of tensor memory.  16 compute warps: thread = (point, 32 of the 128 units);
-// warp 16 only issues MMAs.  Per tile (p = point, i = layer-0 unit, j = layer-1 unit):
+// One tile = 128 data points = the 128 lanes of tensor memory.  H/8 compute warps: thread = (point, 32 of the H units);
+// the warp behind them only issues MMAs.  (H = 64, config 5's net, runs the same code with two blocks per SM.)  Per tile (p = point, i = layer-0 unit, j = layer-1 unit):
 //   L0    tcgen05      DL[p][i] = sum_c X[p][c] W0'[i][c]            A = X image = [x | 1 | 0] (K-major view), B = W0 image = [W0 | b0 | 0]
 //   EPIL  CUDA cores   a0 = tanh(DL)                                 -> a0 image
 //   FWD   tcgen05      D1[p][j] = sum_i a0[p][i] W1[j][i]            A = a0 image (K-major view), B = W image (K-major view)
@@ -48,8 +49,16 @@
 
 #ifdef __CUDACC__
 enum { QB_TG8_BAR_F = 400, QB_TG8_BAR_B = 408, QB_TG8_BAR_W = 416, QB_TG8_BAR_Z = 424, QB_TG8_BAR_RDY = 432, QB_TG8_SLOT = 440, QB_TG8_BAR_L = 448,
-       QB_TG8_HDR = 512, QB_TG8_IMG = 32768, QB_TG8_AIMG = 36864, QB_TG8_XIMG = 4096, QB_TG8_W0IMG = 4096, QB_TG8_NCOMP = 512 };
-enum { QB_TG8_C_D1 = 0, QB_TG8_C_D0 = 128, QB_TG8_C_DW1 = 256, QB_TG8_C_DW0 = 400 };
+       QB_TG8_HDR = 512, QB_TG8_XIMG = 4096 };
+// Hidden width H (128: configs 3 / 4, one block per SM; 64: config 5, two blocks per SM): G = H/32 thread groups of 128 compute
+// threads (thread = point x 32 units), the issue warp comes after them.  Images of 128 points x H units; tensor-memory
+// columns R1 | R0 | G1 (H + 16: the ones block yields db1) | G0 (16)
+template <int H> struct QbTg8Dim {
+    static constexpr int G = H / 32, NCOMP = 128 * G, ISSUER = 4 * G;
+    static constexpr int IMG = 256 * H, AIMG = IMG + 4096, W0IMG = 32 * H, WIMG = 2 * H * H, WSBO = 16 * H;
+    static constexpr int C_D1 = 0, C_D0 = H, C_DW1 = 2 * H, C_DW0 = 3 * H + 16;
+    static constexpr int CPG = 16 / G;                    // X image columns laid out by one thread group
+};
 // float slots behind tp.sc
 enum { QB_TG8_S_C1 = 0, QB_TG8_S_SZ1 = 1, QB_TG8_S_K0 = 2, QB_TG8_S_UW1 = 3, QB_TG8_S_UW0 = 4, QB_TG8_S_SX = 5, QB_TG8_S_C0 = 6 };
 
@@ -66,7 +75,9 @@ __device__ unsigned int qb_tg8_trace_buf[QB_TG8_TR_BLOCKS * QB_TG8_TR_WARPS * QB
 __device__ __forceinline__ float qb_tg8_pow2(int e) { return __uint_as_float((uint32_t)(127 + max(-126, min(127, e))) << 23); }
 
 // all threads: tensor-memory allocation and the mbarriers
+template <int H>
 __device__ __forceinline__ uint32_t qb_tg8_init(const QbTg8Plan& tp, unsigned char* smem) {
+    using D = QbTg8Dim<H>;
     if ((threadIdx.x >> 5) == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      :: "r"(qb_smem_u32(smem + QB_TG8_SLOT)), "r"((uint32_t)tp.tmem_cols) : "memory");
@@ -78,7 +89,7 @@ __device__ __forceinline__ uint32_t qb_tg8_init(const QbTg8Plan& tp, unsigned ch
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB_TG8_BAR_B), "r"(1u) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB_TG8_BAR_W), "r"(1u) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB_TG8_BAR_Z), "r"(1u) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB_TG8_BAR_RDY), "r"((uint32_t)QB_TG8_NCOMP) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB_TG8_BAR_RDY), "r"((uint32_t)D::NCOMP) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB_TG8_BAR_L), "r"(1u) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -94,13 +105,15 @@ __device__ __forceinline__ void qb_tg8_fini(const QbTg8Plan& tp, uint32_t tmem) 
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)tp.tmem_cols) : "memory");
 }
 // thread 0, between two block barriers: every phase of the previous evaluation has completed, start again at parity 0
+template <int H>
 __device__ __forceinline__ void qb_tg8_reset_barriers(unsigned char* smem) {
+    using D = QbTg8Dim<H>;
     const uint32_t b = qb_smem_u32(smem);
     const uint32_t off[6] = {QB_TG8_BAR_F, QB_TG8_BAR_B, QB_TG8_BAR_W, QB_TG8_BAR_Z, QB_TG8_BAR_RDY, QB_TG8_BAR_L};
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
         asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"(b + off[i]) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + off[i]), "r"(i == 4 ? (uint32_t)QB_TG8_NCOMP : 1u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + off[i]), "r"(i == 4 ? (uint32_t)D::NCOMP : 1u) : "memory");
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -150,9 +163,10 @@ __device__ __forceinline__ void qb_tg8_tanh4(float2& a, float2& b, float S) {
 //   A value far below its bound loses nothing until it is ~2^17 below it (fp16 keeps 2^16 .. 2^-24; hi and lo need 22 bits);
 //   further down the lo part runs out of bits one by one (absolute error 2^-25 in image units) - only gradients that are
 //   tiny against these bounds in EVERY entry (saturated units AND residuals far below sigma) see it, at the 1e-5 level.
+template <int H>
 __device__ __forceinline__ void qb_tg8_stage(const QbTg8Plan& tp, unsigned char* smem, const float* __restrict__ theta,
                                              const float* __restrict__ absmax, float is2) {
-    constexpr int H = 128;
+    using D = QbTg8Dim<H>;
     float* F = reinterpret_cast<float*>(smem + tp.fl_base);
     float* sred = reinterpret_cast<float*>(smem);                      // [17][4] + [17]
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
@@ -195,7 +209,7 @@ __device__ __forceinline__ void qb_tg8_stage(const QbTg8Plan& tp, unsigned char*
     // ---- W0 image: element (unit i, column q) at halfword (i/8)*128 + (q/8)*64 + (i%8)*8 + q%8
     {
         uint32_t* hi = reinterpret_cast<uint32_t*>(smem + tp.w0_img);
-        uint32_t* lo = hi + QB_TG8_W0IMG / 4;
+        uint32_t* lo = hi + D::W0IMG / 4;
         const float sc0 = fold * qb_tg8_pow2(s0);
         for (int e = tid; e < H * 8; e += nt) {
             const int i = e >> 3, q = (e & 7) * 2;
@@ -215,9 +229,9 @@ __device__ __forceinline__ void qb_tg8_stage(const QbTg8Plan& tp, unsigned char*
     // ---- W image: word index of the pair (j, i), (j, i + 1)
     {
         uint32_t* hi = reinterpret_cast<uint32_t*>(smem + tp.w_img);
-        uint32_t* lo = hi + QB_TG8_IMG / 4;
+        uint32_t* lo = hi + D::WIMG / 4;
         for (int e = tid; e < H * H / 2; e += nt) {
-            const int j = e >> 6, i = (e & 63) * 2;
+            const int j = e / (H / 2), i = (e % (H / 2)) * 2;
             const float w0 = theta[tp.w1_off + j * H + i], w1 = theta[tp.w1_off + j * H + i + 1];
             uint32_t h2, l2;
             qb_tg8_split(w0 * wscale, w1 * wscale, h2, l2);
@@ -227,7 +241,7 @@ __device__ __forceinline__ void qb_tg8_stage(const QbTg8Plan& tp, unsigned char*
     }
     // ---- ones block of the a0 hi image (the lo image has none: its pass of DW1 runs with N = 128)
     {
-        uint32_t* hi = reinterpret_cast<uint32_t*>(smem + tp.a_img + QB_TG8_IMG);            // units 128 .. 143
+        uint32_t* hi = reinterpret_cast<uint32_t*>(smem + tp.a_img + D::IMG);            // units H .. H + 15
         for (int e = tid; e < 2 * 2048 / 4; e += nt)
             hi[e] = (e < 512 && (e & 3) == 0) ? 0x00007400u : 0u;      // chunk 16: word 0 of every point's 16-byte row = (2^14, 0)
     }
@@ -279,9 +293,11 @@ __device__ __forceinline__ void qb_tg8_issue3(uint32_t d, uint32_t a_hi_img, uin
 // Value + gradient of the data term over points [n0, n1) for the staged parameter vector.  Every thread of the block
 // (512 compute threads + the issue warp) calls it.  Returns the block-wide sum of squared residuals; g[0..P) (global, this
 // block's row) receives d/dtheta of -0.5*ssq/sigma^2.
+template <int H>
 __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem, unsigned char* smem, const float* __restrict__ x,
                                               const float* __restrict__ y, int64_t n0, int64_t n1, float is2, float* __restrict__ g) {
-    constexpr int H = 128;
+    using D = QbTg8Dim<H>;
+    constexpr int G = D::G, KS = H / 16;
     const float* F = reinterpret_cast<const float*>(smem + tp.fl_base);
     const uint32_t sb = qb_smem_u32(smem);
     const uint32_t bar_f = sb + QB_TG8_BAR_F, bar_b = sb + QB_TG8_BAR_B, bar_w = sb + QB_TG8_BAR_W, bar_z = sb + QB_TG8_BAR_Z,
@@ -289,32 +305,33 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = (int)((n1 - n0 + 127) / 128);
     __syncthreads();                               // staging complete; nobody is still inside the previous evaluation
-    if (threadIdx.x == 0) qb_tg8_reset_barriers(smem);
+    if (threadIdx.x == 0) qb_tg8_reset_barriers<H>(smem);
     __syncthreads();
     float ssq = 0.0f, dbl = 0.0f;
     float dwl[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) dwl[i] = 0.0f;
 
-    if (wid == QB_TG8_NCOMP / 32) {
+    if (wid == D::ISSUER) {
         // ================================ issue warp ================================
-        const uint32_t id_base = (1u << 4) | ((128u >> 4) << 24);
-        const uint32_t id_fwd = id_base | ((128u >> 3) << 17);
+        // D = f32; M = 128 (points) for L0 / FWD / BWD, M = H (units) for the weight gradients
+        const uint32_t id_pts = (1u << 4) | ((128u >> 4) << 24), id_unt = (1u << 4) | ((uint32_t)(H >> 4) << 24) | (1u << 15) | (1u << 16);
+        const uint32_t id_fwd = id_pts | ((uint32_t)(H >> 3) << 17);
         const uint32_t id_bwd = id_fwd | (1u << 16);
-        const uint32_t id_dw1 = id_base | (1u << 15) | (1u << 16) | ((144u >> 3) << 17);
-        const uint32_t id_dw1n = id_base | (1u << 15) | (1u << 16) | ((128u >> 3) << 17);
-        const uint32_t id_dw0 = id_base | (1u << 15) | (1u << 16) | ((16u >> 3) << 17);
-        const uint32_t dh_a = qb_tg8_dhi(128u), dh_b = qb_tg8_dhi(2048u);          // (LBO 2048, SBO 128) / (LBO 128, SBO 2048)
+        const uint32_t id_dw1 = id_unt | ((uint32_t)((H + 16) >> 3) << 17);
+        const uint32_t id_dw1n = id_unt | ((uint32_t)(H >> 3) << 17);
+        const uint32_t id_dw0 = id_unt | ((16u >> 3) << 17);
+        const uint32_t dh_a = qb_tg8_dhi(128u), dh_b = qb_tg8_dhi(2048u), dh_w = qb_tg8_dhi((uint32_t)D::WSBO);   // SBO 128 / 2048 / 16 H
         const uint32_t a_img = sb + (uint32_t)tp.a_img, z_img = sb + (uint32_t)tp.z_img, w_img = sb + (uint32_t)tp.w_img,
                        w0_img = sb + (uint32_t)tp.w0_img;
         // K-major views of the point images and the MN-major view of W: LBO 2048; the other views: LBO 128
-        const uint32_t aK_hi = qb_tg8_dlo(a_img, 2048u), aK_lo = qb_tg8_dlo(a_img + QB_TG8_AIMG, 2048u);
-        const uint32_t aM_hi = qb_tg8_dlo(a_img, 128u), aM_lo = qb_tg8_dlo(a_img + QB_TG8_AIMG, 128u);
-        const uint32_t zK_hi = qb_tg8_dlo(z_img, 2048u), zK_lo = qb_tg8_dlo(z_img + QB_TG8_IMG, 2048u);
-        const uint32_t zM_hi = qb_tg8_dlo(z_img, 128u), zM_lo = qb_tg8_dlo(z_img + QB_TG8_IMG, 128u);
-        const uint32_t wK_hi = qb_tg8_dlo(w_img, 128u), wK_lo = qb_tg8_dlo(w_img + QB_TG8_IMG, 128u);
-        const uint32_t wM_hi = qb_tg8_dlo(w_img, 2048u), wM_lo = qb_tg8_dlo(w_img + QB_TG8_IMG, 2048u);
-        const uint32_t w0_hi = qb_tg8_dlo(w0_img, 128u), w0_lo = qb_tg8_dlo(w0_img + QB_TG8_W0IMG, 128u), dh_w0 = qb_tg8_dhi(256u);
+        const uint32_t aK_hi = qb_tg8_dlo(a_img, 2048u), aK_lo = qb_tg8_dlo(a_img + D::AIMG, 2048u);
+        const uint32_t aM_hi = qb_tg8_dlo(a_img, 128u), aM_lo = qb_tg8_dlo(a_img + D::AIMG, 128u);
+        const uint32_t zK_hi = qb_tg8_dlo(z_img, 2048u), zK_lo = qb_tg8_dlo(z_img + D::IMG, 2048u);
+        const uint32_t zM_hi = qb_tg8_dlo(z_img, 128u), zM_lo = qb_tg8_dlo(z_img + D::IMG, 128u);
+        const uint32_t wK_hi = qb_tg8_dlo(w_img, 128u), wK_lo = qb_tg8_dlo(w_img + D::WIMG, 128u);
+        const uint32_t wM_hi = qb_tg8_dlo(w_img, (uint32_t)D::WSBO), wM_lo = qb_tg8_dlo(w_img + D::WIMG, (uint32_t)D::WSBO);
+        const uint32_t w0_hi = qb_tg8_dlo(w0_img, 128u), w0_lo = qb_tg8_dlo(w0_img + D::W0IMG, 128u), dh_w0 = qb_tg8_dhi(256u);
         uint32_t n = 0;
         auto wait_rdy = [&]() {
             qb3_wait(bar_rdy, n & 1u);
@@ -325,7 +342,7 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
         // layer 0 of tile u: X image (K-major view, K = 16: one k-step) x W0 image -> R1
         auto issue_l0 = [&](int u) {
             const uint32_t x_img = sb + (uint32_t)tp.x_img + (uint32_t)(u & 1) * 2u * QB_TG8_XIMG;
-            qb_tg8_issue3<1>(tmem + QB_TG8_C_D1, qb_tg8_dlo(x_img, 2048u), qb_tg8_dlo(x_img + QB_TG8_XIMG, 2048u), dh_a, 0u,
+            qb_tg8_issue3<1>(tmem + D::C_D1, qb_tg8_dlo(x_img, 2048u), qb_tg8_dlo(x_img + QB_TG8_XIMG, 2048u), dh_a, 0u,
                              w0_hi, w0_lo, dh_w0, 0u, id_fwd, id_fwd, 0u);
         };
         if (T > 0) {
@@ -334,7 +351,7 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
             __syncwarp();
             wait_rdy();                                                   // a0(0) is in the a0 image
             if (qb3_elect()) {
-                qb_tg8_issue3<8>(tmem + QB_TG8_C_D1, aK_hi, aK_lo, dh_a, 256u, wK_hi, wK_lo, dh_b, 16u, id_fwd, id_fwd, 0u);
+                qb_tg8_issue3<KS>(tmem + D::C_D1, aK_hi, aK_lo, dh_a, 256u, wK_hi, wK_lo, dh_w, 16u, id_fwd, id_fwd, 0u);
                 qb3_commit(bar_f);
             }
             __syncwarp();
@@ -346,9 +363,9 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
             QB_TG8_STAMP(t, 0);
             if (qb3_elect()) {
                 if (t + 1 < T) issue_l0(t + 1);
-                qb_tg8_issue3<8>(tmem + QB_TG8_C_D0, zK_hi, zK_lo, dh_a, 256u, wM_hi, wM_lo, dh_a, 256u, id_bwd, id_bwd, 0u);
+                qb_tg8_issue3<KS>(tmem + D::C_D0, zK_hi, zK_lo, dh_a, 256u, wM_hi, wM_lo, dh_a, (uint32_t)(2 * D::WSBO) >> 4, id_bwd, id_bwd, 0u);
                 qb3_commit(bar_b);
-                qb_tg8_issue3<8>(tmem + QB_TG8_C_DW1, zM_hi, zM_lo, dh_b, 16u, aM_hi, aM_lo, dh_b, 16u, id_dw1, id_dw1n, acc0);
+                qb_tg8_issue3<8>(tmem + D::C_DW1, zM_hi, zM_lo, dh_b, 16u, aM_hi, aM_lo, dh_b, 16u, id_dw1, id_dw1n, acc0);
                 qb3_commit(bar_w);
             }
             __syncwarp();
@@ -357,11 +374,11 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
             QB_TG8_STAMP(t, 2);
             if (qb3_elect()) {
                 if (t + 1 < T) {
-                    qb_tg8_issue3<8>(tmem + QB_TG8_C_D1, aK_hi, aK_lo, dh_a, 256u, wK_hi, wK_lo, dh_b, 16u, id_fwd, id_fwd, 0u);
+                    qb_tg8_issue3<KS>(tmem + D::C_D1, aK_hi, aK_lo, dh_a, 256u, wK_hi, wK_lo, dh_w, 16u, id_fwd, id_fwd, 0u);
                     qb3_commit(bar_f);
                 }
                 const uint32_t x_img = sb + (uint32_t)tp.x_img + (uint32_t)(t & 1) * 2u * QB_TG8_XIMG;
-                qb_tg8_issue3<8>(tmem + QB_TG8_C_DW0, zM_hi, zM_lo, dh_b, 16u, qb_tg8_dlo(x_img, 128u), qb_tg8_dlo(x_img + QB_TG8_XIMG, 128u),
+                qb_tg8_issue3<8>(tmem + D::C_DW0, zM_hi, zM_lo, dh_b, 16u, qb_tg8_dlo(x_img, 128u), qb_tg8_dlo(x_img + QB_TG8_XIMG, 128u),
                                  dh_b, 16u, id_dw0, id_dw0, acc0);
                 qb3_commit(bar_z);
             }
@@ -376,10 +393,10 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
         const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16);
         const uint32_t prow = (pt >> 3) * 128u + (pt & 7u) * 16u;           // this point's 16-byte row inside an 8-unit chunk
         const uint32_t poff = prow + (uint32_t)(c >> 3) * 2048u;            // chunk j of this thread: + 2048 j
-        unsigned char* a_hi = smem + tp.a_img + poff; unsigned char* a_lo = a_hi + QB_TG8_AIMG;
-        unsigned char* z_hi = smem + tp.z_img + poff; unsigned char* z_lo = z_hi + QB_TG8_IMG;
-        // X image: thread group g lays out columns 4g .. 4g+3 of its point (half of a 16-byte row)
-        unsigned char* x_row = smem + tp.x_img + (grp >> 1) * 2048 + prow + (grp & 1) * 8;
+        unsigned char* a_hi = smem + tp.a_img + poff; unsigned char* a_lo = a_hi + D::AIMG;
+        unsigned char* z_hi = smem + tp.z_img + poff; unsigned char* z_lo = z_hi + D::IMG;
+        // X image: thread group g lays out columns CPG g .. CPG g + CPG - 1 of its point (a 16-byte row, or half of one)
+        unsigned char* x_row = smem + tp.x_img + ((grp * D::CPG) >> 3) * 2048 + prow + ((grp * D::CPG) & 7) * 2;
         float* ybuf = reinterpret_cast<float*>(smem + tp.ybuf);
         const float c1 = F[tp.sc + QB_TG8_S_C1], sz1 = F[tp.sc + QB_TG8_S_SZ1], k0 = F[tp.sc + QB_TG8_S_K0], sx = F[tp.sc + QB_TG8_S_SX],
                     c0 = F[tp.sc + QB_TG8_S_C0];
@@ -407,12 +424,12 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
             }
         };
         // inputs of tile tt: this thread's four columns of its point (x, then the constant 1, then zeros) and the target
-        float xq[4], yn = 0.0f;
+        float xq[D::CPG], yn = 0.0f;
         auto fetch = [&](int tt) {
             const int64_t pp = n0 + (int64_t)tt * 128 + pt;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int q = 4 * grp + j;
+            for (int j = 0; j < D::CPG; ++j) {
+                const int q = D::CPG * grp + j;
                 float v = 0.0f;
                 if (q < tp.in_dim && pp < n1) v = __ldg(x + pp * tp.in_dim + q);
                 xq[j] = (q == tp.in_dim) ? 1.0f : v;
@@ -420,12 +437,17 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
             yn = pp < n1 ? __ldg(y + pp) : 0.0f;
         };
         auto xstore = [&](int tt) {
-            uint32_t h0, l0, h1, l1;
-            qb_tg8_split(xq[0] * sx, xq[1] * sx, h0, l0);
-            qb_tg8_split(xq[2] * sx, xq[3] * sx, h1, l1);
+            uint32_t h[D::CPG / 2], l[D::CPG / 2];
+#pragma unroll
+            for (int j = 0; j < D::CPG / 2; ++j) qb_tg8_split(xq[2 * j] * sx, xq[2 * j + 1] * sx, h[j], l[j]);
             unsigned char* xi = x_row + (tt & 1) * 2 * QB_TG8_XIMG;
-            *reinterpret_cast<uint2*>(xi) = make_uint2(h0, h1);
-            *reinterpret_cast<uint2*>(xi + QB_TG8_XIMG) = make_uint2(l0, l1);
+            if constexpr (D::CPG == 4) {
+                *reinterpret_cast<uint2*>(xi) = make_uint2(h[0], h[1]);
+                *reinterpret_cast<uint2*>(xi + QB_TG8_XIMG) = make_uint2(l[0], l[1]);
+            } else {
+                *reinterpret_cast<uint4*>(xi) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(xi + QB_TG8_XIMG) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
         };
         // EPIL: R1 holds layer 0 of a tile (this thread's 32 columns) -> 2^14 tanh, packed, back into the same columns
         auto epil = [&]() {
@@ -433,7 +455,7 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
                 uint32_t v[16], o[16];
-                qb_tmem_ld16(tl + QB_TG8_C_D1 + c + 16 * hf, v);
+                qb_tmem_ld16(tl + D::C_D1 + c + 16 * hf, v);
                 qb_tmem_ld_wait16(v);
 #pragma unroll
                 for (int gq = 0; gq < 4; ++gq) {
@@ -443,7 +465,7 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
                     qb_tg8_split(z0.x, z0.y, o[2 * gq], o[8 + 2 * gq]);
                     qb_tg8_split(z1.x, z1.y, o[2 * gq + 1], o[8 + 2 * gq + 1]);
                 }
-                qb_tmem_st16(tl + QB_TG8_C_D1 + c + 16 * hf, o);
+                qb_tmem_st16(tl + D::C_D1 + c + 16 * hf, o);
             }
         };
 
@@ -457,7 +479,7 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
             qb_tc_fence_after();
             epil();
             qb_tmem_st_wait();
-            unpark(QB_TG8_C_D1, a_hi, a_lo);
+            unpark(D::C_D1, a_hi, a_lo);
             publish();
         }
 #pragma unroll 1
@@ -477,7 +499,7 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                     uint32_t v[16];
-                    qb_tmem_ld16(tl + QB_TG8_C_D1 + c + 16 * hf, v);
+                    qb_tmem_ld16(tl + D::C_D1 + c + 16 * hf, v);
                     qb_tmem_ld_wait16(v);
 #pragma unroll
                     for (int gq = 0; gq < 4; ++gq) {
@@ -490,15 +512,15 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
                         v[4 * gq] = __float_as_uint(z0.x); v[4 * gq + 1] = __float_as_uint(z0.y);
                         v[4 * gq + 2] = __float_as_uint(z1.x); v[4 * gq + 3] = __float_as_uint(z1.y);
                     }
-                    qb_tmem_st16(tl + QB_TG8_C_D1 + c + 16 * hf, v);           // a1 waits in the accumulator's columns
+                    qb_tmem_st16(tl + D::C_D1 + c + 16 * hf, v);           // a1 waits in the accumulator's columns
                 }
                 ybuf[grp * 128 + pt] = acc.x + acc.y;
                 qb_tmem_st_wait();
                 QB_TG8_STAMP(t, 2);
-                asm volatile("bar.sync %0, %1;" :: "r"(1 + quarter), "n"(128) : "memory");
+                asm volatile("bar.sync %0, %1;" :: "r"(1 + quarter), "n"(32 * G) : "memory");
                 float yo = F[tp.bl];
 #pragma unroll
-                for (int gg = 0; gg < 4; ++gg) yo += ybuf[gg * 128 + pt];
+                for (int gg = 0; gg < G; ++gg) yo += ybuf[gg * 128 + pt];
                 const float r = live ? yv - yo : 0.0f;
                 const float dy = r * is2, dyz = dy * sz1;
                 if (grp == 0) { ssq = fmaf(r, r, ssq); dbl += dy; }
@@ -508,7 +530,7 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                     uint32_t v[16];
-                    qb_tmem_ld16(tl + QB_TG8_C_D1 + c + 16 * hf, v);
+                    qb_tmem_ld16(tl + D::C_D1 + c + 16 * hf, v);
                     qb_tmem_ld_wait16(v);
 #pragma unroll
                     for (int jj = 0; jj < 2; ++jj) {
@@ -544,7 +566,7 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                     uint32_t v[16], o[16];
-                    qb_tmem_ld16(tl + QB_TG8_C_D0 + c + 16 * hf, v);
+                    qb_tmem_ld16(tl + D::C_D0 + c + 16 * hf, v);
                     qb_tmem_ld_wait16(v);
 #pragma unroll
                     for (int jj = 0; jj < 2; ++jj) {
@@ -561,7 +583,7 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
                             qb_tg8_split(z.x, z.y, o[4 * jj + w], o[8 + 4 * jj + w]);
                         }
                     }
-                    qb_tmem_st16(tl + QB_TG8_C_D0 + c + 16 * hf, o);      // the z image is still an operand of DW1(t)
+                    qb_tmem_st16(tl + D::C_D0 + c + 16 * hf, o);      // the z image is still an operand of DW1(t)
                 }
             }
             QB_TG8_STAMP(t, 6);
@@ -571,24 +593,28 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
             qb3_wait(bar_w, (uint32_t)t & 1u);                      // DW1(t) has read the z and a0 images
             qb_tc_fence_after();
             QB_TG8_STAMP(t, 8);
-            unpark(QB_TG8_C_D0, z_hi, z_lo);
-            if (more) unpark(QB_TG8_C_D1, a_hi, a_lo);
+            unpark(D::C_D0, z_hi, z_lo);
+            if (more) unpark(D::C_D1, a_hi, a_lo);
             publish();
             QB_TG8_STAMP(t, 9);
         }
         if (T > 0) { qb3_wait(bar_z, (uint32_t)(T - 1) & 1u); qb_tc_fence_after(); }
 
-        // ---------------- gradient out: row j (G1) / i (G0) = this thread's tensor-memory lane
+        // ---------------- gradient out: row j (G1) / i (G0).  An M = 128 accumulator keeps row m in lane m; an M = 64 one in
+        // lane (m % 16) + 32 (m / 16): the first 16 lanes of every warp quarter
         const int d = tp.in_dim;
         if (T > 0) {
             const float uw1 = F[tp.sc + QB_TG8_S_UW1], uw0 = F[tp.sc + QB_TG8_S_UW0];
+            const int row = H == 128 ? (int)pt : quarter * 16 + lane;
+            const bool rv = H == 128 || lane < 16;
             const bool al16 = (reinterpret_cast<uintptr_t>(g + tp.w1_off) & 15) == 0;
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
                 uint32_t v[16];
-                qb_tmem_ld16(tl + QB_TG8_C_DW1 + c + 16 * hf, v);
+                qb_tmem_ld16(tl + D::C_DW1 + c + 16 * hf, v);
                 qb_tmem_ld_wait16(v);
-                float* dst = g + tp.w1_off + pt * H + c + 16 * hf;
+                float* dst = g + tp.w1_off + row * H + c + 16 * hf;
+                if (!rv) continue;
                 if (al16) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
@@ -601,27 +627,29 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
             }
             if (grp == 0) {
                 uint32_t v[16];
-                qb_tmem_ld16(tl + QB_TG8_C_DW1 + 128, v);              // column 128: db1
+                qb_tmem_ld16(tl + D::C_DW1 + H, v);                    // column H: db1
                 qb_tmem_ld_wait16(v);
-                if (tp.b1_off >= 0) g[tp.b1_off + pt] = __uint_as_float(v[0]) * uw1;
-                qb_tmem_ld16(tl + QB_TG8_C_DW0, v);                    // columns < d: dW0, column d: db0
+                if (rv && tp.b1_off >= 0) g[tp.b1_off + row] = __uint_as_float(v[0]) * uw1;
+                qb_tmem_ld16(tl + D::C_DW0, v);                        // columns < d: dW0, column d: db0
                 qb_tmem_ld_wait16(v);
+                if (rv) {
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    if (q < d) g[tp.w0_off + pt * d + q] = __uint_as_float(v[q]) * uw0;
-                    else if (q == d && tp.b0_off >= 0) g[tp.b0_off + pt] = __uint_as_float(v[q]) * uw0;
+                    for (int q = 0; q < 16; ++q) {
+                        if (q < d) g[tp.w0_off + row * d + q] = __uint_as_float(v[q]) * uw0;
+                        else if (q == d && tp.b0_off >= 0) g[tp.b0_off + row] = __uint_as_float(v[q]) * uw0;
+                    }
                 }
             }
         }
     }
     if (T <= 0)
         for (int i = threadIdx.x; i < tp.n_params; i += blockDim.x) g[i] = 0.0f;
-    // dWl[j] = sum over the 128 point slots of the per-thread partial sums (fixed order); the z / X images are free now
+    // dWl[j] = sum over the 128 point slots of the per-thread partial sums (fixed order); the images are free now
     qb_tc_fence_before();
     __syncthreads();
     if (T > 0) {
-        float* scr = reinterpret_cast<float*>(smem + tp.z_img);            // [128][129] floats: runs into the X images
-        if (wid < QB_TG8_NCOMP / 32) {
+        float* scr = reinterpret_cast<float*>(smem + tp.a_img);            // [H][129] floats over the a0 / z / X images
+        if (wid < D::ISSUER) {
             const int pt = (wid & 3) * 32 + lane, c = (wid >> 2) * 32;
 #pragma unroll
             for (int e = 0; e < 32; ++e) scr[(c + e) * 129 + pt] = dwl[e];

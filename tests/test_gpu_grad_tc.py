@@ -1,6 +1,8 @@
-"""Tensor-core gradient path (quinn_b200/csrc/qb_tcg.cuh: forward, back-propagation and weight-gradient GEMMs on
-tcgen05, 3xTF32) against the fp64 oracle (manual reverse mode pinned to the reference's autograd by
-tests/test_oracle_golden.py) and against the CUDA-core kernel it replaces; HMC / MALA chains on it."""
+"""Tensor-core gradient paths against the fp64 oracle (manual reverse mode pinned to the reference's autograd by
+tests/test_oracle_golden.py) and against the CUDA-core kernel they replace; HMC / MALA chains on them.  Every test runs twice:
+   'tcg'  quinn_b200/csrc/qb_tcg.cuh  (3xTF32; widths 32 / 64, tanh / relu)       -- plan code 3
+   'tg8'  quinn_b200/csrc/qb_tg8.cuh  (3xFP16 with power-of-two scaling; tanh nets of width 64 / 128, the default there) -- plan code 4
+QB_TG8_64=0 sends the 64-wide tanh nets back to qb_tcg.cuh."""
 import os
 
 import numpy as np
@@ -15,6 +17,24 @@ pytestmark = pytest.mark.gpu
 
 TOL_LP = 1e-5        # relative (north_star: 1e-4 in fp32)
 TOL_G = 2e-5         # of the largest gradient entry (north_star: 1e-4)
+
+
+@pytest.fixture(autouse=True, params=['tg8', 'tcg'])
+def grad_path(request):
+    old = os.environ.get('QB_TG8_64')
+    os.environ['QB_TG8_64'] = '1' if request.param == 'tg8' else '0'
+    yield request.param
+    if old is None:
+        del os.environ['QB_TG8_64']
+    else:
+        os.environ['QB_TG8_64'] = old
+
+
+def plan_code(widths, act):
+    """Which tensor-core gradient kernel an eligible net takes under the current QB_TG8_64."""
+    if widths[1] in (64, 128) and act == 'tanh' and (widths[1] == 128 or os.environ.get('QB_TG8_64', '1') != '0'):
+        return 4
+    return 3
 
 
 class no_tcg:
@@ -72,7 +92,7 @@ def test_tc_gradient_matches_oracle(case):
     x, y = _data(rs, N, widths[0])
     th = (0.5 * rs.randn(K, P)).astype(np.float32).astype(np.float64)
     prob = ops.Problem(netdesc_from_layers(layers, P), x, y, 0.2, dtype=torch.float32)
-    assert prob.plan_info(K, True)['tensor_core'] == 3
+    assert prob.plan_info(K, True)['tensor_core'] == plan_code(widths, act)
     lp, g = ops.logpost_grad(prob, th)
     lp, g = lp.cpu().numpy(), g.double().cpu().numpy()
     idx = np.arange(K) if K <= 5 else np.array([0, K // 2, K - 1])
@@ -97,7 +117,7 @@ def test_tc_gradient_without_biases_and_with_prior():
             anchor = anchor.astype(np.float32).astype(np.float64)
             prob = ops.Problem(netdesc_from_layers(layers, P), x, y, 0.3, dtype=torch.float32, prior_sigma=0.7,
                                prior_anchor=anchor, fulldatasize=1200)
-            assert prob.plan_info(K, True)['tensor_core'] == 3
+            assert prob.plan_info(K, True)['tensor_core'] == plan_code([3, 64, 64, 1], 'tanh')
             lp, g = ops.logpost_grad(prob, th)
             _check(layers, P, x, y, th, 0.3, lp.cpu().numpy(), g.double().cpu().numpy(), prior=dict(sigma=0.7, anchor=anchor),
                    nfull=1200)
@@ -106,11 +126,13 @@ def test_tc_gradient_without_biases_and_with_prior():
 def test_tc_gradient_plan_eligibility():
     from quinn_b200 import ops
     rs = np.random.RandomState(1)
-    cases = [([3, 64, 64, 1], ['tanh', 'tanh', 'identity'], 3), ([2, 32, 32, 1], ['relu', 'relu', 'identity'], 3),
+    t64 = plan_code([3, 64, 64, 1], 'tanh')
+    cases = [([3, 64, 64, 1], ['tanh', 'tanh', 'identity'], t64), ([2, 32, 32, 1], ['relu', 'relu', 'identity'], 3),
+             ([3, 64, 64, 1], ['relu', 'relu', 'identity'], 3),          # relu: unbounded activations stay on the tf32 kernel
              ([3, 48, 48, 1], ['tanh', 'tanh', 'identity'], 0),          # width not 32 / 64
              ([3, 64, 32, 1], ['tanh', 'tanh', 'identity'], 0),          # unequal widths
              ([3, 64, 64, 2], ['tanh', 'tanh', 'identity'], 0),          # two outputs
-             ([8, 64, 64, 1], ['tanh', 'tanh', 'identity'], 0),          # more than 7 inputs
+             ([8, 64, 64, 1], ['tanh', 'tanh', 'identity'], 4 if t64 == 4 else 0),   # more than 7 inputs: only the fp16-split kernel
              ([3, 64, 64, 1], ['tanh', 'relu', 'identity'], 0),          # mixed activations
              ([3, 64, 64, 64, 1], ['tanh'] * 3 + ['identity'], 0),       # deeper
              ([10, 128, 128, 1], ['tanh', 'tanh', 'identity'], 4)]       # config 3 / 4 net: the 128-wide kernel (qb_tg8.cuh)
@@ -142,7 +164,7 @@ def test_tc_gradient_full_size_config5_and_config2():
         K = 200
         th = (rs.rand(K, P) if widths[1] == 64 else 0.1 * rs.randn(K, P)).astype(np.float32).astype(np.float64)
         prob = ops.Problem(netdesc_from_layers(layers, P), x.astype(np.float32), y.astype(np.float32), sigma, dtype=torch.float32)
-        assert prob.plan_info(K, True)['tensor_core'] == 3
+        assert prob.plan_info(K, True)['tensor_core'] == plan_code(widths, 'tanh')
         lp, g = ops.logpost_grad(prob, th)
         lp, g = lp.cpu().numpy(), g.double().cpu().numpy()
         xs, ys = x.astype(np.float32).astype(np.float64), y.astype(np.float32).astype(np.float64)
@@ -162,7 +184,7 @@ def test_tc_hmc_replay_matches_oracle_chain(method):
     mom = rs.randn(steps, K, P).astype(np.float32).astype(np.float64)
     u = rs.rand(steps, K)
     prob = ops.Problem(netdesc_from_layers(layers, P), x, y, sigma, dtype=torch.float32)
-    assert prob.plan_info(K, True)['tensor_core'] == 3
+    assert prob.plan_info(K, True)['tensor_core'] == plan_code([3, 64, 64, 1], 'tanh')
     st = ops.ChainState(prob, th0)
     rec = ops.Recorder(st, steps)
     hm = ops.HmcState(st, epsilon=eps, L=3, method=method)

@@ -42,7 +42,7 @@ def test_tc128_gradient_matches_oracle(case):
     th = (0.5 * rs.randn(K, P)).astype(np.float32).astype(np.float64)
     prob = ops.Problem(netdesc_from_layers(layers, P), x, y, 0.2, dtype=torch.float32)
     info = prob.plan_info(K, True)
-    assert info['tensor_core'] == 4 and info['threads'] == 544 and info['tmem_cols'] == 512
+    assert info['tensor_core'] == 4 and info['threads'] == 544 and info['tmem_cols'] == 512 and info['smem_bytes'] <= 227 * 1024
     lp, g = ops.logpost_grad(prob, th)
     lp, g = lp.cpu().numpy(), g.double().cpu().numpy()
     idx = np.arange(K) if K <= 5 else np.array([0, K // 2, K - 1])
@@ -167,3 +167,39 @@ def test_tc128_full_size_config4():
     lp, g = ops.logpost_grad(prob, th)
     lp, g = lp.cpu().numpy(), g.double().cpu().numpy()
     _check(layers, P, x.astype(np.float64), y.astype(np.float64), th[[K - 1]], sigma, lp[[K - 1]], g[[K - 1]])
+
+
+@pytest.mark.parametrize('method', ['hmc', 'mala'])
+def test_tc128_hmc_chain_at_width_128(method):
+    """HMC / MALA with the fused leapfrog on the 128-wide kernel (k_hmc_tc128), Philox momenta: the chains equal the CUDA-core
+    kernel's (decisions can only differ at fp32-noise ties) and recorded log-posteriors equal the oracle's at the stored states."""
+    from quinn_b200 import ops
+    rs = np.random.RandomState(77)
+    layers, P = make_net([10, 128, 128, 1], ACTS)
+    N, K, steps, sigma = 600, 6, 12, 0.3
+    x, y = _data(rs, N, 10)
+    th0 = 0.1 * rs.randn(K, P)
+    prob = ops.Problem(netdesc_from_layers(layers, P), x, y, sigma, dtype=torch.float32)
+    assert prob.plan_info(K, True)['tensor_core'] == 4
+
+    def run():
+        st = ops.ChainState(prob, th0)
+        rec = ops.Recorder(st, steps, store_every=1)
+        ops.hmc_run(st, ops.HmcState(st, epsilon=2e-4, L=3, method=method), steps, rec, seed=23)
+        return st, rec
+
+    st, rec = run()
+    with no_tcg():
+        st2, rec2 = run()
+    a1, a2 = rec.accepted.cpu().numpy().astype(bool), rec2.accepted.cpu().numpy().astype(bool)
+    assert (a1 != a2).mean() < 0.05
+    assert 0.05 < a1.mean() <= 1.0
+    same = (a1 == a2).all(axis=1)
+    assert same.any()
+    np.testing.assert_allclose(rec.logpost.cpu().numpy()[same], rec2.logpost.cpu().numpy()[same], rtol=5e-4)
+    lps = rec.logpost.cpu().numpy()
+    samples = rec.samples.double().cpu().numpy()
+    for k in (0, K - 1):
+        for s in (0, steps - 1):
+            ref = qo.logpost(layers, samples[k, s], x, y, sigma)
+            assert abs(lps[k, s] - ref) <= 1e-5 * abs(ref)

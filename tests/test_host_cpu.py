@@ -135,8 +135,14 @@ def test_tensor_core_plan_selection_is_host_logic():
     c2 = info('mlp_c2', _lib.QB_F32)
     assert c2[6] == 2 and c2[7] == 128
     assert info('mlp_c5', _lib.QB_F64)[6] == 0                  # fp64 stays on the CUDA cores
-    g5 = info('mlp_c5', _lib.QB_F32, grad=1)                    # gradient path: tcgen05 kernel 2 (qb_tcg.cuh)
-    assert g5[6] == 3 and g5[1] == 512 and g5[7] == 512 and g5[2] <= 227 * 1024
+    g5 = info('mlp_c5', _lib.QB_F32, grad=1)                    # gradient path: tcgen05 kernel 2, fp16-split operands (qb_tg8.cuh)
+    assert g5[6] == 4 and g5[1] == 288 and g5[7] == 256 and g5[2] <= 113 * 1024
+    os.environ['QB_TG8_64'] = '0'
+    try:
+        g5 = info('mlp_c5', _lib.QB_F32, grad=1)                # ... or the 3xTF32 kernel (qb_tcg.cuh)
+        assert g5[6] == 3 and g5[1] == 512 and g5[7] == 512 and g5[2] <= 227 * 1024
+    finally:
+        del os.environ['QB_TG8_64']
     g2 = info('mlp_c2', _lib.QB_F32, grad=1)
     assert g2[6] == 3 and g2[1] == 256 and g2[7] == 256
     g3 = info('mlp_c3', _lib.QB_F32, grad=1)                    # 128-wide: fp16-split kernel 2 (qb_tg8.cuh)
