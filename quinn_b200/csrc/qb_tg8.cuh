@@ -34,10 +34,11 @@
 //
 // Pipeline (two block-wide hand-overs per tile, as in qb_tcg.cuh); tensor memory: R1 = columns [0,128), R0 = [128,256),
 // G1 = [256,400), G0 = [400,416):
-//   phase B(t): wait FWD(t) -> EPI1(t) from R1 (a1 waits in R1 across the reduction of y over the four thread groups)
+//   phase B(t): wait FWD(t) -> EPI1(t) from R1 (a1 waits in R1 across the reduction of y over the thread groups)
 //               -> [wait DW0(t-1)] X(t+1) -> X image, z1 -> z image                     => issue L0(t+1) -> R1, BWD(t) -> R0, DW1(t)
-//   phase A(t): wait BWD(t) -> EPI0(t): R0 -> z0, packed, back into R0; EPIL(t+1): R1 -> a0(t+1), packed, back into R1 (DW1(t)
-//               still reads both images) -> wait DW1(t) -> R0 -> z image, R1 -> a0 image   => issue FWD(t+1) -> R1, DW0(t)
+//   phase A(t): wait L0(t+1) -> EPIL(t+1): R1 -> a0(t+1), packed, back into R1 (under BWD(t)); wait BWD(t) -> EPI0(t): R0 -> z0,
+//               packed, back into R0 (under DW1(t), which still reads both images) -> wait DW1(t) -> R1 -> a0 image  => issue FWD(t+1)
+//               -> R0 -> z image                                                                                     => issue DW0(t)
 //   DW0(t) runs under EPI1(t+1).
 #pragma once
 #include <stdint.h>
@@ -48,7 +49,7 @@
 
 
 #ifdef __CUDACC__
-enum { QB_TG8_BAR_F = 400, QB_TG8_BAR_B = 408, QB_TG8_BAR_W = 416, QB_TG8_BAR_Z = 424, QB_TG8_BAR_RDY = 432, QB_TG8_SLOT = 440, QB_TG8_BAR_L = 448,
+enum { QB_TG8_BAR_F = 400, QB_TG8_BAR_B = 408, QB_TG8_BAR_W = 416, QB_TG8_BAR_Z = 424, QB_TG8_BAR_RDY = 432, QB_TG8_SLOT = 440, QB_TG8_BAR_L = 448, QB_TG8_BAR_RDY2 = 456,
        QB_TG8_HDR = 512, QB_TG8_XIMG = 4096 };
 // Hidden width H (128: configs 3 / 4, one block per SM; 64: config 5, two blocks per SM): G = H/32 thread groups of 128 compute
 // threads (thread = point x 32 units), the issue warp comes after them.  Images of 128 points x H units; tensor-memory
@@ -91,6 +92,7 @@ __device__ __forceinline__ uint32_t qb_tg8_init(const QbTg8Plan& tp, unsigned ch
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB_TG8_BAR_Z), "r"(1u) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB_TG8_BAR_RDY), "r"((uint32_t)D::NCOMP) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB_TG8_BAR_L), "r"(1u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB_TG8_BAR_RDY2), "r"((uint32_t)D::NCOMP) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     qb_tc_fence_before();
@@ -109,15 +111,26 @@ template <int H>
 __device__ __forceinline__ void qb_tg8_reset_barriers(unsigned char* smem) {
     using D = QbTg8Dim<H>;
     const uint32_t b = qb_smem_u32(smem);
-    const uint32_t off[6] = {QB_TG8_BAR_F, QB_TG8_BAR_B, QB_TG8_BAR_W, QB_TG8_BAR_Z, QB_TG8_BAR_RDY, QB_TG8_BAR_L};
+    const uint32_t off[7] = {QB_TG8_BAR_F, QB_TG8_BAR_B, QB_TG8_BAR_W, QB_TG8_BAR_Z, QB_TG8_BAR_RDY, QB_TG8_BAR_L, QB_TG8_BAR_RDY2};
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
+    for (int i = 0; i < 7; ++i) {
         asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"(b + off[i]) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + off[i]), "r"(i == 4 ? (uint32_t)D::NCOMP : 1u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + off[i]), "r"((i == 4 || i == 6) ? (uint32_t)D::NCOMP : 1u) : "memory");
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 
+// bounded polling wait (no suspend hint): traps after ~2^28 polls instead of hanging
+__device__ __forceinline__ void qb_tg8_spin(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
+    for (int it = 0; it < (1 << 28); ++it) {
+        uint32_t ok;
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
 __device__ __forceinline__ void qb_tg8_st4(uint32_t taddr, const uint32_t (&v)[4]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
 }
@@ -301,16 +314,16 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
     const float* F = reinterpret_cast<const float*>(smem + tp.fl_base);
     const uint32_t sb = qb_smem_u32(smem);
     const uint32_t bar_f = sb + QB_TG8_BAR_F, bar_b = sb + QB_TG8_BAR_B, bar_w = sb + QB_TG8_BAR_W, bar_z = sb + QB_TG8_BAR_Z,
-                   bar_rdy = sb + QB_TG8_BAR_RDY, bar_l = sb + QB_TG8_BAR_L;
+                   bar_rdy = sb + QB_TG8_BAR_RDY, bar_l = sb + QB_TG8_BAR_L, bar_rdy2 = sb + QB_TG8_BAR_RDY2;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = (int)((n1 - n0 + 127) / 128);
     __syncthreads();                               // staging complete; nobody is still inside the previous evaluation
     if (threadIdx.x == 0) qb_tg8_reset_barriers<H>(smem);
     __syncthreads();
     float ssq = 0.0f, dbl = 0.0f;
-    float dwl[32];
+    float2 dwl2[16];                               // output-layer weight gradient of this thread's 32 units, over its points
 #pragma unroll
-    for (int i = 0; i < 32; ++i) dwl[i] = 0.0f;
+    for (int i = 0; i < 16; ++i) dwl2[i] = make_float2(0.0f, 0.0f);
 
     if (wid == D::ISSUER) {
         // ================================ issue warp ================================
@@ -332,10 +345,20 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
         const uint32_t wK_hi = qb_tg8_dlo(w_img, 128u), wK_lo = qb_tg8_dlo(w_img + D::WIMG, 128u);
         const uint32_t wM_hi = qb_tg8_dlo(w_img, (uint32_t)D::WSBO), wM_lo = qb_tg8_dlo(w_img + D::WIMG, (uint32_t)D::WSBO);
         const uint32_t w0_hi = qb_tg8_dlo(w0_img, 128u), w0_lo = qb_tg8_dlo(w0_img + D::W0IMG, 128u), dh_w0 = qb_tg8_dhi(256u);
-        uint32_t n = 0;
+        // Hand-overs from the compute threads.  Two arrivals of one thread on the same mbarrier must be separated by a wait that
+        // depends on the issue warp having seen the first one (else a fast thread's second arrival completes the phase while a slow
+        // thread has not arrived once): the second hand-over of phase A follows the first without such a wait and has its own barrier.
+        // The issue warp polls without a suspend hint: every hand-over is on the critical path of the tile loop.
+        uint32_t n = 0, n2 = 0;
         auto wait_rdy = [&]() {
-            qb3_wait(bar_rdy, n & 1u);
+            qb_tg8_spin(bar_rdy, n & 1u);
             ++n;
+            qb_tc_fence_after();
+            __syncwarp();
+        };
+        auto wait_rdy2 = [&]() {
+            qb_tg8_spin(bar_rdy2, n2 & 1u);
+            ++n2;
             qb_tc_fence_after();
             __syncwarp();
         };
@@ -362,7 +385,7 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
             wait_rdy();                                                   // z1(t) is in the z image, X(t+1) in the X image; R1 is free
             QB_TG8_STAMP(t, 0);
             if (qb3_elect()) {
-                if (t + 1 < T) issue_l0(t + 1);
+                if (t + 1 < T) { issue_l0(t + 1); qb3_commit(bar_l); }
                 qb_tg8_issue3<KS>(tmem + D::C_D0, zK_hi, zK_lo, dh_a, 256u, wM_hi, wM_lo, dh_a, (uint32_t)(2 * D::WSBO) >> 4, id_bwd, id_bwd, 0u);
                 qb3_commit(bar_b);
                 qb_tg8_issue3<8>(tmem + D::C_DW1, zM_hi, zM_lo, dh_b, 16u, aM_hi, aM_lo, dh_b, 16u, id_dw1, id_dw1n, acc0);
@@ -370,13 +393,17 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
             }
             __syncwarp();
             QB_TG8_STAMP(t, 1);
-            wait_rdy();                                                   // z0(t) is in the z image, a0(t+1) in the a0 image
-            QB_TG8_STAMP(t, 2);
-            if (qb3_elect()) {
-                if (t + 1 < T) {
+            if (t + 1 < T) {
+                wait_rdy();                                               // a0(t+1) is in the a0 image, R1 is free
+                if (qb3_elect()) {
                     qb_tg8_issue3<KS>(tmem + D::C_D1, aK_hi, aK_lo, dh_a, 256u, wK_hi, wK_lo, dh_w, 16u, id_fwd, id_fwd, 0u);
                     qb3_commit(bar_f);
                 }
+                __syncwarp();
+            }
+            wait_rdy2();                                                  // z0(t) is in the z image
+            QB_TG8_STAMP(t, 2);
+            if (qb3_elect()) {
                 const uint32_t x_img = sb + (uint32_t)tp.x_img + (uint32_t)(t & 1) * 2u * QB_TG8_XIMG;
                 qb_tg8_issue3<8>(tmem + D::C_DW0, zM_hi, zM_lo, dh_b, 16u, qb_tg8_dlo(x_img, 128u), qb_tg8_dlo(x_img + QB_TG8_XIMG, 128u),
                                  dh_b, 16u, id_dw0, id_dw0, acc0);
@@ -403,10 +430,10 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
         const float4* B4 = reinterpret_cast<const float4*>(F + tp.b1 + c);
         const float4* W4 = reinterpret_cast<const float4*>(F + tp.wl + c);
 
-        auto publish = [&]() {
+        auto publish = [&](uint32_t bar) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             qb_tc_fence_before();
-            qb_mbar_arrive(bar_rdy);
+            qb_mbar_arrive(bar);
         };
         // this thread's 32 columns of region `col` hold packed results: per half of 16 columns, 8 hi words then 8 lo words
         // (units 16 hf .. 16 hf + 15).  Copy them into the images.
@@ -474,13 +501,13 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
             fetch(0);
             yv = yn;
             xstore(0);
-            publish();
+            publish(bar_rdy);
             qb3_wait(bar_l, 0u);
             qb_tc_fence_after();
             epil();
             qb_tmem_st_wait();
             unpark(D::C_D1, a_hi, a_lo);
-            publish();
+            publish(bar_rdy);
         }
 #pragma unroll 1
         for (int t = 0; t < T; ++t) {
@@ -523,6 +550,7 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
                 for (int gg = 0; gg < G; ++gg) yo += ybuf[gg * 128 + pt];
                 const float r = live ? yv - yo : 0.0f;
                 const float dy = r * is2, dyz = dy * sz1;
+                const float2 dy2 = make_float2(dy, dy), dyz2 = make_float2(dyz, dyz), one2 = make_float2(1.0f, 1.0f);
                 if (grp == 0) { ssq = fmaf(r, r, ssq); dbl += dy; }
                 if (t > 0) { qb3_wait(bar_z, (uint32_t)(t - 1) & 1u); qb_tc_fence_after(); }     // DW0(t-1) has read the z and X images
                 QB_TG8_STAMP(t, 3);
@@ -539,16 +567,14 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
                         for (int g2 = 0; g2 < 2; ++g2) {
                             const int gq = 2 * jj + g2;
                             const float4 w = W4[4 * hf + gq];
-                            const float wv[4] = {w.x, w.y, w.z, w.w};
-                            float z[4];
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float a = __uint_as_float(v[4 * gq + e]);
-                                z[e] = dyz * wv[e] * fmaf(-a, a, 1.0f);
-                                dwl[16 * hf + 4 * gq + e] = fmaf(dy, a, dwl[16 * hf + 4 * gq + e]);
-                            }
-                            qb_tg8_split(z[0], z[1], h[2 * g2], l[2 * g2]);
-                            qb_tg8_split(z[2], z[3], h[2 * g2 + 1], l[2 * g2 + 1]);
+                            const float2 a01 = make_float2(__uint_as_float(v[4 * gq]), __uint_as_float(v[4 * gq + 1]));
+                            const float2 a23 = make_float2(__uint_as_float(v[4 * gq + 2]), __uint_as_float(v[4 * gq + 3]));
+                            const float2 z01 = __fmul2_rn(__fmul2_rn(make_float2(w.x, w.y), dyz2), __ffma2_rn(make_float2(-a01.x, -a01.y), a01, one2));
+                            const float2 z23 = __fmul2_rn(__fmul2_rn(make_float2(w.z, w.w), dyz2), __ffma2_rn(make_float2(-a23.x, -a23.y), a23, one2));
+                            dwl2[8 * hf + 2 * gq] = __ffma2_rn(dy2, a01, dwl2[8 * hf + 2 * gq]);
+                            dwl2[8 * hf + 2 * gq + 1] = __ffma2_rn(dy2, a23, dwl2[8 * hf + 2 * gq + 1]);
+                            qb_tg8_split(z01.x, z01.y, h[2 * g2], l[2 * g2]);
+                            qb_tg8_split(z23.x, z23.y, h[2 * g2 + 1], l[2 * g2 + 1]);
                         }
                         *reinterpret_cast<uint4*>(z_hi + 2048 * (2 * hf + jj)) = make_uint4(h[0], h[1], h[2], h[3]);
                         *reinterpret_cast<uint4*>(z_lo + 2048 * (2 * hf + jj)) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -556,11 +582,19 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
                 }
             }
             QB_TG8_STAMP(t, 4);
-            publish();
-            // ---------------- phase A: EPI0(t) and EPIL(t+1) while DW1(t) runs; results stay in tensor memory until DW1(t) is done
+            publish(bar_rdy);
+            // ---------------- phase A: EPIL(t+1) while BWD(t) runs, EPI0(t) while DW1(t) runs; results stay in tensor memory until
+            // DW1(t) has read the images
+            if (more) {
+                qb3_wait(bar_l, (uint32_t)(t + 1) & 1u);               // layer 0 of tile t+1 is in R1 (issued ahead of BWD(t))
+                qb_tc_fence_after();
+                epil();
+                yv = yn;
+            }
+            QB_TG8_STAMP(t, 5);
             qb3_wait(bar_b, (uint32_t)t & 1u);
             qb_tc_fence_after();
-            QB_TG8_STAMP(t, 5);
+            QB_TG8_STAMP(t, 6);
             {
                 const float2 k2 = make_float2(k0, k0), sa = make_float2(6.103515625e-05f, 6.103515625e-05f), one = make_float2(1.0f, 1.0f);
 #pragma unroll
@@ -586,16 +620,17 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
                     qb_tmem_st16(tl + D::C_D0 + c + 16 * hf, o);      // the z image is still an operand of DW1(t)
                 }
             }
-            QB_TG8_STAMP(t, 6);
-            if (more) { epil(); yv = yn; }
             qb_tmem_st_wait();
             QB_TG8_STAMP(t, 7);
             qb3_wait(bar_w, (uint32_t)t & 1u);                      // DW1(t) has read the z and a0 images
             qb_tc_fence_after();
             QB_TG8_STAMP(t, 8);
+            if (more) {
+                unpark(D::C_D1, a_hi, a_lo);
+                publish(bar_rdy);                                    // => FWD(t+1)
+            }
             unpark(D::C_D0, z_hi, z_lo);
-            if (more) unpark(D::C_D1, a_hi, a_lo);
-            publish();
+            publish(bar_rdy2);                                       // => DW0(t)
             QB_TG8_STAMP(t, 9);
         }
         if (T > 0) { qb3_wait(bar_z, (uint32_t)(T - 1) & 1u); qb_tc_fence_after(); }
@@ -652,7 +687,7 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
         if (wid < D::ISSUER) {
             const int pt = (wid & 3) * 32 + lane, c = (wid >> 2) * 32;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) scr[(c + e) * 129 + pt] = dwl[e];
+            for (int e = 0; e < 16; ++e) { scr[(c + 2 * e) * 129 + pt] = dwl2[e].x; scr[(c + 2 * e + 1) * 129 + pt] = dwl2[e].y; }
         }
         __syncthreads();
         if (threadIdx.x < H) {

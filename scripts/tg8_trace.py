@@ -41,12 +41,12 @@ for b in (0, 1):
         e = buf[b, w]
         per = (e[u + 1, 0] - e[u, 0]).mean()
         d = [(e[u, i + 1] - e[u, i]).mean() for i in range(9)]
-        print(f'  warp {w:2d}: period {per:7.0f} | wait f {d[0]:6.0f} | EPI1a {d[1]:5.0f} sync+zf {d[2]:5.0f} EPI1b {d[3]:5.0f} | pub+wait b {d[4]:6.0f} | EPI0 {d[5]:5.0f} '
-              f'L0 {d[6]:5.0f} | wait w {d[7]:6.0f} | unpark {d[8]:5.0f}')
+        print(f'  warp {w:2d}: period {per:7.0f} | wait f {d[0]:6.0f} | EPI1a {d[1]:5.0f} sync+zf {d[2]:5.0f} EPI1b {d[3]:5.0f} | pub, wait l, EPIL {d[4]:6.0f} | '
+              f'wait b {d[5]:5.0f} EPI0 {d[6]:5.0f} | wait w {d[7]:6.0f} | unpark + pub {d[8]:5.0f}')
     e = buf[b, 16]
     print(f'  issuer : period {(e[u + 1, 0] - e[u, 0]).mean():7.0f} | issue BWD+DW1 {(e[u, 1] - e[u, 0]).mean():5.0f} wait rdy(A) {(e[u, 2] - e[u, 1]).mean():6.0f} '
           f'issue FWD+DW0 {(e[u, 3] - e[u, 2]).mean():5.0f} wait rdy(B) {(e[u + 1, 0] - e[u, 3]).mean():6.0f}')
     # tensor-pipe view: from the issuer's stamps to the first warp that sees each barrier
     w0 = buf[b, 0]
-    print(f'  FWD+DW0 issue start -> warp0 sees f(t+1): {(w0[u + 1, 1] - e[u, 2]).mean():6.0f};  BWD issue start -> warp0 sees b: {(w0[u, 5] - e[u, 0]).mean():6.0f};'
+    print(f'  FWD+DW0 issue start -> warp0 sees f(t+1): {(w0[u + 1, 1] - e[u, 2]).mean():6.0f};  BWD issue start -> warp0 sees b: {(w0[u, 6] - e[u, 0]).mean():6.0f};'
           f'  -> sees w: {(w0[u, 8] - e[u, 0]).mean():6.0f}')
