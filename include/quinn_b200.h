@@ -258,12 +258,15 @@ int qb_fma_peak(int dtype, int variant, int64_t iters, double* flops_out_host, v
 
 /* Launch-plan introspection for DESIGN.md / bench.py: fills out[0..7] =
  * {tile points TM, threads per block, dynamic smem bytes, N-splits S, blocks, inplace flag,
- *  tensor-core path (0: CUDA-core kernel, 1: tcgen05 3xTF32, 2: same, software-pipelined, 3: tcgen05 gradient kernel),
- *  tensor-memory columns}.
+ *  tensor-core path (0: CUDA-core kernel, 1: tcgen05 3xTF32, 2: same, software-pipelined, 3: tcgen05 gradient kernel (3xTF32),
+ *  4: tcgen05 gradient kernel with fp16-split operands), tensor-memory columns}.
  * The tensor-core VALUE path (qb_logpost, qb_amcmc_run, qb_predict) serves fp32 MLPs with <= 15 inputs, hidden widths
  * that are multiples of 16 (<= 128), <= 4 outputs and no residual layers; the tensor-core GRADIENT path
- * (qb_logpost_grad, qb_logpost_members, qb_hmc_run) serves fp32 MLPs in(<= 7) -> H -> H -> 1 with H = 32 or 64 and
- * tanh / relu hidden layers.  QB_NO_TC=1 disables both, QB_NO_TCG=1 only the gradient path. */
+ * (qb_logpost_grad, qb_logpost_members, qb_hmc_run) serves fp32 MLPs in -> H -> H -> 1: tanh nets with H = 64 or 128 and
+ * <= 15 inputs (code 4: 3xFP16; its operand scales come from max|x|, max|y| of the call, found by a small kernel ahead of
+ * the evaluation in 256 bytes that qb_eval_workspace_bytes adds to the workspace), tanh / relu nets with H = 32 or 64 and
+ * <= 7 inputs (code 3).  QB_NO_TC=1 disables both paths, QB_NO_TCG=1 only the gradient path, QB_NO_TG8=1 only code 4,
+ * QB_TG8_64=0 keeps the 64-wide tanh nets on code 3. */
 int qb_plan_info(const qb_net_t* net, int dtype, int64_t K, int64_t N, int want_grad, int64_t* out);
 
 /* ---- device-side post-processing of chains / ensembles -------------------------------------

@@ -65,7 +65,7 @@ enum { QB_TG8_S_C1 = 0, QB_TG8_S_SZ1 = 1, QB_TG8_S_K0 = 2, QB_TG8_S_UW1 = 3, QB_
 
 // Development aid (-DQB_TG8_TRACE, scripts/tg8_trace.py): SM-clock stamps of the phases of every warp of the first blocks.
 #ifdef QB_TG8_TRACE
-enum { QB_TG8_TR_BLOCKS = 8, QB_TG8_TR_WARPS = 17, QB_TG8_TR_TILES = 48, QB_TG8_TR_EV = 10 };
+enum { QB_TG8_TR_BLOCKS = 8, QB_TG8_TR_WARPS = 17, QB_TG8_TR_TILES = 48, QB_TG8_TR_EV = 12 };
 __device__ unsigned int qb_tg8_trace_buf[QB_TG8_TR_BLOCKS * QB_TG8_TR_WARPS * QB_TG8_TR_TILES * QB_TG8_TR_EV];
 #define QB_TG8_STAMP(tile, ev) do { if ((threadIdx.x & 31) == 0 && blockIdx.x < QB_TG8_TR_BLOCKS && blockIdx.y == 0 && (tile) < QB_TG8_TR_TILES) \
     qb_tg8_trace_buf[((blockIdx.x * QB_TG8_TR_WARPS + (threadIdx.x >> 5)) * QB_TG8_TR_TILES + (tile)) * QB_TG8_TR_EV + (ev)] = (unsigned int)clock64(); } while (0)
@@ -588,6 +588,7 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
             if (more) {
                 qb3_wait(bar_l, (uint32_t)(t + 1) & 1u);               // layer 0 of tile t+1 is in R1 (issued ahead of BWD(t))
                 qb_tc_fence_after();
+                QB_TG8_STAMP(t, 10);
                 epil();
                 yv = yn;
             }

@@ -29,7 +29,7 @@ for _ in range(3):
     ops.logpost_grad(prob, th, lp, g)
 torch.cuda.synchronize()
 lib = _lib.load()
-NB, NW, NT, NE = 8, 17, 48, 10
+NB, NW, NT, NE = 8, 17, 48, 12
 buf = np.zeros(NB * NW * NT * NE, dtype=np.uint32)
 lib.qb_tg8_trace_dump.restype = C.c_int
 assert lib.qb_tg8_trace_dump(buf.ctypes.data_as(C.c_void_p)) == 0
@@ -42,7 +42,7 @@ for b in (0, 1):
         per = (e[u + 1, 0] - e[u, 0]).mean()
         d = [(e[u, i + 1] - e[u, i]).mean() for i in range(9)]
         print(f'  warp {w:2d}: period {per:7.0f} | wait f {d[0]:6.0f} | EPI1a {d[1]:5.0f} sync+zf {d[2]:5.0f} EPI1b {d[3]:5.0f} | pub, wait l, EPIL {d[4]:6.0f} | '
-              f'wait b {d[5]:5.0f} EPI0 {d[6]:5.0f} | wait w {d[7]:6.0f} | unpark + pub {d[8]:5.0f}')
+              f'(wait l {(e[u, 10] - e[u, 4]).mean():5.0f}) wait b {d[5]:5.0f} EPI0 {d[6]:5.0f} | wait w {d[7]:6.0f} | unpark + pub {d[8]:5.0f}')
     e = buf[b, 16]
     print(f'  issuer : period {(e[u + 1, 0] - e[u, 0]).mean():7.0f} | issue BWD+DW1 {(e[u, 1] - e[u, 0]).mean():5.0f} wait rdy(A) {(e[u, 2] - e[u, 1]).mean():6.0f} '
           f'issue FWD+DW0 {(e[u, 3] - e[u, 2]).mean():5.0f} wait rdy(B) {(e[u + 1, 0] - e[u, 3]).mean():6.0f}')
