@@ -185,13 +185,31 @@ __device__ __forceinline__ void qb_tg8_stage(const QbTg8Plan& tp, unsigned char*
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
     const float fold = 2.8853900817779268f;
     float mx = 0.0f, cs = 0.0f, wa = 0.0f, m0 = 0.0f;
-    for (int e = tid; e < H * H; e += nt) mx = fmaxf(mx, fabsf(theta[tp.w1_off + e]));
+    {
+        // one coalesced sweep over W1: warps take rows, lanes take columns lane + 32 q; maximum and per-warp column sums of |W1|
+        // (the z image is free during staging: scratch [warps][H])
+        const int nw = nt >> 5;
+        float csum[H / 32];
+#pragma unroll
+        for (int q = 0; q < H / 32; ++q) csum[q] = 0.0f;
+        for (int j = wid; j < H; j += nw) {
+#pragma unroll
+            for (int q = 0; q < H / 32; ++q) {
+                const float w = fabsf(theta[tp.w1_off + j * H + lane + 32 * q]);
+                mx = fmaxf(mx, w);
+                csum[q] += w;
+            }
+        }
+        float* cscr = reinterpret_cast<float*>(smem + tp.z_img);
+#pragma unroll
+        for (int q = 0; q < H / 32; ++q) cscr[wid * H + lane + 32 * q] = csum[q];
+        __syncthreads();
+        if (tid < H)
+            for (int w = 0; w < nw; ++w) cs += cscr[w * H + tid];
+    }
     for (int e = tid; e < H * tp.in_dim; e += nt) m0 = fmaxf(m0, fabsf(theta[tp.w0_off + e]));
     if (tid < H && tp.b0_off >= 0) m0 = fmaxf(m0, fabsf(theta[tp.b0_off + tid]));
-    if (tid < H) {
-        for (int j = 0; j < H; ++j) cs += fabsf(theta[tp.w1_off + j * H + tid]);
-        wa = fabsf(theta[tp.wl_off + tid]);
-    }
+    if (tid < H) wa = fabsf(theta[tp.wl_off + tid]);
     float ws = wa;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
