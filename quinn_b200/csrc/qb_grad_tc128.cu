@@ -5,6 +5,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "quinn_b200.h"
 #include "qb_plan.h"
@@ -28,11 +31,12 @@ bool qb_tg8_make_plan(const qb_net_t* net, int dtype, QbTg8Plan* tp) {
     const qb_layer_t& L2 = net->layers[2];
     if (L0.res_step != 0.0 || L1.res_step != 0.0 || L2.res_step != 0.0) return false;
     if (L0.n_terms > 1 || L1.n_terms > 1 || L2.n_terms > 1) return false;
-    const int H = L0.n_out;
-    if ((H != 128 && H != 64) || L1.n_out != H) return false;
-    if (H == 64 && !tg8_env_int("QB_TG8_64", 1)) return false;
+    const int HR = L0.n_out;
+    if ((HR != 128 && HR != 64 && HR != 32) || L1.n_out != HR) return false;
+    if (HR <= 64 && !tg8_env_int("QB_TG8_64", 1)) return false;
+    const int H = HR == 32 ? 64 : HR;                        // 32-wide nets: zero-padded units on the 64-wide instance
     if (L0.act != QB_ACT_TANH || L1.act != QB_ACT_TANH || L2.act != QB_ACT_IDENTITY) return false;
-    tp->in_dim = net->in_dim; tp->n_params = net->n_params; tp->h = H;
+    tp->in_dim = net->in_dim; tp->n_params = net->n_params; tp->h = H; tp->hr = HR;
     tp->w0_off = L0.w_off; tp->b0_off = L0.b_off; tp->w1_off = L1.w_off; tp->b1_off = L1.b_off;
     tp->wl_off = L2.w_off; tp->bl_off = L2.b_off;
     const int img = 256 * H;
@@ -152,14 +156,25 @@ cudaError_t qb_tg8_launch_eval(const QbTg8Plan& tp, const EvalArgs<float>& a, vo
     return launch_eval_t<128>(tp, a, (const float*)scratch, grid, st);
 }
 
+// 256 bytes of device memory per (device, stream) for max |x|, max |y| of a chain launch: allocated on first use and kept (a
+// stream-ordered allocation per launch went back to the OS at every synchronisation and cost more than a 1024-chain step)
+static void* tg8_stream_scratch(cudaStream_t st) {
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, void*> pool;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    void*& p = pool[std::make_pair(dev, st)];
+    if (!p && cudaMalloc(&p, QB_TG8_SCRATCH_BYTES) != cudaSuccess) p = nullptr;
+    return p;
+}
+
 cudaError_t qb_tg8_launch_hmc(const QbTg8Plan& tp, const ChainArgs<float>& c, const HmcArgs<float>& h, long long K, cudaStream_t st) {
-    void* scratch = nullptr;
-    cudaError_t e = cudaMallocAsync(&scratch, QB_TG8_SCRATCH_BYTES, st);
+    void* scratch = tg8_stream_scratch(st);
+    if (!scratch) return cudaErrorMemoryAllocation;
+    cudaError_t e = tg8_absmax(c.x, c.N * tp.in_dim, c.y, c.N, scratch, st);
     if (e != cudaSuccess) return e;
-    e = tg8_absmax(c.x, c.N * tp.in_dim, c.y, c.N, scratch, st);
-    if (e == cudaSuccess) e = tp.h == 64 ? launch_hmc_t<64>(tp, c, h, K, (const float*)scratch, st) : launch_hmc_t<128>(tp, c, h, K, (const float*)scratch, st);
-    const cudaError_t e2 = cudaFreeAsync(scratch, st);
-    return e != cudaSuccess ? e : e2;
+    return tp.h == 64 ? launch_hmc_t<64>(tp, c, h, K, (const float*)scratch, st) : launch_hmc_t<128>(tp, c, h, K, (const float*)scratch, st);
 }
 
 #ifdef QB_TG8_TRACE

@@ -12,6 +12,6 @@ template <typename T> struct HmcArgs;
 bool qb_tg8_make_plan(const qb_net_t* net, int dtype, QbTg8Plan* tp);
 // scratch: 8 bytes of device memory (max |x|, max |y| of the launch), written by a small kernel ahead of the evaluation
 cudaError_t qb_tg8_launch_eval(const QbTg8Plan& tp, const EvalArgs<float>& a, void* scratch, dim3 grid, cudaStream_t st);
-// HMC / MALA chains on the same evaluation (the scratch words are allocated and freed in stream order)
+// HMC / MALA chains on the same evaluation (the scratch words live in a small per-(device, stream) buffer kept by the library)
 cudaError_t qb_tg8_launch_hmc(const QbTg8Plan& tp, const ChainArgs<float>& c, const HmcArgs<float>& h, long long K, cudaStream_t st);
 enum { QB_TG8_SCRATCH_BYTES = 256 };

@@ -183,6 +183,7 @@ __device__ __forceinline__ void qb_tg8_stage(const QbTg8Plan& tp, unsigned char*
     float* F = reinterpret_cast<float*>(smem + tp.fl_base);
     float* sred = reinterpret_cast<float*>(smem);                      // [17][4] + [17]
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const int hr = tp.hr;                      // the net's own width (32-wide nets run zero-padded on the 64-wide kernel)
     const float fold = 2.8853900817779268f;
     float mx = 0.0f, cs = 0.0f, wa = 0.0f, m0 = 0.0f;
     {
@@ -192,10 +193,10 @@ __device__ __forceinline__ void qb_tg8_stage(const QbTg8Plan& tp, unsigned char*
         float csum[H / 32];
 #pragma unroll
         for (int q = 0; q < H / 32; ++q) csum[q] = 0.0f;
-        for (int j = wid; j < H; j += nw) {
+        for (int j = wid; j < hr; j += nw) {
 #pragma unroll
             for (int q = 0; q < H / 32; ++q) {
-                const float w = fabsf(theta[tp.w1_off + j * H + lane + 32 * q]);
+                const float w = lane + 32 * q < hr ? fabsf(theta[tp.w1_off + j * hr + lane + 32 * q]) : 0.0f;
                 mx = fmaxf(mx, w);
                 csum[q] += w;
             }
@@ -207,9 +208,9 @@ __device__ __forceinline__ void qb_tg8_stage(const QbTg8Plan& tp, unsigned char*
         if (tid < H)
             for (int w = 0; w < nw; ++w) cs += cscr[w * H + tid];
     }
-    for (int e = tid; e < H * tp.in_dim; e += nt) m0 = fmaxf(m0, fabsf(theta[tp.w0_off + e]));
-    if (tid < H && tp.b0_off >= 0) m0 = fmaxf(m0, fabsf(theta[tp.b0_off + tid]));
-    if (tid < H) wa = fabsf(theta[tp.wl_off + tid]);
+    for (int e = tid; e < hr * tp.in_dim; e += nt) m0 = fmaxf(m0, fabsf(theta[tp.w0_off + e]));
+    if (tid < hr && tp.b0_off >= 0) m0 = fmaxf(m0, fabsf(theta[tp.b0_off + tid]));
+    if (tid < hr) wa = fabsf(theta[tp.wl_off + tid]);
     float ws = wa;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -248,6 +249,7 @@ __device__ __forceinline__ void qb_tg8_stage(const QbTg8Plan& tp, unsigned char*
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 v[u] = 0.0f;
+                if (i >= hr) continue;
                 if (q + u < tp.in_dim) v[u] = theta[tp.w0_off + i * tp.in_dim + q + u] * sc0;
                 else if (q + u == tp.in_dim && tp.b0_off >= 0) v[u] = theta[tp.b0_off + i] * sc0;
             }
@@ -263,7 +265,8 @@ __device__ __forceinline__ void qb_tg8_stage(const QbTg8Plan& tp, unsigned char*
         uint32_t* lo = hi + D::WIMG / 4;
         for (int e = tid; e < H * H / 2; e += nt) {
             const int j = e / (H / 2), i = (e % (H / 2)) * 2;
-            const float w0 = theta[tp.w1_off + j * H + i], w1 = theta[tp.w1_off + j * H + i + 1];
+            const bool real = j < hr && i < hr;
+            const float w0 = real ? theta[tp.w1_off + j * hr + i] : 0.0f, w1 = real ? theta[tp.w1_off + j * hr + i + 1] : 0.0f;
             uint32_t h2, l2;
             qb_tg8_split(w0 * wscale, w1 * wscale, h2, l2);
             const int idx = (((j >> 3) * (H / 8) + (i >> 3)) * 64 + (j & 7) * 8 + (i & 7)) >> 1;
@@ -277,8 +280,8 @@ __device__ __forceinline__ void qb_tg8_stage(const QbTg8Plan& tp, unsigned char*
             hi[e] = (e < 512 && (e & 3) == 0) ? 0x00007400u : 0u;      // chunk 16: word 0 of every point's 16-byte row = (2^14, 0)
     }
     for (int j = tid; j < H; j += nt) {
-        F[tp.b1 + j] = tp.b1_off >= 0 ? theta[tp.b1_off + j] * fold : 0.0f;
-        F[tp.wl + j] = theta[tp.wl_off + j];
+        F[tp.b1 + j] = (tp.b1_off >= 0 && j < hr) ? theta[tp.b1_off + j] * fold : 0.0f;
+        F[tp.wl + j] = j < hr ? theta[tp.wl_off + j] : 0.0f;
     }
     if (tid == 0) {
         F[tp.bl] = blv;
@@ -659,16 +662,17 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
         const int d = tp.in_dim;
         if (T > 0) {
             const float uw1 = F[tp.sc + QB_TG8_S_UW1], uw0 = F[tp.sc + QB_TG8_S_UW0];
+            const int hr = tp.hr;
             const int row = H == 128 ? (int)pt : quarter * 16 + lane;
-            const bool rv = H == 128 || lane < 16;
+            const bool rv = (H == 128 || lane < 16) && row < hr;
             const bool al16 = (reinterpret_cast<uintptr_t>(g + tp.w1_off) & 15) == 0;
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
                 uint32_t v[16];
                 qb_tmem_ld16(tl + D::C_DW1 + c + 16 * hf, v);
                 qb_tmem_ld_wait16(v);
-                float* dst = g + tp.w1_off + row * H + c + 16 * hf;
-                if (!rv) continue;
+                float* dst = g + tp.w1_off + row * hr + c + 16 * hf;
+                if (!rv || c + 16 * hf >= hr) continue;
                 if (al16) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
@@ -702,21 +706,40 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
     qb_tc_fence_before();
     __syncthreads();
     if (T > 0) {
-        float* scr = reinterpret_cast<float*>(smem + tp.a_img);            // [H][129] floats over the a0 / z / X images
+        float* scr = reinterpret_cast<float*>(smem + tp.a_img);            // [H][132] floats over the a0 / z / X images
         if (wid < D::ISSUER) {
             const int pt = (wid & 3) * 32 + lane, c = (wid >> 2) * 32;
 #pragma unroll
-            for (int e = 0; e < 16; ++e) { scr[(c + 2 * e) * 129 + pt] = dwl2[e].x; scr[(c + 2 * e + 1) * 129 + pt] = dwl2[e].y; }
+            for (int e = 0; e < 16; ++e) { scr[(c + 2 * e) * 132 + pt] = dwl2[e].x; scr[(c + 2 * e + 1) * 132 + pt] = dwl2[e].y; }
         }
         __syncthreads();
-        if (threadIdx.x < H) {
+        // four threads per unit, each sums every fourth point slot (row stride 132: the 32 lanes of a warp hit 32 banks), then the
+        // four meet through shuffles
+        if (threadIdx.x < 4 * H) {
+            const int u = threadIdx.x >> 2, part = threadIdx.x & 3;
             float s = 0.0f;
-            for (int q = 0; q < 128; ++q) s += scr[threadIdx.x * 129 + q];
-            g[tp.wl_off + threadIdx.x] = s;
+#pragma unroll 8
+            for (int q = 0; q < 32; ++q) s += scr[u * 132 + 4 * q + part];
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (part == 0 && u < tp.hr) g[tp.wl_off + u] = s;
         }
     }
-    const double sbl = qb_block_sum((double)dbl, reinterpret_cast<double*>(smem));
-    if (threadIdx.x == 0 && tp.bl_off >= 0) g[tp.bl_off] = (float)sbl;
-    return qb_block_sum((double)ssq, reinterpret_cast<double*>(smem));
+    // block-wide sums of the squared residuals and of dy (= the output bias gradient) in one pass
+    double* red = reinterpret_cast<double*>(smem);                         // 2 x 17 doubles + 2
+    double v0 = (double)ssq, v1 = (double)dbl;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, off); v1 += __shfl_xor_sync(0xffffffffu, v1, off); }
+    __syncthreads();
+    if (lane == 0) { red[2 * wid] = v0; red[2 * wid + 1] = v1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int w = 0; w < (int)(blockDim.x + 31) >> 5; ++w) { s0 += red[2 * w]; s1 += red[2 * w + 1]; }
+        red[34] = s0;
+        if (tp.bl_off >= 0) g[tp.bl_off] = (float)s1;
+    }
+    __syncthreads();
+    return red[34];
 }
 #endif  // __CUDACC__

@@ -1,8 +1,9 @@
 """Tensor-core gradient paths against the fp64 oracle (manual reverse mode pinned to the reference's autograd by
 tests/test_oracle_golden.py) and against the CUDA-core kernel they replace; HMC / MALA chains on them.  Every test runs twice:
    'tcg'  quinn_b200/csrc/qb_tcg.cuh  (3xTF32; widths 32 / 64, tanh / relu)       -- plan code 3
-   'tg8'  quinn_b200/csrc/qb_tg8.cuh  (3xFP16 with power-of-two scaling; tanh nets of width 64 / 128, the default there) -- plan code 4
-QB_TG8_64=0 sends the 64-wide tanh nets back to qb_tcg.cuh."""
+   'tg8'  quinn_b200/csrc/qb_tg8.cuh  (3xFP16 with power-of-two scaling; tanh nets of width 32 (zero-padded to 64) / 64 / 128, the default
+          there) -- plan code 4
+QB_TG8_64=0 sends the 32- and 64-wide tanh nets back to qb_tcg.cuh."""
 import os
 
 import numpy as np
@@ -32,7 +33,7 @@ def grad_path(request):
 
 def plan_code(widths, act):
     """Which tensor-core gradient kernel an eligible net takes under the current QB_TG8_64."""
-    if widths[1] in (64, 128) and act == 'tanh' and (widths[1] == 128 or os.environ.get('QB_TG8_64', '1') != '0'):
+    if widths[1] in (32, 64, 128) and act == 'tanh' and (widths[1] == 128 or os.environ.get('QB_TG8_64', '1') != '0'):
         return 4
     return 3
 

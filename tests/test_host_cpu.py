@@ -141,10 +141,12 @@ def test_tensor_core_plan_selection_is_host_logic():
     try:
         g5 = info('mlp_c5', _lib.QB_F32, grad=1)                # ... or the 3xTF32 kernel (qb_tcg.cuh)
         assert g5[6] == 3 and g5[1] == 512 and g5[7] == 512 and g5[2] <= 227 * 1024
+        g2 = info('mlp_c2', _lib.QB_F32, grad=1)
+        assert g2[6] == 3 and g2[1] == 256 and g2[7] == 256
     finally:
         del os.environ['QB_TG8_64']
-    g2 = info('mlp_c2', _lib.QB_F32, grad=1)
-    assert g2[6] == 3 and g2[1] == 256 and g2[7] == 256
+    g2 = info('mlp_c2', _lib.QB_F32, grad=1)                    # 32-wide tanh net: zero-padded on the 64-wide fp16-split kernel
+    assert g2[6] == 4 and g2[1] == 288 and g2[7] == 256
     g3 = info('mlp_c3', _lib.QB_F32, grad=1)                    # 128-wide: fp16-split kernel 2 (qb_tg8.cuh)
     assert g3[6] == 4 and g3[1] == 544 and g3[7] == 512 and g3[2] <= 227 * 1024
     assert info('mlp_c5', _lib.QB_F64, grad=1)[6] == 0
