@@ -459,15 +459,17 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
         // this thread's 32 columns of region `col` hold packed results: per half of 16 columns, 8 hi words then 8 lo words
         // (units 16 hf .. 16 hf + 15).  Copy them into the images.
         auto unpark = [&](uint32_t col, unsigned char* hi, unsigned char* lo) {
+            uint32_t v[2][16];
+            qb_tmem_ld16(tl + col + c, v[0]);                  // both halves in flight before the first store
+            qb_tmem_ld16(tl + col + c + 16, v[1]);
+            qb_tmem_ld_wait16(v[0]);
+            qb_tmem_ld_wait16(v[1]);
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
-                uint32_t v[16];
-                qb_tmem_ld16(tl + col + c + 16 * hf, v);
-                qb_tmem_ld_wait16(v);
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj) {
-                    *reinterpret_cast<uint4*>(hi + 2048 * (2 * hf + jj)) = make_uint4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
-                    *reinterpret_cast<uint4*>(lo + 2048 * (2 * hf + jj)) = make_uint4(v[8 + 4 * jj], v[9 + 4 * jj], v[10 + 4 * jj], v[11 + 4 * jj]);
+                    *reinterpret_cast<uint4*>(hi + 2048 * (2 * hf + jj)) = make_uint4(v[hf][4 * jj], v[hf][4 * jj + 1], v[hf][4 * jj + 2], v[hf][4 * jj + 3]);
+                    *reinterpret_cast<uint4*>(lo + 2048 * (2 * hf + jj)) = make_uint4(v[hf][8 + 4 * jj], v[hf][9 + 4 * jj], v[hf][10 + 4 * jj], v[hf][11 + 4 * jj]);
                 }
             }
         };
@@ -563,9 +565,9 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
                     qb_tmem_st16(tl + D::C_D1 + c + 16 * hf, v);           // a1 waits in the accumulator's columns
                 }
                 ybuf[grp * 128 + pt] = acc.x + acc.y;
-                qb_tmem_st_wait();
                 QB_TG8_STAMP(t, 2);
                 asm volatile("bar.sync %0, %1;" :: "r"(1 + quarter), "n"(32 * G) : "memory");
+                qb_tmem_st_wait();                                     // the stash is read back below
                 float yo = F[tp.bl];
 #pragma unroll
                 for (int gg = 0; gg < G; ++gg) yo += ybuf[gg * 128 + pt];
