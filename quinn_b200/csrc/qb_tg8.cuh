@@ -259,18 +259,19 @@ __device__ __forceinline__ void qb_tg8_stage(const QbTg8Plan& tp, unsigned char*
             hi[idx] = h2; lo[idx] = l2;
         }
     }
-    // ---- W image: word index of the pair (j, i), (j, i + 1)
+    // ---- W image: one 128-byte core matrix (8 rows j x 8 columns i) per warp and step, lane = (row, column pair): the 32 words
+    // of a core matrix are contiguous, so the stores are conflict-free
     {
         uint32_t* hi = reinterpret_cast<uint32_t*>(smem + tp.w_img);
         uint32_t* lo = hi + D::WIMG / 4;
-        for (int e = tid; e < H * H / 2; e += nt) {
-            const int j = e / (H / 2), i = (e % (H / 2)) * 2;
+        const int nw = nt >> 5;
+        for (int cm = wid; cm < (H / 8) * (H / 8); cm += nw) {
+            const int j = (cm / (H / 8)) * 8 + (lane >> 2), i = (cm % (H / 8)) * 8 + 2 * (lane & 3);
             const bool real = j < hr && i < hr;
             const float w0 = real ? theta[tp.w1_off + j * hr + i] : 0.0f, w1 = real ? theta[tp.w1_off + j * hr + i + 1] : 0.0f;
             uint32_t h2, l2;
             qb_tg8_split(w0 * wscale, w1 * wscale, h2, l2);
-            const int idx = (((j >> 3) * (H / 8) + (i >> 3)) * 64 + (j & 7) * 8 + (i & 7)) >> 1;
-            hi[idx] = h2; lo[idx] = l2;
+            hi[cm * 32 + lane] = h2; lo[cm * 32 + lane] = l2;
         }
     }
     // ---- ones block of the a0 hi image (the lo image has none: its pass of DW1 runs with N = 128)
