@@ -562,7 +562,7 @@ def run_native(spec, args, steps, warmup, rank, world, local, headline):
             kname = ('k_hmc_tc128' if spec['sampler'] == 'hmc' else 'k_logpost_grad_tc128') + \
                     '<%d> (layer 0, forward, back-propagation and both weight-gradient GEMMs on tcgen05.mma kind::f16 x3 passes, fp16 hi/lo ' \
                     'operands with exact power-of-two scaling, one shared-memory image per matrix for its K-major and MN-major use, ' \
-                    'dedicated issue warp)' % int(spec['hls'][0])
+                    'dedicated issue warp%s)' % (max(64, int(spec['hls'][0])), '; the 32-wide net runs with zero-padded units' if int(spec['hls'][0]) == 32 else '')
         roofline = dict(bound='tensor', kernel=kname, achieved=achieved / 1e12, peak=peak_bf16, unit='TFLOP/s',
                         frac=achieved / 1e12 / peak_bf16, traffic=traffic, peak_source=src,
                         tf32_peak=peak_bf16 / 2.0, frac_of_tf32_peak=achieved / 1e12 / (peak_bf16 / 2.0),
