@@ -204,3 +204,60 @@ def test_tc128_hmc_chain_at_width_128(method):
         for s in (0, steps - 1):
             ref = qo.logpost(layers, samples[k, s], x, y, sigma)
             assert abs(lps[k, s] - ref) <= 1e-5 * abs(ref)
+
+
+def test_tc128_bnet_viloss_fp32_against_the_oracle():
+    """BNet.viloss (bnet.py:181-232) in the fp32 throughput mode on the config-4 net: the nsam weight samples go through the
+    128-wide tensor-core kernel 2; loss and d/d(mu, rho) against the oracle's restatement with the same draws."""
+    from quinn_b200.nns import MLP
+    from quinn_b200.vi import BNet
+    rs = np.random.RandomState(12)
+    torch.manual_seed(0)
+    layers, P = qo.mlp_layers(10, 1, (128, 128), True, 'tanh')
+    m = MLP(10, 1, (128, 128), activ='tanh')
+    b = BNet(m, pi=0.5, sigma1=1.0, sigma2=0.1).float()
+    mu = (0.2 * rs.randn(P)).astype(np.float32)
+    rho = rs.uniform(-5.0, -4.0, size=P).astype(np.float32)
+    off = 0
+    with torch.no_grad():
+        for i in range(b.nparams):
+            n = b.params[2 * i].numel()
+            b.params[2 * i].copy_(torch.as_tensor(mu[off:off + n]).view_as(b.params[2 * i]))
+            b.params[2 * i + 1].copy_(torch.as_tensor(rho[off:off + n]).view_as(b.params[2 * i + 1]))
+            off += n
+    N, nsam, datanoise, num_batches = 700, 5, 0.2, 3
+    x = (rs.rand(N, 10) * 2 - 1).astype(np.float32)
+    y = (np.sin(x.sum(1, keepdims=True)) + 0.1 * rs.randn(N, 1)).astype(np.float32)
+    eps = rs.randn(nsam, P).astype(np.float32)
+    b.loss_params = [datanoise, nsam, num_batches]
+    assert b.params[0].dtype == torch.float32
+    loss = b.viloss(torch.as_tensor(x, device='cuda'), torch.as_tensor(y, device='cuda'), eps=eps)
+    loss.backward()
+    gmu = np.concatenate([b.params[2 * i].grad.double().cpu().numpy().ravel() for i in range(b.nparams)])
+    grho = np.concatenate([b.params[2 * i + 1].grad.double().cpu().numpy().ravel() for i in range(b.nparams)])
+    rl, rgmu, rgrho = qo.vi_loss(layers, mu.astype(np.float64), rho.astype(np.float64), eps.astype(np.float64), x.astype(np.float64),
+                                 y.astype(np.float64), datanoise, num_batches, pi=0.5, sigma1=1.0, sigma2=0.1, want_grad=True)
+    assert abs(loss.item() - rl) <= 1e-4 * abs(rl), (loss.item(), rl)
+    assert np.abs(gmu - rgmu).max() <= 1e-4 * np.abs(rgmu).max()
+    assert np.abs(grho - rgrho).max() <= 1e-4 * np.abs(rgrho).max()
+
+
+def test_tc128_ensemble_training_fp32_follows_fp64():
+    """Batched ensemble training of the config-3 net: a few Adam epochs in fp32 (kernel 2 = the 128-wide
+    tensor-core kernel, per-member data) follow the fp64 run (CUDA-core kernels) to fp32 accuracy."""
+    from quinn_b200.ens.batched import fit_members
+    rs = np.random.RandomState(3)
+    layers, P = qo.mlp_layers(10, 1, (128, 128), True, 'tanh')
+    desc = netdesc_from_layers(layers, P)
+    N, K = 400, 5
+    x = rs.rand(N, 10)
+    y = np.sin(x.sum(1, keepdims=True))
+    th0 = rs.uniform(-0.1, 0.1, size=(K, P))
+    subsets = np.stack([rs.permutation(N)[:320] for _ in range(K)])
+    res = {}
+    for dt in (torch.float64, torch.float32):
+        res[dt] = fit_members(desc, th0, x, y, subsets, val=(x, y), nepochs=6, lrate=0.002, dtype=dt, verbose=False)
+    h64, h32 = res[torch.float64]['history'].cpu().numpy(), res[torch.float32]['history'].cpu().numpy()
+    assert h64.shape == (6, K) and np.isfinite(h32).all()
+    np.testing.assert_allclose(h32, h64, rtol=2e-3)
+    assert (h64[-1] < h64[0]).all()
