@@ -34,8 +34,9 @@
 //
 // Pipeline (two block-wide hand-overs per tile, as in qb_tcg.cuh); tensor memory: R1 = columns [0,128), R0 = [128,256),
 // G1 = [256,400), G0 = [400,416):
-//   phase B(t): wait FWD(t) -> EPI1(t) from R1 (a1 waits in R1 across the reduction of y over the thread groups)
-//               -> [wait DW0(t-1)] X(t+1) -> X image, z1 -> z image                     => issue L0(t+1) -> R1, BWD(t) -> R0, DW1(t)
+//   phase B(t): wait FWD(t) -> EPI1(t), first pass from R1 (a1 waits in R0 across the reduction of y over the thread groups)
+//               -> [wait DW0(t-1)] X(t+1) -> X image                                     => issue L0(t+1) -> R1
+//               -> second pass: z1 -> z image                                            => issue BWD(t) -> R0, DW1(t)
 //   phase A(t): wait L0(t+1) -> EPIL(t+1): R1 -> a0(t+1), packed, back into R1 (under BWD(t)); wait BWD(t) -> EPI0(t): R0 -> z0,
 //               packed, back into R0 (under DW1(t), which still reads both images) -> wait DW1(t) -> R1 -> a0 image  => issue FWD(t+1)
 //               -> R0 -> z image                                                                                     => issue DW0(t)
@@ -49,7 +50,7 @@
 
 
 #ifdef __CUDACC__
-enum { QB_TG8_BAR_F = 400, QB_TG8_BAR_B = 408, QB_TG8_BAR_W = 416, QB_TG8_BAR_Z = 424, QB_TG8_BAR_RDY = 432, QB_TG8_SLOT = 440, QB_TG8_BAR_L = 448, QB_TG8_BAR_RDY2 = 456,
+enum { QB_TG8_BAR_F = 400, QB_TG8_BAR_B = 408, QB_TG8_BAR_W = 416, QB_TG8_BAR_Z = 424, QB_TG8_BAR_RDY = 432, QB_TG8_SLOT = 440, QB_TG8_BAR_L = 448, QB_TG8_BAR_RDY2 = 456, QB_TG8_BAR_RDY3 = 464,
        QB_TG8_HDR = 512, QB_TG8_XIMG = 4096 };
 // Hidden width H (128: configs 3 / 4, one block per SM; 64: config 5, two blocks per SM): G = H/32 thread groups of 128 compute
 // threads (thread = point x 32 units), the issue warp comes after them.  Images of 128 points x H units; tensor-memory
@@ -93,6 +94,7 @@ __device__ __forceinline__ uint32_t qb_tg8_init(const QbTg8Plan& tp, unsigned ch
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB_TG8_BAR_RDY), "r"((uint32_t)D::NCOMP) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB_TG8_BAR_L), "r"(1u) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB_TG8_BAR_RDY2), "r"((uint32_t)D::NCOMP) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + QB_TG8_BAR_RDY3), "r"((uint32_t)D::NCOMP) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     qb_tc_fence_before();
@@ -111,11 +113,11 @@ template <int H>
 __device__ __forceinline__ void qb_tg8_reset_barriers(unsigned char* smem) {
     using D = QbTg8Dim<H>;
     const uint32_t b = qb_smem_u32(smem);
-    const uint32_t off[7] = {QB_TG8_BAR_F, QB_TG8_BAR_B, QB_TG8_BAR_W, QB_TG8_BAR_Z, QB_TG8_BAR_RDY, QB_TG8_BAR_L, QB_TG8_BAR_RDY2};
+    const uint32_t off[8] = {QB_TG8_BAR_F, QB_TG8_BAR_B, QB_TG8_BAR_W, QB_TG8_BAR_Z, QB_TG8_BAR_RDY, QB_TG8_BAR_L, QB_TG8_BAR_RDY2, QB_TG8_BAR_RDY3};
 #pragma unroll
-    for (int i = 0; i < 7; ++i) {
+    for (int i = 0; i < 8; ++i) {
         asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"(b + off[i]) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + off[i]), "r"((i == 4 || i == 6) ? (uint32_t)D::NCOMP : 1u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(b + off[i]), "r"((i == 4 || i >= 6) ? (uint32_t)D::NCOMP : 1u) : "memory");
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -336,7 +338,7 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
     const float* F = reinterpret_cast<const float*>(smem + tp.fl_base);
     const uint32_t sb = qb_smem_u32(smem);
     const uint32_t bar_f = sb + QB_TG8_BAR_F, bar_b = sb + QB_TG8_BAR_B, bar_w = sb + QB_TG8_BAR_W, bar_z = sb + QB_TG8_BAR_Z,
-                   bar_rdy = sb + QB_TG8_BAR_RDY, bar_l = sb + QB_TG8_BAR_L, bar_rdy2 = sb + QB_TG8_BAR_RDY2;
+                   bar_rdy = sb + QB_TG8_BAR_RDY, bar_l = sb + QB_TG8_BAR_L, bar_rdy2 = sb + QB_TG8_BAR_RDY2, bar_rdy3 = sb + QB_TG8_BAR_RDY3;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = (int)((n1 - n0 + 127) / 128);
     __syncthreads();                               // staging complete; nobody is still inside the previous evaluation
@@ -371,10 +373,16 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
         // depends on the issue warp having seen the first one (else a fast thread's second arrival completes the phase while a slow
         // thread has not arrived once): the second hand-over of phase A follows the first without such a wait and has its own barrier.
         // The issue warp polls without a suspend hint: every hand-over is on the critical path of the tile loop.
-        uint32_t n = 0, n2 = 0;
+        uint32_t n = 0, n2 = 0, n3 = 0;
         auto wait_rdy = [&]() {
             qb_tg8_spin(bar_rdy, n & 1u);
             ++n;
+            qb_tc_fence_after();
+            __syncwarp();
+        };
+        auto wait_rdy3 = [&]() {
+            qb_tg8_spin(bar_rdy3, n3 & 1u);
+            ++n3;
             qb_tc_fence_after();
             __syncwarp();
         };
@@ -404,10 +412,14 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
 #pragma unroll 1
         for (int t = 0; t < T; ++t) {
             const uint32_t acc0 = t > 0 ? 1u : 0u;
-            wait_rdy();                                                   // z1(t) is in the z image, X(t+1) in the X image; R1 is free
+            if (t + 1 < T) {
+                wait_rdy3();                                              // X(t+1) is in the X image, R1 has been read (EPI1(t), first pass)
+                if (qb3_elect()) { issue_l0(t + 1); qb3_commit(bar_l); }
+                __syncwarp();
+            }
+            wait_rdy();                                                   // z1(t) is in the z image; R0 is free
             QB_TG8_STAMP(t, 0);
             if (qb3_elect()) {
-                if (t + 1 < T) { issue_l0(t + 1); qb3_commit(bar_l); }
                 qb_tg8_issue3<KS>(tmem + D::C_D0, zK_hi, zK_lo, dh_a, 256u, wM_hi, wM_lo, dh_a, (uint32_t)(2 * D::WSBO) >> 4, id_bwd, id_bwd, 0u);
                 qb3_commit(bar_b);
                 qb_tg8_issue3<8>(tmem + D::C_DW1, zM_hi, zM_lo, dh_b, 16u, aM_hi, aM_lo, dh_b, 16u, id_dw1, id_dw1n, acc0);
@@ -563,7 +575,7 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
                         v[4 * gq] = __float_as_uint(z0.x); v[4 * gq + 1] = __float_as_uint(z0.y);
                         v[4 * gq + 2] = __float_as_uint(z1.x); v[4 * gq + 3] = __float_as_uint(z1.y);
                     }
-                    qb_tmem_st16(tl + D::C_D1 + c + 16 * hf, v);           // a1 waits in the accumulator's columns
+                    qb_tmem_st16(tl + D::C_D0 + c + 16 * hf, v);           // a1 waits in R0 (free until BWD(t)); R1 is released below
                 }
                 ybuf[grp * 128 + pt] = acc.x + acc.y;
                 QB_TG8_STAMP(t, 2);
@@ -578,11 +590,14 @@ __device__ __forceinline__ double qb_tg8_eval(const QbTg8Plan& tp, uint32_t tmem
                 if (grp == 0) { ssq = fmaf(r, r, ssq); dbl += dy; }
                 if (t > 0) { qb3_wait(bar_z, (uint32_t)(t - 1) & 1u); qb_tc_fence_after(); }     // DW0(t-1) has read the z and X images
                 QB_TG8_STAMP(t, 3);
-                if (more) xstore(t + 1);
+                if (more) {
+                    xstore(t + 1);
+                    publish(bar_rdy3);                                 // => L0(t+1) into R1, under the second pass
+                }
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                     uint32_t v[16];
-                    qb_tmem_ld16(tl + D::C_D1 + c + 16 * hf, v);
+                    qb_tmem_ld16(tl + D::C_D0 + c + 16 * hf, v);
                     qb_tmem_ld_wait16(v);
 #pragma unroll
                     for (int jj = 0; jj < 2; ++jj) {
