@@ -629,8 +629,10 @@ def measured_traffic(spec, tc, units):
     """DRAM bytes (read + write) of the dominant kernel for `units` chain-steps / member-points, from the committed
     `ncu --set full` capture of this build (profiles/r2_traffic.json: bytes per unit per kernel), or None."""
     path = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
-    key = {'amcmc': 'k_amcmc_tc3' if tc else 'k_amcmc', 'hmc': 'k_hmc_tc' if tc else 'k_hmc',
+    key = {'amcmc': 'k_amcmc_tc3' if tc else 'k_amcmc', 'hmc': ('k_hmc_tc128' if tc == 4 else 'k_hmc_tc') if tc else 'k_hmc',
            'predict': 'k_predict_tc' if tc else 'k_predict'}.get(spec['sampler'])
+    if key == 'k_hmc_tc128' and int(spec['hls'][0]) != 64:
+        return None                               # the committed capture is the 3-64-64-1 shape (config 5 / c5h)
     try:
         with open(path) as f:
             per_unit = json.load(f)[key]['dram_bytes_per_unit']
