@@ -1,6 +1,15 @@
-import os, sys
-import numpy as np, torch
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/scripts')
+"""Development check of the 64-wide fp16-split gradient kernel with one and two blocks per SM (the hand-over race of
+profiles/README.md showed up here as non-finite gradient rows in the second resident block).
+   python scripts/dbg64.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'scripts'))
 from gpu_probe import mlp_desc
 from quinn_b200 import ops
 def run(K, N, split=None, d=3):
